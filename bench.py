@@ -1,0 +1,324 @@
+#!/usr/bin/env python
+"""bench.py -- the driver-facing benchmark of the fluid-step hot path.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl b200|reference]
+
+A "step" is one timestep of the reference driver loop (main.cpp:236-239): simulate_fluid_step
+(advect, n_diffuse smoothing sweeps, divergence, n_pressure Jacobi sweeps, gradient subtraction)
+followed by advect_color_step.  Metric (BASELINE.json): pressure cell-updates per second,
+    value = W * H * n_pressure / (seconds per WHOLE timestep)
+i.e. the pressure-iteration rate the whole step sustains (every other phase counts against it).
+The pressure solve alone and every phase are reported beside it (`phases`, `pressure_solve`).
+
+Workloads:
+  N = 1 : BASELINE.json configs[2] -- synthetic 4096x4096 grid and image, 100 + 100 sweeps.
+  N > 1 : configs[3] family -- 16384 columns x (2048 * N) rows, row slabs of 16384 x 2048 per GPU
+          (N = 8 is the 16384^2 grid); weak scaling, halo rows exchanged between neighbours.
+Inputs are far larger than L2 (256 MiB per buffer vs 126 MB), so no explicit flush is needed.
+
+Prints ONE JSON line (rank 0).  See the task contract for the keys; `roofline` describes the
+dominant kernel (largest share of the step), `cpu_baseline` the reference's own fluid.cpp compiled
+from /root/reference (oracle/_ref) timed on one host core on a bounded sample.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+METRIC = "cell-updates/s per pressure iter"
+UNIT = "cell-updates/s"
+DT, VISC = 0.1, 0.001
+
+# algorithmic bytes per cell (SURVEY.md 8d / DESIGN.md): compulsory planar traffic, no credit for
+# temporal blocking
+BYTES = {"advect": 16, "diffuse_sweep": 16, "divergence": 12, "pressure_sweep": 12, "project": 20, "advect_color": 40}
+
+
+def measured_peak_gbs():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        try:
+            return float(json.load(open(p))["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+        except Exception:
+            pass
+    return 6650.0, "fallback (B200_PROFILING.md 6.65 TB/s)"
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled every 200 ms during the timed region."""
+
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index: int):
+        self.index = index
+        self.rows = []
+        self.proc = None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), f"--query-gpu={self.Q}",
+                                          "--format=csv,noheader,nounits", "-lms", "200"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.thread = threading.Thread(target=self._read, daemon=True)
+            self.thread.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([x.strip() for x in line.split(",")])
+
+    def stop(self):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.25)
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=5)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for r in self.rows:
+            try:
+                sm.append(float(r[0])); mx.append(float(r[1]))
+                for n, v in zip(names, r[3:7]):
+                    if v.lower().startswith("active"):
+                        reasons.add(n)
+            except Exception:
+                continue
+        sm.sort()
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def make_inputs(h: int, w: int, rank: int = 0):
+    """Synthetic inputs of the named shape (smooth coherent flow + seeded noise, seeded image)."""
+    import numpy as np
+    from probabilistic_fluid_simulation_b200 import fixtures
+    vel = fixtures.smooth_velocity_bytes(h, w)
+    rng = np.random.default_rng(1234 + rank)
+    vel[..., :2] = np.clip(vel[..., :2].astype(np.int16) + rng.integers(-6, 7, size=(h, w, 2)), 0, 255).astype(np.uint8)
+    img = fixtures.random_image_bytes(h, w, 4321 + rank)
+    return fixtures.make_state(vel, img)
+
+
+# --------------------------------------------------------------------------------------------
+# reference arm / cpu baseline: the reference's own fluid.cpp (oracle/_ref) on one host core
+# --------------------------------------------------------------------------------------------
+def cpu_reference_rate(n_iters: int, w: int, sample_rows: int, steps: int, warmup: int):
+    """Times `steps` timesteps of the unmodified reference on a w x sample_rows grid (same dt,
+    viscosity, sweep counts as the GPU workload).  -> (cell-updates/s, ms per step, kind)."""
+    import oracle
+    kind = "reference"
+    if oracle.Reference.available(n_iters):
+        impl = oracle.Reference(n_iters)
+    else:                                   # compiled reference did not travel: use the C port
+        impl = oracle.Oracle(n_iters)
+        kind = "port"
+    vp, vtmp, image, itmp = make_inputs(sample_rows, w)
+    for _ in range(warmup):
+        vp, vtmp, image, itmp = impl.run_steps(vp, vtmp, image, itmp, DT, VISC, 1)
+    t0 = time.perf_counter()
+    for _ in range(steps):
+        vp, vtmp, image, itmp = impl.run_steps(vp, vtmp, image, itmp, DT, VISC, 1)
+    dt_s = (time.perf_counter() - t0) / steps
+    return w * sample_rows * n_iters / dt_s, dt_s * 1e3, kind
+
+
+def run_reference_arm(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    w, h, n = workload_shape(args)
+    sample_rows = max(64, (1 << 20) // w)          # ~1 Mcell per step: ~2-3 s of CPU work at N=100
+    rate, ms, kind = cpu_reference_rate(n, w, sample_rows, args.steps, args.warmup)
+    sample = (f"{w}x{sample_rows} rows of the {w}x{h} workload, {n}+{n} sweeps, dt={DT}, nu={VISC}; "
+              f"one timestep per step; fluid.cpp is single-threaded (SURVEY.md 2.1)")
+    line = {"impl": "reference", "metric": METRIC, "value": rate, "unit": UNIT, "n_gpus": args.gpus,
+            "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": workload_config(args),
+            "cpu_baseline": {"value": rate, "unit": UNIT, "cores": 1, "host_cores": os.cpu_count(), "kind": kind,
+                             "sample": sample},
+            "e2e": {"value": rate, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+            "gpu_launches": 0}
+    print(json.dumps(line), flush=True)
+
+
+# --------------------------------------------------------------------------------------------
+# workload description
+# --------------------------------------------------------------------------------------------
+def workload_shape(args):
+    if args.width and args.height:
+        return args.width, args.height, args.iters
+    if args.gpus == 1:
+        return 4096, 4096, args.iters
+    return 16384, 2048 * args.gpus, args.iters
+
+
+def workload_config(args):
+    w, h, n = workload_shape(args)
+    if args.gpus == 1:
+        name = f"synthetic {w}x{h} grid + {w}x{h} image, {n} diffusion + {n} pressure sweeps/step (BASELINE configs[2])"
+    else:
+        name = (f"synthetic {w}x{h} grid + image, {n}+{n} sweeps/step, row slabs of {w}x{h // args.gpus} per GPU "
+                f"(BASELINE configs[3] family; N=8 is 16384x16384)")
+    return {"workload": name, "grid": [w, h], "image": [w, h], "n_diffuse": n, "n_pressure": n, "dt": DT,
+            "viscosity": VISC, "parallelism": "single GPU" if args.gpus == 1 else f"row slabs x{args.gpus}",
+            "l2": "inputs larger than L2 (no flush needed)"}
+
+
+# --------------------------------------------------------------------------------------------
+# B200 arm, one GPU
+# --------------------------------------------------------------------------------------------
+def run_single_gpu(args):
+    import numpy as np
+    import torch
+
+    import probabilistic_fluid_simulation_b200 as pfs
+
+    torch.cuda.set_device(0)
+    w, h, n = workload_shape(args)
+    cells = w * h
+    vp, vtmp, image, itmp = make_inputs(h, w)
+    fv, ft, fi, fm = (pfs.vp_field(torch.from_numpy(x).cuda()) for x in (vp, vtmp, image, itmp))
+
+    def step():
+        pfs.simulate_fluid_step(fv, ft, DT, VISC, n, n)
+        pfs.advect_color_step(fi, fm, fv, DT)
+
+    for _ in range(args.warmup):
+        step()
+    torch.cuda.synchronize()
+
+    # ---- timed region: K steps, device-resident inputs, CUDA events on the launching stream ----
+    sampler = ClockSampler(0)
+    sampler.start()
+    pfs.phase_timing(True)
+    pfs.phase_times(reset=True)
+    l0 = pfs.kernel_launch_count()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    torch.cuda.synchronize()
+    e0.record()
+    for _ in range(args.steps):
+        step()
+    e1.record()
+    torch.cuda.synchronize()
+    ms_total = e0.elapsed_time(e1)
+    launches = pfs.kernel_launch_count() - l0
+    phase_ms, phase_launches = pfs.phase_times(reset=True)
+    pfs.phase_timing(False)
+    clocks = sampler.stop()
+    ms_step = ms_total / args.steps
+    value = cells * n / (ms_step * 1e-3)
+
+    # ---- roofline of the dominant kernel (largest share of the step) ----
+    peak, peak_src = measured_peak_gbs()
+    per_phase = {k: v / args.steps for k, v in phase_ms.items()}
+    depth = pfs.get_fuse_depth()
+    kernels = {}
+    for phase, key, sweeps in (("diffuse", "diffuse_sweep", n), ("pressure", "pressure_sweep", n)):
+        nl = phase_launches[phase] / args.steps
+        if nl > 0 and per_phase[phase] > 0:
+            bytes_per_launch = BYTES[key] * cells * sweeps / nl       # algorithmic bytes x sweeps fused per launch
+            gbs = bytes_per_launch / (per_phase[phase] / nl * 1e-3) / 1e9
+            kernels[phase] = {"launches_per_step": nl, "avg_launch_ms": per_phase[phase] / nl,
+                              "sweeps_per_launch": sweeps / nl, "alg_bytes_per_launch": bytes_per_launch,
+                              "achieved_gbs": gbs, "frac": gbs / peak, "share_of_step": per_phase[phase] / ms_step}
+    for phase, key in (("advect", "advect"), ("divergence", "divergence"), ("project", "project"),
+                       ("advect_color", "advect_color")):
+        if per_phase[phase] > 0:
+            gbs = BYTES[key] * cells / (per_phase[phase] * 1e-3) / 1e9
+            kernels[phase] = {"launches_per_step": phase_launches[phase] / args.steps, "avg_launch_ms": per_phase[phase],
+                              "alg_bytes_per_launch": BYTES[key] * cells, "achieved_gbs": gbs, "frac": gbs / peak,
+                              "share_of_step": per_phase[phase] / ms_step}
+    dom = max(kernels, key=lambda k: kernels[k]["share_of_step"])
+    traffic = None
+    tpath = os.path.join(ROOT, "profiles", "traffic.json")
+    if os.path.exists(tpath):
+        try:
+            traffic = json.load(open(tpath)).get(dom, {}).get("dram_bytes_per_launch")
+        except Exception:
+            traffic = None
+    roofline = {"bound": "hbm", "kernel": dom, "achieved": kernels[dom]["achieved_gbs"], "peak": peak,
+                "unit": "GB/s", "frac": kernels[dom]["frac"], "traffic": traffic, "peak_source": peak_src,
+                "alg_bytes_per_launch": kernels[dom]["alg_bytes_per_launch"],
+                "avg_launch_ms": kernels[dom]["avg_launch_ms"],
+                "note": "algorithmic bytes give no credit for temporal blocking, so frac may exceed 1"}
+    step_bytes = (88 + 16 * n + 12 * n) * cells
+    whole_step = {"alg_bytes": step_bytes, "achieved_gbs": step_bytes / (ms_step * 1e-3) / 1e9,
+                  "frac": step_bytes / (ms_step * 1e-3) / 1e9 / peak}
+
+    # ---- end to end: host buffers in pinned memory, H2D + kernels + D2H inside the timed region ----
+    hv, ht, hi, hm = (pfs.pinned_empty(x.shape) for x in (vp, vtmp, image, itmp))
+    hv[...] = vp; ht[...] = vtmp; hi[...] = image; hm[...] = itmp
+    gv, gt, gi, gm = (pfs.vp_field(x) for x in (hv, ht, hi, hm))
+    e2e_steps = max(3, min(args.steps, 10))
+    for _ in range(2):
+        pfs.timestep_host(gv, gt, gi, gm, DT, VISC, n, n)
+    t0 = time.perf_counter()
+    for _ in range(e2e_steps):
+        pfs.timestep_host(gv, gt, gi, gm, DT, VISC, n, n)     # synchronises before returning
+    e2e_s = (time.perf_counter() - t0) / e2e_steps
+    e2e = {"value": cells * n / e2e_s, "unit": UNIT, "ms_per_step": e2e_s * 1e3,
+           "h2d_bytes_per_step": 3 * cells * 16, "d2h_bytes_per_step": 3 * cells * 16,
+           "api": "pfs_timestep_host (vp_field structs with pinned host pointers; uploads vp, vtmp, image; "
+                  "downloads vp, vtmp, image)", "steps": e2e_steps}
+
+    # ---- CPU baseline: the reference's fluid.cpp on one host core, bounded sample ----
+    sample_rows = max(64, (1 << 20) // w)
+    cpu_rate, cpu_ms, kind = cpu_reference_rate(n, w, sample_rows, 3, 1)
+    cpu = {"value": cpu_rate, "unit": UNIT, "cores": 1, "host_cores": os.cpu_count(), "kind": kind,
+           "sample": f"3 timesteps of a {w}x{sample_rows} slab of the workload ({n}+{n} sweeps), "
+                     f"{cpu_ms:.0f} ms each; fluid.cpp is single-threaded"}
+
+    line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": 1, "steps": args.steps, "warmup": args.warmup,
+            "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "f32", "data": "synthetic", "config": workload_config(args),
+            "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": int(launches),
+            "clocks": clocks, "whole_step_roofline": whole_step,
+            "pressure_solve": {"ms": per_phase["pressure"], "cell_updates_per_s": cells * n / (per_phase["pressure"] * 1e-3)},
+            "cell_steps_per_s": cells / (ms_step * 1e-3), "phases_ms": per_phase, "kernels": kernels,
+            "fuse_depth": depth}
+    print(json.dumps(line), flush=True)
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--width", type=int, default=0)
+    ap.add_argument("--height", type=int, default=0)
+    ap.add_argument("--iters", type=int, default=100)
+    ap.add_argument("--fuse-depth", type=int, default=None)
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 0)
+    if args.impl == "reference":
+        run_reference_arm(args)
+        return
+    args.warmup = max(args.warmup, 3)
+    if args.fuse_depth is not None:
+        import probabilistic_fluid_simulation_b200 as pfs
+        pfs.set_fuse_depth(args.fuse_depth)
+    if args.gpus == 1 and int(os.environ.get("WORLD_SIZE", "1")) == 1:
+        run_single_gpu(args)
+    else:
+        from probabilistic_fluid_simulation_b200 import slab_bench
+        slab_bench.run(args, sys.modules[__name__])
+
+
+if __name__ == "__main__":
+    main()

@@ -1,0 +1,156 @@
+/*
+ * pfs_b200.h -- C-ABI of libpfs_b200.so: the B200-native (sm_100a) implementation of the
+ * per-timestep fluid update of mdushkoff/Probabilistic_Fluid_Simulation.
+ *
+ * Scope: the hot path that the reference's src/fluid.cpp runs on the CPU (simulate_fluid_step +
+ * advect_color_step and the six operators they call), behind the reference's own operator
+ * interface includes/fluid.hpp.  Every entry point below names the reference declaration it
+ * replaces.  Plain C types only; no torch, no C++ types.  There is NO CPU fallback: every call
+ * either runs hand-written CUDA kernels on the current device or returns an error.
+ *
+ * Data layout at the boundary (unchanged from the reference, fluid.cpp:15-17, main.cpp:25):
+ *   row-major, interleaved, 4 floats per cell:  idx = (j*W + i)*4 + k
+ *   velocity/pressure field:  k = 0 u, 1 v, 2 pressure, 3 divergence
+ *   image:                    k = R,G,B,A in [0,1]
+ * Internally the library works on SoA planes it owns; callers never see them.
+ *
+ * Sweep counts: the reference hard-codes NUM_JACOBI_ITERS = 30 for both loops (fluid.hpp:11);
+ * here they are run-time arguments.  n_diffuse == n_pressure == 30 reproduces the reference.
+ * For any pair of counts the buffer-pointer choreography of fluid.cpp (data pointers swapped
+ * after every sweep but the last, fluid.cpp:188-194, 260-265) is reproduced literally: which of
+ * the two caller buffers ends up holding which iterate, and whether the caller's two pointers
+ * end up exchanged, is exactly what the reference's loops would produce.
+ *
+ * Threading: one host thread per device at a time (the library keeps per-device scratch).
+ * Streams: every device-pointer entry point takes a `stream` (a cudaStream_t passed as void*;
+ * NULL = the legacy default stream, which is what the reference driver uses) and only enqueues
+ * work on it -- no hidden synchronisation.  Host-buffer entry points synchronise before return.
+ *
+ * Errors: every function returns PFS_OK (0) or a pfs_status; pfs_last_error() gives the message
+ * (thread-local).  The reference returns void and ignores CUDA errors (main.cpp:45-49); the
+ * fluid.hpp-compatible C++ shim (host/fluid_shim.cpp) aborts on a non-zero status instead.
+ */
+#ifndef PFS_B200_H_
+#define PFS_B200_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define PFS_B200_VERSION 100 /* major*100 + minor */
+
+typedef enum pfs_status {
+    PFS_OK = 0,
+    PFS_EINVAL = 1,      /* bad argument (null pointer, non-positive size, channels != 4, ...) */
+    PFS_ECUDA = 2,       /* a CUDA runtime call or kernel launch failed */
+    PFS_ENOMEM = 3,      /* device or pinned-host allocation failed */
+    PFS_ENODEVICE = 4,   /* no sm_100-class CUDA device visible: there is no CPU fallback */
+    PFS_ESTATE = 5       /* multi-GPU slab context used before its peers were attached, etc. */
+} pfs_status;
+
+/* Same fields, same order as the reference's vp_field (includes/fluid.hpp:17-22). */
+typedef struct pfs_field {
+    int x;        /* width  */
+    int y;        /* height */
+    int z;        /* channels, must be 4 */
+    float *data;
+} pfs_field;
+
+/* ---- library ------------------------------------------------------------------------------ */
+int pfs_version(void);
+const char *pfs_last_error(void);
+/* Number of kernels this library has launched in the calling process (bench.py gpu_launches). */
+uint64_t pfs_kernel_launch_count(void);
+/* Frees all per-device scratch.  Optional; also runs at process exit. */
+int pfs_shutdown(void);
+/* Tuning knob for tests/benchmarks: maximum number of Jacobi sweeps fused per kernel launch
+ * (temporal blocking depth).  0 = library default.  1 = one sweep per launch.  Results are
+ * bit-identical for every value. */
+int pfs_set_fuse_depth(int max_sweeps_per_launch);
+int pfs_get_fuse_depth(void);
+
+/* Pinned host memory (the reference's CUDA build reads PNGs into cudaMallocHost memory,
+ * includes/utils.hpp:69-76). */
+int pfs_host_alloc(void **ptr, size_t bytes);
+int pfs_host_free(void *ptr);
+
+/* ---- device-pointer step API: replaces the USE_CUDA branch of includes/fluid.hpp ----------- */
+
+/* Replaces: void simulate_fluid_step(float **vp, float **tmp, float dt, float viscosity,
+ *                                    int vx, int vy, int vz)            (fluid.hpp:107)
+ * with the semantics of the CPU implementation (fluid.cpp:298-305):
+ *   advect(vp->tmp); diffuse(tmp->vp); computePressure(vp->tmp); subtractPressureGradient(tmp->vp)
+ * *vp and *tmp are caller-owned DEVICE buffers of vx*vy*vz floats (vz == 4).  On return *vp points
+ * at [u_projected, v_projected, p_{N-1}, divergence] and *tmp at [u_diffused, v_diffused, p_N,
+ * divergence]; the two pointers are exchanged iff the reference's loops would exchange them
+ * (never when n_diffuse and n_pressure have the same parity).  tmp's channel 2 is the warm start
+ * of the pressure solve (main.cpp:188-195 initialises it to -1). */
+int pfs_simulate_fluid_step(float **vp, float **tmp, float dt, float viscosity,
+                            int vx, int vy, int vz, int n_diffuse, int n_pressure, void *stream);
+
+/* Replaces: void advect_color_step(float **image, float **itmp, float **vp, float dt,
+ *                                  int ix, int iy, int iz, int vx, int vy, int vz) (fluid.hpp:116)
+ * (fluid.cpp:312-320: advect_color(image->itmp) then exchange *image and *itmp). */
+int pfs_advect_color_step(float **image, float **itmp, float **vp, float dt,
+                          int ix, int iy, int iz, int vx, int vy, int vz, void *stream);
+
+/* ---- device-pointer operator API: the six operators of includes/fluid.hpp ------------------ */
+/* Each one has the reference CPU operator's exact effect on the caller's interleaved buffers
+ * (which channels are written, which are left untouched, how the pointers end up). */
+
+/* advect (fluid.hpp:32, fluid.cpp:24-70): vp_out ch0,1 <- semi-Lagrangian advection of vp ch0,1. */
+int pfs_advect(const float *vp, float *vp_out, float dt, int vx, int vy, int vz, void *stream);
+/* diffuse (fluid.hpp:58, fluid.cpp:129-196): n_sweeps smoothing sweeps on ch0,1, ping-ponging
+ * between the two buffers; *vp_out ends on the buffer written last, *vp on the other. */
+int pfs_diffuse(float **vp, float **vp_out, float viscosity, float dt,
+                int vx, int vy, int vz, int n_sweeps, void *stream);
+/* addForces (fluid.hpp:70, fluid.cpp:198-208): the reference body is empty and its call site is
+ * commented out (fluid.cpp:302).  Kept as a validated no-op so the operator surface is complete. */
+int pfs_add_forces(float *vp, const float *forces, int vx, int vy, int vz, void *stream);
+/* computePressure (fluid.hpp:81, fluid.cpp:210-267): divergence of *vp ch0,1 into ch3 of BOTH
+ * buffers, then n_sweeps Jacobi sweeps on ch2 starting from *vp ch2; pointer rule as pfs_diffuse. */
+int pfs_compute_pressure(float **vp, float **vp_out, float dt,
+                         int vx, int vy, int vz, int n_sweeps, void *stream);
+/* subtractPressureGradient (fluid.hpp:92, fluid.cpp:269-296): vp_out ch0,1 <- vp ch0,1 - grad(vp ch2)*dt/2 */
+int pfs_subtract_pressure_gradient(const float *vp, float *vp_out, float dt,
+                                   int vx, int vy, int vz, void *stream);
+/* advect_color (fluid.hpp:45, fluid.cpp:72-127): itmp <- image advected through vp ch0,1. */
+int pfs_advect_color(const float *image, float *itmp, const float *vp, float dt,
+                     int ix, int iy, int iz, int vx, int vy, int vz, void *stream);
+
+/* ---- host-buffer API: replaces the non-USE_CUDA branch of includes/fluid.hpp --------------- */
+/* Same semantics as the device-pointer calls, but the pfs_field structs hold HOST pointers, as
+ * in the reference CPU build (fluid.hpp:109,118; main.cpp:236,239).  Each call copies its inputs
+ * to the device, runs the kernels and copies every buffer the reference would have modified
+ * back into the caller's memory, exchanging the structs' data pointers as the reference does.
+ * Pinned host memory (pfs_host_alloc) makes the copies asynchronous and ~2x faster. */
+int pfs_simulate_fluid_step_host(pfs_field *vp, pfs_field *tmp, float dt, float viscosity,
+                                 int n_diffuse, int n_pressure);
+int pfs_advect_color_step_host(pfs_field *image, pfs_field *itmp, pfs_field *vp, float dt);
+/* One whole timestep of the reference driver loop (main.cpp:236-239) on host buffers:
+ * simulate_fluid_step + advect_color_step, with the uploads, kernels and downloads of the two
+ * halves overlapped on separate streams. */
+int pfs_timestep_host(pfs_field *vp, pfs_field *vtmp, pfs_field *image, pfs_field *itmp,
+                      float dt, float viscosity, int n_diffuse, int n_pressure);
+
+/* ---- phase timing (diagnostics for bench.py; not on the reference's surface) --------------- */
+/* When enabled, pfs_simulate_fluid_step / pfs_advect_color_step bracket each phase with CUDA
+ * events on the caller's stream.  pfs_phase_times() synchronises those events and returns the
+ * accumulated milliseconds and launch counts since the last reset. */
+#define PFS_PHASE_ADVECT 0
+#define PFS_PHASE_DIFFUSE 1
+#define PFS_PHASE_DIVERGENCE 2
+#define PFS_PHASE_PRESSURE 3
+#define PFS_PHASE_PROJECT 4
+#define PFS_PHASE_ADVECT_COLOR 5
+#define PFS_NUM_PHASES 6
+int pfs_phase_timing_enable(int on);
+int pfs_phase_times(float ms_out[PFS_NUM_PHASES], uint64_t launches_out[PFS_NUM_PHASES], int reset);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* PFS_B200_H_ */

@@ -1,0 +1,393 @@
+// kernels_basic.cu -- the non-iterated kernels of the fluid step (advect, divergence, project+pack,
+// advect_color, interleaved<->planar movers) and the one-sweep-per-launch Jacobi kernel that is the
+// reference point / remainder path for the temporally blocked sweeps in sweeps_fused.cu.
+//
+// All kernels are HBM-streaming: planar fp32, float4 per thread along x when W % 4 == 0 (V = 4),
+// scalar otherwise (V = 1).  Periodic wrap is resolved by index (no halo copies on one GPU).
+#include "pfs_internal.cuh"
+
+namespace pfs {
+
+namespace {
+
+constexpr int BX = 32;   // threads along x
+constexpr int BY = 8;    // threads along y
+
+template <int V>
+__device__ __forceinline__ void load_vec(const float *p, float (&o)[V])
+{
+    if constexpr (V == 4) {
+        float4 t = __ldg(reinterpret_cast<const float4 *>(p));
+        o[0] = t.x; o[1] = t.y; o[2] = t.z; o[3] = t.w;
+    } else {
+        o[0] = __ldg(p);
+    }
+}
+
+template <int V>
+__device__ __forceinline__ void store_vec(float *p, const float (&o)[V])
+{
+    if constexpr (V == 4) {
+        *reinterpret_cast<float4 *>(p) = make_float4(o[0], o[1], o[2], o[3]);
+    } else {
+        *p = o[0];
+    }
+}
+
+// Common per-thread stencil addressing: this thread owns cells [x, x+V) of row j.
+struct StencilPos {
+    int x, j, xm, xp, jm, jp;
+    bool valid;
+};
+
+template <int V>
+__device__ __forceinline__ StencilPos stencil_pos(int w, int h)
+{
+    StencilPos s;
+    int xv = blockIdx.x * BX + threadIdx.x;
+    s.j = blockIdx.y * BY + threadIdx.y;
+    s.x = xv * V;
+    s.valid = (s.x < w) && (s.j < h);
+    s.xm = (s.x == 0) ? w - 1 : s.x - 1;          // ((i-1) % w + w) % w, fluid.cpp:159
+    s.xp = (s.x + V >= w) ? 0 : s.x + V;          // (i+1) % w, fluid.cpp:160
+    s.jm = (s.j == 0) ? h - 1 : s.j - 1;          // fluid.cpp:161
+    s.jp = (s.j + 1 >= h) ? 0 : s.j + 1;          // fluid.cpp:162
+    return s;
+}
+
+inline dim3 stencil_grid(int w, int h, int v, int planes)
+{
+    int wv = (w + v - 1) / v;
+    return dim3((wv + BX - 1) / BX, (h + BY - 1) / BY, planes);
+}
+
+// ---------------------------------------------------------------------------------------------
+// one Jacobi sweep (fluid.cpp:154-186 diffusion, :239-258 pressure)
+// ---------------------------------------------------------------------------------------------
+template <int OP, int V>
+__global__ void __launch_bounds__(BX *BY)
+    sweep_kernel(const float *__restrict__ in0, const float *__restrict__ in1, float *__restrict__ out0,
+                 float *__restrict__ out1, const float *__restrict__ rhs, int w, int h, float alpha, float beta)
+{
+    StencilPos s = stencil_pos<V>(w, h);
+    if (!s.valid) return;
+    const float *in = blockIdx.z ? in1 : in0;
+    float *out = blockIdx.z ? out1 : out0;
+    const float *rc = in + (size_t)s.j * w;
+    float c[V], t[V], b[V], o[V];
+    load_vec<V>(rc + s.x, c);
+    load_vec<V>(in + (size_t)s.jm * w + s.x, t);
+    load_vec<V>(in + (size_t)s.jp * w + s.x, b);
+    float l = __ldg(rc + s.xm), r = __ldg(rc + s.xp);
+    float q[V];
+    if constexpr (OP == SWEEP_PRESSURE) load_vec<V>(rhs + (size_t)s.j * w + s.x, q);
+#pragma unroll
+    for (int k = 0; k < V; k++) {
+        float left = (k == 0) ? l : c[k - 1];
+        float right = (k == V - 1) ? r : c[k + 1];
+        if constexpr (OP == SWEEP_PRESSURE)
+            o[k] = pressure_update(left, right, t[k], b[k], q[k]);
+        else
+            o[k] = diffuse_update(left, right, t[k], b[k], c[k], alpha, beta);
+    }
+    store_vec<V>(out + (size_t)s.j * w + s.x, o);
+}
+
+// ---------------------------------------------------------------------------------------------
+// divergence (fluid.cpp:221-237) + optional extraction of the warm-start pressure (channel 2)
+// ---------------------------------------------------------------------------------------------
+template <int V>
+__global__ void __launch_bounds__(BX *BY)
+    divergence_kernel(const float *__restrict__ u, const float *__restrict__ v, float *__restrict__ div,
+                      const float *__restrict__ p0_src, float *__restrict__ p0, float gamma, int w, int h)
+{
+    StencilPos s = stencil_pos<V>(w, h);
+    if (!s.valid) return;
+    const float *ur = u + (size_t)s.j * w;
+    float uc[V], vt[V], vb[V], o[V];
+    load_vec<V>(ur + s.x, uc);
+    load_vec<V>(v + (size_t)s.jm * w + s.x, vt);
+    load_vec<V>(v + (size_t)s.jp * w + s.x, vb);
+    float ul = __ldg(ur + s.xm), urr = __ldg(ur + s.xp);
+#pragma unroll
+    for (int k = 0; k < V; k++) {
+        float left = (k == 0) ? ul : uc[k - 1];
+        float right = (k == V - 1) ? urr : uc[k + 1];
+        o[k] = divergence_value(right, left, vb[k], vt[k], gamma);
+    }
+    store_vec<V>(div + (size_t)s.j * w + s.x, o);
+    if (p0 != nullptr) {
+        const float *src = p0_src + ((size_t)s.j * w + s.x) * 4 + 2;
+        float pv[V];
+#pragma unroll
+        for (int k = 0; k < V; k++) pv[k] = __ldg(src + 4 * k);
+        store_vec<V>(p0 + (size_t)s.j * w + s.x, pv);
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// subtract pressure gradient (fluid.cpp:273-294) fused with the write-back of both interleaved
+// post-state buffers (full 16-byte cells, so no read-modify-write of the caller's buffers).
+// ---------------------------------------------------------------------------------------------
+template <int V>
+__global__ void __launch_bounds__(BX *BY)
+    project_pack_kernel(const float *__restrict__ u, const float *__restrict__ v, const float *__restrict__ pn,
+                        const float *__restrict__ pprev, const float *__restrict__ div,
+                        float4 *__restrict__ out_q, float4 *__restrict__ out_p, float dt, int w, int h)
+{
+    StencilPos s = stencil_pos<V>(w, h);
+    if (!s.valid) return;
+    const float *pr = pn + (size_t)s.j * w;
+    float pc[V], pt[V], pb[V], uu[V], vv[V], pp[V], dd[V];
+    size_t off = (size_t)s.j * w + s.x;
+    load_vec<V>(pr + s.x, pc);
+    load_vec<V>(pn + (size_t)s.jm * w + s.x, pt);
+    load_vec<V>(pn + (size_t)s.jp * w + s.x, pb);
+    float pl = __ldg(pr + s.xm), prr = __ldg(pr + s.xp);
+    load_vec<V>(u + off, uu);
+    load_vec<V>(v + off, vv);
+    load_vec<V>(pprev + off, pp);
+    load_vec<V>(div + off, dd);
+#pragma unroll
+    for (int k = 0; k < V; k++) {
+        float left = (k == 0) ? pl : pc[k - 1];
+        float right = (k == V - 1) ? prr : pc[k + 1];
+        float un = project_component(uu[k], right, left, dt);
+        float vn = project_component(vv[k], pb[k], pt[k], dt);
+        out_q[off + k] = make_float4(un, vn, pp[k], dd[k]);
+        out_p[off + k] = make_float4(uu[k], vv[k], pc[k], dd[k]);
+    }
+}
+
+// stand-alone subtractPressureGradient on interleaved buffers (operator API only)
+__global__ void __launch_bounds__(256)
+    subtract_gradient_aos_kernel(const float4 *__restrict__ in, float *__restrict__ out, float dt, int w, int h)
+{
+    int i = blockIdx.x * 64 + threadIdx.x, j = blockIdx.y * 4 + threadIdx.y;
+    if (i >= w || j >= h) return;
+    int im = (i == 0) ? w - 1 : i - 1, ip = (i + 1 >= w) ? 0 : i + 1;
+    int jm = (j == 0) ? h - 1 : j - 1, jp = (j + 1 >= h) ? 0 : j + 1;
+    const float *f = reinterpret_cast<const float *>(in);
+    float pl = __ldg(f + ((size_t)j * w + im) * 4 + 2), pr = __ldg(f + ((size_t)j * w + ip) * 4 + 2);
+    float pt = __ldg(f + ((size_t)jm * w + i) * 4 + 2), pb = __ldg(f + ((size_t)jp * w + i) * 4 + 2);
+    float2 uv = __ldg(reinterpret_cast<const float2 *>(f + ((size_t)j * w + i) * 4));
+    float2 o;
+    o.x = project_component(uv.x, pr, pl, dt);
+    o.y = project_component(uv.y, pb, pt, dt);
+    *reinterpret_cast<float2 *>(out + ((size_t)j * w + i) * 4) = o;
+}
+
+// ---------------------------------------------------------------------------------------------
+// advect (fluid.cpp:24-70): back-trace, periodic wrap, bilinear gather of (u, v) from the
+// interleaved field.  One 8-byte load fetches both components of a corner; neighbouring threads'
+// corners share 32-byte sectors, so the gather runs out of L1 for coherent flows.
+// ---------------------------------------------------------------------------------------------
+template <bool TO_PLANES>
+__global__ void __launch_bounds__(256)
+    advect_kernel(const float *__restrict__ vp, float *__restrict__ u_out, float *__restrict__ v_out,
+                  float *__restrict__ aos_out, float dt, int w, int h)
+{
+    int i = blockIdx.x * 64 + threadIdx.x, j = blockIdx.y * 4 + threadIdx.y;
+    if (i >= w || j >= h) return;
+    const float fw = (float)w, fh = (float)h;
+    size_t cell = (size_t)j * w + i;
+    float2 uv = __ldg(reinterpret_cast<const float2 *>(vp + cell * 4));
+    // fluid.cpp:39,41: (float)i - dt*u/fwidth  ==  i - ((dt*u)/fwidth)
+    float xp = __fsub_rn((float)i, __fdiv_rn(__fmul_rn(dt, uv.x), fw));
+    float yp = __fsub_rn((float)j, __fdiv_rn(__fmul_rn(dt, uv.y), fh));
+    xp = wrap_coord(xp, fw);
+    yp = wrap_coord(yp, fh);
+    Bilinear b = make_bilinear(xp, yp, w, h);
+    const float *r0 = vp + (size_t)b.j0 * w * 4, *r1 = vp + (size_t)b.j1 * w * 4;
+    float2 f00 = __ldg(reinterpret_cast<const float2 *>(r0 + (size_t)b.i0 * 4));
+    float2 f10 = __ldg(reinterpret_cast<const float2 *>(r0 + (size_t)b.i1 * 4));
+    float2 f01 = __ldg(reinterpret_cast<const float2 *>(r1 + (size_t)b.i0 * 4));
+    float2 f11 = __ldg(reinterpret_cast<const float2 *>(r1 + (size_t)b.i1 * 4));
+    float un = bilerp(b, f00.x, f10.x, f01.x, f11.x);
+    float vn = bilerp(b, f00.y, f10.y, f01.y, f11.y);
+    if constexpr (TO_PLANES) {
+        u_out[cell] = un;
+        v_out[cell] = vn;
+    } else {
+        *reinterpret_cast<float2 *>(aos_out + cell * 4) = make_float2(un, vn);
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// advect_color (fluid.cpp:72-127): one thread per pixel, velocity point-sampled at
+// ((int)(i*viw), (int)(j*vih)), four float4 texel gathers, one coalesced float4 store.
+// ---------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256)
+    advect_color_kernel(const float4 *__restrict__ image, float4 *__restrict__ out, const float *__restrict__ vp,
+                        float dt_over_viw, float dt_over_vih, float viw, float vih, int iw, int ih, int vw)
+{
+    int i = blockIdx.x * 64 + threadIdx.x, j = blockIdx.y * 4 + threadIdx.y;
+    if (i >= iw || j >= ih) return;
+    const float fiw = (float)iw, fih = (float)ih;
+    int vi = (int)__fmul_rn((float)i, viw);   // fluid.cpp:89
+    int vj = (int)__fmul_rn((float)j, vih);   // fluid.cpp:90
+    float2 uv = __ldg(reinterpret_cast<const float2 *>(vp + ((size_t)vj * vw + vi) * 4));
+    // fluid.cpp:97-98: (float)i - (dt/viw) * u / fiwidth
+    float xp = __fsub_rn((float)i, __fdiv_rn(__fmul_rn(dt_over_viw, uv.x), fiw));
+    float yp = __fsub_rn((float)j, __fdiv_rn(__fmul_rn(dt_over_vih, uv.y), fih));
+    xp = wrap_coord(xp, fiw);
+    yp = wrap_coord(yp, fih);
+    Bilinear b = make_bilinear(xp, yp, iw, ih);
+    const float4 *r0 = image + (size_t)b.j0 * iw, *r1 = image + (size_t)b.j1 * iw;
+    float4 f00 = __ldg(r0 + b.i0), f10 = __ldg(r0 + b.i1), f01 = __ldg(r1 + b.i0), f11 = __ldg(r1 + b.i1);
+    float4 o;
+    o.x = bilerp(b, f00.x, f10.x, f01.x, f11.x);
+    o.y = bilerp(b, f00.y, f10.y, f01.y, f11.y);
+    o.z = bilerp(b, f00.z, f10.z, f01.z, f11.z);
+    o.w = bilerp(b, f00.w, f10.w, f01.w, f11.w);
+    out[(size_t)j * iw + i] = o;
+}
+
+// ---------------------------------------------------------------------------------------------
+// interleaved <-> planar movers (operator API; the fused step never needs a separate pass)
+// ---------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256)
+    unpack_kernel(const float4 *__restrict__ aos, float *c0, float *c1, float *c2, float *c3, size_t n)
+{
+    size_t i = (size_t)blockIdx.x * 256 + threadIdx.x;
+    if (i >= n) return;
+    float4 v = __ldg(aos + i);
+    if (c0) c0[i] = v.x;
+    if (c1) c1[i] = v.y;
+    if (c2) c2[i] = v.z;
+    if (c3) c3[i] = v.w;
+}
+
+__global__ void __launch_bounds__(256)
+    pack_kernel(float *__restrict__ aos, const float *c0, const float *c1, const float *c2, const float *c3, size_t n)
+{
+    size_t i = (size_t)blockIdx.x * 256 + threadIdx.x;
+    if (i >= n) return;
+    if (c0 && c1 && c2 && c3) {
+        reinterpret_cast<float4 *>(aos)[i] = make_float4(c0[i], c1[i], c2[i], c3[i]);
+        return;
+    }
+    if (c0 && c1) {
+        *reinterpret_cast<float2 *>(aos + i * 4) = make_float2(c0[i], c1[i]);
+    } else {
+        if (c0) aos[i * 4 + 0] = c0[i];
+        if (c1) aos[i * 4 + 1] = c1[i];
+    }
+    if (c2 && c3) {
+        *reinterpret_cast<float2 *>(aos + i * 4 + 2) = make_float2(c2[i], c3[i]);
+    } else {
+        if (c2) aos[i * 4 + 2] = c2[i];
+        if (c3) aos[i * 4 + 3] = c3[i];
+    }
+}
+
+inline bool vec4_ok(int w, const void *a, const void *b = nullptr, const void *c = nullptr, const void *d = nullptr,
+                    const void *e = nullptr, const void *f = nullptr)
+{
+    auto al = [](const void *p) { return (reinterpret_cast<uintptr_t>(p) & 15u) == 0; };
+    return (w % 4 == 0) && al(a) && al(b) && al(c) && al(d) && al(e) && al(f);
+}
+
+}  // namespace
+
+// ---------------------------------------------------------------------------------------------
+// host wrappers
+// ---------------------------------------------------------------------------------------------
+int launch_unpack(const float *aos, float *c0, float *c1, float *c2, float *c3, int w, int h, cudaStream_t s)
+{
+    size_t n = (size_t)w * h;
+    unsigned blocks = (unsigned)((n + 255) / 256);
+    PFS_LAUNCH(unpack_kernel, blocks, 256, 0, s, reinterpret_cast<const float4 *>(aos), c0, c1, c2, c3, n);
+    return PFS_OK;
+}
+
+int launch_pack(float *aos, const float *c0, const float *c1, const float *c2, const float *c3, int w, int h,
+                cudaStream_t s)
+{
+    size_t n = (size_t)w * h;
+    unsigned blocks = (unsigned)((n + 255) / 256);
+    PFS_LAUNCH(pack_kernel, blocks, 256, 0, s, aos, c0, c1, c2, c3, n);
+    return PFS_OK;
+}
+
+int launch_advect(const float *vp_aos, float *u_out, float *v_out, float *aos_out, float dt, int w, int h,
+                  cudaStream_t s)
+{
+    dim3 block(64, 4), grid((w + 63) / 64, (h + 3) / 4);
+    if (aos_out == nullptr)
+        PFS_LAUNCH(advect_kernel<true>, grid, block, 0, s, vp_aos, u_out, v_out, aos_out, dt, w, h);
+    else
+        PFS_LAUNCH(advect_kernel<false>, grid, block, 0, s, vp_aos, u_out, v_out, aos_out, dt, w, h);
+    return PFS_OK;
+}
+
+int launch_sweeps_basic(SweepOp op, float *a0, float *a1, float *b0, float *b1, const float *rhs,
+                        const SweepParams &p, int n, int *flips, cudaStream_t s)
+{
+    const int planes = (op == SWEEP_DIFFUSE) ? 2 : 1;
+    const bool v4 = vec4_ok(p.w, a0, a1, b0, b1, rhs);
+    dim3 block(BX, BY), grid = stencil_grid(p.w, p.h, v4 ? 4 : 1, planes);
+    using SweepFn = void (*)(const float *, const float *, float *, float *, const float *, int, int, float, float);
+    SweepFn fn;
+    if (op == SWEEP_PRESSURE)
+        fn = v4 ? sweep_kernel<SWEEP_PRESSURE, 4> : sweep_kernel<SWEEP_PRESSURE, 1>;
+    else
+        fn = v4 ? sweep_kernel<SWEEP_DIFFUSE, 4> : sweep_kernel<SWEEP_DIFFUSE, 1>;
+    for (int it = 0; it < n; it++) {
+        const float *i0 = (it & 1) ? b0 : a0, *i1 = (it & 1) ? b1 : a1;
+        float *o0 = (it & 1) ? a0 : b0, *o1 = (it & 1) ? a1 : b1;
+        PFS_LAUNCH(fn, grid, block, 0, s, i0, i1, o0, o1, rhs, p.w, p.h, p.alpha, p.beta);
+    }
+    *flips = n;
+    return PFS_OK;
+}
+
+int launch_divergence(const float *u, const float *v, float *div, const float *p0_src_aos, float *p0, float dt,
+                      int w, int h, cudaStream_t s)
+{
+    const float gamma = (float)(-1.0 / (double)dt);   // fluid.cpp:218
+    const bool v4 = vec4_ok(w, u, v, div, p0);
+    dim3 block(BX, BY), grid = stencil_grid(w, h, v4 ? 4 : 1, 1);
+    if (v4)
+        PFS_LAUNCH(divergence_kernel<4>, grid, block, 0, s, u, v, div, p0_src_aos, p0, gamma, w, h);
+    else
+        PFS_LAUNCH(divergence_kernel<1>, grid, block, 0, s, u, v, div, p0_src_aos, p0, gamma, w, h);
+    return PFS_OK;
+}
+
+int launch_project_pack(const float *u, const float *v, const float *p_n, const float *p_prev, const float *div,
+                        float *out_q, float *out_p, float dt, int w, int h, cudaStream_t s)
+{
+    const bool v4 = vec4_ok(w, u, v, p_n, p_prev, div);
+    dim3 block(BX, BY), grid = stencil_grid(w, h, v4 ? 4 : 1, 1);
+    float4 *q4 = reinterpret_cast<float4 *>(out_q), *p4 = reinterpret_cast<float4 *>(out_p);
+    if (v4)
+        PFS_LAUNCH(project_pack_kernel<4>, grid, block, 0, s, u, v, p_n, p_prev, div, q4, p4, dt, w, h);
+    else
+        PFS_LAUNCH(project_pack_kernel<1>, grid, block, 0, s, u, v, p_n, p_prev, div, q4, p4, dt, w, h);
+    return PFS_OK;
+}
+
+int launch_subtract_gradient_aos(const float *vp_aos, float *out_aos, float dt, int w, int h, cudaStream_t s)
+{
+    dim3 block(64, 4), grid((w + 63) / 64, (h + 3) / 4);
+    PFS_LAUNCH(subtract_gradient_aos_kernel, grid, block, 0, s, reinterpret_cast<const float4 *>(vp_aos), out_aos, dt,
+               w, h);
+    return PFS_OK;
+}
+
+int launch_advect_color(const float *image, float *out, const float *vp_aos, float dt, int iw, int ih, int vw, int vh,
+                        cudaStream_t s)
+{
+    // fluid.cpp:82-83 and the (dt/viw), (dt/vih) factors of :97-98, all binary32
+    const float viw = (float)vw / (float)iw;
+    const float vih = (float)vh / (float)ih;
+    const float dt_over_viw = dt / viw;
+    const float dt_over_vih = dt / vih;
+    dim3 block(64, 4), grid((iw + 63) / 64, (ih + 3) / 4);
+    PFS_LAUNCH(advect_color_kernel, grid, block, 0, s, reinterpret_cast<const float4 *>(image),
+               reinterpret_cast<float4 *>(out), vp_aos, dt_over_viw, dt_over_vih, viw, vih, iw, ih, vw);
+    return PFS_OK;
+}
+
+}  // namespace pfs

@@ -1,0 +1,689 @@
+// pfs_api.cu -- the C-ABI of libpfs_b200.so (include/pfs_b200.h): argument validation, per-device
+// planar scratch, the buffer-pointer choreography of the reference (fluid.cpp:188-194, 260-265,
+// 298-305) and the sequencing of the kernels in kernels_basic.cu / sweeps_fused.cu.
+#include <stdarg.h>
+#include <stdlib.h>
+#include <string.h>
+
+#include <map>
+#include <mutex>
+#include <vector>
+
+#include "pfs_internal.cuh"
+
+namespace pfs {
+
+// ---------------------------------------------------------------------------------------------
+// errors, launch accounting
+// ---------------------------------------------------------------------------------------------
+static thread_local char t_error[512] = "";
+unsigned long long g_launches = 0;
+
+void set_error(const char *fmt, ...)
+{
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(t_error, sizeof(t_error), fmt, ap);
+    va_end(ap);
+}
+
+int cuda_fail(cudaError_t e, const char *what, const char *file, int line)
+{
+    set_error("CUDA error %d (%s) at %s:%d: %s", (int)e, cudaGetErrorString(e), file, line, what);
+    if (e == cudaErrorMemoryAllocation) return PFS_ENOMEM;
+    if (e == cudaErrorNoDevice || e == cudaErrorInsufficientDriver || e == cudaErrorNoKernelImageForDevice)
+        return PFS_ENODEVICE;
+    return PFS_ECUDA;
+}
+
+int check_launch(const char *kernel, const char *file, int line)
+{
+    cudaError_t e = cudaGetLastError();
+    if (e == cudaSuccess) return PFS_OK;
+    set_error("launch of %s failed at %s:%d: %s", kernel, file, line, cudaGetErrorString(e));
+    if (e == cudaErrorNoKernelImageForDevice || e == cudaErrorNoDevice) return PFS_ENODEVICE;
+    return PFS_ECUDA;
+}
+
+// ---------------------------------------------------------------------------------------------
+// per-device scratch: seven planes (u,v x2, p x2, divergence) sized for the largest grid seen,
+// plus staging buffers of the host API.
+// ---------------------------------------------------------------------------------------------
+struct DeviceScratch {
+    size_t plane_cells = 0;
+    float *planes = nullptr;          // 7 * plane_cells floats, one allocation
+    float *stage[4] = {nullptr, nullptr, nullptr, nullptr};   // host-API device copies: vp, tmp, image, itmp
+    size_t stage_floats[4] = {0, 0, 0, 0};
+    cudaStream_t streams[2] = {nullptr, nullptr};             // host-API streams
+    cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};
+    float *plane(int k) const { return planes + (size_t)k * plane_cells; }
+};
+
+static std::mutex g_mutex;
+static std::map<int, DeviceScratch> g_scratch;
+static int g_fuse_depth = 0;     // 0 = default
+
+static void free_scratch(DeviceScratch &sc)
+{
+    if (sc.planes) cudaFree(sc.planes);
+    for (int i = 0; i < 4; i++)
+        if (sc.stage[i]) cudaFree(sc.stage[i]);
+    for (int i = 0; i < 2; i++)
+        if (sc.streams[i]) cudaStreamDestroy(sc.streams[i]);
+    for (int i = 0; i < 4; i++)
+        if (sc.ev[i]) cudaEventDestroy(sc.ev[i]);
+    sc = DeviceScratch();
+}
+
+static int current_device(int *dev)
+{
+    cudaError_t e = cudaGetDevice(dev);
+    if (e != cudaSuccess) {
+        set_error("no usable CUDA device (%s); libpfs_b200 has no CPU fallback", cudaGetErrorString(e));
+        (void)cudaGetLastError();
+        return PFS_ENODEVICE;
+    }
+    return PFS_OK;
+}
+
+// Planes are padded so every plane starts 256-byte aligned whatever the cell count.
+static size_t padded_cells(size_t cells) { return (cells + 63) & ~(size_t)63; }
+
+static int get_scratch(size_t cells, DeviceScratch **out)
+{
+    int dev;
+    PFS_TRY(current_device(&dev));
+    std::lock_guard<std::mutex> lock(g_mutex);
+    DeviceScratch &sc = g_scratch[dev];
+    size_t need = padded_cells(cells);
+    if (sc.plane_cells < need) {
+        if (sc.planes) {
+            PFS_CUDA(cudaDeviceSynchronize());   // earlier steps may still be using the old planes
+            PFS_CUDA(cudaFree(sc.planes));
+            sc.planes = nullptr;
+            sc.plane_cells = 0;
+        }
+        PFS_CUDA(cudaMalloc((void **)&sc.planes, 7 * need * sizeof(float)));
+        sc.plane_cells = need;
+    }
+    *out = &sc;
+    return PFS_OK;
+}
+
+// ---------------------------------------------------------------------------------------------
+// phase timing
+// ---------------------------------------------------------------------------------------------
+struct PhaseSpan {
+    int phase;
+    cudaEvent_t a, b;
+    unsigned long long launches;
+};
+static bool g_phase_timing = false;
+static std::vector<PhaseSpan> g_spans;
+static std::vector<cudaEvent_t> g_event_pool;
+
+static cudaEvent_t take_event()
+{
+    if (!g_event_pool.empty()) {
+        cudaEvent_t e = g_event_pool.back();
+        g_event_pool.pop_back();
+        return e;
+    }
+    cudaEvent_t e = nullptr;
+    cudaEventCreate(&e);
+    return e;
+}
+
+struct PhaseScope {
+    int phase;
+    cudaStream_t s;
+    cudaEvent_t a = nullptr;
+    unsigned long long l0 = 0;
+    PhaseScope(int phase_, cudaStream_t s_) : phase(phase_), s(s_)
+    {
+        if (!g_phase_timing) return;
+        a = take_event();
+        l0 = g_launches;
+        cudaEventRecord(a, s);
+    }
+    ~PhaseScope()
+    {
+        if (!a) return;
+        cudaEvent_t b = take_event();
+        cudaEventRecord(b, s);
+        g_spans.push_back({phase, a, b, g_launches - l0});
+    }
+};
+
+// ---------------------------------------------------------------------------------------------
+// argument checks
+// ---------------------------------------------------------------------------------------------
+static int check_dims(const char *fn, int x, int y, int z)
+{
+    if (x <= 0 || y <= 0) {
+        set_error("%s: width and height must be positive (got %d x %d)", fn, x, y);
+        return PFS_EINVAL;
+    }
+    if (z != 4) {
+        set_error("%s: channel count must be 4 (interleaved RGBA / u,v,p,div as in main.cpp:25), got %d", fn, z);
+        return PFS_EINVAL;
+    }
+    if ((size_t)x * (size_t)y > ((size_t)1 << 28)) {
+        // the reference's int indexing (fluid.cpp:15-17) tops out at 2^30 floats = 2^28 cells
+        set_error("%s: %d x %d exceeds 2^28 cells (the reference's int32 index limit)", fn, x, y);
+        return PFS_EINVAL;
+    }
+    return PFS_OK;
+}
+
+static int check_ptr(const char *fn, const char *name, const void *p)
+{
+    if (p == nullptr) {
+        set_error("%s: %s is null", fn, name);
+        return PFS_EINVAL;
+    }
+    if ((reinterpret_cast<uintptr_t>(p) & 15u) != 0) {
+        set_error("%s: %s must be 16-byte aligned (one interleaved cell)", fn, name);
+        return PFS_EINVAL;
+    }
+    return PFS_OK;
+}
+
+static int check_sweeps(const char *fn, int n)
+{
+    if (n < 1) {
+        set_error("%s: sweep count must be >= 1 (got %d)", fn, n);
+        return PFS_EINVAL;
+    }
+    return PFS_OK;
+}
+
+// ---------------------------------------------------------------------------------------------
+// n Jacobi sweeps on planes with the reference's "n-1 swaps" semantics.
+//
+// Start: iterate 0 in planes a*.  The reference loop writes sweep k to the "other" buffer and
+// swaps, so the caller needs BOTH iterate n (the result) and iterate n-1 (left behind in the other
+// buffer, fluid.cpp:188-194).  We run n-1 sweeps with as much temporal blocking as allowed, which
+// leaves iterate n-1 in one plane set, then exactly one sweep into the other set.
+// On return *last points at the planes of iterate n and *prev at those of iterate n-1.
+// ---------------------------------------------------------------------------------------------
+struct PlanePair {
+    float *c0, *c1;   // c1 unused for pressure
+};
+
+static int run_sweeps(SweepOp op, PlanePair a, PlanePair b, const float *rhs, const SweepParams &p, int n,
+                      PlanePair *last, PlanePair *prev, cudaStream_t s)
+{
+    int lead = n - 1;
+    int flips = 0;   // number of a<->b ping-pong hops the lead sweeps took (one per launch)
+    if (lead > 0) {
+        int depth = g_fuse_depth;
+        bool fused = (depth != 1) && fused_sweeps_supported(p.w, p.h);
+        if (fused)
+            PFS_TRY(launch_sweeps_fused(op, a.c0, a.c1, b.c0, b.c1, rhs, p, lead, depth, &flips, s));
+        else
+            PFS_TRY(launch_sweeps_basic(op, a.c0, a.c1, b.c0, b.c1, rhs, p, lead, &flips, s));
+    }
+    // iterate n-1 is in b if the lead sweeps took an odd number of hops, else in a
+    PlanePair cur = (flips & 1) ? b : a, oth = (flips & 1) ? a : b;
+    int one = 0;
+    PFS_TRY(launch_sweeps_basic(op, cur.c0, cur.c1, oth.c0, oth.c1, rhs, p, 1, &one, s));
+    *last = oth;
+    *prev = cur;
+    return PFS_OK;
+}
+
+static SweepParams diffuse_params(int w, int h, float viscosity, float dt)
+{
+    SweepParams p;
+    p.w = w;
+    p.h = h;
+    p.alpha = viscosity * dt;                               // fluid.cpp:144 (binary32 product)
+    p.beta = (float)(1.0 + 4.0 * (double)p.alpha);          // fluid.cpp:145 (double, rounded to float)
+    return p;
+}
+
+}  // namespace pfs
+
+using namespace pfs;
+
+// =============================================================================================
+// library
+// =============================================================================================
+extern "C" int pfs_version(void) { return PFS_B200_VERSION; }
+
+extern "C" const char *pfs_last_error(void) { return t_error; }
+
+extern "C" uint64_t pfs_kernel_launch_count(void) { return g_launches; }
+
+extern "C" int pfs_shutdown(void)
+{
+    std::lock_guard<std::mutex> lock(g_mutex);
+    int cur = 0;
+    bool have = (cudaGetDevice(&cur) == cudaSuccess);
+    for (auto &kv : g_scratch) {
+        if (cudaSetDevice(kv.first) == cudaSuccess) {
+            cudaDeviceSynchronize();
+            free_scratch(kv.second);
+        }
+    }
+    g_scratch.clear();
+    for (auto &sp : g_spans) {
+        cudaEventDestroy(sp.a);
+        cudaEventDestroy(sp.b);
+    }
+    g_spans.clear();
+    for (auto e : g_event_pool) cudaEventDestroy(e);
+    g_event_pool.clear();
+    if (have) cudaSetDevice(cur);
+    (void)cudaGetLastError();
+    return PFS_OK;
+}
+
+extern "C" int pfs_set_fuse_depth(int d)
+{
+    if (d < 0) {
+        set_error("pfs_set_fuse_depth: depth must be >= 0");
+        return PFS_EINVAL;
+    }
+    g_fuse_depth = d;
+    return PFS_OK;
+}
+
+extern "C" int pfs_get_fuse_depth(void) { return g_fuse_depth; }
+
+extern "C" int pfs_host_alloc(void **ptr, size_t bytes)
+{
+    if (!ptr) {
+        set_error("pfs_host_alloc: ptr is null");
+        return PFS_EINVAL;
+    }
+    cudaError_t e = cudaMallocHost(ptr, bytes);
+    if (e != cudaSuccess) return cuda_fail(e, "cudaMallocHost", __FILE__, __LINE__);
+    return PFS_OK;
+}
+
+extern "C" int pfs_host_free(void *ptr)
+{
+    if (ptr) PFS_CUDA(cudaFreeHost(ptr));
+    return PFS_OK;
+}
+
+extern "C" int pfs_phase_timing_enable(int on)
+{
+    g_phase_timing = (on != 0);
+    return PFS_OK;
+}
+
+extern "C" int pfs_phase_times(float ms_out[PFS_NUM_PHASES], uint64_t launches_out[PFS_NUM_PHASES], int reset)
+{
+    for (int i = 0; i < PFS_NUM_PHASES; i++) {
+        if (ms_out) ms_out[i] = 0.f;
+        if (launches_out) launches_out[i] = 0;
+    }
+    for (auto &sp : g_spans) {
+        PFS_CUDA(cudaEventSynchronize(sp.b));
+        float ms = 0.f;
+        PFS_CUDA(cudaEventElapsedTime(&ms, sp.a, sp.b));
+        if (ms_out) ms_out[sp.phase] += ms;
+        if (launches_out) launches_out[sp.phase] += sp.launches;
+    }
+    if (reset) {
+        for (auto &sp : g_spans) {
+            g_event_pool.push_back(sp.a);
+            g_event_pool.push_back(sp.b);
+        }
+        g_spans.clear();
+    }
+    return PFS_OK;
+}
+
+// =============================================================================================
+// device-pointer operator API
+// =============================================================================================
+extern "C" int pfs_advect(const float *vp, float *vp_out, float dt, int vx, int vy, int vz, void *stream)
+{
+    PFS_TRY(check_dims("pfs_advect", vx, vy, vz));
+    PFS_TRY(check_ptr("pfs_advect", "vp", vp));
+    PFS_TRY(check_ptr("pfs_advect", "vp_out", vp_out));
+    return launch_advect(vp, nullptr, nullptr, vp_out, dt, vx, vy, (cudaStream_t)stream);
+}
+
+extern "C" int pfs_add_forces(float *vp, const float *forces, int vx, int vy, int vz, void *stream)
+{
+    // fluid.cpp:198-208: empty loop body; call site commented out (fluid.cpp:302).
+    (void)forces;
+    (void)stream;
+    PFS_TRY(check_dims("pfs_add_forces", vx, vy, vz));
+    PFS_TRY(check_ptr("pfs_add_forces", "vp", vp));
+    return PFS_OK;
+}
+
+extern "C" int pfs_diffuse(float **vp, float **vp_out, float viscosity, float dt, int vx, int vy, int vz, int n_sweeps,
+                           void *stream)
+{
+    const char *fn = "pfs_diffuse";
+    PFS_TRY(check_dims(fn, vx, vy, vz));
+    PFS_TRY(check_sweeps(fn, n_sweeps));
+    if (!vp || !vp_out) {
+        set_error("%s: vp / vp_out handle is null", fn);
+        return PFS_EINVAL;
+    }
+    PFS_TRY(check_ptr(fn, "*vp", *vp));
+    PFS_TRY(check_ptr(fn, "*vp_out", *vp_out));
+    cudaStream_t s = (cudaStream_t)stream;
+    DeviceScratch *sc;
+    PFS_TRY(get_scratch((size_t)vx * vy, &sc));
+    float *in0 = *vp, *out0 = *vp_out;
+    PlanePair a{sc->plane(0), sc->plane(1)}, b{sc->plane(2), sc->plane(3)}, last, prev;
+    PFS_TRY(launch_unpack(in0, a.c0, a.c1, nullptr, nullptr, vx, vy, s));
+    PFS_TRY(run_sweeps(SWEEP_DIFFUSE, a, b, nullptr, diffuse_params(vx, vy, viscosity, dt), n_sweeps, &last, &prev, s));
+    // Sweep k writes the original vp_out buffer when k is odd and the original vp buffer when k is
+    // even (fluid.cpp:188-194).  Only channels 0,1 are ever written.
+    float *buf_last = (n_sweeps & 1) ? out0 : in0;
+    float *buf_prev = (n_sweeps & 1) ? in0 : out0;
+    PFS_TRY(launch_pack(buf_last, last.c0, last.c1, nullptr, nullptr, vx, vy, s));
+    if (n_sweeps >= 2) PFS_TRY(launch_pack(buf_prev, prev.c0, prev.c1, nullptr, nullptr, vx, vy, s));
+    *vp_out = buf_last;
+    *vp = buf_prev;
+    return PFS_OK;
+}
+
+extern "C" int pfs_compute_pressure(float **vp, float **vp_out, float dt, int vx, int vy, int vz, int n_sweeps,
+                                    void *stream)
+{
+    const char *fn = "pfs_compute_pressure";
+    PFS_TRY(check_dims(fn, vx, vy, vz));
+    PFS_TRY(check_sweeps(fn, n_sweeps));
+    if (!vp || !vp_out) {
+        set_error("%s: vp / vp_out handle is null", fn);
+        return PFS_EINVAL;
+    }
+    PFS_TRY(check_ptr(fn, "*vp", *vp));
+    PFS_TRY(check_ptr(fn, "*vp_out", *vp_out));
+    cudaStream_t s = (cudaStream_t)stream;
+    DeviceScratch *sc;
+    PFS_TRY(get_scratch((size_t)vx * vy, &sc));
+    float *in0 = *vp, *out0 = *vp_out;
+    float *u = sc->plane(0), *v = sc->plane(1), *div = sc->plane(6);
+    PlanePair a{sc->plane(4), nullptr}, b{sc->plane(5), nullptr}, last, prev;
+    PFS_TRY(launch_unpack(in0, u, v, nullptr, nullptr, vx, vy, s));
+    PFS_TRY(launch_divergence(u, v, div, in0, a.c0, dt, vx, vy, s));
+    SweepParams p{vx, vy, 1.0f, 4.0f};
+    PFS_TRY(run_sweeps(SWEEP_PRESSURE, a, b, div, p, n_sweeps, &last, &prev, s));
+    float *buf_last = (n_sweeps & 1) ? out0 : in0;
+    float *buf_prev = (n_sweeps & 1) ? in0 : out0;
+    // channel 3 of both buffers <- divergence (fluid.cpp:235-236); channel 2 <- the iterate each
+    // buffer was last written with.  With one sweep the input buffer keeps its pressure.
+    PFS_TRY(launch_pack(buf_last, nullptr, nullptr, last.c0, div, vx, vy, s));
+    PFS_TRY(launch_pack(buf_prev, nullptr, nullptr, (n_sweeps >= 2) ? prev.c0 : nullptr, div, vx, vy, s));
+    *vp_out = buf_last;
+    *vp = buf_prev;
+    return PFS_OK;
+}
+
+extern "C" int pfs_subtract_pressure_gradient(const float *vp, float *vp_out, float dt, int vx, int vy, int vz,
+                                              void *stream)
+{
+    const char *fn = "pfs_subtract_pressure_gradient";
+    PFS_TRY(check_dims(fn, vx, vy, vz));
+    PFS_TRY(check_ptr(fn, "vp", vp));
+    PFS_TRY(check_ptr(fn, "vp_out", vp_out));
+    return launch_subtract_gradient_aos(vp, vp_out, dt, vx, vy, (cudaStream_t)stream);
+}
+
+extern "C" int pfs_advect_color(const float *image, float *itmp, const float *vp, float dt, int ix, int iy, int iz,
+                                int vx, int vy, int vz, void *stream)
+{
+    const char *fn = "pfs_advect_color";
+    PFS_TRY(check_dims(fn, ix, iy, iz));
+    PFS_TRY(check_dims(fn, vx, vy, vz));
+    PFS_TRY(check_ptr(fn, "image", image));
+    PFS_TRY(check_ptr(fn, "itmp", itmp));
+    PFS_TRY(check_ptr(fn, "vp", vp));
+    return launch_advect_color(image, itmp, vp, dt, ix, iy, vx, vy, (cudaStream_t)stream);
+}
+
+// =============================================================================================
+// device-pointer step API
+// =============================================================================================
+extern "C" int pfs_simulate_fluid_step(float **vp, float **tmp, float dt, float viscosity, int vx, int vy, int vz,
+                                       int n_diffuse, int n_pressure, void *stream)
+{
+    const char *fn = "pfs_simulate_fluid_step";
+    PFS_TRY(check_dims(fn, vx, vy, vz));
+    PFS_TRY(check_sweeps(fn, n_diffuse));
+    PFS_TRY(check_sweeps(fn, n_pressure));
+    if (!vp || !tmp) {
+        set_error("%s: vp / tmp handle is null", fn);
+        return PFS_EINVAL;
+    }
+    PFS_TRY(check_ptr(fn, "*vp", *vp));
+    PFS_TRY(check_ptr(fn, "*tmp", *tmp));
+    if (*vp == *tmp) {
+        set_error("%s: vp and tmp must be distinct buffers", fn);
+        return PFS_EINVAL;
+    }
+    cudaStream_t s = (cudaStream_t)stream;
+    DeviceScratch *sc;
+    PFS_TRY(get_scratch((size_t)vx * vy, &sc));
+
+    float *X = *vp, *Y = *tmp;
+    PlanePair ua{sc->plane(0), sc->plane(1)}, ub{sc->plane(2), sc->plane(3)}, d_last, d_prev;
+    PlanePair pa{sc->plane(4), nullptr}, pb{sc->plane(5), nullptr}, p_last, p_prev;
+    float *div = sc->plane(6);
+
+    // advect(vp -> tmp)  (fluid.cpp:299): X.uv gathered, result kept planar (iterate 0 of diffusion)
+    {
+        PhaseScope ph(PFS_PHASE_ADVECT, s);
+        PFS_TRY(launch_advect(X, ua.c0, ua.c1, nullptr, dt, vx, vy, s));
+    }
+    // diffuse(tmp -> vp)  (fluid.cpp:300)
+    {
+        PhaseScope ph(PFS_PHASE_DIFFUSE, s);
+        PFS_TRY(run_sweeps(SWEEP_DIFFUSE, ua, ub, nullptr, diffuse_params(vx, vy, viscosity, dt), n_diffuse, &d_last,
+                           &d_prev, s));
+    }
+    // After diffuse the struct `vp` points at the buffer written last: sweep k writes X for odd k,
+    // Y for even k (sweep 1 writes vp_out = the original vp buffer X).
+    float *Bv = (n_diffuse & 1) ? X : Y;     // holds iterate n_diffuse in ch0,1; its ch2 is the warm start
+    float *Bo = (n_diffuse & 1) ? Y : X;     // holds iterate n_diffuse-1 in ch0,1
+    // computePressure(vp -> tmp)  (fluid.cpp:303): divergence of iterate n_diffuse, p_0 = Bv.ch2
+    {
+        PhaseScope ph(PFS_PHASE_DIVERGENCE, s);
+        PFS_TRY(launch_divergence(d_last.c0, d_last.c1, div, Bv, pa.c0, dt, vx, vy, s));
+    }
+    {
+        PhaseScope ph(PFS_PHASE_PRESSURE, s);
+        SweepParams pp{vx, vy, 1.0f, 4.0f};
+        PFS_TRY(run_sweeps(SWEEP_PRESSURE, pa, pb, div, pp, n_pressure, &p_last, &p_prev, s));
+    }
+    // Pressure sweep k writes Bo for odd k, Bv for even k; struct `tmp` ends on the buffer with p_N.
+    float *Bp = (n_pressure & 1) ? Bo : Bv;
+    float *Bq = (n_pressure & 1) ? Bv : Bo;
+    // subtractPressureGradient(tmp -> vp)  (fluid.cpp:304) reads ch0,1 of the buffer holding p_N,
+    // which carries diffusion iterate n_diffuse if that buffer is Bv, else iterate n_diffuse-1.
+    const PlanePair &uv_p = (Bp == Bv) ? d_last : d_prev;
+    {
+        PhaseScope ph(PFS_PHASE_PROJECT, s);
+        PFS_TRY(launch_project_pack(uv_p.c0, uv_p.c1, p_last.c0, p_prev.c0, div, Bq, Bp, dt, vx, vy, s));
+    }
+    *vp = Bq;
+    *tmp = Bp;
+    return PFS_OK;
+}
+
+extern "C" int pfs_advect_color_step(float **image, float **itmp, float **vp, float dt, int ix, int iy, int iz, int vx,
+                                     int vy, int vz, void *stream)
+{
+    const char *fn = "pfs_advect_color_step";
+    if (!image || !itmp || !vp) {
+        set_error("%s: image / itmp / vp handle is null", fn);
+        return PFS_EINVAL;
+    }
+    cudaStream_t s = (cudaStream_t)stream;
+    {
+        PhaseScope ph(PFS_PHASE_ADVECT_COLOR, s);
+        PFS_TRY(pfs_advect_color(*image, *itmp, *vp, dt, ix, iy, iz, vx, vy, vz, stream));
+    }
+    float *t = *image;     // fluid.cpp:317-319
+    *image = *itmp;
+    *itmp = t;
+    return PFS_OK;
+}
+
+// =============================================================================================
+// host-buffer API
+// =============================================================================================
+namespace pfs {
+
+static int host_ctx(DeviceScratch **out)
+{
+    int dev;
+    PFS_TRY(current_device(&dev));
+    std::lock_guard<std::mutex> lock(g_mutex);
+    DeviceScratch &sc = g_scratch[dev];
+    for (int i = 0; i < 2; i++)
+        if (!sc.streams[i]) PFS_CUDA(cudaStreamCreateWithFlags(&sc.streams[i], cudaStreamNonBlocking));
+    for (int i = 0; i < 4; i++)
+        if (!sc.ev[i]) PFS_CUDA(cudaEventCreateWithFlags(&sc.ev[i], cudaEventDisableTiming));
+    *out = &sc;
+    return PFS_OK;
+}
+
+static int ensure_stage(DeviceScratch *sc, int k, size_t floats)
+{
+    if (sc->stage_floats[k] >= floats) return PFS_OK;
+    if (sc->stage[k]) {
+        PFS_CUDA(cudaDeviceSynchronize());
+        PFS_CUDA(cudaFree(sc->stage[k]));
+        sc->stage[k] = nullptr;
+        sc->stage_floats[k] = 0;
+    }
+    PFS_CUDA(cudaMalloc((void **)&sc->stage[k], floats * sizeof(float)));
+    sc->stage_floats[k] = floats;
+    return PFS_OK;
+}
+
+static int check_field(const char *fn, const char *name, const pfs_field *f)
+{
+    if (!f || !f->data) {
+        set_error("%s: %s (or its data pointer) is null", fn, name);
+        return PFS_EINVAL;
+    }
+    return check_dims(fn, f->x, f->y, f->z);
+}
+
+}  // namespace pfs
+
+extern "C" int pfs_simulate_fluid_step_host(pfs_field *vp, pfs_field *tmp, float dt, float viscosity, int n_diffuse,
+                                            int n_pressure)
+{
+    const char *fn = "pfs_simulate_fluid_step_host";
+    PFS_TRY(check_field(fn, "vp", vp));
+    PFS_TRY(check_field(fn, "tmp", tmp));
+    if (vp->x != tmp->x || vp->y != tmp->y) {
+        set_error("%s: vp and tmp must have the same shape", fn);
+        return PFS_EINVAL;
+    }
+    DeviceScratch *sc;
+    PFS_TRY(host_ctx(&sc));
+    size_t n = (size_t)vp->x * vp->y * 4;
+    PFS_TRY(ensure_stage(sc, 0, n));
+    PFS_TRY(ensure_stage(sc, 1, n));
+    cudaStream_t s = sc->streams[0];
+    float *dvp = sc->stage[0], *dtmp = sc->stage[1];
+    PFS_CUDA(cudaMemcpyAsync(dvp, vp->data, n * sizeof(float), cudaMemcpyHostToDevice, s));
+    PFS_CUDA(cudaMemcpyAsync(dtmp, tmp->data, n * sizeof(float), cudaMemcpyHostToDevice, s));
+    float *a = dvp, *b = dtmp;
+    PFS_TRY(pfs_simulate_fluid_step(&a, &b, dt, viscosity, vp->x, vp->y, 4, n_diffuse, n_pressure, s));
+    // mirror the pointer exchange on the caller's structs, then bring both post-state buffers back
+    float *hvp = vp->data, *htmp = tmp->data;
+    if (a != dvp) {
+        vp->data = htmp;
+        tmp->data = hvp;
+    }
+    PFS_CUDA(cudaMemcpyAsync(vp->data, a, n * sizeof(float), cudaMemcpyDeviceToHost, s));
+    PFS_CUDA(cudaMemcpyAsync(tmp->data, b, n * sizeof(float), cudaMemcpyDeviceToHost, s));
+    PFS_CUDA(cudaStreamSynchronize(s));
+    return PFS_OK;
+}
+
+extern "C" int pfs_advect_color_step_host(pfs_field *image, pfs_field *itmp, pfs_field *vp, float dt)
+{
+    const char *fn = "pfs_advect_color_step_host";
+    PFS_TRY(check_field(fn, "image", image));
+    PFS_TRY(check_field(fn, "itmp", itmp));
+    PFS_TRY(check_field(fn, "vp", vp));
+    if (image->x != itmp->x || image->y != itmp->y) {
+        set_error("%s: image and itmp must have the same shape", fn);
+        return PFS_EINVAL;
+    }
+    DeviceScratch *sc;
+    PFS_TRY(host_ctx(&sc));
+    size_t nv = (size_t)vp->x * vp->y * 4, ni = (size_t)image->x * image->y * 4;
+    PFS_TRY(ensure_stage(sc, 0, nv));
+    PFS_TRY(ensure_stage(sc, 2, ni));
+    PFS_TRY(ensure_stage(sc, 3, ni));
+    cudaStream_t s = sc->streams[0];
+    PFS_CUDA(cudaMemcpyAsync(sc->stage[0], vp->data, nv * sizeof(float), cudaMemcpyHostToDevice, s));
+    PFS_CUDA(cudaMemcpyAsync(sc->stage[2], image->data, ni * sizeof(float), cudaMemcpyHostToDevice, s));
+    PFS_TRY(pfs_advect_color(sc->stage[2], sc->stage[3], sc->stage[0], dt, image->x, image->y, 4, vp->x, vp->y, 4, s));
+    // fluid.cpp:316-319: the result is written to itmp's buffer, then the two data pointers swap
+    PFS_CUDA(cudaMemcpyAsync(itmp->data, sc->stage[3], ni * sizeof(float), cudaMemcpyDeviceToHost, s));
+    PFS_CUDA(cudaStreamSynchronize(s));
+    float *t = image->data;
+    image->data = itmp->data;
+    itmp->data = t;
+    return PFS_OK;
+}
+
+extern "C" int pfs_timestep_host(pfs_field *vp, pfs_field *vtmp, pfs_field *image, pfs_field *itmp, float dt,
+                                 float viscosity, int n_diffuse, int n_pressure)
+{
+    const char *fn = "pfs_timestep_host";
+    PFS_TRY(check_field(fn, "vp", vp));
+    PFS_TRY(check_field(fn, "vtmp", vtmp));
+    PFS_TRY(check_field(fn, "image", image));
+    PFS_TRY(check_field(fn, "itmp", itmp));
+    if (vp->x != vtmp->x || vp->y != vtmp->y || image->x != itmp->x || image->y != itmp->y) {
+        set_error("%s: vp/vtmp and image/itmp must pairwise have the same shape", fn);
+        return PFS_EINVAL;
+    }
+    DeviceScratch *sc;
+    PFS_TRY(host_ctx(&sc));
+    size_t nv = (size_t)vp->x * vp->y * 4, ni = (size_t)image->x * image->y * 4;
+    PFS_TRY(ensure_stage(sc, 0, nv));
+    PFS_TRY(ensure_stage(sc, 1, nv));
+    PFS_TRY(ensure_stage(sc, 2, ni));
+    PFS_TRY(ensure_stage(sc, 3, ni));
+    cudaStream_t s0 = sc->streams[0], s1 = sc->streams[1];
+    float *dvp = sc->stage[0], *dtmp = sc->stage[1], *dimg = sc->stage[2], *ditmp = sc->stage[3];
+
+    // stream 0: velocity field up, fluid step.  stream 1: image up (overlaps the fluid step).
+    PFS_CUDA(cudaMemcpyAsync(dvp, vp->data, nv * sizeof(float), cudaMemcpyHostToDevice, s0));
+    PFS_CUDA(cudaMemcpyAsync(dtmp, vtmp->data, nv * sizeof(float), cudaMemcpyHostToDevice, s0));
+    PFS_CUDA(cudaMemcpyAsync(dimg, image->data, ni * sizeof(float), cudaMemcpyHostToDevice, s1));
+    float *a = dvp, *b = dtmp;
+    PFS_TRY(pfs_simulate_fluid_step(&a, &b, dt, viscosity, vp->x, vp->y, 4, n_diffuse, n_pressure, s0));
+    PFS_CUDA(cudaEventRecord(sc->ev[1], s0));
+    float *hvp = vp->data, *htmp = vtmp->data;
+    if (a != dvp) {
+        vp->data = htmp;
+        vtmp->data = hvp;
+    }
+    // stream 1: advect_color once the image is up and the projected velocity exists, image down.
+    PFS_CUDA(cudaStreamWaitEvent(s1, sc->ev[1], 0));
+    float *di = dimg, *dt2 = ditmp, *dv = a;
+    PFS_TRY(pfs_advect_color_step(&di, &dt2, &dv, dt, image->x, image->y, 4, vp->x, vp->y, 4, s1));
+    PFS_CUDA(cudaMemcpyAsync(itmp->data, di, ni * sizeof(float), cudaMemcpyDeviceToHost, s1));
+    // stream 0: velocity post-state down (overlaps advect_color and the image download)
+    PFS_CUDA(cudaMemcpyAsync(vp->data, a, nv * sizeof(float), cudaMemcpyDeviceToHost, s0));
+    PFS_CUDA(cudaMemcpyAsync(vtmp->data, b, nv * sizeof(float), cudaMemcpyDeviceToHost, s0));
+    PFS_CUDA(cudaStreamSynchronize(s0));
+    PFS_CUDA(cudaStreamSynchronize(s1));
+    float *t = image->data;     // fluid.cpp:317-319
+    image->data = itmp->data;
+    itmp->data = t;
+    return PFS_OK;
+}

@@ -1,0 +1,172 @@
+// pfs_internal.cuh -- shared declarations of libpfs_b200.so (not installed; the public surface
+// is include/pfs_b200.h).
+//
+// Arithmetic contract (DESIGN.md "Parity"): every floating-point operation on the path is written
+// with a round-to-nearest intrinsic (__fadd_rn/__fsub_rn/__fmul_rn/__fdiv_rn), which nvcc never
+// contracts into FMA, in exactly the association order of the reference expression cited next to
+// it.  The translation units are additionally compiled with -fmad=false.  The reference CPU
+// build has no FMA, so results are bit-identical, not merely close.
+#pragma once
+
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+
+#include "../../include/pfs_b200.h"
+
+namespace pfs {
+
+// ---------------------------------------------------------------------------------------------
+// error plumbing
+// ---------------------------------------------------------------------------------------------
+void set_error(const char *fmt, ...);
+int cuda_fail(cudaError_t e, const char *what, const char *file, int line);
+
+#define PFS_CUDA(call)                                                         \
+    do {                                                                       \
+        cudaError_t e__ = (call);                                              \
+        if (e__ != cudaSuccess) return ::pfs::cuda_fail(e__, #call, __FILE__, __LINE__); \
+    } while (0)
+
+#define PFS_TRY(call)                       \
+    do {                                    \
+        int s__ = (call);                   \
+        if (s__ != PFS_OK) return s__;      \
+    } while (0)
+
+extern unsigned long long g_launches;   // kernels launched by this library (host counter)
+int check_launch(const char *kernel, const char *file, int line);
+
+#define PFS_LAUNCH(kernel, grid, block, smem, stream, ...)                     \
+    do {                                                                       \
+        kernel<<<(grid), (block), (smem), (stream)>>>(__VA_ARGS__);            \
+        ++::pfs::g_launches;                                                   \
+        PFS_TRY(::pfs::check_launch(#kernel, __FILE__, __LINE__));             \
+    } while (0)
+
+// ---------------------------------------------------------------------------------------------
+// exact-arithmetic device helpers (each cites the reference expression it reproduces)
+// ---------------------------------------------------------------------------------------------
+
+// fluid.cpp:48-49,105-106: fmod(fmod(x, ext) + ext, ext) on floats.  CUDA fmodf is exact (0 ulp).
+__device__ __forceinline__ float wrap_coord(float x, float ext)
+{
+    return fmodf(__fadd_rn(fmodf(x, ext), ext), ext);
+}
+
+// fluid.cpp:19-21 with alpha = 1, beta = 4 (fluid.cpp:215-216,255): (((pL+pR)+pT)+pB + 1.0f*b)/4.0f.
+// Division by 4 and multiplication by 0.25 round identically (same real value, one rounding).
+__device__ __forceinline__ float pressure_update(float pl, float pr, float pt, float pb, float b)
+{
+    return __fmul_rn(__fadd_rn(__fadd_rn(__fadd_rn(__fadd_rn(pl, pr), pt), pb), b), 0.25f);
+}
+
+// fluid.cpp:175-182: jacobi(alpha*L, alpha*R, alpha*T, alpha*B, 1.0f, beta, u_n)
+//   = ((((aL + aR) + aT) + aB) + u_n) / beta, IEEE division.
+__device__ __forceinline__ float diffuse_update(float l, float r, float t, float b, float c,
+                                                float alpha, float beta)
+{
+    float s = __fadd_rn(__fmul_rn(alpha, l), __fmul_rn(alpha, r));
+    s = __fadd_rn(s, __fmul_rn(alpha, t));
+    s = __fadd_rn(s, __fmul_rn(alpha, b));
+    s = __fadd_rn(s, c);
+    return __fdiv_rn(s, beta);
+}
+
+// fluid.cpp:230-235: gamma * ((uR - uL) + (vB - vT))
+__device__ __forceinline__ float divergence_value(float ur, float ul, float vb, float vt, float gamma)
+{
+    return __fmul_rn(gamma, __fadd_rn(__fsub_rn(ur, ul), __fsub_rn(vb, vt)));
+}
+
+// fluid.cpp:288-293: u - ((pR - pL) * dt) / 2.0f   (x/2 == x*0.5 exactly)
+__device__ __forceinline__ float project_component(float vel, float p_hi, float p_lo, float dt)
+{
+    return __fsub_rn(vel, __fmul_rn(__fmul_rn(__fsub_rn(p_hi, p_lo), dt), 0.5f));
+}
+
+// fluid.cpp:55-66 / :112-124: cell indices and the four bilinear weights of a wrapped departure
+// point.  Weights are formed first ((1-sx)*(1-sy) etc.), each then multiplies its sample, and the
+// four terms are added left to right.
+struct Bilinear {
+    int i0, i1, j0, j1;
+    float w00, w10, w01, w11;
+};
+
+__device__ __forceinline__ Bilinear make_bilinear(float xp, float yp, int w, int h)
+{
+    Bilinear b;
+    b.i0 = (int)xp;
+    b.j0 = (int)yp;
+    b.i1 = b.i0 + 1;
+    if (b.i1 >= w) b.i1 -= w;   // (i0 + 1) % width, i0 in [0, w)
+    b.j1 = b.j0 + 1;
+    if (b.j1 >= h) b.j1 -= h;
+    float sx = __fsub_rn(xp, (float)b.i0), sy = __fsub_rn(yp, (float)b.j0);
+    float ox = __fsub_rn(1.0f, sx), oy = __fsub_rn(1.0f, sy);
+    b.w00 = __fmul_rn(ox, oy);
+    b.w10 = __fmul_rn(sx, oy);
+    b.w01 = __fmul_rn(ox, sy);
+    b.w11 = __fmul_rn(sx, sy);
+    return b;
+}
+
+__device__ __forceinline__ float bilerp(const Bilinear &b, float f00, float f10, float f01, float f11)
+{
+    float s = __fadd_rn(__fmul_rn(b.w00, f00), __fmul_rn(b.w10, f10));
+    s = __fadd_rn(s, __fmul_rn(b.w01, f01));
+    return __fadd_rn(s, __fmul_rn(b.w11, f11));
+}
+
+// ---------------------------------------------------------------------------------------------
+// host-side launch wrappers (kernels_basic.cu, sweeps_fused.cu)
+// ---------------------------------------------------------------------------------------------
+
+enum SweepOp { SWEEP_PRESSURE = 0, SWEEP_DIFFUSE = 1 };
+
+struct SweepParams {
+    int w, h;
+    float alpha, beta;   // diffusion only (fluid.cpp:144-145)
+};
+
+// interleaved (AoS) <-> planar (SoA) movers.  Null plane pointers are skipped.
+int launch_unpack(const float *aos, float *c0, float *c1, float *c2, float *c3, int w, int h, cudaStream_t s);
+int launch_pack(float *aos, const float *c0, const float *c1, const float *c2, const float *c3, int w, int h,
+                cudaStream_t s);
+
+// advect (fluid.cpp:24-70).  Source is always the interleaved field; destination is either two
+// planes (u_out, v_out) or channels 0,1 of an interleaved buffer (aos_out), whichever is non-null.
+int launch_advect(const float *vp_aos, float *u_out, float *v_out, float *aos_out, float dt, int w, int h,
+                  cudaStream_t s);
+
+// n sweeps of the 5-point update on planes, one sweep per launch, ping-ponging a<->b.
+// pressure: planes a0/b0 only, rhs = divergence plane.  diffuse: (a0,a1) <-> (b0,b1), rhs unused.
+// *flips receives the number of a<->b hops taken (= launches): the result is in b* if it is odd.
+int launch_sweeps_basic(SweepOp op, float *a0, float *a1, float *b0, float *b1, const float *rhs,
+                        const SweepParams &p, int n, int *flips, cudaStream_t s);
+
+// Temporally blocked version: up to `depth` sweeps fused per launch.  Same contract and bit-identical
+// results.  Returns PFS_EINVAL if the shape is not supported (caller then uses the basic path).
+int launch_sweeps_fused(SweepOp op, float *a0, float *a1, float *b0, float *b1, const float *rhs,
+                        const SweepParams &p, int n, int depth, int *flips, cudaStream_t s);
+bool fused_sweeps_supported(int w, int h);
+
+// divergence (fluid.cpp:221-237) of planes (u, v) into plane div; optionally also extracts
+// channel 2 of an interleaved buffer into plane p0 (the pressure warm start) in the same pass.
+int launch_divergence(const float *u, const float *v, float *div, const float *p0_src_aos, float *p0,
+                      float dt, int w, int h, cudaStream_t s);
+
+// End of simulate_fluid_step: subtract the gradient of p_n from (u, v) (fluid.cpp:269-296) and write
+// BOTH interleaved post-state buffers with full-cell stores:
+//   out_q = [u - gx, v - gy, p_prev, div]      out_p = [u, v, p_n, div]
+int launch_project_pack(const float *u, const float *v, const float *p_n, const float *p_prev,
+                        const float *div, float *out_q, float *out_p, float dt, int w, int h, cudaStream_t s);
+
+// subtractPressureGradient as a stand-alone operator on interleaved buffers (writes ch0,1 of out).
+int launch_subtract_gradient_aos(const float *vp_aos, float *out_aos, float dt, int w, int h, cudaStream_t s);
+
+// advect_color (fluid.cpp:72-127) on interleaved buffers.
+int launch_advect_color(const float *image, float *out, const float *vp_aos, float dt, int iw, int ih, int vw,
+                        int vh, cudaStream_t s);
+
+}  // namespace pfs

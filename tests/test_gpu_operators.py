@@ -1,0 +1,137 @@
+"""GPU parity, part 2: every operator of includes/fluid.hpp, CUDA (through the C-ABI) vs the CPU
+oracle on the same seeded inputs -- values bit for bit, untouched channels untouched, and the
+data-pointer exchanges of the reference reproduced."""
+import numpy as np
+import pytest
+
+import oracle
+import probabilistic_fluid_simulation_b200 as pfs
+from golden_util import assert_bit_equal
+from gpu_util import to_dev, to_host
+
+pytestmark = pytest.mark.gpu
+
+SHAPES = [(16, 16), (29, 37), (48, 40), (8, 128), (64, 4), (130, 260), (1, 8), (8, 1), (257, 512)]
+
+
+def rand_field(h, w, seed, scale=1.0):
+    rng = np.random.default_rng(seed)
+    return (rng.standard_normal((h, w, 4)) * scale).astype(np.float32)
+
+
+@pytest.mark.parametrize("shape", SHAPES)
+@pytest.mark.parametrize("dt", [0.1, 7.5, 1000.0])
+def test_advect(shape, dt):
+    h, w = shape
+    a, b = rand_field(h, w, 1), rand_field(h, w, 2)
+    fa, fb = pfs.vp_field(to_dev(a)), pfs.vp_field(to_dev(b))
+    pfs.advect(fa, fb, dt)
+    oracle.Oracle().advect(a, b, dt)
+    assert_bit_equal(to_host(fb.data), b, "advect out (ch2,3 must be untouched)")
+    assert_bit_equal(to_host(fa.data), a, "advect in")
+
+
+@pytest.mark.parametrize("n", [1, 2, 3, 4, 7, 30, 31])
+@pytest.mark.parametrize("shape", [(16, 16), (29, 37), (48, 40), (130, 260), (64, 4), (3, 5)])
+def test_diffuse(n, shape):
+    h, w = shape
+    a, b = rand_field(h, w, 3), rand_field(h, w, 4)
+    fa, fb = pfs.vp_field(to_dev(a)), pfs.vp_field(to_dev(b))
+    pa, pb = fa.data.data_ptr(), fb.data.data_ptr()
+    pfs.diffuse(fa, fb, 0.013, 2.5, n)
+    ra, rb = oracle.Oracle().diffuse(a, b, 0.013, 2.5, n)
+    assert_bit_equal(to_host(fa.data), ra, "diffuse vp")
+    assert_bit_equal(to_host(fb.data), rb, "diffuse vp_out")
+    swapped = ra is not a
+    assert (fa.data.data_ptr() == pb) == swapped and (fb.data.data_ptr() == pa) == swapped
+
+
+@pytest.mark.parametrize("visc,dt", [(0.0, 1.0), (0.5, 4.0), (1e-6, 1e-3), (25.0, 10.0)])
+def test_diffuse_parameter_range(visc, dt):
+    a, b = rand_field(40, 64, 13, 3.0), rand_field(40, 64, 14)
+    fa, fb = pfs.vp_field(to_dev(a)), pfs.vp_field(to_dev(b))
+    pfs.diffuse(fa, fb, visc, dt, 6)
+    ra, rb = oracle.Oracle().diffuse(a, b, visc, dt, 6)
+    assert_bit_equal(to_host(fa.data), ra, "diffuse vp")
+    assert_bit_equal(to_host(fb.data), rb, "diffuse vp_out")
+
+
+@pytest.mark.parametrize("n", [1, 2, 3, 4, 7, 30, 31])
+@pytest.mark.parametrize("shape", [(16, 16), (29, 37), (48, 40), (130, 260), (64, 4), (3, 5)])
+def test_compute_pressure(n, shape):
+    h, w = shape
+    a, b = rand_field(h, w, 5), rand_field(h, w, 6)
+    fa, fb = pfs.vp_field(to_dev(a)), pfs.vp_field(to_dev(b))
+    pfs.computePressure(fa, fb, 0.37, n)
+    ra, rb = oracle.Oracle().compute_pressure(a, b, 0.37, n)
+    assert_bit_equal(to_host(fa.data), ra, "pressure vp")
+    assert_bit_equal(to_host(fb.data), rb, "pressure vp_out")
+
+
+@pytest.mark.parametrize("shape", SHAPES)
+def test_subtract_pressure_gradient(shape):
+    h, w = shape
+    a, b = rand_field(h, w, 7), rand_field(h, w, 8)
+    fa, fb = pfs.vp_field(to_dev(a)), pfs.vp_field(to_dev(b))
+    pfs.subtractPressureGradient(fa, fb, 0.9)
+    oracle.Oracle().subtract_pressure_gradient(a, b, 0.9)
+    assert_bit_equal(to_host(fb.data), b, "subtract out")
+
+
+@pytest.mark.parametrize("ishape,vshape", [((32, 48), (16, 16)), ((41, 50), (29, 37)), ((64, 96), (32, 32)),
+                                            ((16, 16), (64, 64)), ((512, 768), (256, 256)), ((100, 7), (3, 300))])
+@pytest.mark.parametrize("dt", [0.1, 250.0])
+def test_advect_color(ishape, vshape, dt):
+    rng = np.random.default_rng(9)
+    img = rng.random((ishape[0], ishape[1], 4)).astype(np.float32)
+    out = np.zeros_like(img)
+    vp = rand_field(vshape[0], vshape[1], 10)
+    fi, fo, fv = pfs.vp_field(to_dev(img)), pfs.vp_field(to_dev(out)), pfs.vp_field(to_dev(vp))
+    pfs.advect_color(fi, fo, fv, dt)
+    oracle.Oracle().advect_color(img, out, vp, dt)
+    assert_bit_equal(to_host(fo.data), out, "advect_color out")
+
+
+def test_add_forces_is_a_noop():
+    a = rand_field(16, 16, 15)
+    fa = pfs.vp_field(to_dev(a))
+    pfs.addForces(fa, None)
+    assert_bit_equal(to_host(fa.data), a, "addForces")
+
+
+@pytest.mark.parametrize("nd,npr", [(1, 1), (1, 2), (2, 1), (2, 2), (3, 3), (3, 4), (4, 3), (5, 8), (30, 30), (7, 30),
+                                     (30, 7), (100, 100)])
+def test_step_with_any_sweep_counts(nd, npr):
+    """Independent diffusion / pressure counts: the pointer choreography decides which diffusion
+    iterate the projection uses and whether the caller's buffers end up exchanged."""
+    h, w = 36, 52
+    vp, vt = rand_field(h, w, 21, 0.8), rand_field(h, w, 22, 0.5)
+    fv, ft = pfs.vp_field(to_dev(vp)), pfs.vp_field(to_dev(vt))
+    p_vp = fv.data.data_ptr()
+    orc = oracle.Oracle(nd, npr)
+    for _ in range(3):
+        pfs.simulate_fluid_step(fv, ft, 1.7, 0.02, nd, npr)
+        vp2, vt2 = orc.simulate_fluid_step(vp, vt, 1.7, 0.02)
+        exchanged = vp2 is not vp
+        vp, vt = vp2, vt2
+        assert (fv.data.data_ptr() != p_vp) == exchanged
+        p_vp = fv.data.data_ptr()
+        assert_bit_equal(to_host(fv.data), vp, "vp")
+        assert_bit_equal(to_host(ft.data), vt, "tmp")
+
+
+@pytest.mark.parametrize("depth", [1, 2, 3, 4, 5, 8, 0])
+def test_fuse_depth_is_invisible(depth):
+    """Temporal blocking must not change a single bit, whatever the depth."""
+    h, w = 96, 256
+    vp, vt = rand_field(h, w, 31, 0.8), rand_field(h, w, 32, 0.5)
+    want_vp, want_vt = oracle.Oracle(13, 21).simulate_fluid_step(vp.copy(), vt.copy(), 0.9, 0.01)
+    old = pfs.get_fuse_depth()
+    try:
+        pfs.set_fuse_depth(depth)
+        fv, ft = pfs.vp_field(to_dev(vp)), pfs.vp_field(to_dev(vt))
+        pfs.simulate_fluid_step(fv, ft, 0.9, 0.01, 13, 21)
+        assert_bit_equal(to_host(fv.data), want_vp, f"vp depth={depth}")
+        assert_bit_equal(to_host(ft.data), want_vt, f"tmp depth={depth}")
+    finally:
+        pfs.set_fuse_depth(old)
