@@ -261,27 +261,31 @@ def run_single_gpu(args):
                   "frac": step_bytes / (ms_step * 1e-3) / 1e9 / peak}
 
     # ---- end to end: host buffers in pinned memory, H2D + kernels + D2H inside the timed region ----
-    hv, ht, hi, hm = (pfs.pinned_empty(x.shape) for x in (vp, vtmp, image, itmp))
-    hv[...] = vp; ht[...] = vtmp; hi[...] = image; hm[...] = itmp
-    gv, gt, gi, gm = (pfs.vp_field(x) for x in (hv, ht, hi, hm))
-    e2e_steps = max(3, min(args.steps, 10))
-    for _ in range(2):
-        pfs.timestep_host(gv, gt, gi, gm, DT, VISC, n, n)
-    t0 = time.perf_counter()
-    for _ in range(e2e_steps):
-        pfs.timestep_host(gv, gt, gi, gm, DT, VISC, n, n)     # synchronises before returning
-    e2e_s = (time.perf_counter() - t0) / e2e_steps
-    e2e = {"value": cells * n / e2e_s, "unit": UNIT, "ms_per_step": e2e_s * 1e3,
-           "h2d_bytes_per_step": 3 * cells * 16, "d2h_bytes_per_step": 3 * cells * 16,
-           "api": "pfs_timestep_host (vp_field structs with pinned host pointers; uploads vp, vtmp, image; "
-                  "downloads vp, vtmp, image)", "steps": e2e_steps}
+    e2e = None
+    if not args.no_e2e:
+        hv, ht, hi, hm = (pfs.pinned_empty(x.shape) for x in (vp, vtmp, image, itmp))
+        hv[...] = vp; ht[...] = vtmp; hi[...] = image; hm[...] = itmp
+        gv, gt, gi, gm = (pfs.vp_field(x) for x in (hv, ht, hi, hm))
+        e2e_steps = max(3, min(args.steps, 10))
+        for _ in range(2):
+            pfs.timestep_host(gv, gt, gi, gm, DT, VISC, n, n)
+        t0 = time.perf_counter()
+        for _ in range(e2e_steps):
+            pfs.timestep_host(gv, gt, gi, gm, DT, VISC, n, n)     # synchronises before returning
+        e2e_s = (time.perf_counter() - t0) / e2e_steps
+        e2e = {"value": cells * n / e2e_s, "unit": UNIT, "ms_per_step": e2e_s * 1e3,
+               "h2d_bytes_per_step": 3 * cells * 16, "d2h_bytes_per_step": 3 * cells * 16,
+               "api": "pfs_timestep_host (vp_field structs with pinned host pointers; uploads vp, vtmp, image; "
+                      "downloads vp, vtmp, image)", "steps": e2e_steps}
 
     # ---- CPU baseline: the reference's fluid.cpp on one host core, bounded sample ----
-    sample_rows = max(64, (1 << 20) // w)
-    cpu_rate, cpu_ms, kind = cpu_reference_rate(n, w, sample_rows, 3, 1)
-    cpu = {"value": cpu_rate, "unit": UNIT, "cores": 1, "host_cores": os.cpu_count(), "kind": kind,
-           "sample": f"3 timesteps of a {w}x{sample_rows} slab of the workload ({n}+{n} sweeps), "
-                     f"{cpu_ms:.0f} ms each; fluid.cpp is single-threaded"}
+    cpu = None
+    if not args.no_cpu:
+        sample_rows = max(64, (1 << 20) // w)
+        cpu_rate, cpu_ms, kind = cpu_reference_rate(n, w, sample_rows, 3, 1)
+        cpu = {"value": cpu_rate, "unit": UNIT, "cores": 1, "host_cores": os.cpu_count(), "kind": kind,
+               "sample": f"3 timesteps of a {w}x{sample_rows} slab of the workload ({n}+{n} sweeps), "
+                         f"{cpu_ms:.0f} ms each; fluid.cpp is single-threaded"}
 
     line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": 1, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
@@ -304,6 +308,8 @@ def main():
     ap.add_argument("--height", type=int, default=0)
     ap.add_argument("--iters", type=int, default=100)
     ap.add_argument("--fuse-depth", type=int, default=None)
+    ap.add_argument("--no-e2e", action="store_true", help="skip the host-buffer end-to-end leg (tuning runs)")
+    ap.add_argument("--no-cpu", action="store_true", help="skip the CPU baseline leg (tuning runs)")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 0)
     if args.impl == "reference":
