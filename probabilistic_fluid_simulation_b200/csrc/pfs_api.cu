@@ -219,7 +219,9 @@ static int run_sweeps(SweepOp op, PlanePair a, PlanePair b, const float *rhs, co
     if (lead > 0) {
         int depth = g_fuse_depth;
         bool fused = (depth != 1) && fused_sweeps_supported(p.w, p.h);
-        if (fused)
+        if (fused && op == SWEEP_DIFFUSE && packed_diffuse_supported(p))
+            PFS_TRY(launch_diffuse_packed(a.c0, a.c1, b.c0, b.c1, p, lead, depth, &flips, s));
+        else if (fused)
             PFS_TRY(launch_sweeps_fused(op, a.c0, a.c1, b.c0, b.c1, rhs, p, lead, depth, &flips, s));
         else
             PFS_TRY(launch_sweeps_basic(op, a.c0, a.c1, b.c0, b.c1, rhs, p, lead, &flips, s));
@@ -268,6 +270,7 @@ extern "C" int pfs_shutdown(void)
         }
     }
     g_scratch.clear();
+    packed_release_device_buffers();
     for (auto &sp : g_spans) {
         cudaEventDestroy(sp.a);
         cudaEventDestroy(sp.b);

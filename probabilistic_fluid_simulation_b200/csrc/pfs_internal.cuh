@@ -151,6 +151,12 @@ int launch_sweeps_fused(SweepOp op, float *a0, float *a1, float *b0, float *b1, 
                         const SweepParams &p, int n, int depth, int *flips, cudaStream_t s);
 bool fused_sweeps_supported(int w, int h);
 
+// Packed-FP32 (f32x2) temporally blocked diffusion: u and v advanced together (sweeps_packed.cu).
+bool packed_diffuse_supported(const SweepParams &p);
+int launch_diffuse_packed(float *a0, float *a1, float *b0, float *b1, const SweepParams &p, int n, int depth,
+                          int *flips, cudaStream_t s);
+void packed_release_device_buffers();
+
 // divergence (fluid.cpp:221-237) of planes (u, v) into plane div; optionally also extracts
 // channel 2 of an interleaved buffer into plane p0 (the pressure warm start) in the same pass.
 int launch_divergence(const float *u, const float *v, float *div, const float *p0_src_aos, float *p0,

@@ -1,0 +1,394 @@
+// sweeps_packed.cu -- temporally blocked smoothing ("diffusion") sweeps on Blackwell's packed-FP32
+// pipe: T sweeps of fluid.cpp:154-186 per launch, u and v advanced together.
+//
+// The diffusion operator applies the same 5-point update with the same coefficients to channel 0
+// (u) and channel 1 (v).  sm_100 has two-wide FP32 instructions (add/mul/fma.rn.f32x2 -> FADD2 /
+// FMUL2 / FFMA2) that round each half exactly like the scalar instruction, so a lane keeps (u, v)
+// of a cell in one 64-bit register pair and issues ONE instruction per pair of updates.  The
+// structure is the warp-streaming scheme of sweeps_fused.cu:
+//   * a warp owns a strip of 128 columns x a chunk of L rows of BOTH planes; each lane holds, for
+//     every time level 0..T-1, the two most recent rows of its 4 cells x (u,v) (16*T registers);
+//   * per stream step one new row of u and of v arrives through a private cp.async ring in shared
+//     memory (no barriers anywhere), level l = 1..T produces row s-l, level T is stored;
+//   * x neighbours across lanes come by warp shuffle of the already-multiplied alpha*value pairs;
+//   * the division by beta = 1 + 4*alpha is the 3-instruction correctly rounded FMA division of
+//     div_const_fast() below, applied to pairs.  Its preconditions (numerator magnitude in
+//     [2^-96, 2^96], not -0) are not branched on in the hot loop: the loop keeps a running FMNMX3
+//     minimum of |numerator| and maximum of |input|; a warp whose extremes leave the safe range
+//     raises a flag for its work item, and a second ("repair") launch recomputes exactly those
+//     items with __fdiv_rn.  Real velocity fields never raise the flag; exact-zero regions do, and
+//     stay correct.
+// Results are bit-identical to the one-sweep kernel and to fluid.cpp for every T.
+#include <stdlib.h>
+
+#include <map>
+#include <mutex>
+
+#include "pfs_internal.cuh"
+
+namespace pfs {
+
+namespace {
+
+constexpr int WARPS_PER_CTA = 4;
+constexpr int RING_SLOTS = 4;
+constexpr int PREFETCH = RING_SLOTS - 2;
+
+struct PackedParams {
+    const float *in_u, *in_v;
+    float *out_u, *out_v;
+    int *flags;                 // one int per work item (main kernel raises, repair kernel consumes)
+    int w, h;
+    int strip_out, halo_cols;
+    int n_strips, n_chunks, chunk_rows;
+    float alpha, beta, rbeta;
+    float guard_lo, guard_hi_in;   // |numerator| >= guard_lo and |input| <= guard_hi_in keep the FMA division exact
+    float neg_zero;             // -0.0f, deliberately a RUN-TIME value: see mulc2()
+};
+
+// ---- packed binary32 x2 arithmetic (each half rounded to nearest-even like the scalar op) ------
+__device__ __forceinline__ unsigned long long pk(float2 a)
+{
+    unsigned long long r;
+    asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(a.x), "f"(a.y));
+    return r;
+}
+__device__ __forceinline__ float2 upk(unsigned long long r)
+{
+    float2 a;
+    asm("mov.b64 {%0, %1}, %2;" : "=f"(a.x), "=f"(a.y) : "l"(r));
+    return a;
+}
+__device__ __forceinline__ float2 add2(float2 a, float2 b)
+{
+    unsigned long long d;
+    asm("add.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(pk(a)), "l"(pk(b)));
+    return upk(d);
+}
+__device__ __forceinline__ float2 mul2(float2 a, float2 b)
+{
+    unsigned long long d;
+    asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(pk(a)), "l"(pk(b)));
+    return upk(d);
+}
+__device__ __forceinline__ float2 fma2(float2 a, float2 b, float2 c)
+{
+    unsigned long long d;
+    asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(d) : "l"(pk(a)), "l"(pk(b)), "l"(pk(c)));
+    return upk(d);
+}
+// alpha * x as RN(x*alpha + (-0)): identical to mul.rn for every input (adding -0 never changes a
+// value, and (+0)+(-0) = +0, (-0)+(-0) = -0 keep the product's zero sign).  Why not mul.rn.f32x2:
+// ptxas 12.9 contracts an explicit mul.rn.f32x2 feeding add.rn.f32x2 into FFMA2 -- even with
+// --fmad=false, and unlike the scalar mul.rn/add.rn pair -- which would round once instead of twice
+// and break parity with fluid.cpp.  An FMA whose addend is a kernel parameter cannot be simplified
+// back into a multiply, and an FMA result cannot be contracted into a following add.
+__device__ __forceinline__ float2 mulc2(float2 x, float2 c, float2 neg_zero) { return fma2(x, c, neg_zero); }
+
+__device__ __forceinline__ float min3abs(float m, float a, float b)
+{
+    float d;
+    asm("min.f32 %0, %1, %2, %3;" : "=f"(d) : "f"(m), "f"(fabsf(a)), "f"(fabsf(b)));
+    return d;
+}
+__device__ __forceinline__ float max3abs(float m, float a, float b)
+{
+    float d;
+    asm("max.f32 %0, %1, %2, %3;" : "=f"(d) : "f"(m), "f"(fabsf(a)), "f"(fabsf(b)));
+    return d;
+}
+__device__ __forceinline__ float2 shfl_up2(float2 v)
+{
+    return make_float2(__shfl_up_sync(0xffffffffu, v.x, 1), __shfl_up_sync(0xffffffffu, v.y, 1));
+}
+__device__ __forceinline__ float2 shfl_down2(float2 v)
+{
+    return make_float2(__shfl_down_sync(0xffffffffu, v.x, 1), __shfl_down_sync(0xffffffffu, v.y, 1));
+}
+
+__device__ __forceinline__ void cp_async16(void *smem, const void *gmem)
+{
+    unsigned s = (unsigned)__cvta_generic_to_shared(smem);
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;\n" ::"r"(s), "l"(gmem) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;\n" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait()
+{
+    asm volatile("cp.async.wait_group %0;\n" ::"n"(N) : "memory");
+}
+
+// ---------------------------------------------------------------------------------------------
+// Correctly rounded division by a loop-invariant constant, 3 instructions (per PAIR here):
+//   y = RN(1/b) (host, binary32);  q0 = RN(a*y);  e = a - b*q0 (exact in one FMA);  q1 = RN(q0 + e*y)
+// q1 == RN(a/b): q0 + e*y = a/b + eps*(a/b - q0) with |eps| <= b*2^-25 (b scaled to [1,2)) and
+// |a/b - q0| < 1.5 ulp, i.e. the FMA rounds a value within 0.75*b^2 (< 3) units of 2^-47 of the true
+// quotient (quotient scaled to [1,2)).  A different rounding needs a rounding midpoint m in that
+// gap, i.e. |A - B*M| <= 2 for the integer significands A, B and the odd 25-bit M of m.
+// tests/exact_div_check.c enumerates EVERY (a, b) with |A - B*M| <= 4 over all 2^23 significands B
+// (23.3 M quotients): no mismatch.  Preconditions: e must not lose bits to underflow
+// (|a| >= 2^-96), nothing overflows (|a| <= 2^96, 2^-20 <= b <= 2^20) and a is not -0 (the final FMA
+// would return +0).  +0 is fine.  The guard below keeps the kernel inside them.
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ float2 div_const_fast2(float2 a, float2 negb, float2 y)
+{
+    const float2 q0 = mul2(a, y);
+    const float2 e = fma2(negb, q0, a);
+    return fma2(e, y, q0);
+}
+
+template <int T, bool EXACT, int MINB>
+__global__ void __launch_bounds__(WARPS_PER_CTA * 32, MINB) diffuse_packed_kernel(const PackedParams P)
+{
+    __shared__ float4 ring[WARPS_PER_CTA][RING_SLOTS][2][32];
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int item = blockIdx.x * WARPS_PER_CTA + warp;
+    if (item >= P.n_strips * P.n_chunks) return;          // whole warp leaves together
+    if constexpr (EXACT) {
+        if (P.flags[item] == 0) return;                   // repair launch: only flagged items
+    }
+    const int strip = item % P.n_strips;
+    const int chunk = item / P.n_strips;
+    const int w = P.w, h = P.h;
+
+    const int x0 = strip * P.strip_out;
+    const int xc = x0 - P.halo_cols + 4 * lane;           // unwrapped first column of this lane
+    int xw = xc % w;
+    if (xw < 0) xw += w;
+    const bool store_lane = (xc >= x0) && (xc < x0 + P.strip_out) && (xc < w);
+
+    const int y0 = chunk * P.chunk_rows;
+    const int L = min(P.chunk_rows, h - y0);
+    int ld_row = (y0 - T) % h;
+    if (ld_row < 0) ld_row += h;
+    const int n_steps = L + 2 * T;
+
+    float4 *my = &ring[warp][0][0][lane];
+    constexpr int SLOT_STRIDE = 2 * 32;                   // float4 units per ring slot
+
+    auto prefetch = [&](int s) {
+        if (s < n_steps) {
+            float4 *dst = my + (s & (RING_SLOTS - 1)) * SLOT_STRIDE;
+            const size_t off = (size_t)ld_row * w + xw;
+            cp_async16(dst, P.in_u + off);
+            cp_async16(dst + 32, P.in_v + off);
+            ld_row = (ld_row + 1 == h) ? 0 : ld_row + 1;
+        }
+        cp_async_commit();
+    };
+#pragma unroll
+    for (int s = 0; s < PREFETCH; s++) prefetch(s);
+
+    // S[l][k][c]: level l, k alternates with the step parity, c = cell 0..3; .x = u, .y = v.
+    // Initialised to 1 (not 0) so that warm-up garbage never looks like a zero numerator.
+    float2 S[T][2][4];
+#pragma unroll
+    for (int l = 0; l < T; l++)
+#pragma unroll
+        for (int c = 0; c < 4; c++) S[l][0][c] = S[l][1][c] = make_float2(1.f, 1.f);
+
+    const float2 alpha2 = make_float2(P.alpha, P.alpha);
+    const float2 nz2 = make_float2(P.neg_zero, P.neg_zero);
+    const float2 negb2 = make_float2(-P.beta, -P.beta);
+    const float2 y2 = make_float2(P.rbeta, P.rbeta);
+    const float beta = P.beta;
+    float num_min = __int_as_float(0x7f800000);           // +inf
+    float in_max = 0.f;
+
+    float *out_u = P.out_u + (size_t)y0 * w + xc;
+    float *out_v = P.out_v + (size_t)y0 * w + xc;
+
+    for (int sb = 0; sb < n_steps; sb += 2) {
+#pragma unroll
+        for (int u = 0; u < 2; u++) {
+            const int s = sb + u;
+            prefetch(s + PREFETCH);
+            cp_async_wait<PREFETCH>();
+            const float4 *slot = my + (s & (RING_SLOTS - 1)) * SLOT_STRIDE;
+            const float4 ru = slot[0], rv = slot[32];
+            float2 fresh[4] = {make_float2(ru.x, rv.x), make_float2(ru.y, rv.y), make_float2(ru.z, rv.z),
+                               make_float2(ru.w, rv.w)};
+            if constexpr (!EXACT) {
+#pragma unroll
+                for (int c = 0; c < 4; c++) in_max = max3abs(in_max, fresh[c].x, fresh[c].y);
+            }
+            const int older = u;
+#pragma unroll
+            for (int l = 1; l <= T; l++) {
+                float2 aC[4], aT[4], aB[4], o[4];
+#pragma unroll
+                for (int c = 0; c < 4; c++) {
+                    aC[c] = mulc2(S[l - 1][older ^ 1][c], alpha2, nz2);   // alpha * centre row (s-l)
+                    aT[c] = mulc2(S[l - 1][older][c], alpha2, nz2);       // alpha * top row (s-l-1)
+                    aB[c] = mulc2(fresh[c], alpha2, nz2);                 // alpha * bottom row (s-l+1)
+                }
+                const float2 aLft = shfl_up2(aC[3]);                  // alpha * (x-1) of cell 0
+                const float2 aRgt = shfl_down2(aC[0]);                // alpha * (x+1) of cell 3
+#pragma unroll
+                for (int c = 0; c < 4; c++) {
+                    const float2 lft = (c == 0) ? aLft : aC[c - 1];
+                    const float2 rgt = (c == 3) ? aRgt : aC[c + 1];
+                    // fluid.cpp:175-182: (((aL + aR) + aT) + aB) + 1.0f*u_n
+                    float2 num = add2(add2(add2(add2(lft, rgt), aT[c]), aB[c]), S[l - 1][older ^ 1][c]);
+                    if constexpr (EXACT) {
+                        o[c] = make_float2(__fdiv_rn(num.x, beta), __fdiv_rn(num.y, beta));
+                    } else {
+                        o[c] = div_const_fast2(num, negb2, y2);
+                        num_min = min3abs(num_min, num.x, num.y);
+                    }
+                }
+#pragma unroll
+                for (int c = 0; c < 4; c++) {
+                    S[l - 1][older][c] = fresh[c];
+                    fresh[c] = o[c];
+                }
+            }
+            const int orow = s - 2 * T;
+            if (store_lane && orow >= 0 && orow < L) {
+                *reinterpret_cast<float4 *>(out_u + (size_t)orow * w) =
+                    make_float4(fresh[0].x, fresh[1].x, fresh[2].x, fresh[3].x);
+                *reinterpret_cast<float4 *>(out_v + (size_t)orow * w) =
+                    make_float4(fresh[0].y, fresh[1].y, fresh[2].y, fresh[3].y);
+            }
+        }
+    }
+    cp_async_wait<0>();
+    if constexpr (!EXACT) {
+        // !(x >= lo) also catches a NaN minimum
+        const bool bad = !(num_min >= P.guard_lo) || !(in_max <= P.guard_hi_in);
+        if (__any_sync(0xffffffffu, bad) && lane == 0) P.flags[item] = 1;
+    }
+}
+
+template <int T>
+int launch_packed(const PackedParams &P, cudaStream_t s)
+{
+    const int total = P.n_strips * P.n_chunks;
+    const unsigned blocks = (unsigned)((total + WARPS_PER_CTA - 1) / WARPS_PER_CTA);
+    constexpr int MINB = (T > 4) ? 2 : 3;
+    PFS_CUDA(cudaMemsetAsync(P.flags, 0, (size_t)total * sizeof(int), s));
+    PFS_LAUNCH((diffuse_packed_kernel<T, false, MINB>), blocks, WARPS_PER_CTA * 32, 0, s, P);
+    PFS_LAUNCH((diffuse_packed_kernel<T, true, MINB>), blocks, WARPS_PER_CTA * 32, 0, s, P);
+    return PFS_OK;
+}
+
+int launch_packed_depth(int t, const PackedParams &P, cudaStream_t s)
+{
+    switch (t) {
+    case 1: return launch_packed<1>(P, s);
+    case 2: return launch_packed<2>(P, s);
+    case 3: return launch_packed<3>(P, s);
+    case 4: return launch_packed<4>(P, s);
+    case 5: return launch_packed<5>(P, s);
+    case 6: return launch_packed<6>(P, s);
+    case 7: return launch_packed<7>(P, s);
+    case 8: return launch_packed<8>(P, s);
+    default: set_error("packed diffusion: unsupported depth %d", t); return PFS_EINVAL;
+    }
+}
+
+// per-device flag buffers (grown on demand)
+struct FlagBuf {
+    int *ptr = nullptr;
+    size_t n = 0;
+};
+std::mutex g_flag_mutex;
+std::map<int, FlagBuf> g_flags;
+
+int get_flags(size_t n, int **out)
+{
+    int dev = 0;
+    PFS_CUDA(cudaGetDevice(&dev));
+    std::lock_guard<std::mutex> lock(g_flag_mutex);
+    FlagBuf &fb = g_flags[dev];
+    if (fb.n < n) {
+        if (fb.ptr) {
+            PFS_CUDA(cudaDeviceSynchronize());
+            PFS_CUDA(cudaFree(fb.ptr));
+            fb.ptr = nullptr;
+            fb.n = 0;
+        }
+        size_t want = n < 16384 ? 16384 : 2 * n;
+        PFS_CUDA(cudaMalloc((void **)&fb.ptr, want * sizeof(int)));
+        fb.n = want;
+    }
+    *out = fb.ptr;
+    return PFS_OK;
+}
+
+int env_int(const char *name, int dflt)
+{
+    const char *v = getenv(name);
+    return (v && *v) ? atoi(v) : dflt;
+}
+
+}  // namespace
+
+void packed_release_device_buffers()
+{
+    std::lock_guard<std::mutex> lock(g_flag_mutex);
+    for (auto &kv : g_flags) {
+        if (kv.second.ptr && cudaSetDevice(kv.first) == cudaSuccess) cudaFree(kv.second.ptr);
+    }
+    g_flags.clear();
+}
+
+bool packed_diffuse_supported(const SweepParams &p)
+{
+    // alpha >= 0 makes every sweep a convex combination (|values| never exceed the input maximum),
+    // which is what lets the guard bound numerators by checking inputs only.
+    return (p.w % 4 == 0) && p.w >= 4 && p.h >= 1 && p.alpha >= 0.f && p.beta >= 1.f && p.beta <= 0x1p20f;
+}
+
+// n diffusion sweeps, up to `depth` per launch, ping-ponging (a0,a1) <-> (b0,b1).
+int launch_diffuse_packed(float *a0, float *a1, float *b0, float *b1, const SweepParams &p, int n, int depth,
+                          int *flips, cudaStream_t s)
+{
+    static const int env_depth = env_int("PFS_DIFFUSE_DEPTH", 0);
+    static const int env_rows = env_int("PFS_DIFFUSE_ROWS", 0);
+    static const int env_warps = env_int("PFS_DIFFUSE_WARPS_PER_SM", 0);
+    if (depth <= 0) depth = env_depth > 0 ? env_depth : 6;
+    if (depth > 8) depth = 8;
+    int hops = 0;
+    float *cur0 = a0, *cur1 = a1, *oth0 = b0, *oth1 = b1;
+    int left = n;
+    while (left > 0) {
+        const int t = left < depth ? left : depth;
+        PackedParams P;
+        P.in_u = cur0; P.in_v = cur1; P.out_u = oth0; P.out_v = oth1;
+        P.w = p.w; P.h = p.h;
+        P.halo_cols = 4 * ((t + 3) / 4);
+        P.strip_out = 128 - 2 * P.halo_cols;
+        P.n_strips = (p.w + P.strip_out - 1) / P.strip_out;
+        // chunk height: one resident wave of warps if the grid allows it, never shorter than 32 rows
+        // (2T halo rows are streamed per chunk) and never taller than 256
+        const int warps_per_sm = env_warps > 0 ? env_warps : ((t > 4) ? 8 : 12);
+        const long long slots = 148LL * warps_per_sm;
+        int rows = env_rows;
+        if (rows <= 0) {
+            long long chunks = slots / P.n_strips;
+            if (chunks < 1) chunks = 1;
+            rows = (int)((p.h + chunks - 1) / chunks);
+            if (rows < 32) rows = 32;
+            if (rows > 256) rows = 256;
+        }
+        if (rows > p.h) rows = p.h;
+        P.chunk_rows = rows;
+        P.n_chunks = (p.h + rows - 1) / rows;
+        P.alpha = p.alpha; P.beta = p.beta; P.rbeta = 1.0f / p.beta;
+        P.guard_lo = 0x1p-96f;
+        P.guard_hi_in = 0x1p60f;
+        P.neg_zero = -0.0f;
+        PFS_TRY(get_flags((size_t)P.n_strips * P.n_chunks, &P.flags));
+        PFS_TRY(launch_packed_depth(t, P, s));
+        float *t0 = cur0, *t1 = cur1;
+        cur0 = oth0; cur1 = oth1; oth0 = t0; oth1 = t1;
+        hops++;
+        left -= t;
+    }
+    *flips = hops;
+    return PFS_OK;
+}
+
+}  // namespace pfs

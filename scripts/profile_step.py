@@ -1,0 +1,21 @@
+#!/usr/bin/env python
+"""One 4096^2 timestep (100+100 sweeps) for ncu.  Usage: profile_step.py [depth] [steps]"""
+import os, sys
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+import torch
+import bench
+import probabilistic_fluid_simulation_b200 as pfs
+
+depth = int(sys.argv[1]) if len(sys.argv) > 1 else 0
+steps = int(sys.argv[2]) if len(sys.argv) > 2 else 1
+size = int(sys.argv[3]) if len(sys.argv) > 3 else 4096
+n = int(sys.argv[4]) if len(sys.argv) > 4 else 100
+pfs.set_fuse_depth(depth)
+vp, vtmp, image, itmp = bench.make_inputs(size, size)
+fv, ft, fi, fm = (pfs.vp_field(torch.from_numpy(x).cuda()) for x in (vp, vtmp, image, itmp))
+for _ in range(steps):
+    pfs.simulate_fluid_step(fv, ft, bench.DT, bench.VISC, n, n)
+    pfs.advect_color_step(fi, fm, fv, bench.DT)
+torch.cuda.synchronize()
+print("done", pfs.kernel_launch_count())
