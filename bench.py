@@ -53,7 +53,7 @@ def measured_peak_gbs():
 
 
 class ClockSampler:
-    """nvidia-smi clocks / throttle reasons sampled every 200 ms during the timed region."""
+    """nvidia-smi clocks / throttle reasons sampled every 50 ms during the timed region."""
 
     Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
          "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
@@ -67,7 +67,7 @@ class ClockSampler:
     def start(self):
         try:
             self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), f"--query-gpu={self.Q}",
-                                          "--format=csv,noheader,nounits", "-lms", "200"],
+                                          "--format=csv,noheader,nounits", "-lms", "50"],
                                          stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             self.thread = threading.Thread(target=self._read, daemon=True)
             self.thread.start()
@@ -76,9 +76,9 @@ class ClockSampler:
 
     def _read(self):
         for line in self.proc.stdout:
-            self.rows.append([x.strip() for x in line.split(",")])
+            self.rows.append((time.perf_counter(), [x.strip() for x in line.split(",")]))
 
-    def stop(self):
+    def stop(self, t0=None, t1=None):
         if not self.proc:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
         time.sleep(0.25)
@@ -89,7 +89,11 @@ class ClockSampler:
             self.proc.kill()
         sm, mx, reasons = [], [], set()
         names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        for r in self.rows:
+        inside = [r for (t, r) in self.rows if t0 is None or (t0 <= t <= t1 + 0.06)]
+        window = "timed region"
+        if not inside:                       # region shorter than the sampling period
+            inside, window = [r for (_, r) in self.rows], "whole run (timed region shorter than one sample)"
+        for r in inside:
             try:
                 sm.append(float(r[0])); mx.append(float(r[1]))
                 for n, v in zip(names, r[3:7]):
@@ -99,7 +103,7 @@ class ClockSampler:
                 continue
         sm.sort()
         return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": max(mx) if mx else None,
-                "reasons": sorted(reasons), "samples": len(sm)}
+                "reasons": sorted(reasons), "samples": len(sm), "window": window}
 
 
 def make_inputs(h: int, w: int, rank: int = 0):
@@ -205,21 +209,24 @@ def run_single_gpu(args):
     # ---- timed region: K steps, device-resident inputs, CUDA events on the launching stream ----
     sampler = ClockSampler(0)
     sampler.start()
+    time.sleep(0.12)          # let nvidia-smi deliver its first sample before the (short) timed region
     pfs.phase_timing(True)
     pfs.phase_times(reset=True)
     l0 = pfs.kernel_launch_count()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     torch.cuda.synchronize()
+    t_begin = time.perf_counter()
     e0.record()
     for _ in range(args.steps):
         step()
     e1.record()
     torch.cuda.synchronize()
+    t_end = time.perf_counter()
     ms_total = e0.elapsed_time(e1)
     launches = pfs.kernel_launch_count() - l0
     phase_ms, phase_launches = pfs.phase_times(reset=True)
     pfs.phase_timing(False)
-    clocks = sampler.stop()
+    clocks = sampler.stop(t_begin, t_end)
     ms_step = ms_total / args.steps
     value = cells * n / (ms_step * 1e-3)
 
@@ -301,8 +308,8 @@ def run_single_gpu(args):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=10)
-    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--steps", type=int, default=100)
+    ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--width", type=int, default=0)
     ap.add_argument("--height", type=int, default=0)

@@ -348,7 +348,7 @@ int launch_diffuse_packed(float *a0, float *a1, float *b0, float *b1, const Swee
     static const int env_depth = env_int("PFS_DIFFUSE_DEPTH", 0);
     static const int env_rows = env_int("PFS_DIFFUSE_ROWS", 0);
     static const int env_warps = env_int("PFS_DIFFUSE_WARPS_PER_SM", 0);
-    if (depth <= 0) depth = env_depth > 0 ? env_depth : 6;
+    if (depth <= 0) depth = env_depth > 0 ? env_depth : 8;
     if (depth > 8) depth = 8;
     int hops = 0;
     float *cur0 = a0, *cur1 = a1, *oth0 = b0, *oth1 = b1;

@@ -1,0 +1,139 @@
+// fluid_shim.cpp -- defines the C++-linkage symbols of fluid.hpp (the reference's operator API) on
+// top of the C-ABI of libpfs_b200.so.  Compile twice: with -DUSE_CUDA (device-pointer entry points,
+// mangled exactly like the reference's: _Z19simulate_fluid_stepPPfS0_ffiii,
+// _Z17advect_color_stepPPfS0_S0_fiiiiii) and without (vp_field* host entry points).
+// Plain g++ + the CUDA runtime headers only; no nvcc needed (as for the reference's main.cpp).
+#include <cstdio>
+#include <cstdlib>
+
+#include <cuda_runtime_api.h>
+
+#include "../../include/pfs_b200.h"
+#include "fluid.hpp"
+
+namespace {
+void die_on(int status, const char *where)
+{
+    if (status == PFS_OK) return;
+    std::fprintf(stderr, "%s failed (status %d): %s\n", where, status, pfs_last_error());
+    std::abort();   // never continue silently, never fall back to a CPU path
+}
+}  // namespace
+
+#ifdef USE_CUDA
+
+void simulate_fluid_step(float **vp, float **tmp, float dt, float viscosity, int vx, int vy, int vz)
+{
+    die_on(pfs_simulate_fluid_step(vp, tmp, dt, viscosity, vx, vy, vz, NUM_JACOBI_ITERS, NUM_JACOBI_ITERS, nullptr),
+           "simulate_fluid_step");
+}
+
+void advect_color_step(float **image, float **itmp, float **vp, float dt, int ix, int iy, int iz, int vx, int vy,
+                       int vz)
+{
+    die_on(pfs_advect_color_step(image, itmp, vp, dt, ix, iy, iz, vx, vy, vz, nullptr), "advect_color_step");
+}
+
+#else  // host-pointer (CPU-build) signatures
+
+namespace {
+// Single operators on host structs: stage through device memory around the device-pointer C-ABI.
+struct Staged {
+    float *d = nullptr;
+    size_t bytes = 0;
+    explicit Staged(const vp_field *f) : bytes(sizeof(float) * (size_t)f->x * f->y * f->z)
+    {
+        if (cudaMalloc((void **)&d, bytes) != cudaSuccess ||
+            cudaMemcpy(d, f->data, bytes, cudaMemcpyHostToDevice) != cudaSuccess) {
+            std::fprintf(stderr, "fluid.hpp shim: cannot stage a %zu-byte field on the GPU\n", bytes);
+            std::abort();
+        }
+    }
+    void download(float *host) const
+    {
+        if (cudaMemcpy(host, d, bytes, cudaMemcpyDeviceToHost) != cudaSuccess) std::abort();
+    }
+    ~Staged() { cudaFree(d); }
+};
+pfs_field as_pfs(vp_field *f) { return pfs_field{f->x, f->y, f->z, f->data}; }
+}  // namespace
+
+void advect(vp_field *vp, vp_field *vp_out, float dt)
+{
+    Staged a(vp), b(vp_out);
+    die_on(pfs_advect(a.d, b.d, dt, vp->x, vp->y, vp->z, nullptr), "advect");
+    b.download(vp_out->data);
+}
+
+void advect_color(vp_field *image, vp_field *out, vp_field *vp, float dt)
+{
+    Staged i(image), o(out), v(vp);
+    die_on(pfs_advect_color(i.d, o.d, v.d, dt, image->x, image->y, image->z, vp->x, vp->y, vp->z, nullptr),
+           "advect_color");
+    o.download(out->data);
+}
+
+void diffuse(vp_field *vp, vp_field *vp_out, float viscosity, float dt)
+{
+    Staged a(vp), b(vp_out);
+    float *pa = a.d, *pb = b.d;
+    die_on(pfs_diffuse(&pa, &pb, viscosity, dt, vp->x, vp->y, vp->z, NUM_JACOBI_ITERS, nullptr), "diffuse");
+    if (pa != a.d) {   // the reference exchanged the two data pointers (fluid.cpp:188-194)
+        float *t = vp->data;
+        vp->data = vp_out->data;
+        vp_out->data = t;
+        b.download(vp->data);
+        a.download(vp_out->data);
+    } else {
+        a.download(vp->data);
+        b.download(vp_out->data);
+    }
+}
+
+void addForces(vp_field *vp, float *forces)
+{
+    (void)forces;   // empty in the reference (fluid.cpp:198-208)
+    (void)vp;
+}
+
+void computePressure(vp_field *vp, vp_field *vp_out, float dt)
+{
+    Staged a(vp), b(vp_out);
+    float *pa = a.d, *pb = b.d;
+    die_on(pfs_compute_pressure(&pa, &pb, dt, vp->x, vp->y, vp->z, NUM_JACOBI_ITERS, nullptr), "computePressure");
+    if (pa != a.d) {
+        float *t = vp->data;
+        vp->data = vp_out->data;
+        vp_out->data = t;
+        b.download(vp->data);
+        a.download(vp_out->data);
+    } else {
+        a.download(vp->data);
+        b.download(vp_out->data);
+    }
+}
+
+void subtractPressureGradient(vp_field *vp, vp_field *vp_out, float dt)
+{
+    Staged a(vp), b(vp_out);
+    die_on(pfs_subtract_pressure_gradient(a.d, b.d, dt, vp->x, vp->y, vp->z, nullptr), "subtractPressureGradient");
+    b.download(vp_out->data);
+}
+
+void simulate_fluid_step(vp_field *vp, vp_field *tmp, float dt, float viscosity)
+{
+    pfs_field a = as_pfs(vp), b = as_pfs(tmp);
+    die_on(pfs_simulate_fluid_step_host(&a, &b, dt, viscosity, NUM_JACOBI_ITERS, NUM_JACOBI_ITERS), "simulate_fluid_step");
+    vp->data = a.data;
+    tmp->data = b.data;
+}
+
+void advect_color_step(vp_field *image, vp_field *itmp, vp_field *vp, float dt)
+{
+    pfs_field i = as_pfs(image), t = as_pfs(itmp), v = as_pfs(vp);
+    die_on(pfs_advect_color_step_host(&i, &t, &v, dt), "advect_color_step");
+    image->data = i.data;
+    itmp->data = t.data;
+}
+
+#endif  // USE_CUDA

@@ -1,0 +1,141 @@
+// fluidsim_b200 -- command-line driver with the interface of the reference's src/main.cpp:
+//
+//   fluidsim_b200 <n_timesteps> <delta_t> <viscosity> <input_image> <velocity_field> [output_dir]
+//
+// Same argument checks and exit codes (main.cpp:105-140), same stdout lines (:214-215, :67, :250),
+// same frames <output_dir>/<i>.png, timing mode when no output_dir is given (:110-113).  It drives
+// the fluid.hpp entry points of the CUDA build (simulate_fluid_step / advect_color_step on device
+// buffers, main.cpp:222,225), which fluid_shim.cpp forwards to libpfs_b200.so.
+// Two deliberate differences from the reference's CUDA driver, both needed to reproduce what its CPU
+// build computes: the temporary velocity buffer IS uploaded (main.cpp:203-210 never initialises
+// d_vtmp although channel 2 of it is the first pressure guess), and the clock stops after the
+// device is idle (main.cpp:247 stops it before cudaDeviceSynchronize, :252-255).
+#include <chrono>
+#include <cmath>
+#include <cstdio>
+#include <cstdlib>
+#include <iostream>
+#include <string>
+
+#include <cuda_runtime_api.h>
+
+#define USE_CUDA
+#include "fluid.hpp"
+#include "png_io.hpp"
+
+#define NUM_CHANNELS (4)
+#define VP_RANGE (2.0)
+
+static void usage(const char *prog)
+{
+    std::cerr << "Usage: " << prog
+              << " <n_timesteps> <delta_t> <viscosity> <input_image> <velocity_field> [output_dir]" << std::endl;
+}
+
+static void *pinned_alloc(size_t bytes)
+{
+    void *p = nullptr;
+    if (cudaMallocHost(&p, bytes) != cudaSuccess) return nullptr;   // utils.hpp:69-76
+    return p;
+}
+
+static bool cuda_ok(cudaError_t e, const char *what)
+{
+    if (e == cudaSuccess) return true;
+    std::cerr << what << ": " << cudaGetErrorString(e) << std::endl;
+    return false;
+}
+
+int main(int argc, char *argv[])
+{
+    int flags = 0;
+    if (argc != 6 && argc != 7) {
+        usage(argv[0]);
+        return 1;
+    }
+    if (argc == 6) flags |= 1;   // timing mode, no file writing
+    int n_timesteps = atoi(argv[1]);
+    float delta_t = atof(argv[2]);
+    float viscosity = atof(argv[3]);
+    if (n_timesteps <= 0) {
+        std::cerr << "Timesteps must be greater than 0." << std::endl;
+        return 1;
+    }
+    if (delta_t <= 0) {
+        std::cerr << "Delta T must be greater than 0." << std::endl;
+        return 1;
+    }
+
+    pngio::png_image input_image, velocity_image;
+    vp_field image, vp, itmp, vtmp;
+    if (pngio::read_png_to_array(&input_image, argv[4], &image.data, pinned_alloc) != 0) {
+        std::cerr << "Something went wrong reading the input image..." << std::endl;
+        return 1;
+    }
+    if (pngio::read_png_to_array(&velocity_image, argv[5], &vp.data, pinned_alloc) != 0) {
+        std::cerr << "Something went wrong reading the initial velocity field..." << std::endl;
+        return 1;
+    }
+    image.x = itmp.x = input_image.width;
+    image.y = itmp.y = input_image.height;
+    vp.x = vtmp.x = velocity_image.width;
+    vp.y = vtmp.y = velocity_image.height;
+    image.z = itmp.z = vp.z = vtmp.z = NUM_CHANNELS;
+
+    // main.cpp:170-179: every channel v <- v*2.0 - 1.0 (double arithmetic, stored as float)
+    const size_t vel_floats = (size_t)vp.x * vp.y * NUM_CHANNELS;
+    const size_t img_floats = (size_t)image.x * image.y * NUM_CHANNELS;
+    for (size_t i = 0; i < vel_floats; i++) {
+        float v = vp.data[i];
+        vp.data[i] = (v * VP_RANGE) - VP_RANGE / 2.0;
+    }
+    const size_t input_bytes = sizeof(float) * img_floats, velocity_bytes = sizeof(float) * vel_floats;
+
+    // main.cpp:186-195: vtmp = (-1,-1,-1,+1) per cell
+    vtmp.data = (float *)pinned_alloc(velocity_bytes);
+    if (!vtmp.data) return 1;
+    for (size_t i = 0; i < vel_floats; i++) vtmp.data[i] = ((i % 4) == 3) ? 1.0f : -1.0f;
+
+    float *d_image = nullptr, *d_vp = nullptr, *d_itmp = nullptr, *d_vtmp = nullptr;
+    if (!cuda_ok(cudaMalloc((void **)&d_image, input_bytes), "cudaMalloc") ||
+        !cuda_ok(cudaMalloc((void **)&d_vp, velocity_bytes), "cudaMalloc") ||
+        !cuda_ok(cudaMalloc((void **)&d_itmp, input_bytes), "cudaMalloc") ||
+        !cuda_ok(cudaMalloc((void **)&d_vtmp, velocity_bytes), "cudaMalloc"))
+        return 1;
+    if (!cuda_ok(cudaMemcpy(d_image, image.data, input_bytes, cudaMemcpyHostToDevice), "H2D image") ||
+        !cuda_ok(cudaMemcpy(d_vp, vp.data, velocity_bytes, cudaMemcpyHostToDevice), "H2D vp") ||
+        !cuda_ok(cudaMemcpy(d_vtmp, vtmp.data, velocity_bytes, cudaMemcpyHostToDevice), "H2D vtmp"))
+        return 1;
+
+    std::cout << "Simulating [" << velocity_image.height << " x " << velocity_image.width << "] domain for "
+              << n_timesteps << " timesteps at dt=" << delta_t << "..." << std::endl;
+
+    auto time_start = std::chrono::high_resolution_clock::now();
+    for (int i = 0; i < n_timesteps; i++) {
+        simulate_fluid_step(&d_vp, &d_vtmp, delta_t, viscosity, vp.x, vp.y, vp.z);
+        advect_color_step(&d_image, &d_itmp, &d_vp, delta_t, image.x, image.y, image.z, vp.x, vp.y, vp.z);
+        if (flags == 0) {
+            cudaDeviceSynchronize();
+            if (!cuda_ok(cudaMemcpy(image.data, d_image, input_bytes, cudaMemcpyDeviceToHost), "D2H image")) return 1;
+            std::string outpath = std::string(argv[6]);
+            if (!outpath.empty() && outpath.back() != '/') outpath += "/";
+            outpath += std::to_string(i) + ".png";
+            std::cout << "[" << i << "] Writing to : " << outpath << std::endl;
+            pngio::write_png_from_array(&input_image, outpath.c_str(), image.data);
+        }
+    }
+    cudaDeviceSynchronize();
+    auto time_end = std::chrono::high_resolution_clock::now();
+    std::cout << n_timesteps << " timesteps took "
+              << std::chrono::duration_cast<std::chrono::microseconds>(time_end - time_start).count() << " us."
+              << std::endl;
+
+    cudaFreeHost(image.data);
+    cudaFreeHost(vp.data);
+    cudaFreeHost(vtmp.data);
+    cudaFree(d_image);
+    cudaFree(d_vp);
+    cudaFree(d_itmp);
+    cudaFree(d_vtmp);
+    return 0;
+}

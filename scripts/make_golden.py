@@ -29,7 +29,7 @@ sys.path.insert(0, ROOT)
 sys.path.insert(0, os.path.join(ROOT, "scripts"))
 
 import oracle  # noqa: E402
-import png_exact  # noqa: E402
+from probabilistic_fluid_simulation_b200 import pngio as png_exact  # noqa: E402
 from probabilistic_fluid_simulation_b200 import fixtures  # noqa: E402
 from tests.golden_util import build_inputs  # noqa: E402
 

@@ -43,5 +43,23 @@ int main(){
         }
     }
     printf("worst-case quotients tested %ld  one-iteration mismatches %ld  two-iteration mismatches %ld\n",tested,bad1,bad2);
-    return 0;
+    /* random numerators over the whole guarded exponent range x random betas of the form 1+4*alpha */
+    uint64_t st = 88172645463325252ULL; long rtested = 0, rbad = 0;
+    for (int bi = 0; bi < 2000; bi++) {
+        st ^= st << 13; st ^= st >> 7; st ^= st << 17;
+        float alpha = u2f(0x30000000u + (uint32_t)(st % 0x10800000u));
+        float b = (float)(1.0 + 4.0 * (double)alpha);
+        if (!(b <= 1048576.0f)) continue;
+        float y = 1.0f / b;
+        for (int i = 0; i < 10000; i++) {
+            st ^= st << 13; st ^= st >> 7; st ^= st << 17;
+            uint32_t m = (uint32_t)(st & 0x7fffffu); int e = 127 - 96 + (int)((st >> 23) % 193); uint32_t sg = (uint32_t)((st >> 40) & 1) << 31;
+            float a = u2f(sg | ((uint32_t)e << 23) | m);
+            float q0 = a * y; float r = fmaf(-b, q0, a); float q1 = fmaf(r, y, q0);
+            rtested++;
+            if (f2u(q1) != f2u(a / b)) rbad++;
+        }
+    }
+    printf("random quotients tested %ld  mismatches %ld\n", rtested, rbad);
+    return (bad1 != 0 || rbad != 0);
 }

@@ -1,0 +1,61 @@
+"""The main.cpp-compatible driver (host/main.cpp -> build/fluidsim_b200): same CLI, stdout lines and
+output frames as the reference driver, checked against frames computed by the CPU oracle."""
+import os
+import subprocess
+
+import numpy as np
+import pytest
+
+import oracle
+from golden_util import GOLD
+from probabilistic_fluid_simulation_b200 import fixtures, pngio
+
+pytestmark = pytest.mark.gpu
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+EXE = os.path.join(ROOT, "probabilistic_fluid_simulation_b200", "host", "build", "fluidsim_b200")
+
+
+@pytest.fixture(scope="module")
+def pngs(tmp_path_factory):
+    d = tmp_path_factory.mktemp("pngs")
+    vel = np.load(os.path.join(GOLD, "png_perlin_t0_64.npz"))["rgba"]
+    img = np.load(os.path.join(GOLD, "png_baboon.npz"))["rgba"][:96, :160].copy()
+    pngio.write_rgba8(str(d / "vel.png"), vel)
+    pngio.write_rgba8(str(d / "img.png"), img)
+    # 8-bit RGBA files decode to the bytes that were written
+    assert np.array_equal(pngio.read_rgba8(str(d / "vel.png")), vel)
+    return d, vel, img
+
+
+def test_driver_frames_match_oracle(pngs, tmp_path):
+    d, vel, img = pngs
+    assert os.path.exists(EXE), "driver not built (run __graft_entry__.build())"
+    out = tmp_path / "frames"
+    out.mkdir()
+    steps, dt, visc = 4, 0.5, 0.001
+    r = subprocess.run([EXE, str(steps), str(dt), str(visc), str(d / "img.png"), str(d / "vel.png"), str(out)],
+                       capture_output=True, text=True, timeout=300)
+    assert r.returncode == 0, r.stderr
+    lines = r.stdout.strip().splitlines()
+    assert lines[0] == f"Simulating [64 x 64] domain for {steps} timesteps at dt={dt}..."      # main.cpp:214-215
+    assert lines[-1].startswith(f"{steps} timesteps took ") and lines[-1].endswith(" us.")       # main.cpp:250
+    vp, vtmp, image, itmp = fixtures.make_state(vel, img)
+    orc = oracle.Oracle(30)
+    for i in range(steps):
+        vp, vtmp, image, itmp = orc.run_steps(vp, vtmp, image, itmp, np.float32(dt), np.float32(visc), 1)
+        assert lines[1 + i] == f"[{i}] Writing to : {out}/{i}.png"                                # main.cpp:67
+        frame = pngio.read_rgba8(str(out / f"{i}.png"))
+        assert np.array_equal(frame, fixtures.unit_float_to_bytes(image)), f"frame {i}"          # utils.hpp:129-131
+
+
+def test_driver_timing_mode_and_errors(pngs):
+    d, _, _ = pngs
+    r = subprocess.run([EXE, "2", "0.1", "0.001", str(d / "img.png"), str(d / "vel.png")], capture_output=True,
+                       text=True, timeout=300)
+    assert r.returncode == 0 and "Writing to" not in r.stdout and "2 timesteps took" in r.stdout
+    assert subprocess.run([EXE], capture_output=True).returncode == 1
+    r = subprocess.run([EXE, "0", "0.1", "0.001", "a", "b"], capture_output=True, text=True)
+    assert r.returncode == 1 and "Timesteps must be greater than 0." in r.stderr
+    r = subprocess.run([EXE, "3", "0.1", "0.001", "/nonexistent.png", "b"], capture_output=True, text=True)
+    assert r.returncode == 1 and "Something went wrong reading the input image..." in r.stderr

@@ -135,3 +135,44 @@ def test_fuse_depth_is_invisible(depth):
         assert_bit_equal(to_host(ft.data), want_vt, f"tmp depth={depth}")
     finally:
         pfs.set_fuse_depth(old)
+
+
+@pytest.mark.parametrize("kind", ["zeros", "neg_zeros", "tiny", "huge", "mixed_patch", "denormal"])
+def test_diffuse_zero_and_tiny_fields(kind):
+    """Inputs outside the safe range of the 3-instruction FMA division (exact zeros, -0, numerators
+    below 2^-96, values above 2^60) must take the repair path and still match fluid.cpp bit for bit."""
+    h, w = 160, 384
+    rng = np.random.default_rng(41)
+    a = (rng.standard_normal((h, w, 4)) * 0.5).astype(np.float32)
+    if kind == "zeros":
+        a[..., :2] = 0.0
+    elif kind == "neg_zeros":
+        a[..., :2] = -0.0
+    elif kind == "tiny":
+        a[..., :2] *= np.float32(1e-36)
+    elif kind == "huge":
+        a[..., :2] *= np.float32(1e25)
+    elif kind == "mixed_patch":
+        a[40:90, 100:300, :2] = 0.0          # a still region inside a moving field
+        a[120:130, 10:20, 0] = -0.0
+    elif kind == "denormal":
+        a[..., :2] *= np.float32(1e-42)
+    b = rng.standard_normal((h, w, 4)).astype(np.float32)
+    for visc, dt, n in ((0.02, 1.5, 19), (0.0, 1.0, 9)):
+        x, y = a.copy(), b.copy()
+        fa, fb = pfs.vp_field(to_dev(x)), pfs.vp_field(to_dev(y))
+        pfs.diffuse(fa, fb, visc, dt, n)
+        ra, rb = oracle.Oracle().diffuse(x, y, visc, dt, n)
+        assert_bit_equal(to_host(fa.data), ra, f"diffuse vp ({kind}, visc={visc})")
+        assert_bit_equal(to_host(fb.data), rb, f"diffuse vp_out ({kind}, visc={visc})")
+
+
+def test_diffuse_negative_viscosity_takes_the_exact_path():
+    """alpha < 0 breaks the convexity argument of the guard: the library must not use the packed
+    fast path, and must still match the reference."""
+    a, b = rand_field(64, 128, 51), rand_field(64, 128, 52)
+    fa, fb = pfs.vp_field(to_dev(a)), pfs.vp_field(to_dev(b))
+    pfs.diffuse(fa, fb, -0.01, 1.0, 7)
+    ra, rb = oracle.Oracle().diffuse(a, b, -0.01, 1.0, 7)
+    assert_bit_equal(to_host(fa.data), ra, "diffuse vp")
+    assert_bit_equal(to_host(fb.data), rb, "diffuse vp_out")
