@@ -106,14 +106,18 @@ class ClockSampler:
                 "reasons": sorted(reasons), "samples": len(sm), "window": window}
 
 
-def make_inputs(h: int, w: int, rank: int = 0):
-    """Synthetic inputs of the named shape (smooth coherent flow + seeded noise, seeded image)."""
+def make_inputs(h: int, w: int, rows=None):
+    """Synthetic inputs of the named shape: smooth coherent flow + position-hashed noise of +-6 byte
+    levels, position-hashed image.  `rows = (r0, r1)` builds only that band of the h x w grid and image
+    (multi-GPU ranks build their own band; it equals the same rows of the whole-grid inputs)."""
     import numpy as np
     from probabilistic_fluid_simulation_b200 import fixtures
-    vel = fixtures.smooth_velocity_bytes(h, w)
-    rng = np.random.default_rng(1234 + rank)
-    vel[..., :2] = np.clip(vel[..., :2].astype(np.int16) + rng.integers(-6, 7, size=(h, w, 2)), 0, 255).astype(np.uint8)
-    img = fixtures.random_image_bytes(h, w, 4321 + rank)
+    r0, r1 = rows if rows is not None else (0, h)
+    vel = fixtures.smooth_velocity_bytes(h, w, rows=(r0, r1))
+    noise = fixtures.hash_bytes(h, w, 2, 1234, rows=(r0, r1)).astype(np.int16) % 13 - 6
+    vel[..., :2] = np.clip(vel[..., :2].astype(np.int16) + noise, 0, 255).astype(np.uint8)
+    img = fixtures.hash_bytes(h, w, 4, 4321, rows=(r0, r1))
+    img[..., 3] = 255
     return fixtures.make_state(vel, img)
 
 

@@ -136,6 +136,33 @@ int pfs_advect_color_step_host(pfs_field *image, pfs_field *itmp, pfs_field *vp,
 int pfs_timestep_host(pfs_field *vp, pfs_field *vtmp, pfs_field *image, pfs_field *itmp,
                       float dt, float viscosity, int n_diffuse, int n_pressure);
 
+/* ---- multi-GPU: one periodic grid as a ring of row slabs (BASELINE configs[3]) ---------------- */
+/* Not on the reference's surface (the reference is single-device); same operators, same
+ * results bit for bit.  Rank r of R owns a contiguous band of velocity rows and the band of image rows
+ * whose velocity look-up (fluid.cpp:89-90) falls into it; the caller's interleaved buffers are split the
+ * same way (band rows x width x 4 floats each).  Halo rows move between ring neighbours before every
+ * fused pass (csrc/slab.cu).  Transports: NCCL, one process per GPU (pfs_slab_connect_nccl), or direct
+ * copies between slabs living in one process on any devices (pfs_slab_connect_local). */
+typedef struct pfs_slab pfs_slab;
+/* Pure host arithmetic: the bands of rank `rank` (works without a GPU). */
+int pfs_slab_partition(int rank, int nranks, int gh, int ih, int *row0, int *rows, int *irow0, int *irows);
+/* Creates the context of one rank on the CURRENT device: gw x gh velocity grid, iw x ih image (0 x 0: none). */
+int pfs_slab_create(pfs_slab **out, int rank, int nranks, int gw, int gh, int iw, int ih);
+int pfs_slab_destroy(pfs_slab *s);
+int pfs_slab_rows(const pfs_slab *s, int *row0, int *rows, int *irow0, int *irows);
+int pfs_slab_connect_local(pfs_slab *const *slabs, int n);         /* all n ranks, in rank order */
+int pfs_slab_nccl_unique_id(char id[128]);                          /* rank 0; ship the bytes to every rank */
+int pfs_slab_connect_nccl(pfs_slab *s, const char id[128]);         /* collective over all ranks */
+/* simulate_fluid_step / advect_color_step (fluid.hpp:107,116) on the bands.  slabs/vp/tmp/streams are
+ * arrays over the LOCAL slabs (all ranks for the in-process transport, exactly one under NCCL); vp[k] and
+ * tmp[k] are exchanged exactly as pfs_simulate_fluid_step exchanges *vp and *tmp. */
+int pfs_slab_simulate_fluid_step(pfs_slab *const *slabs, int n_local, float **vp, float **tmp, float dt,
+                                 float viscosity, int n_diffuse, int n_pressure, void *const *streams);
+int pfs_slab_advect_color_step(pfs_slab *const *slabs, int n_local, float **image, float **itmp,
+                               float *const *vp, float dt, void *const *streams);
+/* Synchronises and reports an internal halo overflow (a bug, never expected). */
+int pfs_slab_check(pfs_slab *const *slabs, int n_local);
+
 /* ---- phase timing (diagnostics for bench.py; not on the reference's surface) --------------- */
 /* When enabled, pfs_simulate_fluid_step / pfs_advect_color_step bracket each phase with CUDA
  * events on the caller's stream.  pfs_phase_times() synchronises those events and returns the

@@ -51,6 +51,16 @@ SIGNATURES = {
     "pfs_simulate_fluid_step_host": (_int, [_F, _F, _f32, _f32, _int, _int]),
     "pfs_advect_color_step_host": (_int, [_F, _F, _F, _f32]),
     "pfs_timestep_host": (_int, [_F, _F, _F, _F, _f32, _f32, _int, _int]),
+    "pfs_slab_partition": (_int, [_int, _int, _int, _int] + [ctypes.POINTER(_int)] * 4),
+    "pfs_slab_create": (_int, [_pp, _int, _int, _int, _int, _int, _int]),
+    "pfs_slab_destroy": (_int, [_vp]),
+    "pfs_slab_rows": (_int, [_vp] + [ctypes.POINTER(_int)] * 4),
+    "pfs_slab_connect_local": (_int, [_pp, _int]),
+    "pfs_slab_nccl_unique_id": (_int, [ctypes.c_char_p]),
+    "pfs_slab_connect_nccl": (_int, [_vp, ctypes.c_char_p]),
+    "pfs_slab_simulate_fluid_step": (_int, [_pp, _int, _pp, _pp, _f32, _f32, _int, _int, _pp]),
+    "pfs_slab_advect_color_step": (_int, [_pp, _int, _pp, _pp, _pp, _f32, _pp]),
+    "pfs_slab_check": (_int, [_pp, _int]),
     "pfs_phase_timing_enable": (_int, [_int]),
     "pfs_phase_times": (_int, [ctypes.POINTER(_f32), ctypes.POINTER(ctypes.c_uint64), _int]),
 }

@@ -35,13 +35,15 @@ __device__ __forceinline__ void store_vec(float *p, const float (&o)[V])
 }
 
 // Common per-thread stencil addressing: this thread owns cells [x, x+V) of row j.
+// j = interior row (0..h-1, what the interleaved caller buffers are indexed with); rj, jm, jp = PLANE
+// rows of the cell and of its vertical neighbours (see SweepParams::y_base / wrap).
 struct StencilPos {
-    int x, j, xm, xp, jm, jp;
+    int x, j, rj, xm, xp, jm, jp;
     bool valid;
 };
 
 template <int V>
-__device__ __forceinline__ StencilPos stencil_pos(int w, int h)
+__device__ __forceinline__ StencilPos stencil_pos(int w, int h, int y_base, int wrap)
 {
     StencilPos s;
     int xv = blockIdx.x * BX + threadIdx.x;
@@ -50,8 +52,14 @@ __device__ __forceinline__ StencilPos stencil_pos(int w, int h)
     s.valid = (s.x < w) && (s.j < h);
     s.xm = (s.x == 0) ? w - 1 : s.x - 1;          // ((i-1) % w + w) % w, fluid.cpp:159
     s.xp = (s.x + V >= w) ? 0 : s.x + V;          // (i+1) % w, fluid.cpp:160
-    s.jm = (s.j == 0) ? h - 1 : s.j - 1;          // fluid.cpp:161
-    s.jp = (s.j + 1 >= h) ? 0 : s.j + 1;          // fluid.cpp:162
+    int jm = s.j - 1, jp = s.j + 1;
+    if (wrap) {
+        if (jm < 0) jm = h - 1;                   // fluid.cpp:161
+        if (jp >= h) jp = 0;                      // fluid.cpp:162
+    }
+    s.rj = y_base + s.j;
+    s.jm = y_base + jm;
+    s.jp = y_base + jp;
     return s;
 }
 
@@ -67,20 +75,21 @@ inline dim3 stencil_grid(int w, int h, int v, int planes)
 template <int OP, int V>
 __global__ void __launch_bounds__(BX *BY)
     sweep_kernel(const float *__restrict__ in0, const float *__restrict__ in1, float *__restrict__ out0,
-                 float *__restrict__ out1, const float *__restrict__ rhs, int w, int h, float alpha, float beta)
+                 float *__restrict__ out1, const float *__restrict__ rhs, int w, int h, float alpha, float beta,
+                 int y_base, int wrap)
 {
-    StencilPos s = stencil_pos<V>(w, h);
+    StencilPos s = stencil_pos<V>(w, h, y_base, wrap);
     if (!s.valid) return;
     const float *in = blockIdx.z ? in1 : in0;
     float *out = blockIdx.z ? out1 : out0;
-    const float *rc = in + (size_t)s.j * w;
+    const float *rc = in + (size_t)s.rj * w;
     float c[V], t[V], b[V], o[V];
     load_vec<V>(rc + s.x, c);
     load_vec<V>(in + (size_t)s.jm * w + s.x, t);
     load_vec<V>(in + (size_t)s.jp * w + s.x, b);
     float l = __ldg(rc + s.xm), r = __ldg(rc + s.xp);
     float q[V];
-    if constexpr (OP == SWEEP_PRESSURE) load_vec<V>(rhs + (size_t)s.j * w + s.x, q);
+    if constexpr (OP == SWEEP_PRESSURE) load_vec<V>(rhs + (size_t)s.rj * w + s.x, q);
 #pragma unroll
     for (int k = 0; k < V; k++) {
         float left = (k == 0) ? l : c[k - 1];
@@ -90,7 +99,7 @@ __global__ void __launch_bounds__(BX *BY)
         else
             o[k] = diffuse_update(left, right, t[k], b[k], c[k], alpha, beta);
     }
-    store_vec<V>(out + (size_t)s.j * w + s.x, o);
+    store_vec<V>(out + (size_t)s.rj * w + s.x, o);
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -99,11 +108,12 @@ __global__ void __launch_bounds__(BX *BY)
 template <int V>
 __global__ void __launch_bounds__(BX *BY)
     divergence_kernel(const float *__restrict__ u, const float *__restrict__ v, float *__restrict__ div,
-                      const float *__restrict__ p0_src, float *__restrict__ p0, float gamma, int w, int h)
+                      const float *__restrict__ p0_src, float *__restrict__ p0, float gamma, int w, int h,
+                      int y_base, int wrap)
 {
-    StencilPos s = stencil_pos<V>(w, h);
+    StencilPos s = stencil_pos<V>(w, h, y_base, wrap);
     if (!s.valid) return;
-    const float *ur = u + (size_t)s.j * w;
+    const float *ur = u + (size_t)s.rj * w;
     float uc[V], vt[V], vb[V], o[V];
     load_vec<V>(ur + s.x, uc);
     load_vec<V>(v + (size_t)s.jm * w + s.x, vt);
@@ -115,13 +125,13 @@ __global__ void __launch_bounds__(BX *BY)
         float right = (k == V - 1) ? urr : uc[k + 1];
         o[k] = divergence_value(right, left, vb[k], vt[k], gamma);
     }
-    store_vec<V>(div + (size_t)s.j * w + s.x, o);
+    store_vec<V>(div + (size_t)s.rj * w + s.x, o);
     if (p0 != nullptr) {
-        const float *src = p0_src + ((size_t)s.j * w + s.x) * 4 + 2;
+        const float *src = p0_src + ((size_t)s.j * w + s.x) * 4 + 2;   // interleaved buffers have no halo rows
         float pv[V];
 #pragma unroll
         for (int k = 0; k < V; k++) pv[k] = __ldg(src + 4 * k);
-        store_vec<V>(p0 + (size_t)s.j * w + s.x, pv);
+        store_vec<V>(p0 + (size_t)s.rj * w + s.x, pv);
     }
 }
 
@@ -133,13 +143,15 @@ template <int V>
 __global__ void __launch_bounds__(BX *BY)
     project_pack_kernel(const float *__restrict__ u, const float *__restrict__ v, const float *__restrict__ pn,
                         const float *__restrict__ pprev, const float *__restrict__ div,
-                        float4 *__restrict__ out_q, float4 *__restrict__ out_p, float dt, int w, int h)
+                        float4 *__restrict__ out_q, float4 *__restrict__ out_p, float dt, int w, int h,
+                        int y_base, int wrap)
 {
-    StencilPos s = stencil_pos<V>(w, h);
+    StencilPos s = stencil_pos<V>(w, h, y_base, wrap);
     if (!s.valid) return;
-    const float *pr = pn + (size_t)s.j * w;
+    const float *pr = pn + (size_t)s.rj * w;
     float pc[V], pt[V], pb[V], uu[V], vv[V], pp[V], dd[V];
-    size_t off = (size_t)s.j * w + s.x;
+    size_t off = (size_t)s.rj * w + s.x;                 // planes (with halo rows)
+    const size_t cell = (size_t)s.j * w + s.x;           // interleaved buffers (no halo rows)
     load_vec<V>(pr + s.x, pc);
     load_vec<V>(pn + (size_t)s.jm * w + s.x, pt);
     load_vec<V>(pn + (size_t)s.jp * w + s.x, pb);
@@ -154,8 +166,8 @@ __global__ void __launch_bounds__(BX *BY)
         float right = (k == V - 1) ? prr : pc[k + 1];
         float un = project_component(uu[k], right, left, dt);
         float vn = project_component(vv[k], pb[k], pt[k], dt);
-        out_q[off + k] = make_float4(un, vn, pp[k], dd[k]);
-        out_p[off + k] = make_float4(uu[k], vv[k], pc[k], dd[k]);
+        out_q[cell + k] = make_float4(un, vn, pp[k], dd[k]);
+        out_p[cell + k] = make_float4(uu[k], vv[k], pc[k], dd[k]);
     }
 }
 
@@ -327,7 +339,8 @@ int launch_sweeps_basic(SweepOp op, float *a0, float *a1, float *b0, float *b1, 
     const int planes = (op == SWEEP_DIFFUSE) ? 2 : 1;
     const bool v4 = vec4_ok(p.w, a0, a1, b0, b1, rhs);
     dim3 block(BX, BY), grid = stencil_grid(p.w, p.h, v4 ? 4 : 1, planes);
-    using SweepFn = void (*)(const float *, const float *, float *, float *, const float *, int, int, float, float);
+    using SweepFn = void (*)(const float *, const float *, float *, float *, const float *, int, int, float, float, int,
+                             int);
     SweepFn fn;
     if (op == SWEEP_PRESSURE)
         fn = v4 ? sweep_kernel<SWEEP_PRESSURE, 4> : sweep_kernel<SWEEP_PRESSURE, 1>;
@@ -336,35 +349,35 @@ int launch_sweeps_basic(SweepOp op, float *a0, float *a1, float *b0, float *b1, 
     for (int it = 0; it < n; it++) {
         const float *i0 = (it & 1) ? b0 : a0, *i1 = (it & 1) ? b1 : a1;
         float *o0 = (it & 1) ? a0 : b0, *o1 = (it & 1) ? a1 : b1;
-        PFS_LAUNCH(fn, grid, block, 0, s, i0, i1, o0, o1, rhs, p.w, p.h, p.alpha, p.beta);
+        PFS_LAUNCH(fn, grid, block, 0, s, i0, i1, o0, o1, rhs, p.w, p.h, p.alpha, p.beta, p.y_base, p.wrap);
     }
     *flips = n;
     return PFS_OK;
 }
 
 int launch_divergence(const float *u, const float *v, float *div, const float *p0_src_aos, float *p0, float dt,
-                      int w, int h, cudaStream_t s)
+                      int w, int h, cudaStream_t s, int y_base, int wrap)
 {
     const float gamma = (float)(-1.0 / (double)dt);   // fluid.cpp:218
     const bool v4 = vec4_ok(w, u, v, div, p0);
     dim3 block(BX, BY), grid = stencil_grid(w, h, v4 ? 4 : 1, 1);
     if (v4)
-        PFS_LAUNCH(divergence_kernel<4>, grid, block, 0, s, u, v, div, p0_src_aos, p0, gamma, w, h);
+        PFS_LAUNCH(divergence_kernel<4>, grid, block, 0, s, u, v, div, p0_src_aos, p0, gamma, w, h, y_base, wrap);
     else
-        PFS_LAUNCH(divergence_kernel<1>, grid, block, 0, s, u, v, div, p0_src_aos, p0, gamma, w, h);
+        PFS_LAUNCH(divergence_kernel<1>, grid, block, 0, s, u, v, div, p0_src_aos, p0, gamma, w, h, y_base, wrap);
     return PFS_OK;
 }
 
 int launch_project_pack(const float *u, const float *v, const float *p_n, const float *p_prev, const float *div,
-                        float *out_q, float *out_p, float dt, int w, int h, cudaStream_t s)
+                        float *out_q, float *out_p, float dt, int w, int h, cudaStream_t s, int y_base, int wrap)
 {
     const bool v4 = vec4_ok(w, u, v, p_n, p_prev, div);
     dim3 block(BX, BY), grid = stencil_grid(w, h, v4 ? 4 : 1, 1);
     float4 *q4 = reinterpret_cast<float4 *>(out_q), *p4 = reinterpret_cast<float4 *>(out_p);
     if (v4)
-        PFS_LAUNCH(project_pack_kernel<4>, grid, block, 0, s, u, v, p_n, p_prev, div, q4, p4, dt, w, h);
+        PFS_LAUNCH(project_pack_kernel<4>, grid, block, 0, s, u, v, p_n, p_prev, div, q4, p4, dt, w, h, y_base, wrap);
     else
-        PFS_LAUNCH(project_pack_kernel<1>, grid, block, 0, s, u, v, p_n, p_prev, div, q4, p4, dt, w, h);
+        PFS_LAUNCH(project_pack_kernel<1>, grid, block, 0, s, u, v, p_n, p_prev, div, q4, p4, dt, w, h, y_base, wrap);
     return PFS_OK;
 }
 

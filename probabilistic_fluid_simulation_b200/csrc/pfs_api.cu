@@ -134,26 +134,21 @@ static cudaEvent_t take_event()
     return e;
 }
 
-struct PhaseScope {
-    int phase;
-    cudaStream_t s;
-    cudaEvent_t a = nullptr;
-    unsigned long long l0 = 0;
-    PhaseScope(int phase_, cudaStream_t s_) : phase(phase_), s(s_)
-    {
-        if (!g_phase_timing) return;
-        a = take_event();
-        l0 = g_launches;
-        cudaEventRecord(a, s);
-    }
-    ~PhaseScope()
-    {
-        if (!a) return;
-        cudaEvent_t b = take_event();
-        cudaEventRecord(b, s);
-        g_spans.push_back({phase, a, b, g_launches - l0});
-    }
-};
+PhaseScope::PhaseScope(int phase_, cudaStream_t s_) : phase(phase_), s(s_)
+{
+    if (!g_phase_timing) return;
+    a = take_event();
+    l0 = g_launches;
+    cudaEventRecord(a, s);
+}
+
+PhaseScope::~PhaseScope()
+{
+    if (!a) return;
+    cudaEvent_t b = take_event();
+    cudaEventRecord(b, s);
+    g_spans.push_back({phase, a, b, g_launches - l0});
+}
 
 // ---------------------------------------------------------------------------------------------
 // argument checks

@@ -44,6 +44,19 @@ int check_launch(const char *kernel, const char *file, int line);
         PFS_TRY(::pfs::check_launch(#kernel, __FILE__, __LINE__));             \
     } while (0)
 
+// Brackets one phase of a step with CUDA events on `s` when pfs_phase_timing_enable(1) is set
+// (pfs_api.cu); a no-op otherwise.
+struct PhaseScope {
+    int phase;
+    cudaStream_t s;
+    cudaEvent_t a = nullptr;
+    unsigned long long l0 = 0;
+    PhaseScope(int phase, cudaStream_t s);
+    ~PhaseScope();
+    PhaseScope(const PhaseScope &) = delete;
+    PhaseScope &operator=(const PhaseScope &) = delete;
+};
+
 // ---------------------------------------------------------------------------------------------
 // exact-arithmetic device helpers (each cites the reference expression it reproduces)
 // ---------------------------------------------------------------------------------------------
@@ -127,6 +140,11 @@ enum SweepOp { SWEEP_PRESSURE = 0, SWEEP_DIFFUSE = 1 };
 struct SweepParams {
     int w, h;
     float alpha, beta;   // diffusion only (fluid.cpp:144-145)
+    // Row map of the planes.  Single GPU: y_base = 0, wrap = 1 (row j-1 of row 0 is row h-1, by index).
+    // Slab of a multi-GPU grid: planes carry halo rows, interior row j lives at plane row y_base + j,
+    // rows -1 and h are real halo rows, wrap = 0.
+    int y_base = 0;
+    int wrap = 1;
 };
 
 // interleaved (AoS) <-> planar (SoA) movers.  Null plane pointers are skipped.
@@ -160,13 +178,14 @@ void packed_release_device_buffers();
 // divergence (fluid.cpp:221-237) of planes (u, v) into plane div; optionally also extracts
 // channel 2 of an interleaved buffer into plane p0 (the pressure warm start) in the same pass.
 int launch_divergence(const float *u, const float *v, float *div, const float *p0_src_aos, float *p0,
-                      float dt, int w, int h, cudaStream_t s);
+                      float dt, int w, int h, cudaStream_t s, int y_base = 0, int wrap = 1);
 
 // End of simulate_fluid_step: subtract the gradient of p_n from (u, v) (fluid.cpp:269-296) and write
 // BOTH interleaved post-state buffers with full-cell stores:
 //   out_q = [u - gx, v - gy, p_prev, div]      out_p = [u, v, p_n, div]
 int launch_project_pack(const float *u, const float *v, const float *p_n, const float *p_prev,
-                        const float *div, float *out_q, float *out_p, float dt, int w, int h, cudaStream_t s);
+                        const float *div, float *out_q, float *out_p, float dt, int w, int h, cudaStream_t s,
+                        int y_base = 0, int wrap = 1);
 
 // subtractPressureGradient as a stand-alone operator on interleaved buffers (writes ch0,1 of out).
 int launch_subtract_gradient_aos(const float *vp_aos, float *out_aos, float dt, int w, int h, cudaStream_t s);

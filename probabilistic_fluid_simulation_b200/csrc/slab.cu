@@ -1,0 +1,967 @@
+// slab.cu -- the fluid step on a row-slab decomposition of one periodic grid over several GPUs
+// (BASELINE.json configs[3]: 16384^2 over 2/4/8 B200).
+//
+// Decomposition: rank r of R owns a contiguous band of rows of the velocity grid and the band of image
+// rows whose velocity look-up (fluid.cpp:89-90) falls into it; x stays whole, so a halo row is one
+// contiguous run of W floats per plane and the x wrap stays local.  The domain is periodic, so the
+// ranks form a ring (R = 1 wraps onto itself).  Planes carry HALO rows above and below the band; the
+// kernels are the single-GPU kernels with the row map (y_base = HALO, wrap = 0).
+//
+// What moves between neighbours each timestep (rows are W*4 bytes per plane):
+//   advect        D rows of (u,v) each way, D = ceil(max|dt*v/H|) + 2 from an all-reduce(max)
+//   diffusion     t rows x 2 planes before every fused pass of depth t, 1 row before the last sweep
+//   divergence    1 row of v; then HALO rows of the divergence (the fused pressure passes need the
+//                 right-hand side inside their halo trapezoid)
+//   pressure      t rows before every fused pass, 1 row before the last sweep, 1 row of p_N for the
+//                 gradient
+//   advect_color  D_i rows of the image each way
+// Results are bit-identical to the single-GPU path (same per-cell arithmetic, global indices).
+//
+// Transports: NCCL send/recv between one process per GPU (resolved with dlopen, so the single-GPU
+// library has no NCCL dependency), or direct copies between slabs that live in one process (any
+// devices; used by the tests to run R slabs on one GPU and by single-process multi-GPU callers).
+#include <dlfcn.h>
+#include <nccl.h>   // types and enums only; every function is resolved at run time
+#include <stdlib.h>
+
+#include <algorithm>
+#include <cmath>
+#include <vector>
+
+#include "pfs_internal.cuh"
+
+namespace pfs {
+
+constexpr int HALO = 8;   // >= the deepest fused pass
+
+// ---------------------------------------------------------------------------------------------
+// NCCL through dlopen
+// ---------------------------------------------------------------------------------------------
+struct NcclApi {
+    ncclResult_t (*GetUniqueId)(ncclUniqueId *) = nullptr;
+    ncclResult_t (*CommInitRank)(ncclComm_t *, int, ncclUniqueId, int) = nullptr;
+    ncclResult_t (*CommDestroy)(ncclComm_t) = nullptr;
+    ncclResult_t (*GroupStart)() = nullptr;
+    ncclResult_t (*GroupEnd)() = nullptr;
+    ncclResult_t (*Send)(const void *, size_t, ncclDataType_t, int, ncclComm_t, cudaStream_t) = nullptr;
+    ncclResult_t (*Recv)(void *, size_t, ncclDataType_t, int, ncclComm_t, cudaStream_t) = nullptr;
+    ncclResult_t (*AllReduce)(const void *, void *, size_t, ncclDataType_t, ncclRedOp_t, ncclComm_t, cudaStream_t) = nullptr;
+    ncclResult_t (*Broadcast)(const void *, void *, size_t, ncclDataType_t, int, ncclComm_t, cudaStream_t) = nullptr;
+    const char *(*GetErrorString)(ncclResult_t) = nullptr;
+    bool loaded = false;
+};
+
+static NcclApi &nccl()
+{
+    static NcclApi a;
+    static bool tried = false;
+    if (tried) return a;
+    tried = true;
+    void *h = nullptr;
+    const char *env = getenv("PFS_NCCL_LIB");
+    for (const char *name : {env ? env : "libnccl.so.2", "libnccl.so.2", "libnccl.so"}) {
+        h = dlopen(name, RTLD_NOW | RTLD_GLOBAL);
+        if (h) break;
+    }
+    if (!h) return a;
+#define PFS_NCCL_SYM(field, sym) a.field = (decltype(a.field))dlsym(h, sym)
+    PFS_NCCL_SYM(GetUniqueId, "ncclGetUniqueId");
+    PFS_NCCL_SYM(CommInitRank, "ncclCommInitRank");
+    PFS_NCCL_SYM(CommDestroy, "ncclCommDestroy");
+    PFS_NCCL_SYM(GroupStart, "ncclGroupStart");
+    PFS_NCCL_SYM(GroupEnd, "ncclGroupEnd");
+    PFS_NCCL_SYM(Send, "ncclSend");
+    PFS_NCCL_SYM(Recv, "ncclRecv");
+    PFS_NCCL_SYM(AllReduce, "ncclAllReduce");
+    PFS_NCCL_SYM(Broadcast, "ncclBroadcast");
+    PFS_NCCL_SYM(GetErrorString, "ncclGetErrorString");
+#undef PFS_NCCL_SYM
+    a.loaded = a.GetUniqueId && a.CommInitRank && a.CommDestroy && a.GroupStart && a.GroupEnd && a.Send && a.Recv &&
+               a.AllReduce && a.Broadcast && a.GetErrorString;
+    return a;
+}
+
+#define PFS_NCCL(call)                                                                            \
+    do {                                                                                          \
+        ncclResult_t r__ = (call);                                                                \
+        if (r__ != ncclSuccess) {                                                                 \
+            set_error("NCCL error %d (%s) at %s:%d: %s", (int)r__, nccl().GetErrorString(r__), __FILE__, __LINE__, #call); \
+            return PFS_ECUDA;                                                                     \
+        }                                                                                         \
+    } while (0)
+
+// ---------------------------------------------------------------------------------------------
+// partition (pure host logic; exported for the CPU tests)
+// ---------------------------------------------------------------------------------------------
+static void band(int total, int parts, int r, int *first, int *count)
+{
+    const int base = total / parts, rem = total % parts;
+    *first = r * base + std::min(r, rem);
+    *count = base + (r < rem ? 1 : 0);
+}
+
+// image rows j whose velocity row (int)((float)j * vih) lies in [row0, row0+rows)  (fluid.cpp:83,90)
+static void image_band(int ih, int gh, int row0, int rows, int *irow0, int *irows)
+{
+    const float vih = (float)gh / (float)ih;
+    int first = ih, last = -1;
+    for (int j = 0; j < ih; j++) {
+        const int vj = (int)((float)j * vih);
+        if (vj >= row0 && vj < row0 + rows) {
+            first = std::min(first, j);
+            last = std::max(last, j);
+        }
+    }
+    if (last < first) {
+        *irow0 = 0;
+        *irows = 0;
+    } else {
+        *irow0 = first;
+        *irows = last - first + 1;
+    }
+}
+
+}  // namespace pfs
+
+// ---------------------------------------------------------------------------------------------
+// slab context
+// ---------------------------------------------------------------------------------------------
+struct pfs_slab {
+    int rank = 0, nranks = 1;
+    int gw = 0, gh = 0, row0 = 0, rows = 0;
+    int iw = 0, ih = 0, irow0 = 0, irows = 0;
+    int device = 0;
+    size_t plane_floats = 0;
+    float *planes = nullptr;              // 7 planes of (rows + 2*HALO) x gw
+    float2 *uvx = nullptr;                // advect source: (u,v) rows [row0-D, row0+rows+D) (or the whole grid)
+    size_t uvx_rows = 0;
+    float4 *imgx = nullptr;               // advect_color source: image rows [irow0-Di, irow0+irows+Di)
+    size_t imgx_rows = 0;
+    float *d_scalars = nullptr;           // [0] max|v| (advect), [1] max|v| (advect_color), [2] overflow flag (as int)
+    float *h_scalars = nullptr;           // pinned mirror
+    ncclComm_t comm = nullptr;
+    std::vector<pfs_slab *> group;        // in-process transport: all ranks, indexed by rank (empty under NCCL)
+    cudaStream_t stream = nullptr;        // stream of the call in flight
+    cudaEvent_t ev_ready = nullptr, ev_done = nullptr;
+    float *plane(int k) const { return planes + (size_t)k * plane_floats; }
+    int up() const { return (rank + nranks - 1) % nranks; }
+    int down() const { return (rank + 1) % nranks; }
+};
+
+namespace pfs {
+
+namespace {
+
+struct Guard {   // cudaSetDevice for the scope of one slab's work
+    int prev = -1;
+    explicit Guard(int dev)
+    {
+        cudaGetDevice(&prev);
+        if (prev != dev) cudaSetDevice(dev);
+    }
+    ~Guard()
+    {
+        if (prev >= 0) cudaSetDevice(prev);
+    }
+};
+
+// ---- small kernels of the slab path -----------------------------------------------------------
+__global__ void __launch_bounds__(256) max_abs_v_kernel(const float4 *__restrict__ vp, size_t n, float *out)
+{
+    float m = 0.f;
+    for (size_t i = (size_t)blockIdx.x * 256 + threadIdx.x; i < n; i += (size_t)gridDim.x * 256) {
+        const float v = fabsf(__ldg(vp + i).y);
+        m = (v > m || v != v) ? v : m;           // NaN propagates: the host then takes the all-gather path
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        const float t = __shfl_xor_sync(0xffffffffu, m, o);
+        m = (t > m || t != t) ? t : m;
+    }
+    if ((threadIdx.x & 31) == 0) {
+        if (m != m) m = __int_as_float(0x7f800000);   // NaN -> +inf, so that every rank takes the same decision
+        atomicMax(reinterpret_cast<int *>(out), __float_as_int(m));   // non-negative floats order like their bits
+    }
+}
+
+__global__ void __launch_bounds__(256) unpack_uv_kernel(const float4 *__restrict__ vp, float2 *__restrict__ uv, size_t n)
+{
+    const size_t i = (size_t)blockIdx.x * 256 + threadIdx.x;
+    if (i >= n) return;
+    const float4 c = __ldg(vp + i);
+    uv[i] = make_float2(c.x, c.y);
+}
+
+// advect (fluid.cpp:24-70) with GLOBAL indices: this rank produces rows [row0, row0+rows) of the
+// gh-row grid; the gather source holds rows [src_row0, src_row0+src_rows) (mod gh) of (u,v).
+__global__ void __launch_bounds__(256)
+    advect_slab_kernel(const float2 *__restrict__ src, int src_row0, int src_rows, float *__restrict__ u_out,
+                       float *__restrict__ v_out, float dt, int w, int gh, int row0, int rows, int y_base,
+                       int *overflow)
+{
+    const int i = blockIdx.x * 64 + threadIdx.x, jl = blockIdx.y * 4 + threadIdx.y;
+    if (i >= w || jl >= rows) return;
+    const int j = row0 + jl;
+    const float fw = (float)w, fh = (float)gh;
+    int lj = j - src_row0;
+    if (lj < 0) lj += gh;
+    const float2 uv = __ldg(src + (size_t)lj * w + i);
+    float xp = __fsub_rn((float)i, __fdiv_rn(__fmul_rn(dt, uv.x), fw));
+    float yp = __fsub_rn((float)j, __fdiv_rn(__fmul_rn(dt, uv.y), fh));
+    xp = wrap_coord(xp, fw);
+    yp = wrap_coord(yp, fh);
+    const Bilinear b = make_bilinear(xp, yp, w, gh);
+    int l0 = b.j0 - src_row0, l1 = b.j1 - src_row0;
+    if (l0 < 0) l0 += gh;
+    if (l1 < 0) l1 += gh;
+    if (l0 >= src_rows || l1 >= src_rows) {      // cannot happen if D was computed correctly; never read out of bounds
+        atomicExch(overflow, 1);
+        return;
+    }
+    const float2 *r0 = src + (size_t)l0 * w, *r1 = src + (size_t)l1 * w;
+    const float2 f00 = __ldg(r0 + b.i0), f10 = __ldg(r0 + b.i1), f01 = __ldg(r1 + b.i0), f11 = __ldg(r1 + b.i1);
+    const size_t o = (size_t)(y_base + jl) * w + i;
+    u_out[o] = bilerp(b, f00.x, f10.x, f01.x, f11.x);
+    v_out[o] = bilerp(b, f00.y, f10.y, f01.y, f11.y);
+}
+
+// advect_color (fluid.cpp:72-127) with GLOBAL indices: image rows [irow0, irow0+irows), velocity rows
+// [row0, row0+rows) (interleaved, local), image gather source rows [src_row0, +src_rows) (mod ih).
+__global__ void __launch_bounds__(256)
+    advect_color_slab_kernel(const float4 *__restrict__ src, int src_row0, int src_rows, float4 *__restrict__ out,
+                             const float *__restrict__ vp, float dt_over_viw, float dt_over_vih, float viw, float vih,
+                             int iw, int ih, int irow0, int irows, int vw, int row0, int rows, int *overflow)
+{
+    const int i = blockIdx.x * 64 + threadIdx.x, jl = blockIdx.y * 4 + threadIdx.y;
+    if (i >= iw || jl >= irows) return;
+    const int j = irow0 + jl;
+    const float fiw = (float)iw, fih = (float)ih;
+    const int vi = (int)__fmul_rn((float)i, viw);
+    const int vj = (int)__fmul_rn((float)j, vih) - row0;
+    if (vj < 0 || vj >= rows) {
+        atomicExch(overflow, 2);
+        return;
+    }
+    const float2 uv = __ldg(reinterpret_cast<const float2 *>(vp + ((size_t)vj * vw + vi) * 4));
+    float xp = __fsub_rn((float)i, __fdiv_rn(__fmul_rn(dt_over_viw, uv.x), fiw));
+    float yp = __fsub_rn((float)j, __fdiv_rn(__fmul_rn(dt_over_vih, uv.y), fih));
+    xp = wrap_coord(xp, fiw);
+    yp = wrap_coord(yp, fih);
+    const Bilinear b = make_bilinear(xp, yp, iw, ih);
+    int l0 = b.j0 - src_row0, l1 = b.j1 - src_row0;
+    if (l0 < 0) l0 += ih;
+    if (l1 < 0) l1 += ih;
+    if (l0 >= src_rows || l1 >= src_rows) {
+        atomicExch(overflow, 3);
+        return;
+    }
+    const float4 *r0 = src + (size_t)l0 * iw, *r1 = src + (size_t)l1 * iw;
+    const float4 f00 = __ldg(r0 + b.i0), f10 = __ldg(r0 + b.i1), f01 = __ldg(r1 + b.i0), f11 = __ldg(r1 + b.i1);
+    float4 o;
+    o.x = bilerp(b, f00.x, f10.x, f01.x, f11.x);
+    o.y = bilerp(b, f00.y, f10.y, f01.y, f11.y);
+    o.z = bilerp(b, f00.z, f10.z, f01.z, f11.z);
+    o.w = bilerp(b, f00.w, f10.w, f01.w, f11.w);
+    out[(size_t)jl * iw + i] = o;
+}
+
+// ---- transport ----------------------------------------------------------------------------------
+// One exchange = for every local slab a list of segments; a segment sends `bytes` from send_up to the
+// upper neighbour's recv_from_down and from send_down to the lower neighbour's recv_from_up.
+struct Segment {
+    const char *send_up, *send_down;
+    char *recv_from_up, *recv_from_down;
+    size_t bytes;
+};
+
+int ring_exchange(const std::vector<pfs_slab *> &local, const std::vector<std::vector<Segment>> &segs)
+{
+    if (local.empty()) return PFS_OK;
+    if (local[0]->comm != nullptr) {
+        // NCCL: one process per rank.  Order inside the group: all sends (up, down per segment), then all
+        // receives (from_down, from_up per segment) -- with two ranks both neighbours are the same
+        // peer, and NCCL pairs sends and receives to one peer in issue order.
+        pfs_slab *s = local[0];
+        Guard g(s->device);
+        const std::vector<Segment> &v = segs[0];
+        PFS_NCCL(nccl().GroupStart());
+        for (const Segment &sg : v) {
+            PFS_NCCL(nccl().Send(sg.send_up, sg.bytes, ncclUint8, s->up(), s->comm, s->stream));
+            PFS_NCCL(nccl().Send(sg.send_down, sg.bytes, ncclUint8, s->down(), s->comm, s->stream));
+        }
+        for (const Segment &sg : v) {
+            PFS_NCCL(nccl().Recv(sg.recv_from_down, sg.bytes, ncclUint8, s->down(), s->comm, s->stream));
+            PFS_NCCL(nccl().Recv(sg.recv_from_up, sg.bytes, ncclUint8, s->up(), s->comm, s->stream));
+        }
+        PFS_NCCL(nccl().GroupEnd());
+        return PFS_OK;
+    }
+    // in-process: every rank is local.  Producer streams publish "ready", consumers copy on their own
+    // stream, then publish "done" so that a producer never overwrites rows a neighbour is still reading.
+    const std::vector<pfs_slab *> &all = local[0]->group;
+    for (pfs_slab *s : local) {
+        Guard g(s->device);
+        PFS_CUDA(cudaEventRecord(s->ev_ready, s->stream));
+    }
+    for (size_t k = 0; k < local.size(); k++) {
+        pfs_slab *s = local[k];
+        pfs_slab *up = all[s->up()], *dn = all[s->down()];
+        size_t ku = 0, kd = 0;
+        for (size_t q = 0; q < local.size(); q++) {
+            if (local[q] == up) ku = q;
+            if (local[q] == dn) kd = q;
+        }
+        Guard g(s->device);
+        PFS_CUDA(cudaStreamWaitEvent(s->stream, up->ev_ready, 0));
+        PFS_CUDA(cudaStreamWaitEvent(s->stream, dn->ev_ready, 0));
+        for (size_t i = 0; i < segs[k].size(); i++) {
+            const Segment &mine = segs[k][i];
+            // my top halo <- the upper neighbour's bottom rows; my bottom halo <- the lower neighbour's top rows
+            PFS_CUDA(cudaMemcpyAsync(mine.recv_from_up, segs[ku][i].send_down, mine.bytes, cudaMemcpyDefault, s->stream));
+            PFS_CUDA(cudaMemcpyAsync(mine.recv_from_down, segs[kd][i].send_up, mine.bytes, cudaMemcpyDefault, s->stream));
+        }
+        PFS_CUDA(cudaEventRecord(s->ev_done, s->stream));
+    }
+    for (pfs_slab *s : local) {
+        Guard g(s->device);
+        PFS_CUDA(cudaStreamWaitEvent(s->stream, all[s->up()]->ev_done, 0));
+        PFS_CUDA(cudaStreamWaitEvent(s->stream, all[s->down()]->ev_done, 0));
+    }
+    return PFS_OK;
+}
+
+// halo exchange of `t` rows of the given planes (same plane indices on every slab)
+int exchange_planes(const std::vector<pfs_slab *> &local, const std::vector<std::vector<float *>> &planes, int t)
+{
+    std::vector<std::vector<Segment>> segs(local.size());
+    for (size_t k = 0; k < local.size(); k++) {
+        pfs_slab *s = local[k];
+        const size_t row = (size_t)s->gw * sizeof(float);
+        for (float *p : planes[k]) {
+            char *b = reinterpret_cast<char *>(p);
+            Segment sg;
+            sg.send_up = b + (size_t)HALO * row;
+            sg.send_down = b + (size_t)(HALO + s->rows - t) * row;
+            sg.recv_from_up = b + (size_t)(HALO - t) * row;
+            sg.recv_from_down = b + (size_t)(HALO + s->rows) * row;
+            sg.bytes = (size_t)t * row;
+            segs[k].push_back(sg);
+        }
+    }
+    return ring_exchange(local, segs);
+}
+
+// max over all ranks of a non-negative device scalar; returns it on the host (synchronises the streams)
+int global_max(const std::vector<pfs_slab *> &local, int slot, float *out)
+{
+    float m = 0.f;
+    bool nan = false;
+    for (pfs_slab *s : local) {
+        Guard g(s->device);
+        if (s->comm != nullptr)
+            PFS_NCCL(nccl().AllReduce(s->d_scalars + slot, s->d_scalars + slot, 1, ncclFloat, ncclMax, s->comm, s->stream));
+        PFS_CUDA(cudaMemcpyAsync(s->h_scalars + slot, s->d_scalars + slot, sizeof(float), cudaMemcpyDeviceToHost, s->stream));
+    }
+    for (pfs_slab *s : local) {
+        Guard g(s->device);
+        PFS_CUDA(cudaStreamSynchronize(s->stream));
+        const float v = s->h_scalars[slot];
+        if (v != v) nan = true;
+        m = std::max(m, v);
+    }
+    *out = nan ? INFINITY : m;
+    return PFS_OK;
+}
+
+int ensure_bytes(void **ptr, size_t *have_rows, size_t want_rows, size_t row_bytes)
+{
+    if (*have_rows >= want_rows && *ptr) return PFS_OK;
+    if (*ptr) {
+        PFS_CUDA(cudaDeviceSynchronize());
+        PFS_CUDA(cudaFree(*ptr));
+        *ptr = nullptr;
+        *have_rows = 0;
+    }
+    PFS_CUDA(cudaMalloc(ptr, want_rows * row_bytes));
+    *have_rows = want_rows;
+    return PFS_OK;
+}
+
+// Fill the gather source of one field: local band in the middle, D halo rows from the ring neighbours,
+// or -- when D exceeds a band -- every rank's band (all-gather), which is always sufficient.
+// `elem` = bytes per cell.  On return *src_row0 / *src_rows describe what `buf` holds.
+int fill_gather_source(const std::vector<pfs_slab *> &local, const std::vector<char *> &buf, int width, int total_rows,
+                       const std::vector<int> &first, const std::vector<int> &count, int D, size_t elem, bool whole,
+                       std::vector<int> *src_row0, std::vector<int> *src_rows)
+{
+    const size_t row = (size_t)width * elem;
+    if (!whole) {
+        std::vector<std::vector<Segment>> segs(local.size());
+        for (size_t k = 0; k < local.size(); k++) {
+            char *b = buf[k];
+            Segment sg;
+            sg.send_up = b + (size_t)D * row;
+            sg.send_down = b + (size_t)(D + count[k] - D) * row;
+            sg.recv_from_up = b;
+            sg.recv_from_down = b + (size_t)(D + count[k]) * row;
+            sg.bytes = (size_t)D * row;
+            segs[k].push_back(sg);
+            (*src_row0)[k] = ((first[k] - D) % total_rows + total_rows) % total_rows;
+            (*src_rows)[k] = count[k] + 2 * D;
+        }
+        return ring_exchange(local, segs);
+    }
+    // all-gather: buf holds the whole field in global row order; the local band is already in place
+    for (size_t k = 0; k < local.size(); k++) {
+        pfs_slab *s = local[k];
+        Guard g(s->device);
+        (*src_row0)[k] = 0;
+        (*src_rows)[k] = total_rows;
+        if (s->comm != nullptr) {
+            for (int r = 0; r < s->nranks; r++) {
+                int f, c;
+                if (elem == sizeof(float2))
+                    band(s->gh, s->nranks, r, &f, &c);
+                else {
+                    int vf, vc;
+                    band(s->gh, s->nranks, r, &vf, &vc);
+                    image_band(s->ih, s->gh, vf, vc, &f, &c);
+                }
+                if (c == 0) continue;
+                char *p = buf[k] + (size_t)f * row;
+                PFS_NCCL(nccl().Broadcast(p, p, (size_t)c * row, ncclUint8, r, s->comm, s->stream));
+            }
+        } else {
+            PFS_CUDA(cudaEventRecord(s->ev_ready, s->stream));
+        }
+    }
+    if (local[0]->comm == nullptr) {
+        const std::vector<pfs_slab *> &all = local[0]->group;
+        for (size_t k = 0; k < local.size(); k++) {
+            pfs_slab *s = local[k];
+            Guard g(s->device);
+            for (size_t q = 0; q < local.size(); q++) {
+                if (q == k || count[q] == 0) continue;
+                PFS_CUDA(cudaStreamWaitEvent(s->stream, all[local[q]->rank]->ev_ready, 0));
+                PFS_CUDA(cudaMemcpyAsync(buf[k] + (size_t)first[q] * row, buf[q] + (size_t)first[q] * row,
+                                         (size_t)count[q] * row, cudaMemcpyDefault, s->stream));
+            }
+            PFS_CUDA(cudaEventRecord(s->ev_done, s->stream));
+        }
+        for (pfs_slab *s : local) {
+            Guard g(s->device);
+            for (pfs_slab *o : local)
+                if (o != s) PFS_CUDA(cudaStreamWaitEvent(s->stream, o->ev_done, 0));
+        }
+    }
+    return PFS_OK;
+}
+
+int check_local(const char *fn, pfs_slab *const *slabs, int n_local, std::vector<pfs_slab *> *out)
+{
+    if (!slabs || n_local < 1) {
+        set_error("%s: no slabs given", fn);
+        return PFS_EINVAL;
+    }
+    for (int k = 0; k < n_local; k++) {
+        if (!slabs[k]) {
+            set_error("%s: slab %d is null", fn, k);
+            return PFS_EINVAL;
+        }
+        out->push_back(slabs[k]);
+    }
+    pfs_slab *s0 = slabs[0];
+    if (s0->comm == nullptr) {
+        if ((int)s0->group.size() != s0->nranks || n_local != s0->nranks) {
+            set_error("%s: in-process transport needs every rank of the ring in the call (got %d of %d); "
+                      "call pfs_slab_connect_local or pfs_slab_connect_nccl first", fn, n_local, s0->nranks);
+            return PFS_ESTATE;
+        }
+        for (int k = 0; k < n_local; k++) {
+            if (slabs[k]->rank != k) {
+                set_error("%s: slabs must be passed in rank order", fn);
+                return PFS_EINVAL;
+            }
+        }
+    } else if (n_local != 1) {
+        set_error("%s: the NCCL transport drives exactly one slab per process", fn);
+        return PFS_EINVAL;
+    }
+    return PFS_OK;
+}
+
+}  // namespace
+}  // namespace pfs
+
+using namespace pfs;
+
+// =============================================================================================
+// C-ABI
+// =============================================================================================
+extern "C" int pfs_slab_partition(int rank, int nranks, int gh, int ih, int *row0, int *rows, int *irow0, int *irows)
+{
+    if (nranks < 1 || rank < 0 || rank >= nranks || gh < 1) {
+        set_error("pfs_slab_partition: bad rank/nranks/height");
+        return PFS_EINVAL;
+    }
+    int f, c;
+    band(gh, nranks, rank, &f, &c);
+    if (row0) *row0 = f;
+    if (rows) *rows = c;
+    if (ih > 0) {
+        int jf, jc;
+        image_band(ih, gh, f, c, &jf, &jc);
+        if (irow0) *irow0 = jf;
+        if (irows) *irows = jc;
+    }
+    return PFS_OK;
+}
+
+extern "C" int pfs_slab_destroy(pfs_slab *s);
+
+extern "C" int pfs_slab_create(pfs_slab **out, int rank, int nranks, int gw, int gh, int iw, int ih)
+{
+    const char *fn = "pfs_slab_create";
+    if (!out || nranks < 1 || rank < 0 || rank >= nranks || gw < 1 || gh < 1 || iw < 0 || ih < 0) {
+        set_error("%s: bad arguments", fn);
+        return PFS_EINVAL;
+    }
+    if ((size_t)gw * gh > ((size_t)1 << 28) || (size_t)iw * ih > ((size_t)1 << 28)) {
+        set_error("%s: grid exceeds 2^28 cells (the reference's int32 index limit)", fn);
+        return PFS_EINVAL;
+    }
+    if (gh / nranks < HALO) {
+        set_error("%s: every slab needs at least %d rows (grid height %d over %d ranks)", fn, HALO, gh, nranks);
+        return PFS_EINVAL;
+    }
+    pfs_slab *s = new pfs_slab();
+    s->rank = rank;
+    s->nranks = nranks;
+    s->gw = gw;
+    s->gh = gh;
+    s->iw = iw;
+    s->ih = ih;
+    band(gh, nranks, rank, &s->row0, &s->rows);
+    if (ih > 0) image_band(ih, gh, s->row0, s->rows, &s->irow0, &s->irows);
+    cudaError_t e = cudaGetDevice(&s->device);
+    if (e != cudaSuccess) {
+        delete s;
+        set_error("%s: no usable CUDA device (%s); there is no CPU fallback", fn, cudaGetErrorString(e));
+        return PFS_ENODEVICE;
+    }
+    s->plane_floats = ((size_t)(s->rows + 2 * HALO) * gw + 63) & ~(size_t)63;
+    int st = PFS_OK;
+    auto fail = [&](cudaError_t ce, const char *what) {
+        st = cuda_fail(ce, what, __FILE__, __LINE__);
+    };
+    if ((e = cudaMalloc((void **)&s->planes, 7 * s->plane_floats * sizeof(float))) != cudaSuccess) fail(e, "cudaMalloc planes");
+    if (st == PFS_OK && (e = cudaMemset(s->planes, 0, 7 * s->plane_floats * sizeof(float))) != cudaSuccess) fail(e, "cudaMemset");
+    if (st == PFS_OK && (e = cudaMalloc((void **)&s->d_scalars, 4 * sizeof(float))) != cudaSuccess) fail(e, "cudaMalloc scalars");
+    if (st == PFS_OK && (e = cudaMemset(s->d_scalars, 0, 4 * sizeof(float))) != cudaSuccess) fail(e, "cudaMemset");
+    if (st == PFS_OK && (e = cudaMallocHost((void **)&s->h_scalars, 4 * sizeof(float))) != cudaSuccess) fail(e, "cudaMallocHost");
+    if (st == PFS_OK && (e = cudaEventCreateWithFlags(&s->ev_ready, cudaEventDisableTiming)) != cudaSuccess) fail(e, "event");
+    if (st == PFS_OK && (e = cudaEventCreateWithFlags(&s->ev_done, cudaEventDisableTiming)) != cudaSuccess) fail(e, "event");
+    if (st != PFS_OK) {
+        pfs_slab_destroy(s);
+        return st;
+    }
+    if (nranks == 1) s->group.assign(1, s);   // a single slab is its own ring
+    *out = s;
+    return PFS_OK;
+}
+
+extern "C" int pfs_slab_destroy(pfs_slab *s)
+{
+    if (!s) return PFS_OK;
+    Guard g(s->device);
+    cudaDeviceSynchronize();
+    if (s->comm && nccl().loaded) nccl().CommDestroy(s->comm);
+    if (s->planes) cudaFree(s->planes);
+    if (s->uvx) cudaFree(s->uvx);
+    if (s->imgx) cudaFree(s->imgx);
+    if (s->d_scalars) cudaFree(s->d_scalars);
+    if (s->h_scalars) cudaFreeHost(s->h_scalars);
+    if (s->ev_ready) cudaEventDestroy(s->ev_ready);
+    if (s->ev_done) cudaEventDestroy(s->ev_done);
+    (void)cudaGetLastError();
+    delete s;
+    return PFS_OK;
+}
+
+extern "C" int pfs_slab_rows(const pfs_slab *s, int *row0, int *rows, int *irow0, int *irows)
+{
+    if (!s) {
+        set_error("pfs_slab_rows: slab is null");
+        return PFS_EINVAL;
+    }
+    if (row0) *row0 = s->row0;
+    if (rows) *rows = s->rows;
+    if (irow0) *irow0 = s->irow0;
+    if (irows) *irows = s->irows;
+    return PFS_OK;
+}
+
+extern "C" int pfs_slab_connect_local(pfs_slab *const *slabs, int n)
+{
+    const char *fn = "pfs_slab_connect_local";
+    if (!slabs || n < 1) {
+        set_error("%s: no slabs", fn);
+        return PFS_EINVAL;
+    }
+    for (int k = 0; k < n; k++) {
+        if (!slabs[k] || slabs[k]->nranks != n || slabs[k]->rank != k) {
+            set_error("%s: need all %d ranks of one ring, in rank order", fn, n);
+            return PFS_EINVAL;
+        }
+    }
+    for (int k = 0; k < n; k++) slabs[k]->group.assign(slabs, slabs + n);
+    return PFS_OK;
+}
+
+extern "C" int pfs_slab_nccl_unique_id(char id[128])
+{
+    if (!nccl().loaded) {
+        set_error("pfs_slab_nccl_unique_id: libnccl.so.2 could not be loaded (set PFS_NCCL_LIB)");
+        return PFS_ESTATE;
+    }
+    ncclUniqueId u;
+    PFS_NCCL(nccl().GetUniqueId(&u));
+    memcpy(id, u.internal, 128);
+    return PFS_OK;
+}
+
+extern "C" int pfs_slab_connect_nccl(pfs_slab *s, const char id[128])
+{
+    if (!s || !id) {
+        set_error("pfs_slab_connect_nccl: null argument");
+        return PFS_EINVAL;
+    }
+    if (!nccl().loaded) {
+        set_error("pfs_slab_connect_nccl: libnccl.so.2 could not be loaded (set PFS_NCCL_LIB)");
+        return PFS_ESTATE;
+    }
+    Guard g(s->device);
+    ncclUniqueId u;
+    memcpy(u.internal, id, 128);
+    PFS_NCCL(nccl().CommInitRank(&s->comm, s->nranks, u, s->rank));
+    s->group.clear();
+    return PFS_OK;
+}
+
+extern "C" int pfs_slab_check(pfs_slab *const *slabs, int n_local)
+{
+    std::vector<pfs_slab *> local;
+    PFS_TRY(check_local("pfs_slab_check", slabs, n_local, &local));
+    for (pfs_slab *s : local) {
+        Guard g(s->device);
+        PFS_CUDA(cudaDeviceSynchronize());
+        int flag = 0;
+        PFS_CUDA(cudaMemcpy(&flag, s->d_scalars + 2, sizeof(int), cudaMemcpyDeviceToHost));
+        if (flag != 0) {
+            set_error("slab rank %d: a gather left its halo (code %d) -- this is a bug in the displacement bound", s->rank, flag);
+            return PFS_ESTATE;
+        }
+    }
+    return PFS_OK;
+}
+
+// ---------------------------------------------------------------------------------------------
+// simulate_fluid_step on slabs.  vp[k] / tmp[k]: the k-th local slab's band of the interleaved buffers
+// (rows x gw x 4 floats, device memory of that slab's device).  Pointer exchange as pfs_simulate_fluid_step.
+// ---------------------------------------------------------------------------------------------
+extern "C" int pfs_slab_simulate_fluid_step(pfs_slab *const *slabs, int n_local, float **vp, float **tmp, float dt,
+                                            float viscosity, int n_diffuse, int n_pressure, void *const *streams)
+{
+    const char *fn = "pfs_slab_simulate_fluid_step";
+    std::vector<pfs_slab *> L;
+    PFS_TRY(check_local(fn, slabs, n_local, &L));
+    if (n_diffuse < 1 || n_pressure < 1) {
+        set_error("%s: sweep counts must be >= 1", fn);
+        return PFS_EINVAL;
+    }
+    if (!vp || !tmp) {
+        set_error("%s: vp / tmp arrays are null", fn);
+        return PFS_EINVAL;
+    }
+    const int n = n_local;
+    for (int k = 0; k < n; k++) {
+        if (!vp[k] || !tmp[k] || vp[k] == tmp[k] || ((uintptr_t)vp[k] & 15) || ((uintptr_t)tmp[k] & 15)) {
+            set_error("%s: slab %d: vp/tmp must be distinct, non-null, 16-byte aligned device buffers", fn, k);
+            return PFS_EINVAL;
+        }
+        L[k]->stream = streams ? (cudaStream_t)streams[k] : nullptr;
+    }
+    const int gw = L[0]->gw, gh = L[0]->gh;
+
+    // phase timing (pfs_phase_times) follows the first local slab's stream
+    cudaStream_t ts = L[0]->stream;
+    PhaseScope *ph = new PhaseScope(PFS_PHASE_ADVECT, ts);
+    struct PhaseHolder {
+        PhaseScope **p;
+        ~PhaseHolder() { delete *p; }
+    } holder{&ph};
+    auto next_phase = [&](int phase) {
+        delete ph;
+        ph = new PhaseScope(phase, ts);
+    };
+
+    // ---- advect: displacement bound -> halo depth D of the (u,v) gather source ----
+    for (int k = 0; k < n; k++) {
+        pfs_slab *s = L[k];
+        Guard g(s->device);
+        PFS_CUDA(cudaMemsetAsync(s->d_scalars, 0, sizeof(float), s->stream));
+        const size_t cells = (size_t)s->rows * gw;
+        PFS_LAUNCH(max_abs_v_kernel, 592, 256, 0, s->stream, reinterpret_cast<const float4 *>(vp[k]), cells, s->d_scalars);
+    }
+    float vmax = 0.f;
+    PFS_TRY(global_max(L, 0, &vmax));
+    // |dt*v/H| in cells, with slack for the float roundings of the kernel's own expression; +2 for the
+    // bilinear neighbour and the wrap
+    const double disp = std::fabs((double)dt) * (double)vmax / (double)gh;
+    int min_rows = gh;
+    for (int r = 0; r < L[0]->nranks; r++) {
+        int f, c;
+        band(gh, L[0]->nranks, r, &f, &c);
+        min_rows = std::min(min_rows, c);
+    }
+    const bool whole = !(disp * 1.001 + 3.0 < (double)min_rows) || L[0]->nranks == 1;
+    const int D = whole ? 0 : (int)std::ceil(disp * 1.001) + 2;
+    {
+        std::vector<char *> buf(n);
+        std::vector<int> first(n), count(n), src_row0(n), src_rows(n);
+        for (int k = 0; k < n; k++) {
+            pfs_slab *s = L[k];
+            Guard g(s->device);
+            const size_t want = whole ? (size_t)gh : (size_t)s->rows + 2 * (size_t)D;
+            PFS_TRY(ensure_bytes((void **)&s->uvx, &s->uvx_rows, want, (size_t)gw * sizeof(float2)));
+            first[k] = s->row0;
+            count[k] = s->rows;
+            float2 *interior = s->uvx + (size_t)(whole ? s->row0 : D) * gw;
+            const size_t cells = (size_t)s->rows * gw;
+            PFS_LAUNCH(unpack_uv_kernel, (unsigned)((cells + 255) / 256), 256, 0, s->stream,
+                       reinterpret_cast<const float4 *>(vp[k]), interior, cells);
+            buf[k] = reinterpret_cast<char *>(s->uvx);
+        }
+        if (whole && L[0]->nranks == 1) {
+            src_row0[0] = 0;
+            src_rows[0] = gh;
+        } else {
+            PFS_TRY(fill_gather_source(L, buf, gw, gh, first, count, D, sizeof(float2), whole, &src_row0, &src_rows));
+        }
+        for (int k = 0; k < n; k++) {
+            pfs_slab *s = L[k];
+            Guard g(s->device);
+            dim3 block(64, 4), grid((gw + 63) / 64, (s->rows + 3) / 4);
+            PFS_LAUNCH(advect_slab_kernel, grid, block, 0, s->stream, s->uvx, src_row0[k], src_rows[k], s->plane(0),
+                       s->plane(1), dt, gw, gh, s->row0, s->rows, HALO, reinterpret_cast<int *>(s->d_scalars + 2));
+        }
+    }
+
+    // ---- sweeps with halo exchange before every pass ----
+    auto run_sweeps = [&](SweepOp op, int pa0, int pa1, int pb0, int pb1, const SweepParams &proto, int count,
+                          int *last_is_b) -> int {
+        // plane indices; iterate 0 in (pa0, pa1).  n-1 sweeps in passes, then one sweep into the other set.
+        int cur0 = pa0, cur1 = pa1, oth0 = pb0, oth1 = pb1;
+        int left = count - 1;
+        const bool vec = (gw % 4 == 0);
+        SweepParams p0 = proto;
+        const bool packed = (op == SWEEP_DIFFUSE) && vec && packed_diffuse_supported(p0);
+        const int user_depth = pfs_get_fuse_depth();
+        int depth = user_depth > 0 ? std::min(user_depth, HALO) : HALO;
+        if (!vec) depth = 1;
+        auto one_pass = [&](int t) -> int {
+            std::vector<std::vector<float *>> pl(n);
+            for (int k = 0; k < n; k++) {
+                pl[k].push_back(L[k]->plane(cur0));
+                if (op == SWEEP_DIFFUSE) pl[k].push_back(L[k]->plane(cur1));
+            }
+            PFS_TRY(exchange_planes(L, pl, t));
+            for (int k = 0; k < n; k++) {
+                pfs_slab *s = L[k];
+                Guard g(s->device);
+                SweepParams p = proto;
+                p.w = gw;
+                p.h = s->rows;
+                p.y_base = HALO;
+                p.wrap = 0;
+                int flips = 0;
+                float *a0 = s->plane(cur0), *a1 = s->plane(cur1), *b0 = s->plane(oth0), *b1 = s->plane(oth1);
+                const float *rhs = (op == SWEEP_PRESSURE) ? s->plane(6) : nullptr;
+                if (t == 1)
+                    PFS_TRY(launch_sweeps_basic(op, a0, a1, b0, b1, rhs, p, 1, &flips, s->stream));
+                else if (packed)
+                    PFS_TRY(launch_diffuse_packed(a0, a1, b0, b1, p, t, t, &flips, s->stream));
+                else
+                    PFS_TRY(launch_sweeps_fused(op, a0, a1, b0, b1, rhs, p, t, t, &flips, s->stream));
+                if (flips != 1) {
+                    set_error("slab sweeps: a pass of depth %d took %d hops", t, flips);
+                    return PFS_ESTATE;
+                }
+            }
+            std::swap(cur0, oth0);
+            std::swap(cur1, oth1);
+            return PFS_OK;
+        };
+        while (left > 0) {
+            int t = std::min(left, depth);
+            if (t > 1 && !packed) t &= ~1;          // the scalar fused kernel takes even depths
+            if (t < 1) t = 1;
+            PFS_TRY(one_pass(t));
+            left -= t;
+        }
+        PFS_TRY(one_pass(1));
+        *last_is_b = (cur0 == pb0) ? 1 : 0;
+        return PFS_OK;
+    };
+
+    SweepParams dp;
+    dp.w = gw;
+    dp.h = L[0]->rows;
+    dp.alpha = viscosity * dt;
+    dp.beta = (float)(1.0 + 4.0 * (double)dp.alpha);
+    int d_last_is_b = 0;
+    next_phase(PFS_PHASE_DIFFUSE);
+    PFS_TRY(run_sweeps(SWEEP_DIFFUSE, 0, 1, 2, 3, dp, n_diffuse, &d_last_is_b));
+    next_phase(PFS_PHASE_DIVERGENCE);
+    const int dl0 = d_last_is_b ? 2 : 0, dl1 = d_last_is_b ? 3 : 1;      // iterate n_d
+    const int dp0 = d_last_is_b ? 0 : 2, dp1 = d_last_is_b ? 1 : 3;      // iterate n_d - 1
+
+    // pointer choreography (pfs_simulate_fluid_step)
+    std::vector<float *> Bv(n), Bo(n), Bp(n), Bq(n);
+    for (int k = 0; k < n; k++) {
+        Bv[k] = (n_diffuse & 1) ? vp[k] : tmp[k];
+        Bo[k] = (n_diffuse & 1) ? tmp[k] : vp[k];
+        Bp[k] = (n_pressure & 1) ? Bo[k] : Bv[k];
+        Bq[k] = (n_pressure & 1) ? Bv[k] : Bo[k];
+    }
+
+    // ---- divergence (needs one halo row of v) + warm-start pressure; then the divergence halo ----
+    {
+        std::vector<std::vector<float *>> pl(n);
+        for (int k = 0; k < n; k++) pl[k].push_back(L[k]->plane(dl1));
+        PFS_TRY(exchange_planes(L, pl, 1));
+        for (int k = 0; k < n; k++) {
+            pfs_slab *s = L[k];
+            Guard g(s->device);
+            PFS_TRY(launch_divergence(s->plane(dl0), s->plane(dl1), s->plane(6), Bv[k], s->plane(4), dt, gw, s->rows,
+                                      s->stream, HALO, 0));
+        }
+        for (int k = 0; k < n; k++) pl[k][0] = L[k]->plane(6);
+        PFS_TRY(exchange_planes(L, pl, HALO));
+    }
+    SweepParams pp;
+    pp.w = gw;
+    pp.h = L[0]->rows;
+    pp.alpha = 1.0f;
+    pp.beta = 4.0f;
+    int p_last_is_b = 0;
+    next_phase(PFS_PHASE_PRESSURE);
+    PFS_TRY(run_sweeps(SWEEP_PRESSURE, 4, 4, 5, 5, pp, n_pressure, &p_last_is_b));
+    next_phase(PFS_PHASE_PROJECT);
+    const int pl_last = p_last_is_b ? 5 : 4, pl_prev = p_last_is_b ? 4 : 5;
+
+    // ---- gradient subtraction + write-back (needs one halo row of p_N) ----
+    {
+        std::vector<std::vector<float *>> pl(n);
+        for (int k = 0; k < n; k++) pl[k].push_back(L[k]->plane(pl_last));
+        PFS_TRY(exchange_planes(L, pl, 1));
+        for (int k = 0; k < n; k++) {
+            pfs_slab *s = L[k];
+            Guard g(s->device);
+            const bool use_last = (Bp[k] == Bv[k]);
+            const float *u = s->plane(use_last ? dl0 : dp0), *v = s->plane(use_last ? dl1 : dp1);
+            PFS_TRY(launch_project_pack(u, v, s->plane(pl_last), s->plane(pl_prev), s->plane(6), Bq[k], Bp[k], dt, gw,
+                                        s->rows, s->stream, HALO, 0));
+        }
+    }
+    for (int k = 0; k < n; k++) {
+        vp[k] = Bq[k];
+        tmp[k] = Bp[k];
+    }
+    return PFS_OK;
+}
+
+// ---------------------------------------------------------------------------------------------
+// advect_color_step on slabs.  image[k] / itmp[k]: the k-th slab's band of image rows (irows x iw x 4);
+// vp[k]: its band of the (already stepped) velocity field.  image[k] and itmp[k] are exchanged.
+// ---------------------------------------------------------------------------------------------
+extern "C" int pfs_slab_advect_color_step(pfs_slab *const *slabs, int n_local, float **image, float **itmp,
+                                          float *const *vp, float dt, void *const *streams)
+{
+    const char *fn = "pfs_slab_advect_color_step";
+    std::vector<pfs_slab *> L;
+    PFS_TRY(check_local(fn, slabs, n_local, &L));
+    if (!image || !itmp || !vp) {
+        set_error("%s: null array argument", fn);
+        return PFS_EINVAL;
+    }
+    const int n = n_local;
+    const int iw = L[0]->iw, ih = L[0]->ih, gw = L[0]->gw, gh = L[0]->gh;
+    if (iw < 1 || ih < 1) {
+        set_error("%s: the slabs were created without an image", fn);
+        return PFS_EINVAL;
+    }
+    for (int k = 0; k < n; k++) {
+        if (!vp[k] || (L[k]->irows > 0 && (!image[k] || !itmp[k]))) {
+            set_error("%s: slab %d: null buffer", fn, k);
+            return PFS_EINVAL;
+        }
+        L[k]->stream = streams ? (cudaStream_t)streams[k] : nullptr;
+    }
+    const float viw = (float)gw / (float)iw, vih = (float)gh / (float)ih;
+    const float dt_over_viw = dt / viw, dt_over_vih = dt / vih;
+    PhaseScope ph(PFS_PHASE_ADVECT_COLOR, L[0]->stream);
+
+    for (int k = 0; k < n; k++) {
+        pfs_slab *s = L[k];
+        Guard g(s->device);
+        PFS_CUDA(cudaMemsetAsync(s->d_scalars + 1, 0, sizeof(float), s->stream));
+        const size_t cells = (size_t)s->rows * gw;
+        PFS_LAUNCH(max_abs_v_kernel, 592, 256, 0, s->stream, reinterpret_cast<const float4 *>(vp[k]), cells,
+                   s->d_scalars + 1);
+    }
+    float vmax = 0.f;
+    PFS_TRY(global_max(L, 1, &vmax));
+    const double disp = std::fabs((double)dt_over_vih) * (double)vmax / (double)ih;
+    int min_rows = ih;
+    for (int r = 0; r < L[0]->nranks; r++) {
+        int f, c, jf, jc;
+        band(gh, L[0]->nranks, r, &f, &c);
+        image_band(ih, gh, f, c, &jf, &jc);
+        min_rows = std::min(min_rows, jc);
+    }
+    const bool whole = !(disp * 1.001 + 3.0 < (double)min_rows) || L[0]->nranks == 1;
+    const int D = whole ? 0 : (int)std::ceil(disp * 1.001) + 2;
+
+    std::vector<char *> buf(n);
+    std::vector<int> first(n), count(n), src_row0(n), src_rows(n);
+    for (int k = 0; k < n; k++) {
+        pfs_slab *s = L[k];
+        Guard g(s->device);
+        const size_t want = whole ? (size_t)ih : (size_t)s->irows + 2 * (size_t)D;
+        PFS_TRY(ensure_bytes((void **)&s->imgx, &s->imgx_rows, want, (size_t)iw * sizeof(float4)));
+        first[k] = s->irow0;
+        count[k] = s->irows;
+        if (s->irows > 0)
+            PFS_CUDA(cudaMemcpyAsync(s->imgx + (size_t)(whole ? s->irow0 : D) * iw, image[k],
+                                     (size_t)s->irows * iw * sizeof(float4), cudaMemcpyDeviceToDevice, s->stream));
+        buf[k] = reinterpret_cast<char *>(s->imgx);
+    }
+    if (whole && L[0]->nranks == 1) {
+        src_row0[0] = 0;
+        src_rows[0] = ih;
+    } else {
+        PFS_TRY(fill_gather_source(L, buf, iw, ih, first, count, D, sizeof(float4), whole, &src_row0, &src_rows));
+    }
+    for (int k = 0; k < n; k++) {
+        pfs_slab *s = L[k];
+        if (s->irows == 0) continue;
+        Guard g(s->device);
+        dim3 block(64, 4), grid((iw + 63) / 64, (s->irows + 3) / 4);
+        PFS_LAUNCH(advect_color_slab_kernel, grid, block, 0, s->stream, s->imgx, src_row0[k], src_rows[k],
+                   reinterpret_cast<float4 *>(itmp[k]), vp[k], dt_over_viw, dt_over_vih, viw, vih, iw, ih, s->irow0,
+                   s->irows, gw, s->row0, s->rows, reinterpret_cast<int *>(s->d_scalars + 2));
+    }
+    for (int k = 0; k < n; k++) std::swap(image[k], itmp[k]);   // fluid.cpp:317-319
+    return PFS_OK;
+}

@@ -41,6 +41,7 @@ struct FusedParams {
     int strip_out;              // columns stored per strip = 128 - 2*HL
     int halo_cols;              // HL
     int n_strips, n_chunks, chunk_rows, n_planes;
+    int y_base, wrap;           // row map of the planes (SweepParams)
     float alpha, beta;
     float rbeta;                // RN(1/beta), binary32
     float div_lo, div_hi;       // |numerator| range in which the FMA division is exact (lo = +inf disables it)
@@ -165,8 +166,14 @@ __global__ void __launch_bounds__(WARPS_PER_CTA * 32, MINB) fused_sweeps_kernel(
     // rows: chunk outputs rows [y0, y0+L); the stream starts T rows above
     const int y0 = chunk * P.chunk_rows;
     const int L = min(P.chunk_rows, h - y0);
-    int ld_row = (y0 - T) % h;                        // wrapped row of the next prefetch
-    if (ld_row < 0) ld_row += h;
+    // plane row of the next prefetch: wraps by index on a single GPU, walks into the halo rows of a slab
+    int ld_row = y0 - T;
+    if (P.wrap) {
+        ld_row %= h;
+        if (ld_row < 0) ld_row += h;
+    }
+    ld_row += P.y_base;
+    const int wrap_at = P.wrap ? h : 0x7fffffff;
     const int n_steps = L + 2 * T;
 
     float4 *my = &ring[warp][0][0][lane];
@@ -179,7 +186,7 @@ __global__ void __launch_bounds__(WARPS_PER_CTA * 32, MINB) fused_sweeps_kernel(
             const size_t off = (size_t)ld_row * w + xw;
             cp_async16(dst, in + off);
             if constexpr (OP == SWEEP_PRESSURE) cp_async16(dst + 32, P.rhs + off);
-            ld_row = (ld_row + 1 == h) ? 0 : ld_row + 1;
+            ld_row = (ld_row + 1 == wrap_at) ? 0 : ld_row + 1;
         }
         cp_async_commit();
     };
@@ -195,7 +202,7 @@ __global__ void __launch_bounds__(WARPS_PER_CTA * 32, MINB) fused_sweeps_kernel(
         Q[l] = make_float4(0.f, 0.f, 0.f, 0.f);
     }
 
-    float *out_ptr = out + (size_t)y0 * w + xc;       // row y0 of this lane's columns (store lanes only)
+    float *out_ptr = out + (size_t)(P.y_base + y0) * w + xc;   // row y0 of this lane's columns (store lanes only)
 
     for (int sb = 0; sb < n_steps; sb += U) {
 #pragma unroll
@@ -288,7 +295,7 @@ int launch_sweeps_fused(SweepOp op, float *a0, float *a1, float *b0, float *b1, 
         } else {
             FusedParams P;
             P.in0 = cur0; P.in1 = cur1; P.out0 = oth0; P.out1 = oth1; P.rhs = rhs;
-            P.w = p.w; P.h = p.h;
+            P.w = p.w; P.h = p.h; P.y_base = p.y_base; P.wrap = p.wrap;
             P.halo_cols = 4 * ((t + 3) / 4);
             P.strip_out = 128 - 2 * P.halo_cols;
             P.n_strips = (p.w + P.strip_out - 1) / P.strip_out;

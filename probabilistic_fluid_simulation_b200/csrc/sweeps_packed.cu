@@ -41,6 +41,7 @@ struct PackedParams {
     int w, h;
     int strip_out, halo_cols;
     int n_strips, n_chunks, chunk_rows;
+    int y_base, wrap;           // row map of the planes (SweepParams)
     float alpha, beta, rbeta;
     float guard_lo, guard_hi_in;   // |numerator| >= guard_lo and |input| <= guard_hi_in keep the FMA division exact
     float neg_zero;             // -0.0f, deliberately a RUN-TIME value: see mulc2()
@@ -160,8 +161,13 @@ __global__ void __launch_bounds__(WARPS_PER_CTA * 32, MINB) diffuse_packed_kerne
 
     const int y0 = chunk * P.chunk_rows;
     const int L = min(P.chunk_rows, h - y0);
-    int ld_row = (y0 - T) % h;
-    if (ld_row < 0) ld_row += h;
+    int ld_row = y0 - T;
+    if (P.wrap) {
+        ld_row %= h;
+        if (ld_row < 0) ld_row += h;
+    }
+    ld_row += P.y_base;
+    const int wrap_at = P.wrap ? h : 0x7fffffff;
     const int n_steps = L + 2 * T;
 
     float4 *my = &ring[warp][0][0][lane];
@@ -173,7 +179,7 @@ __global__ void __launch_bounds__(WARPS_PER_CTA * 32, MINB) diffuse_packed_kerne
             const size_t off = (size_t)ld_row * w + xw;
             cp_async16(dst, P.in_u + off);
             cp_async16(dst + 32, P.in_v + off);
-            ld_row = (ld_row + 1 == h) ? 0 : ld_row + 1;
+            ld_row = (ld_row + 1 == wrap_at) ? 0 : ld_row + 1;
         }
         cp_async_commit();
     };
@@ -196,8 +202,8 @@ __global__ void __launch_bounds__(WARPS_PER_CTA * 32, MINB) diffuse_packed_kerne
     float num_min = __int_as_float(0x7f800000);           // +inf
     float in_max = 0.f;
 
-    float *out_u = P.out_u + (size_t)y0 * w + xc;
-    float *out_v = P.out_v + (size_t)y0 * w + xc;
+    float *out_u = P.out_u + (size_t)(P.y_base + y0) * w + xc;
+    float *out_v = P.out_v + (size_t)(P.y_base + y0) * w + xc;
 
     for (int sb = 0; sb < n_steps; sb += 2) {
 #pragma unroll
@@ -357,7 +363,7 @@ int launch_diffuse_packed(float *a0, float *a1, float *b0, float *b1, const Swee
         const int t = left < depth ? left : depth;
         PackedParams P;
         P.in_u = cur0; P.in_v = cur1; P.out_u = oth0; P.out_v = oth1;
-        P.w = p.w; P.h = p.h;
+        P.w = p.w; P.h = p.h; P.y_base = p.y_base; P.wrap = p.wrap;
         P.halo_cols = 4 * ((t + 3) / 4);
         P.strip_out = 128 - 2 * P.halo_cols;
         P.n_strips = (p.w + P.strip_out - 1) / P.strip_out;

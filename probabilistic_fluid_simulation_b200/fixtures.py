@@ -65,19 +65,37 @@ def _triangle(t: np.ndarray, period: int) -> np.ndarray:
     return (up * 255) // max(half, 1)
 
 
-def smooth_velocity_bytes(h: int, w: int) -> np.ndarray:
+def smooth_velocity_bytes(h: int, w: int, rows: tuple[int, int] | None = None) -> np.ndarray:
     """Sum of four integer-phase triangle waves per component (coherent flow: neighbouring cells
-    have neighbouring departure points).  Periodic in both axes when h, w are multiples of 64."""
+    have neighbouring departure points).  Periodic in both axes when h, w are multiples of 64.
+    `rows = (r0, r1)` returns only rows r0..r1-1 of the h x w field (multi-GPU bands)."""
+    r0, r1 = rows if rows is not None else (0, h)
     i = np.arange(w, dtype=np.int64)[None, :]
-    j = np.arange(h, dtype=np.int64)[:, None]
+    j = np.arange(r0, r1, dtype=np.int64)[:, None]
     px, py = max(w // 4, 2), max(h // 4, 2)
     u = (_triangle(i + 0 * j, px) + _triangle(j + 0 * i, py) + _triangle(i + j, max(w // 2, 2)) + _triangle(3 * i - j + 7 * w, max(w // 8, 2))) // 4
     v = (_triangle(j + 0 * i + py // 3, py) + _triangle(i + 0 * j + px // 5, px) + _triangle(2 * j - i + 5 * h, max(h // 2, 2)) + _triangle(i + 3 * j, max(h // 8, 2))) // 4
-    b = np.zeros((h, w, 4), np.uint8)
+    b = np.zeros((r1 - r0, w, 4), np.uint8)
     b[..., 0] = np.clip(u, 0, 255)
     b[..., 1] = np.clip(v, 0, 255)
     b[..., 3] = 255
     return b
+
+
+def hash_bytes(h: int, w: int, channels: int, seed: int, rows: tuple[int, int] | None = None) -> np.ndarray:
+    """Position-hashed pseudo-random bytes [rows, w, channels]: value(i, j, k) depends only on the
+    cell, so any band of rows equals the same rows of the whole field (multi-GPU inputs)."""
+    r0, r1 = rows if rows is not None else (0, h)
+    i = np.arange(w, dtype=np.uint32)[None, :, None]
+    j = np.arange(r0, r1, dtype=np.uint32)[:, None, None]
+    k = np.arange(channels, dtype=np.uint32)[None, None, :]
+    x = i * np.uint32(0x9E3779B1) + j * np.uint32(0x85EBCA77) + k * np.uint32(0xC2B2AE3D) + np.uint32(seed & 0xFFFFFFFF)
+    x ^= x >> np.uint32(15)
+    x *= np.uint32(0x2C1B3C6D)
+    x ^= x >> np.uint32(12)
+    x *= np.uint32(0x297A2D39)
+    x ^= x >> np.uint32(15)
+    return (x & np.uint32(255)).astype(np.uint8)
 
 
 def random_velocity_bytes(h: int, w: int, seed: int = 1234) -> np.ndarray:

@@ -1,0 +1,162 @@
+"""Row-slab decomposition of one periodic grid over several GPUs (csrc/slab.cu).
+
+Two ways to drive it, both through the C-ABI (``pfs_slab_*`` in include/pfs_b200.h):
+
+* :class:`SlabRank` -- one process per GPU (torchrun): every process creates its rank's slab, rank 0
+  creates an NCCL id that the caller broadcasts (torch.distributed, any backend), and each timestep is
+  ``simulate_fluid_step`` / ``advect_color_step`` on the rank's band of the interleaved buffers.
+* :class:`SlabRing` -- all ranks inside one process (on one or several devices); halo rows move by
+  direct device copies.  This is what the single-GPU tests use to check the multi-rank logic bit for bit.
+
+The partition itself is host arithmetic (:func:`partition`) and works without a GPU.
+"""
+from __future__ import annotations
+
+import ctypes
+
+import numpy as np
+
+from . import _cabi
+from ._cabi import check
+from .fluid import NUM_JACOBI_ITERS, vp_field
+
+
+def partition(rank: int, nranks: int, gh: int, ih: int = 0):
+    """-> (row0, rows, irow0, irows): the band of velocity rows of `rank` and the band of image rows
+    whose velocity look-up (int)((float)j * (gh/ih)) (fluid.cpp:83,90) falls into it."""
+    vals = [ctypes.c_int(0) for _ in range(4)]
+    check(_cabi.lib().pfs_slab_partition(rank, nranks, gh, ih, *(ctypes.byref(v) for v in vals)))
+    return tuple(v.value for v in vals)
+
+
+def _ptr_array(values):
+    arr = (ctypes.c_void_p * len(values))(*values)
+    return arr
+
+
+class _SlabBase:
+    def __init__(self):
+        self._handles = []
+
+    def _create(self, rank, nranks, gw, gh, iw, ih):
+        h = ctypes.c_void_p()
+        check(_cabi.lib().pfs_slab_create(ctypes.byref(h), rank, nranks, gw, gh, iw, ih))
+        self._handles.append(h)
+        return h
+
+    def close(self):
+        L = _cabi.lib()
+        for h in self._handles:
+            L.pfs_slab_destroy(h)
+        self._handles = []
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
+class SlabRing(_SlabBase):
+    """All `nranks` slabs of a gw x gh grid (+ iw x ih image) in this process."""
+
+    def __init__(self, nranks: int, gw: int, gh: int, iw: int = 0, ih: int = 0, devices=None):
+        import torch
+        super().__init__()
+        self.nranks, self.gw, self.gh, self.iw, self.ih = nranks, gw, gh, iw, ih
+        self.devices = list(devices) if devices is not None else [torch.cuda.current_device()] * nranks
+        assert len(self.devices) == nranks
+        self.bands = [partition(r, nranks, gh, ih) for r in range(nranks)]
+        for r in range(nranks):
+            with torch.cuda.device(self.devices[r]):
+                self._create(r, nranks, gw, gh, iw, ih)
+        if nranks > 1:
+            check(_cabi.lib().pfs_slab_connect_local(_ptr_array([h.value for h in self._handles]), nranks))
+
+    # -- host <-> bands -------------------------------------------------------------------------
+    def split(self, field: np.ndarray, image: bool = False):
+        import torch
+        out = []
+        for r, (row0, rows, irow0, irows) in enumerate(self.bands):
+            a, n = (irow0, irows) if image else (row0, rows)
+            out.append(torch.from_numpy(np.ascontiguousarray(field[a:a + n])).to(f"cuda:{self.devices[r]}"))
+        return out
+
+    @staticmethod
+    def gather(bands) -> np.ndarray:
+        return np.concatenate([b.detach().cpu().numpy() for b in bands], axis=0)
+
+    # -- steps ----------------------------------------------------------------------------------
+    def _streams(self):
+        import torch
+        return _ptr_array([torch.cuda.current_stream(d).cuda_stream for d in self.devices])
+
+    def simulate_fluid_step(self, vp: list, tmp: list, dt: float, viscosity: float,
+                            n_diffuse: int = NUM_JACOBI_ITERS, n_pressure: int | None = None) -> None:
+        """vp / tmp: lists of the bands (CUDA tensors); entries are exchanged as the reference would."""
+        n_pressure = n_diffuse if n_pressure is None else n_pressure
+        by_ptr = {t.data_ptr(): t for t in vp + tmp}
+        pv, pt = _ptr_array([t.data_ptr() for t in vp]), _ptr_array([t.data_ptr() for t in tmp])
+        check(_cabi.lib().pfs_slab_simulate_fluid_step(_ptr_array([h.value for h in self._handles]), self.nranks, pv, pt,
+                                                       dt, viscosity, n_diffuse, n_pressure, self._streams()))
+        for k in range(self.nranks):
+            vp[k], tmp[k] = by_ptr[pv[k]], by_ptr[pt[k]]
+
+    def advect_color_step(self, image: list, itmp: list, vp: list, dt: float) -> None:
+        by_ptr = {t.data_ptr(): t for t in image + itmp}
+        pi, pm = _ptr_array([t.data_ptr() for t in image]), _ptr_array([t.data_ptr() for t in itmp])
+        pv = _ptr_array([t.data_ptr() for t in vp])
+        check(_cabi.lib().pfs_slab_advect_color_step(_ptr_array([h.value for h in self._handles]), self.nranks, pi, pm,
+                                                     pv, dt, self._streams()))
+        for k in range(self.nranks):
+            image[k], itmp[k] = by_ptr[pi[k]], by_ptr[pm[k]]
+
+    def check(self) -> None:
+        check(_cabi.lib().pfs_slab_check(_ptr_array([h.value for h in self._handles]), self.nranks))
+
+
+class SlabRank(_SlabBase):
+    """This process's slab of a ring of `nranks` processes (one GPU each), connected through NCCL."""
+
+    def __init__(self, rank: int, nranks: int, gw: int, gh: int, iw: int = 0, ih: int = 0):
+        super().__init__()
+        self.rank, self.nranks, self.gw, self.gh, self.iw, self.ih = rank, nranks, gw, gh, iw, ih
+        self.row0, self.rows, self.irow0, self.irows = partition(rank, nranks, gh, ih)
+        self._h = self._create(rank, nranks, gw, gh, iw, ih)
+
+    @staticmethod
+    def unique_id() -> bytes:
+        """Rank 0 only.  Ship the 128 bytes to every rank (e.g. torch.distributed.broadcast)."""
+        buf = ctypes.create_string_buffer(128)
+        check(_cabi.lib().pfs_slab_nccl_unique_id(buf))
+        return buf.raw
+
+    def connect(self, unique_id: bytes) -> None:
+        """Collective: every rank calls it with rank 0's id."""
+        assert len(unique_id) == 128
+        if self.nranks > 1:
+            check(_cabi.lib().pfs_slab_connect_nccl(self._h, ctypes.create_string_buffer(unique_id, 128)))
+
+    def _stream(self, t):
+        import torch
+        return _ptr_array([torch.cuda.current_stream(t.device).cuda_stream])
+
+    def simulate_fluid_step(self, vp: vp_field, tmp: vp_field, dt: float, viscosity: float,
+                            n_diffuse: int = NUM_JACOBI_ITERS, n_pressure: int | None = None) -> None:
+        n_pressure = n_diffuse if n_pressure is None else n_pressure
+        by_ptr = {vp.data.data_ptr(): vp.data, tmp.data.data_ptr(): tmp.data}
+        pv, pt = _ptr_array([vp.data.data_ptr()]), _ptr_array([tmp.data.data_ptr()])
+        check(_cabi.lib().pfs_slab_simulate_fluid_step(_ptr_array([self._h.value]), 1, pv, pt, dt, viscosity,
+                                                       n_diffuse, n_pressure, self._stream(vp.data)))
+        vp.data, tmp.data = by_ptr[pv[0]], by_ptr[pt[0]]
+
+    def advect_color_step(self, image: vp_field, itmp: vp_field, vp: vp_field, dt: float) -> None:
+        by_ptr = {image.data.data_ptr(): image.data, itmp.data.data_ptr(): itmp.data}
+        pi, pm = _ptr_array([image.data.data_ptr()]), _ptr_array([itmp.data.data_ptr()])
+        pv = _ptr_array([vp.data.data_ptr()])
+        check(_cabi.lib().pfs_slab_advect_color_step(_ptr_array([self._h.value]), 1, pi, pm, pv, dt,
+                                                     self._stream(vp.data)))
+        image.data, itmp.data = by_ptr[pi[0]], by_ptr[pm[0]]
+
+    def check(self) -> None:
+        check(_cabi.lib().pfs_slab_check(_ptr_array([self._h.value]), 1))

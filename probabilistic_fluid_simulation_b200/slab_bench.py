@@ -1,0 +1,169 @@
+"""bench.py's multi-GPU arm: one process per GPU (torchrun), a ring of row slabs connected by NCCL.
+
+Workload (BASELINE.json configs[3] family): a 16384-column grid of 2048 rows PER GPU (weak scaling; 8 GPUs
+is the 16384 x 16384 grid), image of the same size, 100 + 100 sweeps.  Every rank builds only its own
+band of the synthetic inputs.  Timing: barrier + synchronize on both sides, CUDA events on every rank,
+the MAX over ranks is the step time; value = (cells of the WHOLE grid) * n_pressure / time.
+"""
+from __future__ import annotations
+
+import json
+import os
+import time
+
+
+# ---- rendezvous helpers (backend-agnostic; exercised over gloo by tests/test_slab_partition.py) -----
+def _tensor(data, dtype, device):
+    import torch
+    return torch.tensor(data, dtype=dtype, device=device)
+
+
+def broadcast_bytes(payload: bytes | None, n: int, device="cuda") -> bytes:
+    """Rank 0 passes `payload` (n bytes); every rank returns it."""
+    import torch
+    import torch.distributed as dist
+    buf = torch.zeros(n, dtype=torch.uint8, device=device)
+    if dist.get_rank() == 0:
+        buf.copy_(torch.frombuffer(bytearray(payload), dtype=torch.uint8))
+    dist.broadcast(buf, 0)
+    return bytes(buf.cpu().numpy().tobytes())
+
+
+def max_over_ranks(x: float, device="cuda") -> float:
+    import torch
+    import torch.distributed as dist
+    t = _tensor([x], torch.float64, device)
+    dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    return float(t.item())
+
+
+def sum_over_ranks(x: float, device="cuda") -> float:
+    import torch
+    import torch.distributed as dist
+    t = _tensor([x], torch.float64, device)
+    dist.all_reduce(t, op=dist.ReduceOp.SUM)
+    return float(t.item())
+
+
+# ---- the bench arm ---------------------------------------------------------------------------------
+def run(args, bench) -> None:
+    import numpy as np
+    import torch
+    import torch.distributed as dist
+
+    import probabilistic_fluid_simulation_b200 as pfs
+    from probabilistic_fluid_simulation_b200.slab import SlabRank
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", str(rank)))
+    if world != args.gpus:
+        raise SystemExit(f"bench.py --gpus {args.gpus} needs WORLD_SIZE={args.gpus} (launch with torch.distributed.run); "
+                         f"got WORLD_SIZE={world}")
+    torch.cuda.set_device(local)
+    dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    w, h, n = bench.workload_shape(args)
+    slab = SlabRank(rank, world, w, h, w, h)
+    uid = broadcast_bytes(SlabRank.unique_id() if rank == 0 else None, 128)
+    slab.connect(uid)
+
+    vp, vtmp, image, itmp = bench.make_inputs(h, w, rows=(slab.row0, slab.row0 + slab.rows))
+    assert slab.irow0 == slab.row0 and slab.irows == slab.rows        # image res == grid res in this workload
+    fv, ft, fi, fm = (pfs.vp_field(torch.from_numpy(x).cuda()) for x in (vp, vtmp, image, itmp))
+    DT, VISC = bench.DT, bench.VISC
+
+    def step():
+        slab.simulate_fluid_step(fv, ft, DT, VISC, n, n)
+        slab.advect_color_step(fi, fm, fv, DT)
+
+    for _ in range(args.warmup):
+        step()
+    slab.check()
+    torch.cuda.synchronize()
+    dist.barrier()
+
+    sampler = bench.ClockSampler(local) if rank == 0 else None
+    if sampler:
+        sampler.start()
+        time.sleep(0.12)
+    pfs.phase_timing(True)
+    pfs.phase_times(reset=True)
+    l0 = pfs.kernel_launch_count()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    torch.cuda.synchronize()
+    dist.barrier()
+    t_begin = time.perf_counter()
+    e0.record()
+    for _ in range(args.steps):
+        step()
+    e1.record()
+    torch.cuda.synchronize()
+    dist.barrier()
+    t_end = time.perf_counter()
+    ms_local = e0.elapsed_time(e1)
+    launches = pfs.kernel_launch_count() - l0
+    phase_ms, phase_launches = pfs.phase_times(reset=True)
+    pfs.phase_timing(False)
+    clocks = sampler.stop(t_begin, t_end) if sampler else None
+    ms_total = max_over_ranks(ms_local)
+    ms_step = ms_total / args.steps
+    cells_global = w * h
+    cells_local = w * slab.rows
+    value = cells_global * n / (ms_step * 1e-3)
+    total_launches = int(sum_over_ranks(float(launches)))
+
+    # ---- end to end: every rank uploads its bands from pinned memory, steps, downloads them ----
+    e2e = None
+    if not args.no_e2e:
+        hv, ht, hi = (torch.from_numpy(x).pin_memory() for x in (vp, vtmp, image))
+        e2e_steps = max(2, min(args.steps, 5))
+        def e2e_step():
+            fv.data.copy_(hv, non_blocking=True); ft.data.copy_(ht, non_blocking=True); fi.data.copy_(hi, non_blocking=True)
+            step()
+            hv.copy_(fv.data, non_blocking=True); ht.copy_(ft.data, non_blocking=True); hi.copy_(fi.data, non_blocking=True)
+            torch.cuda.synchronize()
+        e2e_step()
+        dist.barrier()
+        t0 = time.perf_counter()
+        for _ in range(e2e_steps):
+            e2e_step()
+        dist.barrier()
+        e2e_s = max_over_ranks((time.perf_counter() - t0) / e2e_steps)
+        e2e = {"value": cells_global * n / e2e_s, "unit": bench.UNIT, "ms_per_step": e2e_s * 1e3,
+               "h2d_bytes_per_step": 3 * cells_global * 16, "d2h_bytes_per_step": 3 * cells_global * 16,
+               "api": "SlabRank.simulate_fluid_step + advect_color_step on each rank's band; every rank uploads vp, "
+                      "vtmp, image from pinned host memory and downloads them again each step", "steps": e2e_steps}
+
+    if rank == 0:
+        peak, peak_src = bench.measured_peak_gbs()
+        per_phase = {k: v / args.steps for k, v in phase_ms.items()}
+        kernels = {}
+        for phase, key in (("diffuse", "diffuse_sweep"), ("pressure", "pressure_sweep")):
+            nl = phase_launches[phase] / args.steps
+            if nl > 0 and per_phase[phase] > 0:
+                b = bench.BYTES[key] * cells_local * n
+                gbs = b / (per_phase[phase] * 1e-3) / 1e9
+                kernels[phase] = {"launches_per_step": nl, "phase_ms": per_phase[phase], "alg_bytes_per_phase": b,
+                                  "achieved_gbs": gbs, "frac": gbs / peak, "share_of_step": per_phase[phase] / ms_step,
+                                  "note": "rank 0, includes the halo exchanges between passes"}
+        dom = max(kernels, key=lambda k: kernels[k]["share_of_step"]) if kernels else None
+        roofline = None
+        if dom:
+            roofline = {"bound": "hbm", "kernel": dom + " phase (fused passes + halo exchanges), per GPU",
+                        "achieved": kernels[dom]["achieved_gbs"], "peak": peak, "unit": "GB/s", "frac": kernels[dom]["frac"],
+                        "traffic": None, "peak_source": peak_src}
+        step_bytes = (88 + 16 * n + 12 * n) * cells_local
+        line = {"metric": bench.METRIC, "value": value, "unit": bench.UNIT, "n_gpus": world, "steps": args.steps,
+                "warmup": args.warmup, "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak",
+                "vs_baseline": None, "dtype": "f32", "data": "synthetic", "config": bench.workload_config(args),
+                "roofline": roofline, "cpu_baseline": None, "e2e": e2e, "gpu_launches": total_launches, "clocks": clocks,
+                "whole_step_roofline_per_gpu": {"alg_bytes": step_bytes,
+                                                "achieved_gbs": step_bytes / (ms_step * 1e-3) / 1e9,
+                                                "frac": step_bytes / (ms_step * 1e-3) / 1e9 / peak},
+                "cell_steps_per_s": cells_global / (ms_step * 1e-3), "phases_ms_rank0": per_phase, "kernels": kernels,
+                "transport": "NCCL send/recv of halo rows between ring neighbours (one process per GPU)",
+                "rows_per_gpu": slab.rows}
+        print(json.dumps(line), flush=True)
+    dist.barrier()
+    slab.close()
+    dist.destroy_process_group()

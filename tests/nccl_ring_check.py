@@ -1,0 +1,55 @@
+"""torchrun worker for tests/test_gpu_slabs.py::test_nccl_two_ranks: one process per GPU, NCCL halo
+exchange, result gathered on rank 0 and compared with the CPU oracle bit for bit."""
+import os
+import sys
+
+import numpy as np
+import torch
+import torch.distributed as dist
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, "tests"))
+
+import oracle  # noqa: E402
+from probabilistic_fluid_simulation_b200 import fixtures, vp_field  # noqa: E402
+from probabilistic_fluid_simulation_b200.slab import SlabRank  # noqa: E402
+
+
+def main():
+    rank, world = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"])
+    torch.cuda.set_device(int(os.environ.get("LOCAL_RANK", rank)))
+    dist.init_process_group("nccl")
+    h, w, ih, iw = 128, 256, 192, 256
+    vel = fixtures.smooth_velocity_bytes(h, w)
+    img = fixtures.random_image_bytes(ih, iw, 11)
+    vp, vtmp, image, itmp = fixtures.make_state(vel, img)
+    slab = SlabRank(rank, world, w, h, iw, ih)
+    uid = torch.zeros(128, dtype=torch.uint8, device="cuda")
+    if rank == 0:
+        uid.copy_(torch.frombuffer(bytearray(SlabRank.unique_id()), dtype=torch.uint8))
+    dist.broadcast(uid, 0)
+    slab.connect(bytes(uid.cpu().numpy().tobytes()))
+    r0, rows, i0, irows = slab.row0, slab.rows, slab.irow0, slab.irows
+    fv, ft = vp_field(torch.from_numpy(vp[r0:r0 + rows].copy()).cuda()), vp_field(torch.from_numpy(vtmp[r0:r0 + rows].copy()).cuda())
+    fi, fm = vp_field(torch.from_numpy(image[i0:i0 + irows].copy()).cuda()), vp_field(torch.from_numpy(itmp[i0:i0 + irows].copy()).cuda())
+    dt, visc, nd, npr, steps = 2.0, 0.002, 30, 30, 3
+    for _ in range(steps):
+        slab.simulate_fluid_step(fv, ft, dt, visc, nd, npr)
+        slab.advect_color_step(fi, fm, fv, dt)
+    slab.check()
+    parts = [None] * world
+    dist.all_gather_object(parts, (fv.data.cpu().numpy(), ft.data.cpu().numpy(), fi.data.cpu().numpy()))
+    if rank == 0:
+        got = [np.concatenate([p[k] for p in parts], axis=0) for k in range(3)]
+        want = oracle.Oracle(nd, npr).run_steps(vp, vtmp, image, itmp, dt, visc, steps)
+        for name, g, wv in zip(("vp", "vtmp", "image"), got, want):
+            assert np.array_equal(g.view(np.uint32), wv.view(np.uint32)), name
+        print("NCCL ring matches oracle")
+    dist.barrier()
+    slab.close()
+    dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

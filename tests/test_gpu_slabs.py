@@ -1,0 +1,101 @@
+"""GPU parity, part 4: the row-slab (multi-GPU) path.  R slabs of one periodic grid, driven inside one
+process on ONE GPU (direct-copy transport), must reproduce the CPU oracle bit for bit -- the same check
+as the single-GPU path, so it also proves slab result == single-GPU result.  The NCCL transport is
+exercised by test_nccl_two_ranks when two GPUs are visible."""
+import os
+import subprocess
+import sys
+
+import numpy as np
+import pytest
+
+import oracle
+from golden_util import assert_bit_equal
+from probabilistic_fluid_simulation_b200 import fixtures
+from probabilistic_fluid_simulation_b200.slab import SlabRing
+
+pytestmark = pytest.mark.gpu
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _state(h, w, ih, iw, seed):
+    vel = fixtures.smooth_velocity_bytes(h, w)
+    rng = np.random.default_rng(seed)
+    vel[..., :2] = np.clip(vel[..., :2].astype(np.int16) + rng.integers(-9, 10, size=(h, w, 2)), 0, 255).astype(np.uint8)
+    img = fixtures.random_image_bytes(ih, iw, seed + 1)
+    return fixtures.make_state(vel, img)
+
+
+def _run_ring(nranks, state, dt, visc, nd, npr, steps):
+    vp, vtmp, image, itmp = state
+    h, w = vp.shape[:2]
+    ih, iw = image.shape[:2]
+    ring = SlabRing(nranks, w, h, iw, ih)
+    bv, bt = ring.split(vp), ring.split(vtmp)
+    bi, bm = ring.split(image, image=True), ring.split(itmp, image=True)
+    for _ in range(steps):
+        ring.simulate_fluid_step(bv, bt, dt, visc, nd, npr)
+        ring.advect_color_step(bi, bm, bv, dt)
+    ring.check()
+    out = ring.gather(bv), ring.gather(bt), ring.gather(bi)
+    ring.close()
+    return out
+
+
+@pytest.mark.parametrize("nranks", [1, 2, 3, 4])
+@pytest.mark.parametrize("dt,visc,nd,npr", [(0.5, 0.003, 30, 30), (40.0, 0.01, 7, 10), (3.0, 0.0, 3, 4)])
+def test_ring_matches_oracle(nranks, dt, visc, nd, npr):
+    h, w, ih, iw = 96, 128, 96, 128
+    state = _state(h, w, ih, iw, 3)
+    got = _run_ring(nranks, [x.copy() for x in state], dt, visc, nd, npr, 3)
+    want = oracle.Oracle(nd, npr).run_steps(*state, dt, visc, 3)
+    for name, g, wv in zip(("vp", "vtmp", "image"), got, want):
+        assert_bit_equal(g, wv, f"{name} (R={nranks})")
+
+
+@pytest.mark.parametrize("nranks", [2, 4])
+def test_ring_large_displacement_uses_all_gather(nranks):
+    """dt so large that departure points leave the neighbouring slabs: the gather source becomes the whole
+    field (all-gather path)."""
+    h, w, ih, iw = 64, 96, 64, 96
+    state = _state(h, w, ih, iw, 5)
+    dt = 3000.0
+    got = _run_ring(nranks, [x.copy() for x in state], dt, 0.001, 4, 4, 2)
+    want = oracle.Oracle(4, 4).run_steps(*state, dt, 0.001, 2)
+    for name, g, wv in zip(("vp", "vtmp", "image"), got, want):
+        assert_bit_equal(g, wv, f"{name} (R={nranks})")
+
+
+@pytest.mark.parametrize("nranks", [2, 3])
+def test_ring_image_ratio_not_integer(nranks):
+    """768x512-style image on a 256-wide grid: viw = 1/3 is inexact in binary32;
+    the image bands follow the float look-up of fluid.cpp:89-90."""
+    h, w, ih, iw = 72, 64, 96, 192
+    state = _state(h, w, ih, iw, 7)
+    got = _run_ring(nranks, [x.copy() for x in state], 10.0, 0.001, 30, 30, 2)
+    want = oracle.Oracle(30, 30).run_steps(*state, 10.0, 0.001, 2)
+    for name, g, wv in zip(("vp", "vtmp", "image"), got, want):
+        assert_bit_equal(g, wv, f"{name} (R={nranks})")
+
+
+def test_ring_wide_grid_fused_depth():
+    """A 2048-wide grid over 4 slabs with 100+100 sweeps (the fused passes and their halo depth 8)."""
+    h, w = 128, 2048
+    state = _state(h, w, h, w, 9)
+    got = _run_ring(4, [x.copy() for x in state], 0.1, 0.001, 100, 100, 1)
+    want = oracle.Oracle(100, 100).run_steps(*state, 0.1, 0.001, 1)
+    for name, g, wv in zip(("vp", "vtmp", "image"), got, want):
+        assert_bit_equal(g, wv, name)
+
+
+def test_nccl_two_ranks(tmp_path):
+    import torch
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs two GPUs")
+    out = tmp_path / "nccl.json"
+    cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node=2", "--master-addr", "127.0.0.1",
+           "--master-port", "29541", os.path.join(ROOT, "tests", "nccl_ring_check.py"), str(out)]
+    r = subprocess.run(cmd, capture_output=True, text=True, timeout=600, cwd=ROOT)
+    assert r.returncode == 0, r.stdout[-3000:] + r.stderr[-3000:]
+    assert "NCCL ring matches oracle" in r.stdout
