@@ -144,6 +144,39 @@ def cpu_reference_rate(n_iters: int, w: int, sample_rows: int, steps: int, warmu
     return w * sample_rows * n_iters / dt_s, dt_s * 1e3, kind
 
 
+def fluid_cu_baseline(n_iters: int, w: int, h: int, steps: int = 5, warmup: int = 2):
+    """Times the reference's OWN CUDA backend (src/fluid.cu, written for sm_75, recompiled unmodified for
+    sm_100a into oracle/_ref/libfluid_refcu_<N>.so) on the same workload -- a reported baseline only: it is
+    not numerically equal to fluid.cpp.  -> dict or None if the library did not travel."""
+    import ctypes
+    import torch
+    path = os.path.join(ROOT, "oracle", "_ref", f"libfluid_refcu_{n_iters}.so")
+    if not os.path.exists(path):
+        return None
+    lib = ctypes.CDLL(path)
+    pp = ctypes.POINTER(ctypes.c_void_p)
+    lib.refcu_timestep.argtypes = [pp, pp, pp, pp, ctypes.c_float, ctypes.c_float] + [ctypes.c_int] * 4
+    lib.refcu_timestep.restype = None
+    vp, vtmp, image, itmp = make_inputs(h, w)
+    bufs = [torch.from_numpy(x).cuda() for x in (vp, vtmp, image, itmp)]
+    ptrs = [ctypes.c_void_p(t.data_ptr()) for t in bufs]
+
+    def step():
+        lib.refcu_timestep(*(ctypes.byref(p) for p in ptrs), DT, VISC, w, h, w, h)
+
+    for _ in range(warmup):
+        step()
+    torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    for _ in range(steps):
+        step()
+    torch.cuda.synchronize()       # the reference's own driver stops its clock before this (main.cpp:247)
+    ms = (time.perf_counter() - t0) / steps * 1e3
+    return {"value": w * h * n_iters / (ms * 1e-3), "unit": UNIT, "ms_per_step": ms, "launches_per_step": 2 * n_iters + 4,
+            "what": "reference src/fluid.cu compiled unmodified with nvcc -O3 for sm_100a, same grid and sweep counts; "
+                    "timed baseline only (its results differ from fluid.cpp, SURVEY.md 2.2)"}
+
+
 def run_reference_arm(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
@@ -298,6 +331,13 @@ def run_single_gpu(args):
                "sample": f"3 timesteps of a {w}x{sample_rows} slab of the workload ({n}+{n} sweeps), "
                          f"{cpu_ms:.0f} ms each; fluid.cpp is single-threaded"}
 
+    refcu = None
+    if not args.no_cpu:
+        try:
+            refcu = fluid_cu_baseline(n, w, h)
+        except Exception as e:                      # a baseline must never take the bench down
+            refcu = {"error": repr(e)}
+
     line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": 1, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "f32", "data": "synthetic", "config": workload_config(args),
@@ -305,7 +345,7 @@ def run_single_gpu(args):
             "clocks": clocks, "whole_step_roofline": whole_step,
             "pressure_solve": {"ms": per_phase["pressure"], "cell_updates_per_s": cells * n / (per_phase["pressure"] * 1e-3)},
             "cell_steps_per_s": cells / (ms_step * 1e-3), "phases_ms": per_phase, "kernels": kernels,
-            "fuse_depth": depth}
+            "fuse_depth": depth, "fluid_cu_baseline": refcu}
     print(json.dumps(line), flush=True)
 
 

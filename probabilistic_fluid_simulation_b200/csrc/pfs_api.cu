@@ -18,6 +18,7 @@ namespace pfs {
 // ---------------------------------------------------------------------------------------------
 static thread_local char t_error[512] = "";
 unsigned long long g_launches = 0;
+unsigned long long g_passes = 0;
 
 void set_error(const char *fmt, ...)
 {
@@ -138,7 +139,7 @@ PhaseScope::PhaseScope(int phase_, cudaStream_t s_) : phase(phase_), s(s_)
 {
     if (!g_phase_timing) return;
     a = take_event();
-    l0 = g_launches;
+    l0 = g_passes;
     cudaEventRecord(a, s);
 }
 
@@ -147,7 +148,7 @@ PhaseScope::~PhaseScope()
     if (!a) return;
     cudaEvent_t b = take_event();
     cudaEventRecord(b, s);
-    g_spans.push_back({phase, a, b, g_launches - l0});
+    g_spans.push_back({phase, a, b, g_passes - l0});
 }
 
 // ---------------------------------------------------------------------------------------------

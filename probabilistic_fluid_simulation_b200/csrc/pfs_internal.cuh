@@ -35,12 +35,14 @@ int cuda_fail(cudaError_t e, const char *what, const char *file, int line);
     } while (0)
 
 extern unsigned long long g_launches;   // kernels launched by this library (host counter)
+extern unsigned long long g_passes;     // same, minus the guard-repair launches (what pfs_phase_times reports)
 int check_launch(const char *kernel, const char *file, int line);
 
 #define PFS_LAUNCH(kernel, grid, block, smem, stream, ...)                     \
     do {                                                                       \
         kernel<<<(grid), (block), (smem), (stream)>>>(__VA_ARGS__);            \
         ++::pfs::g_launches;                                                   \
+        ++::pfs::g_passes;                                                     \
         PFS_TRY(::pfs::check_launch(#kernel, __FILE__, __LINE__));             \
     } while (0)
 

@@ -4,16 +4,17 @@
 // Decomposition: rank r of R owns a contiguous band of rows of the velocity grid and the band of image
 // rows whose velocity look-up (fluid.cpp:89-90) falls into it; x stays whole, so a halo row is one
 // contiguous run of W floats per plane and the x wrap stays local.  The domain is periodic, so the
-// ranks form a ring (R = 1 wraps onto itself).  Planes carry HALO rows above and below the band; the
-// kernels are the single-GPU kernels with the row map (y_base = HALO, wrap = 0).
+// ranks form a ring (R = 1 wraps onto itself).  Planes carry `halo` rows above and below the band; the
+// kernels are the single-GPU kernels with the row map (y_base = halo, wrap = 0).
 //
 // What moves between neighbours each timestep (rows are W*4 bytes per plane):
 //   advect        D rows of (u,v) each way, D = ceil(max|dt*v/H|) + 2 from an all-reduce(max)
-//   diffusion     t rows x 2 planes before every fused pass of depth t, 1 row before the last sweep
-//   divergence    1 row of v; then HALO rows of the divergence (the fused pressure passes need the
-//                 right-hand side inside their halo trapezoid)
-//   pressure      t rows before every fused pass, 1 row before the last sweep, 1 row of p_N for the
-//                 gradient
+//   diffusion     `halo` (32) rows x 2 planes; a pass of depth t then also recomputes the halo-t rows next to
+//                 the band (an "extended interior"), so the next passes find valid halos without another
+//                 exchange: one exchange per 32/t passes, ~1.5 % redundant rows on a 2048-row band
+//   divergence    nothing if the last diffusion sweep left >= 1 valid halo row; then `halo` rows of the
+//                 divergence (the fused pressure passes need the right-hand side in their halo trapezoid)
+//   pressure      as diffusion, 1 plane; the gradient needs 1 valid halo row of p_N
 //   advect_color  D_i rows of the image each way
 // Results are bit-identical to the single-GPU path (same per-cell arithmetic, global indices).
 //
@@ -32,7 +33,8 @@
 
 namespace pfs {
 
-constexpr int HALO = 8;   // >= the deepest fused pass
+constexpr int MAX_HALO = 32;   // halo rows per side: one exchange feeds MAX_HALO / depth fused passes
+constexpr int MIN_HALO = 8;    // >= the deepest fused pass
 
 // ---------------------------------------------------------------------------------------------
 // NCCL through dlopen
@@ -131,12 +133,15 @@ struct pfs_slab {
     int gw = 0, gh = 0, row0 = 0, rows = 0;
     int iw = 0, ih = 0, irow0 = 0, irows = 0;
     int device = 0;
+    int halo = pfs::MIN_HALO;             // halo rows per side of every plane (multiple of 8, <= the thinnest band)
     size_t plane_floats = 0;
-    float *planes = nullptr;              // 7 planes of (rows + 2*HALO) x gw
-    float2 *uvx = nullptr;                // advect source: (u,v) rows [row0-D, row0+rows+D) (or the whole grid)
-    size_t uvx_rows = 0;
-    float4 *imgx = nullptr;               // advect_color source: image rows [irow0-Di, irow0+irows+Di)
-    size_t imgx_rows = 0;
+    float *planes = nullptr;              // 7 planes of (rows + 2*halo) x gw
+    // gather sources of advect / advect_color: D halo rows received from each ring neighbour (interleaved
+    // cells, [above | below]); or -- when D exceeds a band -- a copy of the whole field (all-gather)
+    float4 *vhalo = nullptr, *ihalo = nullptr;
+    size_t vhalo_rows = 0, ihalo_rows = 0;         // capacity in rows (both sides together)
+    float4 *vwhole = nullptr, *iwhole = nullptr;
+    size_t vwhole_rows = 0, iwhole_rows = 0;
     float *d_scalars = nullptr;           // [0] max|v| (advect), [1] max|v| (advect_color), [2] overflow flag (as int)
     float *h_scalars = nullptr;           // pinned mirror
     ncclComm_t comm = nullptr;
@@ -184,53 +189,61 @@ __global__ void __launch_bounds__(256) max_abs_v_kernel(const float4 *__restrict
     }
 }
 
-__global__ void __launch_bounds__(256) unpack_uv_kernel(const float4 *__restrict__ vp, float2 *__restrict__ uv, size_t n)
+// Rows of a periodic field of `total` rows, interleaved cells: the local band plus d halo rows received
+// from each ring neighbour (or the whole field: band0 = 0, band_n = total, d = 0).
+struct RowSource {
+    const float4 *band, *above, *below;
+    int band0, band_n, d, total, width;
+};
+
+__device__ __forceinline__ const float4 *source_row(const RowSource &S, int grow, int *overflow, int code)
 {
-    const size_t i = (size_t)blockIdx.x * 256 + threadIdx.x;
-    if (i >= n) return;
-    const float4 c = __ldg(vp + i);
-    uv[i] = make_float2(c.x, c.y);
+    int r = grow - S.band0;
+    if (r < -S.d) r += S.total;
+    if (r >= S.band_n + S.d) r -= S.total;
+    if (r >= 0 && r < S.band_n) return S.band + (size_t)r * S.width;
+    if (r < 0 && r >= -S.d) return S.above + (size_t)(r + S.d) * S.width;
+    if (r >= S.band_n && r < S.band_n + S.d) return S.below + (size_t)(r - S.band_n) * S.width;
+    atomicExch(overflow, code);          // cannot happen if D was computed correctly; never read out of bounds
+    return nullptr;
 }
 
-// advect (fluid.cpp:24-70) with GLOBAL indices: this rank produces rows [row0, row0+rows) of the
-// gh-row grid; the gather source holds rows [src_row0, src_row0+src_rows) (mod gh) of (u,v).
+// advect (fluid.cpp:24-70) with GLOBAL indices: this rank produces rows [row0, row0+rows) of the gh-row
+// grid from the interleaved field (u,v in the first 8 bytes of a cell, as in the single-GPU kernel).
 __global__ void __launch_bounds__(256)
-    advect_slab_kernel(const float2 *__restrict__ src, int src_row0, int src_rows, float *__restrict__ u_out,
-                       float *__restrict__ v_out, float dt, int w, int gh, int row0, int rows, int y_base,
-                       int *overflow)
+    advect_slab_kernel(const RowSource S, float *__restrict__ u_out, float *__restrict__ v_out, float dt, int w, int gh,
+                       int row0, int rows, int y_base, int *overflow)
 {
     const int i = blockIdx.x * 64 + threadIdx.x, jl = blockIdx.y * 4 + threadIdx.y;
     if (i >= w || jl >= rows) return;
     const int j = row0 + jl;
     const float fw = (float)w, fh = (float)gh;
-    int lj = j - src_row0;
-    if (lj < 0) lj += gh;
-    const float2 uv = __ldg(src + (size_t)lj * w + i);
+    const float4 *own = source_row(S, j, overflow, 1);
+    if (!own) return;
+    const float2 uv = __ldg(reinterpret_cast<const float2 *>(own + i));
     float xp = __fsub_rn((float)i, __fdiv_rn(__fmul_rn(dt, uv.x), fw));
     float yp = __fsub_rn((float)j, __fdiv_rn(__fmul_rn(dt, uv.y), fh));
     xp = wrap_coord(xp, fw);
     yp = wrap_coord(yp, fh);
     const Bilinear b = make_bilinear(xp, yp, w, gh);
-    int l0 = b.j0 - src_row0, l1 = b.j1 - src_row0;
-    if (l0 < 0) l0 += gh;
-    if (l1 < 0) l1 += gh;
-    if (l0 >= src_rows || l1 >= src_rows) {      // cannot happen if D was computed correctly; never read out of bounds
-        atomicExch(overflow, 1);
-        return;
-    }
-    const float2 *r0 = src + (size_t)l0 * w, *r1 = src + (size_t)l1 * w;
-    const float2 f00 = __ldg(r0 + b.i0), f10 = __ldg(r0 + b.i1), f01 = __ldg(r1 + b.i0), f11 = __ldg(r1 + b.i1);
+    const float4 *r0 = source_row(S, b.j0, overflow, 1), *r1 = source_row(S, b.j1, overflow, 1);
+    if (!r0 || !r1) return;
+    const float2 f00 = __ldg(reinterpret_cast<const float2 *>(r0 + b.i0));
+    const float2 f10 = __ldg(reinterpret_cast<const float2 *>(r0 + b.i1));
+    const float2 f01 = __ldg(reinterpret_cast<const float2 *>(r1 + b.i0));
+    const float2 f11 = __ldg(reinterpret_cast<const float2 *>(r1 + b.i1));
     const size_t o = (size_t)(y_base + jl) * w + i;
     u_out[o] = bilerp(b, f00.x, f10.x, f01.x, f11.x);
     v_out[o] = bilerp(b, f00.y, f10.y, f01.y, f11.y);
 }
 
-// advect_color (fluid.cpp:72-127) with GLOBAL indices: image rows [irow0, irow0+irows), velocity rows
-// [row0, row0+rows) (interleaved, local), image gather source rows [src_row0, +src_rows) (mod ih).
+// advect_color (fluid.cpp:72-127) with GLOBAL indices: image rows [irow0, irow0+irows) of the ih-row
+// image; velocity rows [row0, row0+rows) (interleaved, local: the image bands are built so that the
+// look-up of fluid.cpp:89-90 never leaves the rank's own velocity band).
 __global__ void __launch_bounds__(256)
-    advect_color_slab_kernel(const float4 *__restrict__ src, int src_row0, int src_rows, float4 *__restrict__ out,
-                             const float *__restrict__ vp, float dt_over_viw, float dt_over_vih, float viw, float vih,
-                             int iw, int ih, int irow0, int irows, int vw, int row0, int rows, int *overflow)
+    advect_color_slab_kernel(const RowSource S, float4 *__restrict__ out, const float *__restrict__ vp,
+                             float dt_over_viw, float dt_over_vih, float viw, float vih, int iw, int ih, int irow0,
+                             int irows, int vw, int row0, int rows, int *overflow)
 {
     const int i = blockIdx.x * 64 + threadIdx.x, jl = blockIdx.y * 4 + threadIdx.y;
     if (i >= iw || jl >= irows) return;
@@ -248,14 +261,8 @@ __global__ void __launch_bounds__(256)
     xp = wrap_coord(xp, fiw);
     yp = wrap_coord(yp, fih);
     const Bilinear b = make_bilinear(xp, yp, iw, ih);
-    int l0 = b.j0 - src_row0, l1 = b.j1 - src_row0;
-    if (l0 < 0) l0 += ih;
-    if (l1 < 0) l1 += ih;
-    if (l0 >= src_rows || l1 >= src_rows) {
-        atomicExch(overflow, 3);
-        return;
-    }
-    const float4 *r0 = src + (size_t)l0 * iw, *r1 = src + (size_t)l1 * iw;
+    const float4 *r0 = source_row(S, b.j0, overflow, 3), *r1 = source_row(S, b.j1, overflow, 3);
+    if (!r0 || !r1) return;
     const float4 f00 = __ldg(r0 + b.i0), f10 = __ldg(r0 + b.i1), f01 = __ldg(r1 + b.i0), f11 = __ldg(r1 + b.i1);
     float4 o;
     o.x = bilerp(b, f00.x, f10.x, f01.x, f11.x);
@@ -340,10 +347,10 @@ int exchange_planes(const std::vector<pfs_slab *> &local, const std::vector<std:
         for (float *p : planes[k]) {
             char *b = reinterpret_cast<char *>(p);
             Segment sg;
-            sg.send_up = b + (size_t)HALO * row;
-            sg.send_down = b + (size_t)(HALO + s->rows - t) * row;
-            sg.recv_from_up = b + (size_t)(HALO - t) * row;
-            sg.recv_from_down = b + (size_t)(HALO + s->rows) * row;
+            sg.send_up = b + (size_t)s->halo * row;
+            sg.send_down = b + (size_t)(s->halo + s->rows - t) * row;
+            sg.recv_from_up = b + (size_t)(s->halo - t) * row;
+            sg.recv_from_down = b + (size_t)(s->halo + s->rows) * row;
             sg.bytes = (size_t)t * row;
             segs[k].push_back(sg);
         }
@@ -387,45 +394,65 @@ int ensure_bytes(void **ptr, size_t *have_rows, size_t want_rows, size_t row_byt
     return PFS_OK;
 }
 
-// Fill the gather source of one field: local band in the middle, D halo rows from the ring neighbours,
-// or -- when D exceeds a band -- every rank's band (all-gather), which is always sufficient.
-// `elem` = bytes per cell.  On return *src_row0 / *src_rows describe what `buf` holds.
-int fill_gather_source(const std::vector<pfs_slab *> &local, const std::vector<char *> &buf, int width, int total_rows,
-                       const std::vector<int> &first, const std::vector<int> &count, int D, size_t elem, bool whole,
-                       std::vector<int> *src_row0, std::vector<int> *src_rows)
+// Build the gather source of one interleaved field on every local slab: the band itself (read in place
+// from the caller's buffer) plus D halo rows from the ring neighbours, or -- when D exceeds a band -- a
+// copy of the whole field assembled from every rank's band (always sufficient).
+struct FieldBands {
+    int width, total;                         // cells per row, rows of the whole field
+    std::vector<const float4 *> band;         // local slabs' bands (caller memory)
+    std::vector<int> first, count;            // global first row / rows of each local band
+    bool image;                               // selects the halo / whole buffers of the slab
+};
+
+int build_row_sources(const std::vector<pfs_slab *> &local, const FieldBands &F, int D, bool whole,
+                      std::vector<RowSource> *out)
 {
-    const size_t row = (size_t)width * elem;
+    const size_t n = local.size();
+    const size_t row = (size_t)F.width * sizeof(float4);
+    out->resize(n);
     if (!whole) {
-        std::vector<std::vector<Segment>> segs(local.size());
-        for (size_t k = 0; k < local.size(); k++) {
-            char *b = buf[k];
+        std::vector<std::vector<Segment>> segs(n);
+        for (size_t k = 0; k < n; k++) {
+            pfs_slab *s = local[k];
+            Guard g(s->device);
+            float4 **hb = F.image ? &s->ihalo : &s->vhalo;
+            size_t *cap = F.image ? &s->ihalo_rows : &s->vhalo_rows;
+            PFS_TRY(ensure_bytes((void **)hb, cap, 2 * (size_t)D, row));
+            float4 *above = *hb, *below = *hb + (size_t)D * F.width;
+            const char *b = reinterpret_cast<const char *>(F.band[k]);
             Segment sg;
-            sg.send_up = b + (size_t)D * row;
-            sg.send_down = b + (size_t)(D + count[k] - D) * row;
-            sg.recv_from_up = b;
-            sg.recv_from_down = b + (size_t)(D + count[k]) * row;
+            sg.send_up = b;
+            sg.send_down = b + (size_t)(F.count[k] - D) * row;
+            sg.recv_from_up = reinterpret_cast<char *>(above);
+            sg.recv_from_down = reinterpret_cast<char *>(below);
             sg.bytes = (size_t)D * row;
             segs[k].push_back(sg);
-            (*src_row0)[k] = ((first[k] - D) % total_rows + total_rows) % total_rows;
-            (*src_rows)[k] = count[k] + 2 * D;
+            (*out)[k] = RowSource{F.band[k], above, below, F.first[k], F.count[k], D, F.total, F.width};
         }
         return ring_exchange(local, segs);
     }
-    // all-gather: buf holds the whole field in global row order; the local band is already in place
-    for (size_t k = 0; k < local.size(); k++) {
+    // whole field: every slab assembles all bands in global row order
+    std::vector<char *> buf(n);
+    for (size_t k = 0; k < n; k++) {
         pfs_slab *s = local[k];
         Guard g(s->device);
-        (*src_row0)[k] = 0;
-        (*src_rows)[k] = total_rows;
+        float4 **wb = F.image ? &s->iwhole : &s->vwhole;
+        size_t *cap = F.image ? &s->iwhole_rows : &s->vwhole_rows;
+        PFS_TRY(ensure_bytes((void **)wb, cap, (size_t)F.total, row));
+        buf[k] = reinterpret_cast<char *>(*wb);
+        if (F.count[k] > 0)
+            PFS_CUDA(cudaMemcpyAsync(buf[k] + (size_t)F.first[k] * row, F.band[k], (size_t)F.count[k] * row,
+                                     cudaMemcpyDeviceToDevice, s->stream));
+        (*out)[k] = RowSource{*wb, nullptr, nullptr, 0, F.total, 0, F.total, F.width};
         if (s->comm != nullptr) {
             for (int r = 0; r < s->nranks; r++) {
                 int f, c;
-                if (elem == sizeof(float2))
-                    band(s->gh, s->nranks, r, &f, &c);
-                else {
-                    int vf, vc;
-                    band(s->gh, s->nranks, r, &vf, &vc);
-                    image_band(s->ih, s->gh, vf, vc, &f, &c);
+                band(s->gh, s->nranks, r, &f, &c);
+                if (F.image) {
+                    int jf, jc;
+                    image_band(s->ih, s->gh, f, c, &jf, &jc);
+                    f = jf;
+                    c = jc;
                 }
                 if (c == 0) continue;
                 char *p = buf[k] + (size_t)f * row;
@@ -435,16 +462,15 @@ int fill_gather_source(const std::vector<pfs_slab *> &local, const std::vector<c
             PFS_CUDA(cudaEventRecord(s->ev_ready, s->stream));
         }
     }
-    if (local[0]->comm == nullptr) {
-        const std::vector<pfs_slab *> &all = local[0]->group;
-        for (size_t k = 0; k < local.size(); k++) {
+    if (local[0]->comm == nullptr && n > 1) {
+        for (size_t k = 0; k < n; k++) {
             pfs_slab *s = local[k];
             Guard g(s->device);
-            for (size_t q = 0; q < local.size(); q++) {
-                if (q == k || count[q] == 0) continue;
-                PFS_CUDA(cudaStreamWaitEvent(s->stream, all[local[q]->rank]->ev_ready, 0));
-                PFS_CUDA(cudaMemcpyAsync(buf[k] + (size_t)first[q] * row, buf[q] + (size_t)first[q] * row,
-                                         (size_t)count[q] * row, cudaMemcpyDefault, s->stream));
+            for (size_t q = 0; q < n; q++) {
+                if (q == k || F.count[q] == 0) continue;
+                PFS_CUDA(cudaStreamWaitEvent(s->stream, local[q]->ev_ready, 0));
+                PFS_CUDA(cudaMemcpyAsync(buf[k] + (size_t)F.first[q] * row, buf[q] + (size_t)F.first[q] * row,
+                                         (size_t)F.count[q] * row, cudaMemcpyDefault, s->stream));
             }
             PFS_CUDA(cudaEventRecord(s->ev_done, s->stream));
         }
@@ -530,8 +556,8 @@ extern "C" int pfs_slab_create(pfs_slab **out, int rank, int nranks, int gw, int
         set_error("%s: grid exceeds 2^28 cells (the reference's int32 index limit)", fn);
         return PFS_EINVAL;
     }
-    if (gh / nranks < HALO) {
-        set_error("%s: every slab needs at least %d rows (grid height %d over %d ranks)", fn, HALO, gh, nranks);
+    if (gh / nranks < MIN_HALO) {
+        set_error("%s: every slab needs at least %d rows (grid height %d over %d ranks)", fn, MIN_HALO, gh, nranks);
         return PFS_EINVAL;
     }
     pfs_slab *s = new pfs_slab();
@@ -549,7 +575,12 @@ extern "C" int pfs_slab_create(pfs_slab **out, int rank, int nranks, int gw, int
         set_error("%s: no usable CUDA device (%s); there is no CPU fallback", fn, cudaGetErrorString(e));
         return PFS_ENODEVICE;
     }
-    s->plane_floats = ((size_t)(s->rows + 2 * HALO) * gw + 63) & ~(size_t)63;
+    s->halo = std::min(MAX_HALO, ((gh / nranks) / 8) * 8);      // same on every rank: the thinnest band decides
+    if (const char *e = getenv("PFS_SLAB_HALO")) {
+        const int v = atoi(e);
+        if (v >= MIN_HALO && v <= s->halo) s->halo = (v / 8) * 8;
+    }
+    s->plane_floats = ((size_t)(s->rows + 2 * s->halo) * gw + 63) & ~(size_t)63;
     int st = PFS_OK;
     auto fail = [&](cudaError_t ce, const char *what) {
         st = cuda_fail(ce, what, __FILE__, __LINE__);
@@ -577,8 +608,10 @@ extern "C" int pfs_slab_destroy(pfs_slab *s)
     cudaDeviceSynchronize();
     if (s->comm && nccl().loaded) nccl().CommDestroy(s->comm);
     if (s->planes) cudaFree(s->planes);
-    if (s->uvx) cudaFree(s->uvx);
-    if (s->imgx) cudaFree(s->imgx);
+    if (s->vhalo) cudaFree(s->vhalo);
+    if (s->ihalo) cudaFree(s->ihalo);
+    if (s->vwhole) cudaFree(s->vwhole);
+    if (s->iwhole) cudaFree(s->iwhole);
     if (s->d_scalars) cudaFree(s->d_scalars);
     if (s->h_scalars) cudaFreeHost(s->h_scalars);
     if (s->ev_ready) cudaEventDestroy(s->ev_ready);
@@ -724,65 +757,60 @@ extern "C" int pfs_slab_simulate_fluid_step(pfs_slab *const *slabs, int n_local,
         band(gh, L[0]->nranks, r, &f, &c);
         min_rows = std::min(min_rows, c);
     }
-    const bool whole = !(disp * 1.001 + 3.0 < (double)min_rows) || L[0]->nranks == 1;
+    const bool whole = !(disp * 1.001 + 3.0 < (double)min_rows);
     const int D = whole ? 0 : (int)std::ceil(disp * 1.001) + 2;
     {
-        std::vector<char *> buf(n);
-        std::vector<int> first(n), count(n), src_row0(n), src_rows(n);
+        FieldBands F{gw, gh, {}, {}, {}, false};
         for (int k = 0; k < n; k++) {
-            pfs_slab *s = L[k];
-            Guard g(s->device);
-            const size_t want = whole ? (size_t)gh : (size_t)s->rows + 2 * (size_t)D;
-            PFS_TRY(ensure_bytes((void **)&s->uvx, &s->uvx_rows, want, (size_t)gw * sizeof(float2)));
-            first[k] = s->row0;
-            count[k] = s->rows;
-            float2 *interior = s->uvx + (size_t)(whole ? s->row0 : D) * gw;
-            const size_t cells = (size_t)s->rows * gw;
-            PFS_LAUNCH(unpack_uv_kernel, (unsigned)((cells + 255) / 256), 256, 0, s->stream,
-                       reinterpret_cast<const float4 *>(vp[k]), interior, cells);
-            buf[k] = reinterpret_cast<char *>(s->uvx);
+            F.band.push_back(reinterpret_cast<const float4 *>(vp[k]));
+            F.first.push_back(L[k]->row0);
+            F.count.push_back(L[k]->rows);
         }
-        if (whole && L[0]->nranks == 1) {
-            src_row0[0] = 0;
-            src_rows[0] = gh;
-        } else {
-            PFS_TRY(fill_gather_source(L, buf, gw, gh, first, count, D, sizeof(float2), whole, &src_row0, &src_rows));
-        }
+        std::vector<RowSource> src;
+        PFS_TRY(build_row_sources(L, F, D, whole, &src));
         for (int k = 0; k < n; k++) {
             pfs_slab *s = L[k];
             Guard g(s->device);
             dim3 block(64, 4), grid((gw + 63) / 64, (s->rows + 3) / 4);
-            PFS_LAUNCH(advect_slab_kernel, grid, block, 0, s->stream, s->uvx, src_row0[k], src_rows[k], s->plane(0),
-                       s->plane(1), dt, gw, gh, s->row0, s->rows, HALO, reinterpret_cast<int *>(s->d_scalars + 2));
+            PFS_LAUNCH(advect_slab_kernel, grid, block, 0, s->stream, src[k], s->plane(0), s->plane(1), dt, gw, gh,
+                       s->row0, s->rows, s->halo, reinterpret_cast<int *>(s->d_scalars + 2));
         }
     }
 
-    // ---- sweeps with halo exchange before every pass ----
+    // n sweeps starting from iterate 0 in planes (pa0, pa1): n-1 in fused passes, then one sweep into the
+    // other set.  `valid` tracks how many halo rows of the current iterate are correct on every slab: an
+    // exchange makes it `halo`; a pass of depth t needs t of them and -- by also recomputing the e = valid-t
+    // rows just outside the band -- leaves e valid rows on its result.
+    const int halo = L[0]->halo;
     auto run_sweeps = [&](SweepOp op, int pa0, int pa1, int pb0, int pb1, const SweepParams &proto, int count,
-                          int *last_is_b) -> int {
-        // plane indices; iterate 0 in (pa0, pa1).  n-1 sweeps in passes, then one sweep into the other set.
+                          int *last_is_b, int *valid_out) -> int {
         int cur0 = pa0, cur1 = pa1, oth0 = pb0, oth1 = pb1;
         int left = count - 1;
+        int valid = 0;
         const bool vec = (gw % 4 == 0);
         SweepParams p0 = proto;
         const bool packed = (op == SWEEP_DIFFUSE) && vec && packed_diffuse_supported(p0);
         const int user_depth = pfs_get_fuse_depth();
-        int depth = user_depth > 0 ? std::min(user_depth, HALO) : HALO;
+        int depth = user_depth > 0 ? std::min(user_depth, MIN_HALO) : MIN_HALO;
         if (!vec) depth = 1;
         auto one_pass = [&](int t) -> int {
-            std::vector<std::vector<float *>> pl(n);
-            for (int k = 0; k < n; k++) {
-                pl[k].push_back(L[k]->plane(cur0));
-                if (op == SWEEP_DIFFUSE) pl[k].push_back(L[k]->plane(cur1));
+            if (valid < t) {
+                std::vector<std::vector<float *>> pl(n);
+                for (int k = 0; k < n; k++) {
+                    pl[k].push_back(L[k]->plane(cur0));
+                    if (op == SWEEP_DIFFUSE) pl[k].push_back(L[k]->plane(cur1));
+                }
+                PFS_TRY(exchange_planes(L, pl, halo));
+                valid = halo;
             }
-            PFS_TRY(exchange_planes(L, pl, t));
+            const int e = valid - t;                    // extra rows recomputed on each side of the band
             for (int k = 0; k < n; k++) {
                 pfs_slab *s = L[k];
                 Guard g(s->device);
                 SweepParams p = proto;
                 p.w = gw;
-                p.h = s->rows;
-                p.y_base = HALO;
+                p.h = s->rows + 2 * e;
+                p.y_base = halo - e;
                 p.wrap = 0;
                 int flips = 0;
                 float *a0 = s->plane(cur0), *a1 = s->plane(cur1), *b0 = s->plane(oth0), *b1 = s->plane(oth1);
@@ -798,6 +826,7 @@ extern "C" int pfs_slab_simulate_fluid_step(pfs_slab *const *slabs, int n_local,
                     return PFS_ESTATE;
                 }
             }
+            valid = e;
             std::swap(cur0, oth0);
             std::swap(cur1, oth1);
             return PFS_OK;
@@ -811,6 +840,7 @@ extern "C" int pfs_slab_simulate_fluid_step(pfs_slab *const *slabs, int n_local,
         }
         PFS_TRY(one_pass(1));
         *last_is_b = (cur0 == pb0) ? 1 : 0;
+        *valid_out = valid;
         return PFS_OK;
     };
 
@@ -819,9 +849,9 @@ extern "C" int pfs_slab_simulate_fluid_step(pfs_slab *const *slabs, int n_local,
     dp.h = L[0]->rows;
     dp.alpha = viscosity * dt;
     dp.beta = (float)(1.0 + 4.0 * (double)dp.alpha);
-    int d_last_is_b = 0;
+    int d_last_is_b = 0, d_valid = 0;
     next_phase(PFS_PHASE_DIFFUSE);
-    PFS_TRY(run_sweeps(SWEEP_DIFFUSE, 0, 1, 2, 3, dp, n_diffuse, &d_last_is_b));
+    PFS_TRY(run_sweeps(SWEEP_DIFFUSE, 0, 1, 2, 3, dp, n_diffuse, &d_last_is_b, &d_valid));
     next_phase(PFS_PHASE_DIVERGENCE);
     const int dl0 = d_last_is_b ? 2 : 0, dl1 = d_last_is_b ? 3 : 1;      // iterate n_d
     const int dp0 = d_last_is_b ? 0 : 2, dp1 = d_last_is_b ? 1 : 3;      // iterate n_d - 1
@@ -839,24 +869,24 @@ extern "C" int pfs_slab_simulate_fluid_step(pfs_slab *const *slabs, int n_local,
     {
         std::vector<std::vector<float *>> pl(n);
         for (int k = 0; k < n; k++) pl[k].push_back(L[k]->plane(dl1));
-        PFS_TRY(exchange_planes(L, pl, 1));
+        if (d_valid < 1) PFS_TRY(exchange_planes(L, pl, 1));
         for (int k = 0; k < n; k++) {
             pfs_slab *s = L[k];
             Guard g(s->device);
             PFS_TRY(launch_divergence(s->plane(dl0), s->plane(dl1), s->plane(6), Bv[k], s->plane(4), dt, gw, s->rows,
-                                      s->stream, HALO, 0));
+                                      s->stream, halo, 0));
         }
         for (int k = 0; k < n; k++) pl[k][0] = L[k]->plane(6);
-        PFS_TRY(exchange_planes(L, pl, HALO));
+        PFS_TRY(exchange_planes(L, pl, halo));
     }
     SweepParams pp;
     pp.w = gw;
     pp.h = L[0]->rows;
     pp.alpha = 1.0f;
     pp.beta = 4.0f;
-    int p_last_is_b = 0;
+    int p_last_is_b = 0, p_valid = 0;
     next_phase(PFS_PHASE_PRESSURE);
-    PFS_TRY(run_sweeps(SWEEP_PRESSURE, 4, 4, 5, 5, pp, n_pressure, &p_last_is_b));
+    PFS_TRY(run_sweeps(SWEEP_PRESSURE, 4, 4, 5, 5, pp, n_pressure, &p_last_is_b, &p_valid));
     next_phase(PFS_PHASE_PROJECT);
     const int pl_last = p_last_is_b ? 5 : 4, pl_prev = p_last_is_b ? 4 : 5;
 
@@ -864,14 +894,14 @@ extern "C" int pfs_slab_simulate_fluid_step(pfs_slab *const *slabs, int n_local,
     {
         std::vector<std::vector<float *>> pl(n);
         for (int k = 0; k < n; k++) pl[k].push_back(L[k]->plane(pl_last));
-        PFS_TRY(exchange_planes(L, pl, 1));
+        if (p_valid < 1) PFS_TRY(exchange_planes(L, pl, 1));
         for (int k = 0; k < n; k++) {
             pfs_slab *s = L[k];
             Guard g(s->device);
             const bool use_last = (Bp[k] == Bv[k]);
             const float *u = s->plane(use_last ? dl0 : dp0), *v = s->plane(use_last ? dl1 : dp1);
             PFS_TRY(launch_project_pack(u, v, s->plane(pl_last), s->plane(pl_prev), s->plane(6), Bq[k], Bp[k], dt, gw,
-                                        s->rows, s->stream, HALO, 0));
+                                        s->rows, s->stream, halo, 0));
         }
     }
     for (int k = 0; k < n; k++) {
@@ -930,37 +960,25 @@ extern "C" int pfs_slab_advect_color_step(pfs_slab *const *slabs, int n_local, f
         image_band(ih, gh, f, c, &jf, &jc);
         min_rows = std::min(min_rows, jc);
     }
-    const bool whole = !(disp * 1.001 + 3.0 < (double)min_rows) || L[0]->nranks == 1;
+    const bool whole = !(disp * 1.001 + 3.0 < (double)min_rows);
     const int D = whole ? 0 : (int)std::ceil(disp * 1.001) + 2;
 
-    std::vector<char *> buf(n);
-    std::vector<int> first(n), count(n), src_row0(n), src_rows(n);
+    FieldBands F{iw, ih, {}, {}, {}, true};
     for (int k = 0; k < n; k++) {
-        pfs_slab *s = L[k];
-        Guard g(s->device);
-        const size_t want = whole ? (size_t)ih : (size_t)s->irows + 2 * (size_t)D;
-        PFS_TRY(ensure_bytes((void **)&s->imgx, &s->imgx_rows, want, (size_t)iw * sizeof(float4)));
-        first[k] = s->irow0;
-        count[k] = s->irows;
-        if (s->irows > 0)
-            PFS_CUDA(cudaMemcpyAsync(s->imgx + (size_t)(whole ? s->irow0 : D) * iw, image[k],
-                                     (size_t)s->irows * iw * sizeof(float4), cudaMemcpyDeviceToDevice, s->stream));
-        buf[k] = reinterpret_cast<char *>(s->imgx);
+        F.band.push_back(reinterpret_cast<const float4 *>(image[k]));
+        F.first.push_back(L[k]->irow0);
+        F.count.push_back(L[k]->irows);
     }
-    if (whole && L[0]->nranks == 1) {
-        src_row0[0] = 0;
-        src_rows[0] = ih;
-    } else {
-        PFS_TRY(fill_gather_source(L, buf, iw, ih, first, count, D, sizeof(float4), whole, &src_row0, &src_rows));
-    }
+    std::vector<RowSource> src;
+    PFS_TRY(build_row_sources(L, F, D, whole, &src));
     for (int k = 0; k < n; k++) {
         pfs_slab *s = L[k];
         if (s->irows == 0) continue;
         Guard g(s->device);
         dim3 block(64, 4), grid((iw + 63) / 64, (s->irows + 3) / 4);
-        PFS_LAUNCH(advect_color_slab_kernel, grid, block, 0, s->stream, s->imgx, src_row0[k], src_rows[k],
-                   reinterpret_cast<float4 *>(itmp[k]), vp[k], dt_over_viw, dt_over_vih, viw, vih, iw, ih, s->irow0,
-                   s->irows, gw, s->row0, s->rows, reinterpret_cast<int *>(s->d_scalars + 2));
+        PFS_LAUNCH(advect_color_slab_kernel, grid, block, 0, s->stream, src[k], reinterpret_cast<float4 *>(itmp[k]), vp[k],
+                   dt_over_viw, dt_over_vih, viw, vih, iw, ih, s->irow0, s->irows, gw, s->row0, s->rows,
+                   reinterpret_cast<int *>(s->d_scalars + 2));
     }
     for (int k = 0; k < n; k++) std::swap(image[k], itmp[k]);   // fluid.cpp:317-319
     return PFS_OK;

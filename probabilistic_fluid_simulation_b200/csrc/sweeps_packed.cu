@@ -276,6 +276,7 @@ int launch_packed(const PackedParams &P, cudaStream_t s)
     PFS_CUDA(cudaMemsetAsync(P.flags, 0, (size_t)total * sizeof(int), s));
     PFS_LAUNCH((diffuse_packed_kernel<T, false, MINB>), blocks, WARPS_PER_CTA * 32, 0, s, P);
     PFS_LAUNCH((diffuse_packed_kernel<T, true, MINB>), blocks, WARPS_PER_CTA * 32, 0, s, P);
+    --g_passes;     // the repair launch belongs to the same pass
     return PFS_OK;
 }
 

@@ -61,11 +61,24 @@ def run(args, bench) -> None:
         raise SystemExit(f"bench.py --gpus {args.gpus} needs WORLD_SIZE={args.gpus} (launch with torch.distributed.run); "
                          f"got WORLD_SIZE={world}")
     torch.cuda.set_device(local)
-    dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     w, h, n = bench.workload_shape(args)
-    slab = SlabRank(rank, world, w, h, w, h)
-    uid = broadcast_bytes(SlabRank.unique_id() if rank == 0 else None, 128)
-    slab.connect(uid)
+    # NCCL announces its version on stdout when a communicator is created; stdout must carry exactly one
+    # JSON line, so fd 1 points at stderr until both communicators (torch's and the library's) exist.
+    import sys
+    sys.stdout.flush()
+    saved_stdout = os.dup(1)
+    os.dup2(2, 1)
+    try:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+        slab = SlabRank(rank, world, w, h, w, h)
+        uid = broadcast_bytes(SlabRank.unique_id() if rank == 0 else None, 128)
+        slab.connect(uid)
+        dist.barrier()
+        torch.cuda.synchronize()
+    finally:
+        sys.stdout.flush()
+        os.dup2(saved_stdout, 1)
+        os.close(saved_stdout)
 
     vp, vtmp, image, itmp = bench.make_inputs(h, w, rows=(slab.row0, slab.row0 + slab.rows))
     assert slab.irow0 == slab.row0 and slab.irows == slab.rows        # image res == grid res in this workload
