@@ -121,6 +121,21 @@ int pfs_subtract_pressure_gradient(const float *vp, float *vp_out, float dt,
 int pfs_advect_color(const float *image, float *itmp, const float *vp, float dt,
                      int ix, int iy, int iz, int vx, int vy, int vz, void *stream);
 
+/* ---- opt-in stochastic forcing at the addForces slot (NOT in the reference) ------------------- */
+/* The reference's addForces is an empty stub whose call is commented out (fluid.cpp:198-208, :302) and the
+ * project has no random term anywhere.  These two entry points fill that slot with an
+ * additive Gaussian forcing of (u, v): u += sigma*g, g ~ N(0,1) approximated by an Irwin-Hall sum of 8
+ * uniform 16-bit integers drawn from Philox-4x32-10 keyed by `seed` with counter (cell, step).  Counter
+ * based, so any decomposition draws the same numbers; restated in oracle/fluid_oracle.c and checked bit
+ * for bit.  sigma == 0 is exactly the deterministic path. */
+int pfs_add_forces_stochastic(float *vp, float sigma, uint64_t seed, uint32_t step, int vx, int vy, int vz,
+                              void *stream);
+/* pfs_simulate_fluid_step with the forcing applied where fluid.cpp:302 would call addForces (after
+ * diffuse, before computePressure). */
+int pfs_simulate_fluid_step_stochastic(float **vp, float **tmp, float dt, float viscosity, int vx, int vy, int vz,
+                                       int n_diffuse, int n_pressure, float sigma, uint64_t seed, uint32_t step,
+                                       void *stream);
+
 /* ---- host-buffer API: replaces the non-USE_CUDA branch of includes/fluid.hpp --------------- */
 /* Same semantics as the device-pointer calls, but the pfs_field structs hold HOST pointers, as
  * in the reference CPU build (fluid.hpp:109,118; main.cpp:236,239).  Each call copies its inputs

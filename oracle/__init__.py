@@ -92,6 +92,13 @@ class Oracle:
             lib.oracle_simulate_fluid_step.argtypes = [F, F, f32, f32, ctypes.c_int, ctypes.c_int]
             lib.oracle_advect_color_step.argtypes = [F, F, F, f32]
             lib.oracle_run_steps.argtypes = [F, F, F, F, f32, f32, ctypes.c_int, ctypes.c_int, ctypes.c_int]
+            lib.oracle_add_forces_stochastic.argtypes = [F, f32, ctypes.c_uint64, ctypes.c_uint32, ctypes.c_int]
+            lib.oracle_add_forces_stochastic.restype = None
+            lib.oracle_simulate_fluid_step_stochastic.argtypes = [F, F, f32, f32, ctypes.c_int, ctypes.c_int, f32,
+                                                                  ctypes.c_uint64, ctypes.c_uint32]
+            lib.oracle_simulate_fluid_step_stochastic.restype = None
+            lib.oracle_philox4x32_10.argtypes = [ctypes.POINTER(ctypes.c_uint32)] * 3
+            lib.oracle_philox4x32_10.restype = None
             lib.oracle_channel_hash.argtypes = [ctypes.POINTER(f32), ctypes.c_size_t, ctypes.c_int, ctypes.c_int]
             lib.oracle_channel_hash.restype = ctypes.c_uint64
             lib.oracle_init_velocity_from_unit.argtypes = [ctypes.POINTER(f32), ctypes.c_size_t]
@@ -147,6 +154,17 @@ class Oracle:
         p = _Pair(image, itmp)
         fv = _as_field(vp)
         self.L.oracle_advect_color_step(p.fa, p.fb, fv, dt)
+        return p.resolve()
+
+    # --- opt-in stochastic forcing (extension; the reference has no random term) ---
+    def add_forces_stochastic(self, vp, sigma, seed, step, row0=0):
+        self.L.oracle_add_forces_stochastic(_as_field(vp), sigma, seed, step, row0)
+        return vp
+
+    def simulate_fluid_step_stochastic(self, vp, tmp, dt, viscosity, sigma, seed, step):
+        p = _Pair(vp, tmp)
+        self.L.oracle_simulate_fluid_step_stochastic(p.fa, p.fb, dt, viscosity, self.n_diffuse, self.n_pressure, sigma,
+                                                     seed, step)
         return p.resolve()
 
     def run_steps(self, vp, vtmp, image, itmp, dt, viscosity, n_steps):

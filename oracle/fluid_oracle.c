@@ -291,3 +291,84 @@ void oracle_run_steps(pfs_oracle_field *vp, pfs_oracle_field *vtmp, pfs_oracle_f
         if (image && itmp) oracle_advect_color_step(image, itmp, vp, dt);
     }
 }
+
+/* ------------------------------------------------------------------------------------------------
+ * Opt-in stochastic forcing at the reference's addForces slot (src/fluid.cpp:198-208, call site
+ * commented out at :302).  THE REFERENCE HAS NO STOCHASTIC TERM: this restates the
+ * extension implemented by libpfs_b200.so (csrc/kernels_basic.cu: stochastic_force_kernel) so that the
+ * CUDA path can be checked bit for bit; "reference parity" for sigma > 0 is UNPINNED by construction.
+ * sigma == 0 leaves the deterministic path untouched.
+ *
+ * Noise: Philox-4x32-10 (Salmon et al., SC'11), key = (seed_lo, seed_hi), counter =
+ * (cell_lo, cell_hi, step, draw) with cell = j*W + i (global index) and draw = 0,1 -> 8 words = 16
+ * uniform 16-bit integers; component u sums the first 8, v the last 8 (Irwin-Hall, n = 8):
+ *   g = (float)(2*S - 8*65535) * norm,  norm = (float)(1/sqrt(4 * 8 * (65536^2 - 1)/12))  -> mean 0, var 1
+ *   u += sigma * g        (binary32: one multiply by norm, one by sigma, one add)
+ * Everything before the three float operations is integer arithmetic, so CPU and GPU agree exactly.
+ * ------------------------------------------------------------------------------------------------ */
+static inline void philox4x32_10(const uint32_t ctr_in[4], const uint32_t key_in[2], uint32_t out[4])
+{
+    uint32_t c0 = ctr_in[0], c1 = ctr_in[1], c2 = ctr_in[2], c3 = ctr_in[3];
+    uint32_t k0 = key_in[0], k1 = key_in[1];
+    for (int r = 0; r < 10; r++) {
+        uint64_t p0 = (uint64_t)0xD2511F53u * c0, p1 = (uint64_t)0xCD9E8D57u * c2;
+        uint32_t n0 = (uint32_t)(p1 >> 32) ^ c1 ^ k0, n1 = (uint32_t)p1;
+        uint32_t n2 = (uint32_t)(p0 >> 32) ^ c3 ^ k1, n3 = (uint32_t)p0;
+        c0 = n0; c1 = n1; c2 = n2; c3 = n3;
+        k0 += 0x9E3779B9u;
+        k1 += 0xBB67AE85u;
+    }
+    out[0] = c0; out[1] = c1; out[2] = c2; out[3] = c3;
+}
+
+void oracle_philox4x32_10(const uint32_t ctr[4], const uint32_t key[2], uint32_t out[4]) { philox4x32_10(ctr, key, out); }
+
+float oracle_stochastic_norm(void)
+{
+    return (float)(1.0 / sqrt(4.0 * 8.0 * (65536.0 * 65536.0 - 1.0) / 12.0));
+}
+
+static inline void gaussian_pair(uint64_t cell, uint64_t seed, uint32_t step, float norm, float *gu, float *gv)
+{
+    uint32_t key[2] = {(uint32_t)seed, (uint32_t)(seed >> 32)};
+    uint32_t w[8];
+    for (uint32_t d = 0; d < 2; d++) {
+        uint32_t ctr[4] = {(uint32_t)cell, (uint32_t)(cell >> 32), step, d};
+        philox4x32_10(ctr, key, w + 4 * d);
+    }
+    int32_t su = 0, sv = 0;
+    for (int k = 0; k < 4; k++) {
+        su += (int32_t)(w[k] & 0xffffu) + (int32_t)(w[k] >> 16);
+        sv += (int32_t)(w[4 + k] & 0xffffu) + (int32_t)(w[4 + k] >> 16);
+    }
+    *gu = (float)(2 * su - 8 * 65535) * norm;
+    *gv = (float)(2 * sv - 8 * 65535) * norm;
+}
+
+/* vp ch0,1 += sigma * N(0,1), independently per cell and component.  row0 = global row of vp's first
+ * row, gw = width (cell index = (row0 + j)*gw + i), so a band of a larger grid draws the same numbers. */
+void oracle_add_forces_stochastic(pfs_oracle_field *vp, float sigma, uint64_t seed, uint32_t step, int row0)
+{
+    const float norm = oracle_stochastic_norm();
+    for (int j = 0; j < vp->y; j++) {
+        for (int i = 0; i < vp->x; i++) {
+            float gu, gv;
+            gaussian_pair((uint64_t)(row0 + j) * (uint64_t)vp->x + (uint64_t)i, seed, step, norm, &gu, &gv);
+            float *c = vp->data + as_idx(i, j, 0, vp->x, vp->z);
+            c[0] = c[0] + sigma * gu;
+            c[1] = c[1] + sigma * gv;
+        }
+    }
+}
+
+/* simulate_fluid_step with the forcing where fluid.cpp:302 would call addForces: on struct `vp` after
+ * diffuse, before computePressure. */
+void oracle_simulate_fluid_step_stochastic(pfs_oracle_field *vp, pfs_oracle_field *tmp, float dt, float viscosity,
+                                           int n_diffuse, int n_pressure, float sigma, uint64_t seed, uint32_t step)
+{
+    oracle_advect(vp, tmp, dt);
+    oracle_diffuse(tmp, vp, viscosity, dt, n_diffuse);
+    if (sigma != 0.0f) oracle_add_forces_stochastic(vp, sigma, seed, step, 0);
+    oracle_compute_pressure(vp, tmp, dt, n_pressure);
+    oracle_subtract_pressure_gradient(tmp, vp, dt);
+}

@@ -48,6 +48,9 @@ SIGNATURES = {
     "pfs_compute_pressure": (_int, [_pp, _pp, _f32, _int, _int, _int, _int, _vp]),
     "pfs_subtract_pressure_gradient": (_int, [_vp, _vp, _f32, _int, _int, _int, _vp]),
     "pfs_advect_color": (_int, [_vp, _vp, _vp, _f32, _int, _int, _int, _int, _int, _int, _vp]),
+    "pfs_add_forces_stochastic": (_int, [_vp, _f32, ctypes.c_uint64, ctypes.c_uint32, _int, _int, _int, _vp]),
+    "pfs_simulate_fluid_step_stochastic": (_int, [_pp, _pp, _f32, _f32, _int, _int, _int, _int, _int, _f32,
+                                                   ctypes.c_uint64, ctypes.c_uint32, _vp]),
     "pfs_simulate_fluid_step_host": (_int, [_F, _F, _f32, _f32, _int, _int]),
     "pfs_advect_color_step_host": (_int, [_F, _F, _F, _f32]),
     "pfs_timestep_host": (_int, [_F, _F, _F, _F, _f32, _f32, _int, _int]),

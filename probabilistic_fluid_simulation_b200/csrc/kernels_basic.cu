@@ -4,6 +4,8 @@
 //
 // All kernels are HBM-streaming: planar fp32, float4 per thread along x when W % 4 == 0 (V = 4),
 // scalar otherwise (V = 1).  Periodic wrap is resolved by index (no halo copies on one GPU).
+#include <math.h>
+
 #include "pfs_internal.cuh"
 
 namespace pfs {
@@ -293,6 +295,52 @@ __global__ void __launch_bounds__(256)
     }
 }
 
+// ---------------------------------------------------------------------------------------------
+// Opt-in stochastic forcing at the reference's (empty) addForces slot, fluid.cpp:198-208 / :302.
+// The reference has no stochastic term; oracle/fluid_oracle.c restates THIS definition (Philox-4x32-10,
+// counter = (cell_lo, cell_hi, step, draw), key = seed; 16 uniform 16-bit integers per cell, 8 summed per
+// component) so that the two agree bit for bit.  Integer arithmetic up to the last three float operations.
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ void philox4x32_10(uint32_t c0, uint32_t c1, uint32_t c2, uint32_t c3, uint32_t k0,
+                                              uint32_t k1, uint32_t (&out)[4])
+{
+#pragma unroll
+    for (int r = 0; r < 10; r++) {
+        const uint32_t hi0 = __umulhi(0xD2511F53u, c0), lo0 = 0xD2511F53u * c0;
+        const uint32_t hi1 = __umulhi(0xCD9E8D57u, c2), lo1 = 0xCD9E8D57u * c2;
+        const uint32_t n0 = hi1 ^ c1 ^ k0, n2 = hi0 ^ c3 ^ k1;
+        c0 = n0; c1 = lo1; c2 = n2; c3 = lo0;
+        k0 += 0x9E3779B9u;
+        k1 += 0xBB67AE85u;
+    }
+    out[0] = c0; out[1] = c1; out[2] = c2; out[3] = c3;
+}
+
+// u, v: either two planes (stride 1, row pitch w, first row y_base) or channels 0,1 of an interleaved
+// buffer (stride 4).  row0 = global row of local row 0 (cell index = (row0 + j) * w + i).
+__global__ void __launch_bounds__(256)
+    stochastic_force_kernel(float *__restrict__ u, float *__restrict__ v, int stride, float sigma, float norm,
+                            uint32_t seed_lo, uint32_t seed_hi, uint32_t step, int w, int h, int row0, int y_base)
+{
+    const int i = blockIdx.x * 64 + threadIdx.x, j = blockIdx.y * 4 + threadIdx.y;
+    if (i >= w || j >= h) return;
+    const unsigned long long cell = (unsigned long long)(row0 + j) * (unsigned long long)w + (unsigned long long)i;
+    uint32_t a[4], b[4];
+    philox4x32_10((uint32_t)cell, (uint32_t)(cell >> 32), step, 0u, seed_lo, seed_hi, a);
+    philox4x32_10((uint32_t)cell, (uint32_t)(cell >> 32), step, 1u, seed_lo, seed_hi, b);
+    int su = 0, sv = 0;
+#pragma unroll
+    for (int q = 0; q < 4; q++) {
+        su += (int)(a[q] & 0xffffu) + (int)(a[q] >> 16);
+        sv += (int)(b[q] & 0xffffu) + (int)(b[q] >> 16);
+    }
+    const float gu = __fmul_rn((float)(2 * su - 8 * 65535), norm);
+    const float gv = __fmul_rn((float)(2 * sv - 8 * 65535), norm);
+    const size_t o = ((size_t)(y_base + j) * w + i) * (size_t)stride;
+    u[o] = __fadd_rn(u[o], __fmul_rn(sigma, gu));
+    v[o] = __fadd_rn(v[o], __fmul_rn(sigma, gv));
+}
+
 inline bool vec4_ok(int w, const void *a, const void *b = nullptr, const void *c = nullptr, const void *d = nullptr,
                     const void *e = nullptr, const void *f = nullptr)
 {
@@ -386,6 +434,17 @@ int launch_subtract_gradient_aos(const float *vp_aos, float *out_aos, float dt, 
     dim3 block(64, 4), grid((w + 63) / 64, (h + 3) / 4);
     PFS_LAUNCH(subtract_gradient_aos_kernel, grid, block, 0, s, reinterpret_cast<const float4 *>(vp_aos), out_aos, dt,
                w, h);
+    return PFS_OK;
+}
+
+int launch_stochastic_force(float *u, float *v, int stride, float sigma, unsigned long long seed, unsigned step, int w,
+                            int h, int row0, int y_base, cudaStream_t s)
+{
+    // same expression as oracle_stochastic_norm()
+    const float norm = (float)(1.0 / sqrt(4.0 * 8.0 * (65536.0 * 65536.0 - 1.0) / 12.0));
+    dim3 block(64, 4), grid((w + 63) / 64, (h + 3) / 4);
+    PFS_LAUNCH(stochastic_force_kernel, grid, block, 0, s, u, v, stride, sigma, norm, (uint32_t)seed,
+               (uint32_t)(seed >> 32), (uint32_t)step, w, h, row0, y_base);
     return PFS_OK;
 }
 

@@ -215,8 +215,14 @@ static int run_sweeps(SweepOp op, PlanePair a, PlanePair b, const float *rhs, co
     if (lead > 0) {
         int depth = g_fuse_depth;
         bool fused = (depth != 1) && fused_sweeps_supported(p.w, p.h);
+        // The packed (f32x2) pressure kernel is bit-exact but register-bound (255 registers, 8 warps/SM) and
+        // measured no faster than the scalar fused kernel at 4096^2 (0.91 vs 0.89 ms per 100 sweeps,
+        // profiles/r01_tuning.md), so it is opt-in: PFS_PRESSURE_KERNEL=packed.
+        static const bool scalar_pressure = !(getenv("PFS_PRESSURE_KERNEL") && !strcmp(getenv("PFS_PRESSURE_KERNEL"), "packed"));
         if (fused && op == SWEEP_DIFFUSE && packed_diffuse_supported(p))
             PFS_TRY(launch_diffuse_packed(a.c0, a.c1, b.c0, b.c1, p, lead, depth, &flips, s));
+        else if (fused && op == SWEEP_PRESSURE && !scalar_pressure && packed_pressure_supported(p))
+            PFS_TRY(launch_pressure_packed(a.c0, b.c0, rhs, p, lead, depth, &flips, s));
         else if (fused)
             PFS_TRY(launch_sweeps_fused(op, a.c0, a.c1, b.c0, b.c1, rhs, p, lead, depth, &flips, s));
         else
@@ -446,10 +452,10 @@ extern "C" int pfs_advect_color(const float *image, float *itmp, const float *vp
 // =============================================================================================
 // device-pointer step API
 // =============================================================================================
-extern "C" int pfs_simulate_fluid_step(float **vp, float **tmp, float dt, float viscosity, int vx, int vy, int vz,
-                                       int n_diffuse, int n_pressure, void *stream)
+static int simulate_fluid_step_impl(const char *fn, float **vp, float **tmp, float dt, float viscosity, int vx, int vy,
+                                    int vz, int n_diffuse, int n_pressure, float sigma, unsigned long long seed,
+                                    unsigned step, void *stream)
 {
-    const char *fn = "pfs_simulate_fluid_step";
     PFS_TRY(check_dims(fn, vx, vy, vz));
     PFS_TRY(check_sweeps(fn, n_diffuse));
     PFS_TRY(check_sweeps(fn, n_pressure));
@@ -487,6 +493,12 @@ extern "C" int pfs_simulate_fluid_step(float **vp, float **tmp, float dt, float 
     // Y for even k (sweep 1 writes vp_out = the original vp buffer X).
     float *Bv = (n_diffuse & 1) ? X : Y;     // holds iterate n_diffuse in ch0,1; its ch2 is the warm start
     float *Bo = (n_diffuse & 1) ? Y : X;     // holds iterate n_diffuse-1 in ch0,1
+    // addForces slot (fluid.cpp:302, commented out in the reference): optional stochastic forcing of the
+    // field struct `vp` points at after diffuse, i.e. diffusion iterate n_diffuse
+    if (sigma != 0.0f) {
+        PhaseScope ph(PFS_PHASE_DIFFUSE, s);
+        PFS_TRY(launch_stochastic_force(d_last.c0, d_last.c1, 1, sigma, seed, step, vx, vy, 0, 0, s));
+    }
     // computePressure(vp -> tmp)  (fluid.cpp:303): divergence of iterate n_diffuse, p_0 = Bv.ch2
     {
         PhaseScope ph(PFS_PHASE_DIVERGENCE, s);
@@ -510,6 +522,31 @@ extern "C" int pfs_simulate_fluid_step(float **vp, float **tmp, float dt, float 
     *vp = Bq;
     *tmp = Bp;
     return PFS_OK;
+}
+
+extern "C" int pfs_simulate_fluid_step(float **vp, float **tmp, float dt, float viscosity, int vx, int vy, int vz,
+                                       int n_diffuse, int n_pressure, void *stream)
+{
+    return simulate_fluid_step_impl("pfs_simulate_fluid_step", vp, tmp, dt, viscosity, vx, vy, vz, n_diffuse, n_pressure,
+                                    0.0f, 0ull, 0u, stream);
+}
+
+extern "C" int pfs_simulate_fluid_step_stochastic(float **vp, float **tmp, float dt, float viscosity, int vx, int vy,
+                                                  int vz, int n_diffuse, int n_pressure, float sigma, uint64_t seed,
+                                                  uint32_t step, void *stream)
+{
+    return simulate_fluid_step_impl("pfs_simulate_fluid_step_stochastic", vp, tmp, dt, viscosity, vx, vy, vz, n_diffuse,
+                                    n_pressure, sigma, seed, step, stream);
+}
+
+extern "C" int pfs_add_forces_stochastic(float *vp, float sigma, uint64_t seed, uint32_t step, int vx, int vy, int vz,
+                                         void *stream)
+{
+    const char *fn = "pfs_add_forces_stochastic";
+    PFS_TRY(check_dims(fn, vx, vy, vz));
+    PFS_TRY(check_ptr(fn, "vp", vp));
+    if (sigma == 0.0f) return PFS_OK;
+    return launch_stochastic_force(vp, vp + 1, 4, sigma, seed, step, vx, vy, 0, 0, (cudaStream_t)stream);
 }
 
 extern "C" int pfs_advect_color_step(float **image, float **itmp, float **vp, float dt, int ix, int iy, int iz, int vx,

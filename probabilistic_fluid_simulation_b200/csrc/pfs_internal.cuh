@@ -176,6 +176,10 @@ bool packed_diffuse_supported(const SweepParams &p);
 int launch_diffuse_packed(float *a0, float *a1, float *b0, float *b1, const SweepParams &p, int n, int depth,
                           int *flips, cudaStream_t s);
 void packed_release_device_buffers();
+// Packed-FP32 temporally blocked pressure sweeps: two strips of the plane per warp (sweeps_packed.cu).
+bool packed_pressure_supported(const SweepParams &p);
+int launch_pressure_packed(float *a, float *b, const float *rhs, const SweepParams &p, int n, int depth, int *flips,
+                           cudaStream_t s);
 
 // divergence (fluid.cpp:221-237) of planes (u, v) into plane div; optionally also extracts
 // channel 2 of an interleaved buffer into plane p0 (the pressure warm start) in the same pass.
@@ -191,6 +195,10 @@ int launch_project_pack(const float *u, const float *v, const float *p_n, const 
 
 // subtractPressureGradient as a stand-alone operator on interleaved buffers (writes ch0,1 of out).
 int launch_subtract_gradient_aos(const float *vp_aos, float *out_aos, float dt, int w, int h, cudaStream_t s);
+
+// Opt-in Gaussian forcing of (u, v) at the addForces slot (kernels_basic.cu).  stride 1 = planes, 4 = interleaved.
+int launch_stochastic_force(float *u, float *v, int stride, float sigma, unsigned long long seed, unsigned step, int w,
+                            int h, int row0, int y_base, cudaStream_t s);
 
 // advect_color (fluid.cpp:72-127) on interleaved buffers.
 int launch_advect_color(const float *image, float *out, const float *vp_aos, float dt, int iw, int ih, int vw,

@@ -23,6 +23,7 @@
 
 #include <map>
 #include <mutex>
+#include <utility>
 
 #include "pfs_internal.cuh"
 
@@ -267,6 +268,157 @@ __global__ void __launch_bounds__(WARPS_PER_CTA * 32, MINB) diffuse_packed_kerne
     }
 }
 
+// ---------------------------------------------------------------------------------------------
+// Packed pressure sweeps (fluid.cpp:239-258): the pressure field is one plane, so the two halves of a
+// register pair are two DIFFERENT strips (A = strip 2k, B = strip 2k+1) of the same rows: identical
+// instruction stream, independent data.  State per lane: 16*T registers of pressure rows plus 8*T of
+// divergence rows (window of T rows, rotating with period T; the step loop is unrolled by lcm(2,T)).
+// (((pL + pR) + pT) + pB) + b, then *0.25 -- the scaling is written as FFMA2(x, 0.25, -0) with a
+// run-time -0 so that ptxas cannot contract it into the next level's first add (see mulc2()).
+// ---------------------------------------------------------------------------------------------
+struct PressurePackedParams {
+    const float *in;
+    float *out;
+    const float *rhs;
+    int w, h;
+    int strip_out, halo_cols;
+    int n_strips, n_pairs, n_chunks, chunk_rows;
+    int y_base, wrap;
+    float neg_zero;
+};
+
+template <int T>
+struct PressureUnroll {
+    static constexpr int value = (T % 2 == 0) ? T : 2 * T;
+};
+
+template <int T, int MINB>
+__global__ void __launch_bounds__(WARPS_PER_CTA * 32, MINB) pressure_packed_kernel(const PressurePackedParams P)
+{
+    constexpr int U = PressureUnroll<T>::value;
+    __shared__ float4 ring[WARPS_PER_CTA][RING_SLOTS][4][32];   // per slot: p(A), p(B), div(A), div(B)
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int item = blockIdx.x * WARPS_PER_CTA + warp;
+    if (item >= P.n_pairs * P.n_chunks) return;
+    const int pair = item % P.n_pairs;
+    const int chunk = item / P.n_pairs;
+    const int w = P.w, h = P.h;
+
+    const int stripA = 2 * pair;
+    const bool haveB = (stripA + 1 < P.n_strips);
+    const int stripB = haveB ? stripA + 1 : stripA;          // an odd last strip is computed twice, stored once
+    const int x0A = stripA * P.strip_out, x0B = stripB * P.strip_out;
+    const int xcA = x0A - P.halo_cols + 4 * lane, xcB = x0B - P.halo_cols + 4 * lane;
+    int xwA = xcA % w, xwB = xcB % w;
+    if (xwA < 0) xwA += w;
+    if (xwB < 0) xwB += w;
+    const bool storeA = (xcA >= x0A) && (xcA < x0A + P.strip_out) && (xcA < w);
+    const bool storeB = haveB && (xcB >= x0B) && (xcB < x0B + P.strip_out) && (xcB < w);
+
+    const int y0 = chunk * P.chunk_rows;
+    const int L = min(P.chunk_rows, h - y0);
+    int ld_row = y0 - T;
+    if (P.wrap) {
+        ld_row %= h;
+        if (ld_row < 0) ld_row += h;
+    }
+    ld_row += P.y_base;
+    const int wrap_at = P.wrap ? h : 0x7fffffff;
+    const int n_steps = L + 2 * T;
+
+    float4 *my = &ring[warp][0][0][lane];
+    constexpr int SLOT_STRIDE = 4 * 32;
+
+    auto prefetch = [&](int s) {
+        if (s < n_steps) {
+            float4 *dst = my + (s & (RING_SLOTS - 1)) * SLOT_STRIDE;
+            const size_t row = (size_t)ld_row * w;
+            cp_async16(dst, P.in + row + xwA);
+            cp_async16(dst + 32, P.in + row + xwB);
+            cp_async16(dst + 64, P.rhs + row + xwA);
+            cp_async16(dst + 96, P.rhs + row + xwB);
+            ld_row = (ld_row + 1 == wrap_at) ? 0 : ld_row + 1;
+        }
+        cp_async_commit();
+    };
+#pragma unroll
+    for (int s = 0; s < PREFETCH; s++) prefetch(s);
+
+    float2 S[T][2][4];      // pressure rows: level, parity slot, cell; .x = strip A, .y = strip B
+    float2 Q[T][4];         // divergence rows s-T .. s-1; row r lives in Q[r mod T]
+#pragma unroll
+    for (int l = 0; l < T; l++)
+#pragma unroll
+        for (int c = 0; c < 4; c++) {
+            S[l][0][c] = S[l][1][c] = make_float2(0.f, 0.f);
+            Q[l][c] = make_float2(0.f, 0.f);
+        }
+    const float2 quarter2 = make_float2(0.25f, 0.25f);
+    const float2 nz2 = make_float2(P.neg_zero, P.neg_zero);
+
+    float *outA = P.out + (size_t)(P.y_base + y0) * w + xcA;
+    float *outB = P.out + (size_t)(P.y_base + y0) * w + xcB;
+
+    for (int sb = 0; sb < n_steps; sb += U) {
+#pragma unroll
+        for (int u = 0; u < U; u++) {
+            const int s = sb + u;
+            prefetch(s + PREFETCH);
+            cp_async_wait<PREFETCH>();
+            const float4 *slot = my + (s & (RING_SLOTS - 1)) * SLOT_STRIDE;
+            const float4 pa = slot[0], pb = slot[32], qa = slot[64], qb = slot[96];
+            float2 fresh[4] = {make_float2(pa.x, pb.x), make_float2(pa.y, pb.y), make_float2(pa.z, pb.z),
+                               make_float2(pa.w, pb.w)};
+            const float2 qnew[4] = {make_float2(qa.x, qb.x), make_float2(qa.y, qb.y), make_float2(qa.z, qb.z),
+                                    make_float2(qa.w, qb.w)};
+            const int older = u & 1;
+#pragma unroll
+            for (int l = 1; l <= T; l++) {
+                float2 o[4];
+                const float2 lft = shfl_up2(S[l - 1][older ^ 1][3]);
+                const float2 rgt = shfl_down2(S[l - 1][older ^ 1][0]);
+#pragma unroll
+                for (int c = 0; c < 4; c++) {
+                    const float2 pl = (c == 0) ? lft : S[l - 1][older ^ 1][c - 1];
+                    const float2 pr = (c == 3) ? rgt : S[l - 1][older ^ 1][c + 1];
+                    // fluid.cpp:249-255: ((((pL + pR) + pT) + pB) + 1.0f*b) / 4.0f
+                    float2 sum = add2(add2(add2(pl, pr), S[l - 1][older][c]), fresh[c]);
+                    sum = add2(sum, Q[(u - l + 2 * U * T) % T][c]);
+                    o[c] = mulc2(sum, quarter2, nz2);
+                }
+#pragma unroll
+                for (int c = 0; c < 4; c++) {
+                    S[l - 1][older][c] = fresh[c];
+                    fresh[c] = o[c];
+                }
+            }
+#pragma unroll
+            for (int c = 0; c < 4; c++) Q[u % T][c] = qnew[c];
+            const int orow = s - 2 * T;
+            if (orow >= 0 && orow < L) {
+                if (storeA)
+                    *reinterpret_cast<float4 *>(outA + (size_t)orow * w) =
+                        make_float4(fresh[0].x, fresh[1].x, fresh[2].x, fresh[3].x);
+                if (storeB)
+                    *reinterpret_cast<float4 *>(outB + (size_t)orow * w) =
+                        make_float4(fresh[0].y, fresh[1].y, fresh[2].y, fresh[3].y);
+            }
+        }
+    }
+    cp_async_wait<0>();
+}
+
+template <int T>
+int launch_pressure_packed_t(const PressurePackedParams &P, cudaStream_t s)
+{
+    const int total = P.n_pairs * P.n_chunks;
+    const unsigned blocks = (unsigned)((total + WARPS_PER_CTA - 1) / WARPS_PER_CTA);
+    constexpr int MINB = (T > 2) ? 2 : 3;
+    PFS_LAUNCH((pressure_packed_kernel<T, MINB>), blocks, WARPS_PER_CTA * 32, 0, s, P);
+    return PFS_OK;
+}
+
 template <int T>
 int launch_packed(const PackedParams &P, cudaStream_t s)
 {
@@ -391,6 +543,66 @@ int launch_diffuse_packed(float *a0, float *a1, float *b0, float *b1, const Swee
         PFS_TRY(launch_packed_depth(t, P, s));
         float *t0 = cur0, *t1 = cur1;
         cur0 = oth0; cur1 = oth1; oth0 = t0; oth1 = t1;
+        hops++;
+        left -= t;
+    }
+    *flips = hops;
+    return PFS_OK;
+}
+
+bool packed_pressure_supported(const SweepParams &p) { return (p.w % 4 == 0) && p.w >= 4 && p.h >= 1; }
+
+// n pressure sweeps, up to `depth` (even, <= 6) per launch, ping-ponging a <-> b; an odd remainder is one
+// plain sweep.
+int launch_pressure_packed(float *a, float *b, const float *rhs, const SweepParams &p, int n, int depth, int *flips,
+                           cudaStream_t s)
+{
+    static const int env_depth = env_int("PFS_PRESSURE_DEPTH", 0);
+    static const int env_rows = env_int("PFS_PRESSURE_ROWS", 0);
+    static const int env_warps = env_int("PFS_PRESSURE_WARPS_PER_SM", 0);
+    if (depth <= 0) depth = env_depth > 0 ? env_depth : 6;
+    if (depth > 8) depth = 8;
+    depth &= ~1;
+    int hops = 0;
+    float *cur = a, *oth = b;
+    int left = n;
+    while (left > 0) {
+        int t = (left >= depth) ? depth : (left & ~1);
+        if (depth < 2 || t < 2) {
+            int one = 0;
+            PFS_TRY(launch_sweeps_basic(SWEEP_PRESSURE, cur, cur, oth, oth, rhs, p, 1, &one, s));
+            t = 1;
+        } else {
+            PressurePackedParams P;
+            P.in = cur; P.out = oth; P.rhs = rhs;
+            P.w = p.w; P.h = p.h; P.y_base = p.y_base; P.wrap = p.wrap;
+            P.halo_cols = 4 * ((t + 3) / 4);
+            P.strip_out = 128 - 2 * P.halo_cols;
+            P.n_strips = (p.w + P.strip_out - 1) / P.strip_out;
+            P.n_pairs = (P.n_strips + 1) / 2;
+            const int warps_per_sm = env_warps > 0 ? env_warps : 8;
+            const long long slots = 148LL * warps_per_sm;
+            int rows = env_rows;
+            if (rows <= 0) {
+                long long chunks = slots / P.n_pairs;
+                if (chunks < 1) chunks = 1;
+                rows = (int)((p.h + chunks - 1) / chunks);
+                if (rows < 32) rows = 32;
+                if (rows > 256) rows = 256;
+            }
+            if (rows > p.h) rows = p.h;
+            P.chunk_rows = rows;
+            P.n_chunks = (p.h + rows - 1) / rows;
+            P.neg_zero = -0.0f;
+            switch (t) {
+            case 2: PFS_TRY(launch_pressure_packed_t<2>(P, s)); break;
+            case 4: PFS_TRY(launch_pressure_packed_t<4>(P, s)); break;
+            case 6: PFS_TRY(launch_pressure_packed_t<6>(P, s)); break;
+            case 8: PFS_TRY(launch_pressure_packed_t<8>(P, s)); break;
+            default: set_error("packed pressure: unsupported depth %d", t); return PFS_EINVAL;
+            }
+        }
+        std::swap(cur, oth);
         hops++;
         left -= t;
     }

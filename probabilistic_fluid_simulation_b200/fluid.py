@@ -167,8 +167,20 @@ def subtractPressureGradient(vp: vp_field, vp_out: vp_field, dt: float) -> None:
 # the two entry points the reference driver calls (main.cpp:222,225 / :236,239)
 # ------------------------------------------------------------------------------------------------
 
+def add_forces_stochastic(vp: vp_field, sigma: float, seed: int, step: int) -> None:
+    """Opt-in extension (not in the reference): vp ch0,1 += sigma * N(0,1), Philox-4x32-10 keyed by
+    `seed`, counter (cell, step).  See include/pfs_b200.h."""
+    L = _cabi.lib()
+    _check_buf(vp, "vp")
+    _require_device("add_forces_stochastic", vp)
+    with _dev_guard(vp.data):
+        check(L.pfs_add_forces_stochastic(vp.data.data_ptr(), sigma, seed, step, vp.x, vp.y, vp.z, _stream_of(vp.data)))
+
+
 def simulate_fluid_step(vp: vp_field, tmp: vp_field, dt: float, viscosity: float,
-                        n_diffuse: int = NUM_JACOBI_ITERS, n_pressure: int | None = None) -> None:
+                        n_diffuse: int = NUM_JACOBI_ITERS, n_pressure: int | None = None,
+                        sigma: float = 0.0, seed: int = 0, step: int = 0) -> None:
+    """sigma != 0 (device buffers only) adds the opt-in stochastic forcing at the addForces slot."""
     L = _cabi.lib()
     n_pressure = n_diffuse if n_pressure is None else n_pressure
     _check_buf(vp, "vp"); _check_buf(tmp, "tmp")
@@ -179,10 +191,17 @@ def simulate_fluid_step(vp: vp_field, tmp: vp_field, dt: float, viscosity: float
     if vp.on_device:
         h = _Handles(vp, tmp)
         with _dev_guard(vp.data):
-            check(L.pfs_simulate_fluid_step(h.ref(0), h.ref(1), dt, viscosity, vp.x, vp.y, vp.z,
-                                            n_diffuse, n_pressure, _stream_of(vp.data)))
+            if sigma != 0.0:
+                check(L.pfs_simulate_fluid_step_stochastic(h.ref(0), h.ref(1), dt, viscosity, vp.x, vp.y, vp.z,
+                                                           n_diffuse, n_pressure, sigma, seed, step,
+                                                           _stream_of(vp.data)))
+            else:
+                check(L.pfs_simulate_fluid_step(h.ref(0), h.ref(1), dt, viscosity, vp.x, vp.y, vp.z,
+                                                n_diffuse, n_pressure, _stream_of(vp.data)))
         h.commit()
     else:
+        if sigma != 0.0:
+            raise ValueError("the stochastic forcing is available on device buffers only")
         sv, st = _host_struct(vp), _host_struct(tmp)
         pairs = [(vp, sv), (tmp, st)]
         check(L.pfs_simulate_fluid_step_host(ctypes.byref(sv), ctypes.byref(st), dt, viscosity, n_diffuse, n_pressure))

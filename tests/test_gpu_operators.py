@@ -176,3 +176,61 @@ def test_diffuse_negative_viscosity_takes_the_exact_path():
     ra, rb = oracle.Oracle().diffuse(a, b, -0.01, 1.0, 7)
     assert_bit_equal(to_host(fa.data), ra, "diffuse vp")
     assert_bit_equal(to_host(fb.data), rb, "diffuse vp_out")
+
+
+def test_packed_pressure_kernel_opt_in(monkeypatch):
+    """The opt-in packed pressure kernel (PFS_PRESSURE_KERNEL=packed, read once per process) must be
+    bit-identical too: run it in a child process."""
+    import subprocess, sys, os
+    code = r'''
+import sys, numpy as np
+sys.path.insert(0, %r); sys.path.insert(0, %r)
+import oracle, probabilistic_fluid_simulation_b200 as pfs
+from gpu_util import to_dev, to_host
+rng = np.random.default_rng(77)
+a = rng.standard_normal((200, 512, 4)).astype(np.float32); b = rng.standard_normal((200, 512, 4)).astype(np.float32)
+for n in (7, 30, 31):
+    x, y = a.copy(), b.copy()
+    fa, fb = pfs.vp_field(to_dev(x)), pfs.vp_field(to_dev(y))
+    pfs.computePressure(fa, fb, 0.37, n)
+    ra, rb = oracle.Oracle().compute_pressure(x, y, 0.37, n)
+    assert np.array_equal(to_host(fa.data).view(np.uint32), ra.view(np.uint32)), n
+    assert np.array_equal(to_host(fb.data).view(np.uint32), rb.view(np.uint32)), n
+print("packed pressure ok")
+''' % (os.path.dirname(os.path.dirname(os.path.abspath(__file__))), os.path.dirname(os.path.abspath(__file__)))
+    env = dict(os.environ, PFS_PRESSURE_KERNEL="packed")
+    r = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, env=env, timeout=300)
+    assert r.returncode == 0 and "packed pressure ok" in r.stdout, r.stdout[-2000:] + r.stderr[-2000:]
+
+
+def test_step_is_cuda_graph_capturable():
+    """The device-pointer step only enqueues work on the caller's stream (no hidden synchronisation, no
+    allocation once the scratch planes exist), so a whole timestep can be captured into a CUDA graph; a
+    replay must give exactly what the eager calls give."""
+    import torch
+    h, w = 128, 256
+    vp, vt = rand_field(h, w, 61, 0.8), rand_field(h, w, 62, 0.5)
+    img = np.random.default_rng(63).random((h, w, 4)).astype(np.float32)
+
+    def fields():
+        return (pfs.vp_field(to_dev(vp)), pfs.vp_field(to_dev(vt)), pfs.vp_field(to_dev(img)),
+                pfs.vp_field(to_dev(np.zeros_like(img))))
+
+    ev, et, ei, em = fields()                       # eager (also sizes the library's scratch planes)
+    pfs.simulate_fluid_step(ev, et, 0.7, 0.01, 30, 30)
+    pfs.advect_color_step(ei, em, ev, 0.7)
+    torch.cuda.synchronize()
+
+    gv, gt, gi, gm = fields()                       # captured: nothing runs until replay
+    graph = torch.cuda.CUDAGraph()
+    side = torch.cuda.Stream()
+    side.wait_stream(torch.cuda.current_stream())
+    with torch.cuda.stream(side):
+        with torch.cuda.graph(graph, stream=side):
+            pfs.simulate_fluid_step(gv, gt, 0.7, 0.01, 30, 30)
+            pfs.advect_color_step(gi, gm, gv, 0.7)
+    graph.replay()
+    torch.cuda.synchronize()
+    assert_bit_equal(to_host(gv.data), to_host(ev.data), "graph vp")
+    assert_bit_equal(to_host(gt.data), to_host(et.data), "graph vtmp")
+    assert_bit_equal(to_host(gi.data), to_host(ei.data), "graph image")
