@@ -452,9 +452,12 @@ extern "C" int pfs_advect_color(const float *image, float *itmp, const float *vp
 // =============================================================================================
 // device-pointer step API
 // =============================================================================================
+// wait_tmp: optional event the stream must wait for before the first read of *tmp (its channel 2 is the
+// pressure warm start, first touched by the divergence kernel) -- lets pfs_timestep_host upload tmp while
+// advect and the diffusion sweeps already run on vp.
 static int simulate_fluid_step_impl(const char *fn, float **vp, float **tmp, float dt, float viscosity, int vx, int vy,
                                     int vz, int n_diffuse, int n_pressure, float sigma, unsigned long long seed,
-                                    unsigned step, void *stream)
+                                    unsigned step, void *stream, cudaEvent_t wait_tmp = nullptr)
 {
     PFS_TRY(check_dims(fn, vx, vy, vz));
     PFS_TRY(check_sweeps(fn, n_diffuse));
@@ -500,6 +503,7 @@ static int simulate_fluid_step_impl(const char *fn, float **vp, float **tmp, flo
         PFS_TRY(launch_stochastic_force(d_last.c0, d_last.c1, 1, sigma, seed, step, vx, vy, 0, 0, s));
     }
     // computePressure(vp -> tmp)  (fluid.cpp:303): divergence of iterate n_diffuse, p_0 = Bv.ch2
+    if (wait_tmp) PFS_CUDA(cudaStreamWaitEvent(s, wait_tmp, 0));
     {
         PhaseScope ph(PFS_PHASE_DIVERGENCE, s);
         PFS_TRY(launch_divergence(d_last.c0, d_last.c1, div, Bv, pa.c0, dt, vx, vy, s));
@@ -696,12 +700,20 @@ extern "C" int pfs_timestep_host(pfs_field *vp, pfs_field *vtmp, pfs_field *imag
     cudaStream_t s0 = sc->streams[0], s1 = sc->streams[1];
     float *dvp = sc->stage[0], *dtmp = sc->stage[1], *dimg = sc->stage[2], *ditmp = sc->stage[3];
 
-    // stream 0: velocity field up, fluid step.  stream 1: image up (overlaps the fluid step).
+    // PCIe is the bottleneck of this call (3 buffers up, 3 down), so the copies are ordered to keep both
+    // directions busy and the kernels hidden behind them:
+    //   stream 0: vp up | advect + diffusion (need only vp) | wait for vtmp | divergence .. project | vp, vtmp down
+    //   stream 1:          vtmp up | image up                | wait for the step | advect_color | image down
+    // The first read of vtmp (pressure warm start) waits for its upload through an event.
     PFS_CUDA(cudaMemcpyAsync(dvp, vp->data, nv * sizeof(float), cudaMemcpyHostToDevice, s0));
-    PFS_CUDA(cudaMemcpyAsync(dtmp, vtmp->data, nv * sizeof(float), cudaMemcpyHostToDevice, s0));
+    PFS_CUDA(cudaEventRecord(sc->ev[2], s0));
+    PFS_CUDA(cudaStreamWaitEvent(s1, sc->ev[2], 0));          // keep the H2D engine order vp, vtmp, image
+    PFS_CUDA(cudaMemcpyAsync(dtmp, vtmp->data, nv * sizeof(float), cudaMemcpyHostToDevice, s1));
+    PFS_CUDA(cudaEventRecord(sc->ev[0], s1));
     PFS_CUDA(cudaMemcpyAsync(dimg, image->data, ni * sizeof(float), cudaMemcpyHostToDevice, s1));
     float *a = dvp, *b = dtmp;
-    PFS_TRY(pfs_simulate_fluid_step(&a, &b, dt, viscosity, vp->x, vp->y, 4, n_diffuse, n_pressure, s0));
+    PFS_TRY(simulate_fluid_step_impl(fn, &a, &b, dt, viscosity, vp->x, vp->y, 4, n_diffuse, n_pressure, 0.0f, 0ull, 0u,
+                                     s0, sc->ev[0]));
     PFS_CUDA(cudaEventRecord(sc->ev[1], s0));
     float *hvp = vp->data, *htmp = vtmp->data;
     if (a != dvp) {
@@ -712,10 +724,10 @@ extern "C" int pfs_timestep_host(pfs_field *vp, pfs_field *vtmp, pfs_field *imag
     PFS_CUDA(cudaStreamWaitEvent(s1, sc->ev[1], 0));
     float *di = dimg, *dt2 = ditmp, *dv = a;
     PFS_TRY(pfs_advect_color_step(&di, &dt2, &dv, dt, image->x, image->y, 4, vp->x, vp->y, 4, s1));
-    PFS_CUDA(cudaMemcpyAsync(itmp->data, di, ni * sizeof(float), cudaMemcpyDeviceToHost, s1));
-    // stream 0: velocity post-state down (overlaps advect_color and the image download)
+    // stream 0: velocity post-state down (starts while the image is still going up / being advected)
     PFS_CUDA(cudaMemcpyAsync(vp->data, a, nv * sizeof(float), cudaMemcpyDeviceToHost, s0));
     PFS_CUDA(cudaMemcpyAsync(vtmp->data, b, nv * sizeof(float), cudaMemcpyDeviceToHost, s0));
+    PFS_CUDA(cudaMemcpyAsync(itmp->data, di, ni * sizeof(float), cudaMemcpyDeviceToHost, s1));
     PFS_CUDA(cudaStreamSynchronize(s0));
     PFS_CUDA(cudaStreamSynchronize(s1));
     float *t = image->data;     // fluid.cpp:317-319

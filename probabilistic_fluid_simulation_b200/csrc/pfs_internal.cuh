@@ -170,6 +170,7 @@ int launch_sweeps_basic(SweepOp op, float *a0, float *a1, float *b0, float *b1, 
 int launch_sweeps_fused(SweepOp op, float *a0, float *a1, float *b0, float *b1, const float *rhs,
                         const SweepParams &p, int n, int depth, int *flips, cudaStream_t s);
 bool fused_sweeps_supported(int w, int h);
+int pick_chunk_rows(int h, int columns_of_items, long long slots, int forced_rows);   // sweeps_packed.cu
 
 // Packed-FP32 (f32x2) temporally blocked diffusion: u and v advanced together (sweeps_packed.cu).
 bool packed_diffuse_supported(const SweepParams &p);

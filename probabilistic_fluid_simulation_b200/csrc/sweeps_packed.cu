@@ -29,6 +29,8 @@
 
 namespace pfs {
 
+int pick_chunk_rows(int h, int columns_of_items, long long slots, int forced_rows);
+
 namespace {
 
 constexpr int WARPS_PER_CTA = 4;
@@ -484,6 +486,25 @@ int env_int(const char *name, int dflt)
 
 }  // namespace
 
+// Rows per work item: every warp streams rows + 2T input rows for `rows` output rows, so chunks should be
+// tall; but there should also be about one resident wave of warps (`slots`), and all chunks should be the
+// same height (a short last chunk costs a whole extra wave).  -> as few chunks as fill the machine once,
+// equal heights, 32 <= rows <= 512.
+int pick_chunk_rows(int h, int columns_of_items, long long slots, int forced_rows)
+{
+    int rows = forced_rows;
+    if (rows <= 0) {
+        long long chunks = slots / (columns_of_items > 0 ? columns_of_items : 1);
+        if (chunks < 1) chunks = 1;
+        rows = (int)((h + chunks - 1) / chunks);
+        if (rows < 32) rows = 32;
+        if (rows > 512) rows = 512;
+    }
+    if (rows > h) rows = h;
+    const int n = (h + rows - 1) / rows;
+    return (h + n - 1) / n;            // equalise
+}
+
 void packed_release_device_buffers()
 {
     std::lock_guard<std::mutex> lock(g_flag_mutex);
@@ -524,17 +545,8 @@ int launch_diffuse_packed(float *a0, float *a1, float *b0, float *b1, const Swee
         // (2T halo rows are streamed per chunk) and never taller than 256
         const int warps_per_sm = env_warps > 0 ? env_warps : ((t > 4) ? 8 : 12);
         const long long slots = 148LL * warps_per_sm;
-        int rows = env_rows;
-        if (rows <= 0) {
-            long long chunks = slots / P.n_strips;
-            if (chunks < 1) chunks = 1;
-            rows = (int)((p.h + chunks - 1) / chunks);
-            if (rows < 32) rows = 32;
-            if (rows > 256) rows = 256;
-        }
-        if (rows > p.h) rows = p.h;
-        P.chunk_rows = rows;
-        P.n_chunks = (p.h + rows - 1) / rows;
+        P.chunk_rows = pick_chunk_rows(p.h, P.n_strips, slots, env_rows);
+        P.n_chunks = (p.h + P.chunk_rows - 1) / P.chunk_rows;
         P.alpha = p.alpha; P.beta = p.beta; P.rbeta = 1.0f / p.beta;
         P.guard_lo = 0x1p-96f;
         P.guard_hi_in = 0x1p60f;
@@ -582,17 +594,8 @@ int launch_pressure_packed(float *a, float *b, const float *rhs, const SweepPara
             P.n_pairs = (P.n_strips + 1) / 2;
             const int warps_per_sm = env_warps > 0 ? env_warps : 8;
             const long long slots = 148LL * warps_per_sm;
-            int rows = env_rows;
-            if (rows <= 0) {
-                long long chunks = slots / P.n_pairs;
-                if (chunks < 1) chunks = 1;
-                rows = (int)((p.h + chunks - 1) / chunks);
-                if (rows < 32) rows = 32;
-                if (rows > 256) rows = 256;
-            }
-            if (rows > p.h) rows = p.h;
-            P.chunk_rows = rows;
-            P.n_chunks = (p.h + rows - 1) / rows;
+            P.chunk_rows = pick_chunk_rows(p.h, P.n_pairs, slots, env_rows);
+            P.n_chunks = (p.h + P.chunk_rows - 1) / P.chunk_rows;
             P.neg_zero = -0.0f;
             switch (t) {
             case 2: PFS_TRY(launch_pressure_packed_t<2>(P, s)); break;
