@@ -791,7 +791,7 @@ extern "C" int pfs_slab_simulate_fluid_step(pfs_slab *const *slabs, int n_local,
         SweepParams p0 = proto;
         const bool packed = (op == SWEEP_DIFFUSE) && vec && packed_diffuse_supported(p0);
         const int user_depth = pfs_get_fuse_depth();
-        int depth = user_depth > 0 ? std::min(user_depth, MIN_HALO) : MIN_HALO;
+        int depth = user_depth > 0 ? std::min(user_depth, MIN_HALO) : (packed ? default_diffuse_depth() : MIN_HALO);
         if (!vec) depth = 1;
         auto one_pass = [&](int t) -> int {
             if (valid < t) {

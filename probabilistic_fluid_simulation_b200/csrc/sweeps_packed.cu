@@ -223,23 +223,37 @@ __global__ void __launch_bounds__(WARPS_PER_CTA * 32, MINB) diffuse_packed_kerne
                 for (int c = 0; c < 4; c++) in_max = max3abs(in_max, fresh[c].x, fresh[c].y);
             }
             const int older = u;
-#pragma unroll
-            for (int l = 1; l <= T; l++) {
-                float2 aC[4], aT[4], aB[4], o[4];
+            // Software pipeline over the levels: the part of level l+1 that only needs rows stored in
+            // earlier steps -- the alpha products of its centre and top rows, the lane shuffles and
+            // (aL + aR) + aT -- is issued before the tail of level l, which depends on the row level l-1
+            // has just produced.  Two independent instruction streams per warp instead of one.
+            float2 part[4], part_next[4];
+            auto prefix = [&](int l, float2(&dst)[4]) {
+                float2 aC[4], aT[4];
 #pragma unroll
                 for (int c = 0; c < 4; c++) {
                     aC[c] = mulc2(S[l - 1][older ^ 1][c], alpha2, nz2);   // alpha * centre row (s-l)
                     aT[c] = mulc2(S[l - 1][older][c], alpha2, nz2);       // alpha * top row (s-l-1)
-                    aB[c] = mulc2(fresh[c], alpha2, nz2);                 // alpha * bottom row (s-l+1)
                 }
-                const float2 aLft = shfl_up2(aC[3]);                  // alpha * (x-1) of cell 0
-                const float2 aRgt = shfl_down2(aC[0]);                // alpha * (x+1) of cell 3
+                const float2 aLft = shfl_up2(aC[3]);                      // alpha * (x-1) of cell 0
+                const float2 aRgt = shfl_down2(aC[0]);                    // alpha * (x+1) of cell 3
 #pragma unroll
                 for (int c = 0; c < 4; c++) {
                     const float2 lft = (c == 0) ? aLft : aC[c - 1];
                     const float2 rgt = (c == 3) ? aRgt : aC[c + 1];
-                    // fluid.cpp:175-182: (((aL + aR) + aT) + aB) + 1.0f*u_n
-                    float2 num = add2(add2(add2(add2(lft, rgt), aT[c]), aB[c]), S[l - 1][older ^ 1][c]);
+                    dst[c] = add2(add2(lft, rgt), aT[c]);                 // (aL + aR) + aT, fluid.cpp:175-182
+                }
+            };
+            prefix(1, part);
+#pragma unroll
+            for (int l = 1; l <= T; l++) {
+                float2 o[4];
+                if (l < T) prefix(l + 1, part_next);
+#pragma unroll
+                for (int c = 0; c < 4; c++) {
+                    const float2 aB = mulc2(fresh[c], alpha2, nz2);       // alpha * bottom row (s-l+1)
+                    // ... + aB) + 1.0f*u_n
+                    const float2 num = add2(add2(part[c], aB), S[l - 1][older ^ 1][c]);
                     if constexpr (EXACT) {
                         o[c] = make_float2(__fdiv_rn(num.x, beta), __fdiv_rn(num.y, beta));
                     } else {
@@ -251,6 +265,7 @@ __global__ void __launch_bounds__(WARPS_PER_CTA * 32, MINB) diffuse_packed_kerne
                 for (int c = 0; c < 4; c++) {
                     S[l - 1][older][c] = fresh[c];
                     fresh[c] = o[c];
+                    part[c] = part_next[c];
                 }
             }
             const int orow = s - 2 * T;
@@ -421,12 +436,11 @@ int launch_pressure_packed_t(const PressurePackedParams &P, cudaStream_t s)
     return PFS_OK;
 }
 
-template <int T>
-int launch_packed(const PackedParams &P, cudaStream_t s)
+template <int T, int MINB>
+int launch_packed_mb(const PackedParams &P, cudaStream_t s)
 {
     const int total = P.n_strips * P.n_chunks;
     const unsigned blocks = (unsigned)((total + WARPS_PER_CTA - 1) / WARPS_PER_CTA);
-    constexpr int MINB = (T > 4) ? 2 : 3;
     PFS_CUDA(cudaMemsetAsync(P.flags, 0, (size_t)total * sizeof(int), s));
     PFS_LAUNCH((diffuse_packed_kernel<T, false, MINB>), blocks, WARPS_PER_CTA * 32, 0, s, P);
     PFS_LAUNCH((diffuse_packed_kernel<T, true, MINB>), blocks, WARPS_PER_CTA * 32, 0, s, P);
@@ -434,17 +448,30 @@ int launch_packed(const PackedParams &P, cudaStream_t s)
     return PFS_OK;
 }
 
-int launch_packed_depth(int t, const PackedParams &P, cudaStream_t s)
+// resident CTAs per SM the kernel is compiled for (register cap 65536 / (128 * MINB)): depth <= 4 fits
+// three CTAs (12 warps/SM) without spilling, deeper passes get two (8 warps/SM, up to 255 registers)
+constexpr int packed_minb(int t) { return t > 4 ? 2 : 3; }
+
+template <int T>
+int launch_packed(const PackedParams &P, int minb, cudaStream_t s)
+{
+    if constexpr (T == 5 || T == 6) {
+        if (minb == 3) return launch_packed_mb<T, 3>(P, s);
+    }
+    return launch_packed_mb<T, packed_minb(T)>(P, s);
+}
+
+int launch_packed_depth(int t, const PackedParams &P, int minb, cudaStream_t s)
 {
     switch (t) {
-    case 1: return launch_packed<1>(P, s);
-    case 2: return launch_packed<2>(P, s);
-    case 3: return launch_packed<3>(P, s);
-    case 4: return launch_packed<4>(P, s);
-    case 5: return launch_packed<5>(P, s);
-    case 6: return launch_packed<6>(P, s);
-    case 7: return launch_packed<7>(P, s);
-    case 8: return launch_packed<8>(P, s);
+    case 1: return launch_packed<1>(P, minb, s);
+    case 2: return launch_packed<2>(P, minb, s);
+    case 3: return launch_packed<3>(P, minb, s);
+    case 4: return launch_packed<4>(P, minb, s);
+    case 5: return launch_packed<5>(P, minb, s);
+    case 6: return launch_packed<6>(P, minb, s);
+    case 7: return launch_packed<7>(P, minb, s);
+    case 8: return launch_packed<8>(P, minb, s);
     default: set_error("packed diffusion: unsupported depth %d", t); return PFS_EINVAL;
     }
 }
@@ -521,14 +548,19 @@ bool packed_diffuse_supported(const SweepParams &p)
     return (p.w % 4 == 0) && p.w >= 4 && p.h >= 1 && p.alpha >= 0.f && p.beta >= 1.f && p.beta <= 0x1p20f;
 }
 
+int default_diffuse_depth()
+{
+    static const int d = env_int("PFS_DIFFUSE_DEPTH", 0);
+    return (d > 0 && d <= 8) ? d : 6;      // measured best at 4096^2 (profiles/r01_tuning.md)
+}
+
 // n diffusion sweeps, up to `depth` per launch, ping-ponging (a0,a1) <-> (b0,b1).
 int launch_diffuse_packed(float *a0, float *a1, float *b0, float *b1, const SweepParams &p, int n, int depth,
                           int *flips, cudaStream_t s)
 {
-    static const int env_depth = env_int("PFS_DIFFUSE_DEPTH", 0);
     static const int env_rows = env_int("PFS_DIFFUSE_ROWS", 0);
     static const int env_warps = env_int("PFS_DIFFUSE_WARPS_PER_SM", 0);
-    if (depth <= 0) depth = env_depth > 0 ? env_depth : 8;
+    if (depth <= 0) depth = default_diffuse_depth();
     if (depth > 8) depth = 8;
     int hops = 0;
     float *cur0 = a0, *cur1 = a1, *oth0 = b0, *oth1 = b1;
@@ -543,7 +575,9 @@ int launch_diffuse_packed(float *a0, float *a1, float *b0, float *b1, const Swee
         P.n_strips = (p.w + P.strip_out - 1) / P.strip_out;
         // chunk height: one resident wave of warps if the grid allows it, never shorter than 32 rows
         // (2T halo rows are streamed per chunk) and never taller than 256
-        const int warps_per_sm = env_warps > 0 ? env_warps : ((t > 4) ? 8 : 12);
+        static const int env_minb = env_int("PFS_DIFFUSE_MINB", 0);
+        const int minb = (env_minb == 3 && (t == 5 || t == 6)) ? 3 : packed_minb(t);
+        const int warps_per_sm = env_warps > 0 ? env_warps : 4 * minb;
         const long long slots = 148LL * warps_per_sm;
         P.chunk_rows = pick_chunk_rows(p.h, P.n_strips, slots, env_rows);
         P.n_chunks = (p.h + P.chunk_rows - 1) / P.chunk_rows;
@@ -552,7 +586,7 @@ int launch_diffuse_packed(float *a0, float *a1, float *b0, float *b1, const Swee
         P.guard_hi_in = 0x1p60f;
         P.neg_zero = -0.0f;
         PFS_TRY(get_flags((size_t)P.n_strips * P.n_chunks, &P.flags));
-        PFS_TRY(launch_packed_depth(t, P, s));
+        PFS_TRY(launch_packed_depth(t, P, minb, s));
         float *t0 = cur0, *t1 = cur1;
         cur0 = oth0; cur1 = oth1; oth0 = t0; oth1 = t1;
         hops++;
