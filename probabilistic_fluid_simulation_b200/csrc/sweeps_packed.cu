@@ -516,7 +516,8 @@ int env_int(const char *name, int dflt)
 // Rows per work item: every warp streams rows + 2T input rows for `rows` output rows, so chunks should be
 // tall; but there should also be about one resident wave of warps (`slots`), and all chunks should be the
 // same height (a short last chunk costs a whole extra wave).  -> as few chunks as fill the machine once,
-// equal heights, 32 <= rows <= 512.
+// equal heights, 8 <= rows <= 512 (small grids cannot fill the machine with tall chunks: there parallelism
+// beats halo overhead, 1024^2 runs 1.6x faster with 9-row chunks than with 32-row ones).
 int pick_chunk_rows(int h, int columns_of_items, long long slots, int forced_rows)
 {
     int rows = forced_rows;
@@ -524,7 +525,7 @@ int pick_chunk_rows(int h, int columns_of_items, long long slots, int forced_row
         long long chunks = slots / (columns_of_items > 0 ? columns_of_items : 1);
         if (chunks < 1) chunks = 1;
         rows = (int)((h + chunks - 1) / chunks);
-        if (rows < 32) rows = 32;
+        if (rows < 8) rows = 8;
         if (rows > 512) rows = 512;
     }
     if (rows > h) rows = h;

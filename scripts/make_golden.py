@@ -45,6 +45,10 @@ PNGS = {
     "png_voronoi_256": "velocity_fields/voronoi/T0/VoronoiRG_256.png",
     "png_circular_128": "velocity_fields/functions/T3/CircularFields_128.png",
     "png_solid_r64": "velocity_fields/solid/T0/R64.png",
+    "png_peppers": "images/peppers.png",
+    "png_checker16_1024": "images/Checker16_1024.png",
+    "png_perlin_t1_512": "velocity_fields/perlin/T1/PerlinRG_512.png",
+    "png_ramp_t0_1024": "velocity_fields/ramps/T0/RampRG_1024.png",
 }
 
 
@@ -62,6 +66,17 @@ CASES = [
     ("tulips_voronoi_100", _png("png_voronoi_256", "png_tulips"), 10.0, 0.001, 30, 100),
     ("baboon_circular_100", _png("png_circular_128", "png_baboon"), 0.1, 0.0, 30, 100),
     ("perlin64_solid64_dt10", _png("png_perlin_t0_64", "png_solid_r64"), 10.0, 0.001, 30, 20),
+    # BASELINE configs[0] (SURVEY.md 8d "Config 1"): the five bundled pairs at native resolution, 100 steps,
+    # dt in {0.1, 10} x nu in {0, 0.001}, N = 30.  "heavy": checked on the GPU only (the CPU suite skips them).
+    ("cfg1_baboon_perlin256_dt0.1_nu0", _png("png_perlin_t0_256", "png_baboon"), 0.1, 0.0, 30, 100),
+    ("cfg1_baboon_perlin256_dt10_nu0.001", _png("png_perlin_t0_256", "png_baboon"), 10.0, 0.001, 30, 100),
+    ("cfg1_baboon_perlin256_dt10_nu0", _png("png_perlin_t0_256", "png_baboon"), 10.0, 0.0, 30, 100),
+    ("cfg1_peppers_perlin512_dt0.1_nu0.001", _png("png_perlin_t1_512", "png_peppers"), 0.1, 0.001, 30, 100),
+    ("cfg1_peppers_perlin512_dt10_nu0", _png("png_perlin_t1_512", "png_peppers"), 10.0, 0.0, 30, 100),
+    ("cfg1_checker_ramp1024_dt0.1_nu0.001", _png("png_ramp_t0_1024", "png_checker16_1024"), 0.1, 0.001, 30, 100),
+    ("cfg1_checker_ramp1024_dt10_nu0", _png("png_ramp_t0_1024", "png_checker16_1024"), 10.0, 0.0, 30, 100),
+    ("cfg1_tulips_voronoi_dt0.1_nu0", _png("png_voronoi_256", "png_tulips"), 0.1, 0.0, 30, 100),
+    ("cfg1_baboon_circular_dt10_nu0.001", _png("png_circular_128", "png_baboon"), 10.0, 0.001, 30, 100),
     ("n1", {"kind": "formula", "vel_hw": [40, 48], "img_hw": [60, 96]}, 10.0, 0.05, 1, 4),
     ("n2", {"kind": "formula", "vel_hw": [40, 48], "img_hw": [60, 96]}, 10.0, 0.05, 2, 4),
     ("n3", {"kind": "formula", "vel_hw": [40, 48], "img_hw": [60, 96]}, 10.0, 0.05, 3, 4),
@@ -111,7 +126,7 @@ def main():
         t0 = time.time()
         hashes, sums = run_case(spec, dt, visc, n, steps)
         cases.append({"name": name, "inputs": spec, "dt": dt, "viscosity": visc, "n_iters": n, "steps": steps,
-                      "hashes": hashes, "sums": sums})
+                      "heavy": bool(time.time() - t0 > 12.0), "hashes": hashes, "sums": sums})
         print(f"{name:24s} N={n:3d} steps={steps:3d}  {time.time() - t0:6.1f}s  vp.u={hashes['vp'][0]}")
     doc = {"generator": "scripts/make_golden.py", "source": "oracle/_ref (unmodified reference src/fluid.cpp)",
            "hash": "64-bit FNV-1a over the 32-bit words of one channel, row-major (SURVEY.md 4.4)",

@@ -28,7 +28,9 @@ def test_golden_file_agrees_with_survey_pins():
         assert CASES[name]["hashes"] == pins, name
 
 
-@pytest.mark.parametrize("name", list(CASES))
+# "heavy" cases (>12 s of single-core CPU time when generated) are checked against the reference hashes by
+# the GPU suite only; the CPU suite keeps to the light ones so that it finishes within a few minutes.
+@pytest.mark.parametrize("name", [n for n, c in CASES.items() if not c.get("heavy")])
 def test_oracle_reproduces_reference_hashes(name):
     c = CASES[name]
     vp, vtmp, image, itmp = case_state(c)
