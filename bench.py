@@ -243,27 +243,68 @@ def run_single_gpu(args):
         step()
     torch.cuda.synchronize()
 
+    graph = None
+    if args.graph:
+        # Two timesteps per graph: the image/itmp exchange of advect_color_step returns to the captured
+        # pointers after an even number of steps (vp/tmp are never exchanged for equal sweep parities).
+        if args.steps % 2:
+            args.steps += 1
+        graph = torch.cuda.CUDAGraph()
+        side = torch.cuda.Stream()
+        side.wait_stream(torch.cuda.current_stream())
+        with torch.cuda.stream(side):
+            with torch.cuda.graph(graph, stream=side):
+                step()
+                step()
+        torch.cuda.synchronize()
+        graph.replay()
+        torch.cuda.synchronize()
+
     # ---- timed region: K steps, device-resident inputs, CUDA events on the launching stream ----
+    # (the library replays its cached step graph here; per-phase events would force it to launch eagerly,
+    #  so the per-phase / per-kernel figures come from a second region right after, see below)
     sampler = ClockSampler(0)
     sampler.start()
     time.sleep(0.12)          # let nvidia-smi deliver its first sample before the (short) timed region
-    pfs.phase_timing(True)
-    pfs.phase_times(reset=True)
     l0 = pfs.kernel_launch_count()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     torch.cuda.synchronize()
     t_begin = time.perf_counter()
     e0.record()
-    for _ in range(args.steps):
-        step()
+    if graph is None:
+        for _ in range(args.steps):
+            step()
+    else:
+        for _ in range(args.steps // 2):
+            graph.replay()
     e1.record()
     torch.cuda.synchronize()
     t_end = time.perf_counter()
     ms_total = e0.elapsed_time(e1)
     launches = pfs.kernel_launch_count() - l0
+    if graph is not None:       # an outer torch graph replays without going through the library's counter
+        l1 = pfs.kernel_launch_count()
+        step(); step()
+        torch.cuda.synchronize()
+        launches = (pfs.kernel_launch_count() - l1) * (args.steps // 2)
+    clocks = sampler.stop(t_begin, t_end)
+
+    # ---- second region: the same steps with per-phase CUDA events on the launching stream (eager launches) ----
+    phase_steps = max(2, min(args.steps, 20))
+    pfs.phase_timing(True)
+    pfs.phase_times(reset=True)
+    p0, p1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    torch.cuda.synchronize()
+    p0.record()
+    for _ in range(phase_steps):
+        step()
+    p1.record()
+    torch.cuda.synchronize()
+    ms_step_eager = p0.elapsed_time(p1) / phase_steps
     phase_ms, phase_launches = pfs.phase_times(reset=True)
     pfs.phase_timing(False)
-    clocks = sampler.stop(t_begin, t_end)
+    phase_ms = {k: v * args.steps / phase_steps for k, v in phase_ms.items()}            # scaled to K steps
+    phase_launches = {k: v * args.steps / phase_steps for k, v in phase_launches.items()}
     ms_step = ms_total / args.steps
     value = cells * n / (ms_step * 1e-3)
 
@@ -279,14 +320,14 @@ def run_single_gpu(args):
             gbs = bytes_per_launch / (per_phase[phase] / nl * 1e-3) / 1e9
             kernels[phase] = {"launches_per_step": nl, "avg_launch_ms": per_phase[phase] / nl,
                               "sweeps_per_launch": sweeps / nl, "alg_bytes_per_launch": bytes_per_launch,
-                              "achieved_gbs": gbs, "frac": gbs / peak, "share_of_step": per_phase[phase] / ms_step}
+                              "achieved_gbs": gbs, "frac": gbs / peak, "share_of_step": per_phase[phase] / ms_step_eager}
     for phase, key in (("advect", "advect"), ("divergence", "divergence"), ("project", "project"),
                        ("advect_color", "advect_color")):
         if per_phase[phase] > 0:
             gbs = BYTES[key] * cells / (per_phase[phase] * 1e-3) / 1e9
             kernels[phase] = {"launches_per_step": phase_launches[phase] / args.steps, "avg_launch_ms": per_phase[phase],
                               "alg_bytes_per_launch": BYTES[key] * cells, "achieved_gbs": gbs, "frac": gbs / peak,
-                              "share_of_step": per_phase[phase] / ms_step}
+                              "share_of_step": per_phase[phase] / ms_step_eager}
     dom = max(kernels, key=lambda k: kernels[k]["share_of_step"])
     traffic = None
     tpath = os.path.join(ROOT, "profiles", "traffic.json")
@@ -345,7 +386,11 @@ def run_single_gpu(args):
             "clocks": clocks, "whole_step_roofline": whole_step,
             "pressure_solve": {"ms": per_phase["pressure"], "cell_updates_per_s": cells * n / (per_phase["pressure"] * 1e-3)},
             "cell_steps_per_s": cells / (ms_step * 1e-3), "phases_ms": per_phase, "kernels": kernels,
-            "fuse_depth": depth, "fluid_cu_baseline": refcu}
+            "fuse_depth": depth, "fluid_cu_baseline": refcu,
+            "launch_mode": ("torch CUDA graph of two timesteps (--graph)" if graph is not None else
+                            "library step graph: the 2nd identical pfs_simulate_fluid_step call is captured, later "
+                            "calls replay it (PFS_STEP_GRAPH=0 disables)"),
+            "phase_region": {"steps": phase_steps, "ms_per_step_eager_with_phase_events": ms_step_eager}}
     print(json.dumps(line), flush=True)
 
 
@@ -359,6 +404,8 @@ def main():
     ap.add_argument("--height", type=int, default=0)
     ap.add_argument("--iters", type=int, default=100)
     ap.add_argument("--fuse-depth", type=int, default=None)
+    ap.add_argument("--graph", action="store_true",
+                    help="replay the timed steps from a CUDA graph of two captured timesteps (small, launch-bound grids)")
     ap.add_argument("--no-e2e", action="store_true", help="skip the host-buffer end-to-end leg (tuning runs)")
     ap.add_argument("--no-cpu", action="store_true", help="skip the CPU baseline leg (tuning runs)")
     args = ap.parse_args()

@@ -150,7 +150,14 @@ __global__ void __launch_bounds__(WARPS_PER_CTA * 32, MINB) diffuse_packed_kerne
     const int item = blockIdx.x * WARPS_PER_CTA + warp;
     if (item >= P.n_strips * P.n_chunks) return;          // whole warp leaves together
     if constexpr (EXACT) {
-        if (P.flags[item] == 0) return;                   // repair launch: only flagged items
+        // repair launch: only flagged items.  It also clears the flag, so the buffer is all zero again when
+        // the next pass starts (no memset launch per pass).
+        int f = 0;
+        if (lane == 0) {
+            f = P.flags[item];
+            if (f) P.flags[item] = 0;
+        }
+        if (__shfl_sync(0xffffffffu, f, 0) == 0) return;
     }
     const int strip = item % P.n_strips;
     const int chunk = item / P.n_strips;
@@ -441,7 +448,6 @@ int launch_packed_mb(const PackedParams &P, cudaStream_t s)
 {
     const int total = P.n_strips * P.n_chunks;
     const unsigned blocks = (unsigned)((total + WARPS_PER_CTA - 1) / WARPS_PER_CTA);
-    PFS_CUDA(cudaMemsetAsync(P.flags, 0, (size_t)total * sizeof(int), s));
     PFS_LAUNCH((diffuse_packed_kernel<T, false, MINB>), blocks, WARPS_PER_CTA * 32, 0, s, P);
     PFS_LAUNCH((diffuse_packed_kernel<T, true, MINB>), blocks, WARPS_PER_CTA * 32, 0, s, P);
     --g_passes;     // the repair launch belongs to the same pass
@@ -499,6 +505,7 @@ int get_flags(size_t n, int **out)
         }
         size_t want = n < 16384 ? 16384 : 2 * n;
         PFS_CUDA(cudaMalloc((void **)&fb.ptr, want * sizeof(int)));
+        PFS_CUDA(cudaMemset(fb.ptr, 0, want * sizeof(int)));   // flags stay zero between passes: the repair kernel clears what it consumes
         fb.n = want;
     }
     *out = fb.ptr;
