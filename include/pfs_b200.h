@@ -21,7 +21,8 @@
  * the two caller buffers ends up holding which iterate, and whether the caller's two pointers
  * end up exchanged, is exactly what the reference's loops would produce.
  *
- * Threading: one host thread per device at a time (the library keeps per-device scratch).
+ * Threading: one host thread and one in-flight step per device at a time (the library keeps per-device
+ * scratch planes, a per-device guard-flag buffer and a cache of step graphs; none of it is locked).
  * Streams: every device-pointer entry point takes a `stream` (a cudaStream_t passed as void*;
  * NULL = the legacy default stream, which is what the reference driver uses) and only enqueues
  * work on it -- no hidden synchronisation.  Host-buffer entry points synchronise before return.
@@ -64,7 +65,8 @@ int pfs_version(void);
 const char *pfs_last_error(void);
 /* Number of kernels this library has launched in the calling process (bench.py gpu_launches). */
 uint64_t pfs_kernel_launch_count(void);
-/* Frees all per-device scratch.  Optional; also runs at process exit. */
+/* Frees all per-device scratch, cached step graphs and internal streams.  Optional: the driver releases
+ * everything at process exit anyway. */
 int pfs_shutdown(void);
 /* Tuning knob for tests/benchmarks: maximum number of Jacobi sweeps fused per kernel launch
  * (temporal blocking depth).  0 = library default.  1 = one sweep per launch.  Results are
@@ -87,7 +89,11 @@ int pfs_host_free(void *ptr);
  * at [u_projected, v_projected, p_{N-1}, divergence] and *tmp at [u_diffused, v_diffused, p_N,
  * divergence]; the two pointers are exchanged iff the reference's loops would exchange them
  * (never when n_diffuse and n_pressure have the same parity).  tmp's channel 2 is the warm start
- * of the pressure solve (main.cpp:188-195 initialises it to -1). */
+ * of the pressure solve (main.cpp:188-195 initialises it to -1).
+ * Launch behaviour: the call only enqueues work on `stream`.  When it is repeated with identical arguments
+ * (the reference driver's loop, main.cpp:219-226) the library captures the kernel sequence into a CUDA graph
+ * on the second call and replays that graph on `stream` afterwards (PFS_STEP_GRAPH=0 disables this); a
+ * caller that is itself capturing `stream` gets plain launches, so the step can be part of a user graph. */
 int pfs_simulate_fluid_step(float **vp, float **tmp, float dt, float viscosity,
                             int vx, int vy, int vz, int n_diffuse, int n_pressure, void *stream);
 
