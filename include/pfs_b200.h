@@ -184,6 +184,15 @@ int pfs_slab_advect_color_step(pfs_slab *const *slabs, int n_local, float **imag
 /* Synchronises and reports an internal halo overflow (a bug, never expected). */
 int pfs_slab_check(pfs_slab *const *slabs, int n_local);
 
+/* ---- step diagnostics (not in the reference: it runs a fixed sweep count, no convergence test) ---- */
+/* From the two post-state buffers of pfs_simulate_fluid_step (*vp = [u, v, p_{N-1}, div], *tmp = [.., p_N, ..]):
+ * out = { ||div||_2, ||p_N - p_{N-1}||_2 (the last Jacobi update, a residual proxy), ||(u,v)||_2, max(|u|,|v|) }.
+ * Warp-shuffle + fixed-order block reduction in double; synchronises `stream`.  The slab variant all-reduces
+ * over the ring (NCCL) and returns the norms of the whole grid on every rank. */
+int pfs_step_norms(const float *vp, const float *tmp, int vx, int vy, int vz, double out[4], void *stream);
+int pfs_slab_step_norms(pfs_slab *const *slabs, int n_local, float *const *vp, float *const *tmp, double out[4],
+                        void *const *streams);
+
 /* ---- phase timing (diagnostics for bench.py; not on the reference's surface) --------------- */
 /* When enabled, pfs_simulate_fluid_step / pfs_advect_color_step bracket each phase with CUDA
  * events on the caller's stream.  pfs_phase_times() synchronises those events and returns the

@@ -341,6 +341,61 @@ __global__ void __launch_bounds__(256)
     v[o] = __fadd_rn(v[o], __fmul_rn(sigma, gv));
 }
 
+// ---------------------------------------------------------------------------------------------
+// Step diagnostics (not in the reference, which runs a fixed sweep count with no convergence test,
+// fluid.cpp:239): from the two post-state buffers of simulate_fluid_step,
+//   [0] sum div^2          (vp ch3)                 [1] sum (p_N - p_{N-1})^2  (tmp ch2 - vp ch2)
+//   [2] sum (u^2 + v^2)    (vp ch0,1, projected)    [3] max(|u|, |v|)
+// Warp-shuffle tree + one partial per block (double), then a single block folds the partials in a fixed
+// order, so the result does not depend on scheduling.
+// ---------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256)
+    norms_partial_kernel(const float4 *__restrict__ vp, const float4 *__restrict__ tmp, size_t n, double *partials)
+{
+    double s0 = 0.0, s1 = 0.0, s2 = 0.0;
+    float m = 0.f;
+    for (size_t i = (size_t)blockIdx.x * 256 + threadIdx.x; i < n; i += (size_t)gridDim.x * 256) {
+        const float4 a = __ldg(vp + i), b = __ldg(tmp + i);
+        s0 += (double)a.w * (double)a.w;
+        const double r = (double)b.z - (double)a.z;
+        s1 += r * r;
+        s2 += (double)a.x * (double)a.x + (double)a.y * (double)a.y;
+        m = fmaxf(m, fmaxf(fabsf(a.x), fabsf(a.y)));
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        s0 += __shfl_xor_sync(0xffffffffu, s0, o);
+        s1 += __shfl_xor_sync(0xffffffffu, s1, o);
+        s2 += __shfl_xor_sync(0xffffffffu, s2, o);
+        m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, o));
+    }
+    __shared__ double sh[8][4];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    if (lane == 0) {
+        sh[warp][0] = s0; sh[warp][1] = s1; sh[warp][2] = s2; sh[warp][3] = (double)m;
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        double t0 = 0, t1 = 0, t2 = 0, t3 = 0;
+        for (int q = 0; q < 8; q++) {
+            t0 += sh[q][0]; t1 += sh[q][1]; t2 += sh[q][2]; t3 = fmax(t3, sh[q][3]);
+        }
+        double *o = partials + 4 * (size_t)blockIdx.x;
+        o[0] = t0; o[1] = t1; o[2] = t2; o[3] = t3;
+    }
+}
+
+__global__ void norms_final_kernel(const double *partials, int nblocks, double *out)
+{
+    if (threadIdx.x != 0 || blockIdx.x != 0) return;
+    double t0 = 0, t1 = 0, t2 = 0, t3 = 0;
+    for (int q = 0; q < nblocks; q++) {
+        t0 += partials[4 * q + 0]; t1 += partials[4 * q + 1]; t2 += partials[4 * q + 2];
+        t3 = fmax(t3, partials[4 * q + 3]);
+    }
+    out[0] = t0; out[1] = t1; out[2] = t2; out[3] = t3;
+}
+
 inline bool vec4_ok(int w, const void *a, const void *b = nullptr, const void *c = nullptr, const void *d = nullptr,
                     const void *e = nullptr, const void *f = nullptr)
 {
@@ -434,6 +489,18 @@ int launch_subtract_gradient_aos(const float *vp_aos, float *out_aos, float dt, 
     dim3 block(64, 4), grid((w + 63) / 64, (h + 3) / 4);
     PFS_LAUNCH(subtract_gradient_aos_kernel, grid, block, 0, s, reinterpret_cast<const float4 *>(vp_aos), out_aos, dt,
                w, h);
+    return PFS_OK;
+}
+
+int launch_step_norms(const float *vp_aos, const float *tmp_aos, size_t cells, double *partials, int max_blocks,
+                      double *out4, cudaStream_t s)
+{
+    int blocks = (int)((cells + 255) / 256);
+    if (blocks > max_blocks) blocks = max_blocks;
+    if (blocks < 1) blocks = 1;
+    PFS_LAUNCH(norms_partial_kernel, blocks, 256, 0, s, reinterpret_cast<const float4 *>(vp_aos),
+               reinterpret_cast<const float4 *>(tmp_aos), cells, partials);
+    PFS_LAUNCH(norms_final_kernel, 1, 32, 0, s, partials, blocks, out4);
     return PFS_OK;
 }
 

@@ -1,6 +1,7 @@
 // pfs_api.cu -- the C-ABI of libpfs_b200.so (include/pfs_b200.h): argument validation, per-device
 // planar scratch, the buffer-pointer choreography of the reference (fluid.cpp:188-194, 260-265,
 // 298-305) and the sequencing of the kernels in kernels_basic.cu / sweeps_fused.cu.
+#include <math.h>
 #include <stdarg.h>
 #include <stdlib.h>
 #include <string.h>
@@ -689,6 +690,35 @@ extern "C" int pfs_add_forces_stochastic(float *vp, float sigma, uint64_t seed, 
     PFS_TRY(check_ptr(fn, "vp", vp));
     if (sigma == 0.0f) return PFS_OK;
     return launch_stochastic_force(vp, vp + 1, 4, sigma, seed, step, vx, vy, 0, 0, (cudaStream_t)stream);
+}
+
+extern "C" int pfs_step_norms(const float *vp, const float *tmp, int vx, int vy, int vz, double out[4], void *stream)
+{
+    const char *fn = "pfs_step_norms";
+    PFS_TRY(check_dims(fn, vx, vy, vz));
+    PFS_TRY(check_ptr(fn, "vp", vp));
+    PFS_TRY(check_ptr(fn, "tmp", tmp));
+    if (!out) {
+        set_error("%s: out is null", fn);
+        return PFS_EINVAL;
+    }
+    cudaStream_t s = (cudaStream_t)stream;
+    constexpr int kBlocks = 1184;
+    double *scratch = nullptr;
+    PFS_CUDA(cudaMalloc((void **)&scratch, (4 * (size_t)kBlocks + 4) * sizeof(double)));
+    int rc = launch_step_norms(vp, tmp, (size_t)vx * vy, scratch, kBlocks, scratch + 4 * (size_t)kBlocks, s);
+    double host[4] = {0, 0, 0, 0};
+    cudaError_t e = cudaSuccess;
+    if (rc == PFS_OK) e = cudaMemcpyAsync(host, scratch + 4 * (size_t)kBlocks, sizeof(host), cudaMemcpyDeviceToHost, s);
+    if (rc == PFS_OK && e == cudaSuccess) e = cudaStreamSynchronize(s);
+    cudaFree(scratch);
+    if (rc != PFS_OK) return rc;
+    if (e != cudaSuccess) return cuda_fail(e, "pfs_step_norms", __FILE__, __LINE__);
+    out[0] = sqrt(host[0]);
+    out[1] = sqrt(host[1]);
+    out[2] = sqrt(host[2]);
+    out[3] = host[3];
+    return PFS_OK;
 }
 
 extern "C" int pfs_advect_color_step(float **image, float **itmp, float **vp, float dt, int ix, int iy, int iz, int vx,

@@ -699,6 +699,67 @@ extern "C" int pfs_slab_check(pfs_slab *const *slabs, int n_local)
 }
 
 // ---------------------------------------------------------------------------------------------
+// Step diagnostics over the whole ring: local partial sums (kernels_basic.cu), then all-reduce across the
+// ranks (NCCL sum / max, or a host fold for slabs living in this process).
+// out = {||div||_2, ||p_N - p_{N-1}||_2, ||(u,v)||_2, max(|u|,|v|)} of the WHOLE grid, the same on every rank.
+// ---------------------------------------------------------------------------------------------
+extern "C" int pfs_slab_step_norms(pfs_slab *const *slabs, int n_local, float *const *vp, float *const *tmp,
+                                   double out[4], void *const *streams)
+{
+    const char *fn = "pfs_slab_step_norms";
+    std::vector<pfs_slab *> L;
+    PFS_TRY(check_local(fn, slabs, n_local, &L));
+    if (!vp || !tmp || !out) {
+        set_error("%s: null argument", fn);
+        return PFS_EINVAL;
+    }
+    constexpr int kBlocks = 1184;
+    double sums[3] = {0, 0, 0}, mx = 0;
+    std::vector<double *> scratch(n_local, nullptr);
+    int rc = PFS_OK;
+    for (int k = 0; k < n_local && rc == PFS_OK; k++) {
+        pfs_slab *s = L[k];
+        Guard g(s->device);
+        s->stream = streams ? (cudaStream_t)streams[k] : nullptr;
+        if (cudaMalloc((void **)&scratch[k], (4 * (size_t)kBlocks + 4) * sizeof(double)) != cudaSuccess) {
+            rc = cuda_fail(cudaGetLastError(), "cudaMalloc", __FILE__, __LINE__);
+            break;
+        }
+        double *res = scratch[k] + 4 * (size_t)kBlocks;
+        rc = launch_step_norms(vp[k], tmp[k], (size_t)s->rows * s->gw, scratch[k], kBlocks, res, s->stream);
+        if (rc == PFS_OK && s->comm != nullptr) {
+            if (nccl().AllReduce(res, res, 3, ncclDouble, ncclSum, s->comm, s->stream) != ncclSuccess ||
+                nccl().AllReduce(res + 3, res + 3, 1, ncclDouble, ncclMax, s->comm, s->stream) != ncclSuccess) {
+                set_error("%s: NCCL all-reduce failed", fn);
+                rc = PFS_ECUDA;
+            }
+        }
+    }
+    for (int k = 0; k < n_local; k++) {
+        pfs_slab *s = L[k];
+        Guard g(s->device);
+        if (rc == PFS_OK && scratch[k]) {
+            double host[4];
+            if (cudaMemcpyAsync(host, scratch[k] + 4 * (size_t)kBlocks, sizeof(host), cudaMemcpyDeviceToHost, s->stream) != cudaSuccess ||
+                cudaStreamSynchronize(s->stream) != cudaSuccess) {
+                rc = cuda_fail(cudaGetLastError(), "norms readback", __FILE__, __LINE__);
+            } else if (s->comm != nullptr) {
+                sums[0] = host[0]; sums[1] = host[1]; sums[2] = host[2]; mx = host[3];
+            } else {
+                sums[0] += host[0]; sums[1] += host[1]; sums[2] += host[2]; mx = std::max(mx, host[3]);
+            }
+        }
+        if (scratch[k]) cudaFree(scratch[k]);
+    }
+    if (rc != PFS_OK) return rc;
+    out[0] = std::sqrt(sums[0]);
+    out[1] = std::sqrt(sums[1]);
+    out[2] = std::sqrt(sums[2]);
+    out[3] = mx;
+    return PFS_OK;
+}
+
+// ---------------------------------------------------------------------------------------------
 // simulate_fluid_step on slabs.  vp[k] / tmp[k]: the k-th local slab's band of the interleaved buffers
 // (rows x gw x 4 floats, device memory of that slab's device).  Pointer exchange as pfs_simulate_fluid_step.
 // ---------------------------------------------------------------------------------------------

@@ -246,6 +246,18 @@ def timestep_host(vp: vp_field, vtmp: vp_field, image: vp_field, itmp: vp_field,
     _commit_host(list(zip(fs[2:], structs[2:])))
 
 
+def step_norms(vp: vp_field, tmp: vp_field) -> dict:
+    """Diagnostics of the step that produced (vp, tmp): L2 norm of the divergence, of the last Jacobi update
+    p_N - p_{N-1}, of the projected velocity, and the maximum speed component (pfs_step_norms)."""
+    L = _cabi.lib()
+    _check_buf(vp, "vp"); _check_buf(tmp, "tmp")
+    _require_device("step_norms", vp, tmp)
+    out = (ctypes.c_double * 4)()
+    with _dev_guard(vp.data):
+        check(L.pfs_step_norms(vp.data.data_ptr(), tmp.data.data_ptr(), vp.x, vp.y, vp.z, out, _stream_of(vp.data)))
+    return {"div_l2": out[0], "pressure_update_l2": out[1], "velocity_l2": out[2], "speed_max": out[3]}
+
+
 def _require_device(op: str, *fields: vp_field) -> None:
     for f in fields:
         if not f.on_device:

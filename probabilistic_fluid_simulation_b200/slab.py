@@ -114,6 +114,13 @@ class SlabRing(_SlabBase):
     def check(self) -> None:
         check(_cabi.lib().pfs_slab_check(_ptr_array([h.value for h in self._handles]), self.nranks))
 
+    def step_norms(self, vp: list, tmp: list) -> dict:
+        out = (ctypes.c_double * 4)()
+        check(_cabi.lib().pfs_slab_step_norms(_ptr_array([h.value for h in self._handles]), self.nranks,
+                                              _ptr_array([t.data_ptr() for t in vp]), _ptr_array([t.data_ptr() for t in tmp]),
+                                              out, self._streams()))
+        return {"div_l2": out[0], "pressure_update_l2": out[1], "velocity_l2": out[2], "speed_max": out[3]}
+
 
 class SlabRank(_SlabBase):
     """This process's slab of a ring of `nranks` processes (one GPU each), connected through NCCL."""
@@ -160,3 +167,10 @@ class SlabRank(_SlabBase):
 
     def check(self) -> None:
         check(_cabi.lib().pfs_slab_check(_ptr_array([self._h.value]), 1))
+
+    def step_norms(self, vp: vp_field, tmp: vp_field) -> dict:
+        """Norms of the WHOLE grid (all-reduced over the ring); the same on every rank."""
+        out = (ctypes.c_double * 4)()
+        check(_cabi.lib().pfs_slab_step_norms(_ptr_array([self._h.value]), 1, _ptr_array([vp.data.data_ptr()]),
+                                              _ptr_array([tmp.data.data_ptr()]), out, self._stream(vp.data)))
+        return {"div_l2": out[0], "pressure_update_l2": out[1], "velocity_l2": out[2], "speed_max": out[3]}

@@ -38,6 +38,7 @@ def main():
         slab.simulate_fluid_step(fv, ft, dt, visc, nd, npr)
         slab.advect_color_step(fi, fm, fv, dt)
     slab.check()
+    norms = slab.step_norms(fv, ft)          # all-reduced over the ring: identical on every rank
     parts = [None] * world
     dist.all_gather_object(parts, (fv.data.cpu().numpy(), ft.data.cpu().numpy(), fi.data.cpu().numpy()))
     if rank == 0:
@@ -45,7 +46,15 @@ def main():
         want = oracle.Oracle(nd, npr).run_steps(vp, vtmp, image, itmp, dt, visc, steps)
         for name, g, wv in zip(("vp", "vtmp", "image"), got, want):
             assert np.array_equal(g.view(np.uint32), wv.view(np.uint32)), name
+        d = want[0][..., 3].astype(np.float64)
+        r = want[1][..., 2].astype(np.float64) - want[0][..., 2].astype(np.float64)
+        assert abs(norms["div_l2"] - np.sqrt((d * d).sum())) <= 1e-11 * np.sqrt((d * d).sum())
+        assert abs(norms["pressure_update_l2"] - np.sqrt((r * r).sum())) <= 1e-11 * np.sqrt((r * r).sum())
+        assert norms["speed_max"] == float(max(np.abs(want[0][..., 0]).max(), np.abs(want[0][..., 1]).max()))
         print("NCCL ring matches oracle")
+    all_norms = [None] * world
+    dist.all_gather_object(all_norms, norms)
+    assert all(n == all_norms[0] for n in all_norms), all_norms
     dist.barrier()
     slab.close()
     dist.destroy_process_group()
