@@ -5,6 +5,7 @@
 // All kernels are HBM-streaming: planar fp32, float4 per thread along x when W % 4 == 0 (V = 4),
 // scalar otherwise (V = 1).  Periodic wrap is resolved by index (no halo copies on one GPU).
 #include <math.h>
+#include <stdlib.h>
 
 #include "pfs_internal.cuh"
 
@@ -207,8 +208,8 @@ __global__ void __launch_bounds__(256)
     size_t cell = (size_t)j * w + i;
     float2 uv = __ldg(reinterpret_cast<const float2 *>(vp + cell * 4));
     // fluid.cpp:39,41: (float)i - dt*u/fwidth  ==  i - ((dt*u)/fwidth)
-    float xp = __fsub_rn((float)i, __fdiv_rn(__fmul_rn(dt, uv.x), fw));
-    float yp = __fsub_rn((float)j, __fdiv_rn(__fmul_rn(dt, uv.y), fh));
+    float xp = __fsub_rn((float)i, div_extent(__fmul_rn(dt, uv.x), fw, __frcp_rn(fw)));
+    float yp = __fsub_rn((float)j, div_extent(__fmul_rn(dt, uv.y), fh, __frcp_rn(fh)));
     xp = wrap_coord(xp, fw);
     yp = wrap_coord(yp, fh);
     Bilinear b = make_bilinear(xp, yp, w, h);
@@ -242,8 +243,8 @@ __global__ void __launch_bounds__(256)
     int vj = (int)__fmul_rn((float)j, vih);   // fluid.cpp:90
     float2 uv = __ldg(reinterpret_cast<const float2 *>(vp + ((size_t)vj * vw + vi) * 4));
     // fluid.cpp:97-98: (float)i - (dt/viw) * u / fiwidth
-    float xp = __fsub_rn((float)i, __fdiv_rn(__fmul_rn(dt_over_viw, uv.x), fiw));
-    float yp = __fsub_rn((float)j, __fdiv_rn(__fmul_rn(dt_over_vih, uv.y), fih));
+    float xp = __fsub_rn((float)i, div_extent(__fmul_rn(dt_over_viw, uv.x), fiw, __frcp_rn(fiw)));
+    float yp = __fsub_rn((float)j, div_extent(__fmul_rn(dt_over_vih, uv.y), fih, __frcp_rn(fih)));
     xp = wrap_coord(xp, fiw);
     yp = wrap_coord(yp, fih);
     Bilinear b = make_bilinear(xp, yp, iw, ih);
@@ -474,7 +475,11 @@ int launch_divergence(const float *u, const float *v, float *div, const float *p
 int launch_project_pack(const float *u, const float *v, const float *p_n, const float *p_prev, const float *div,
                         float *out_q, float *out_p, float dt, int w, int h, cudaStream_t s, int y_base, int wrap)
 {
-    const bool v4 = vec4_ok(w, u, v, p_n, p_prev, div);
+    // One cell per thread unless PFS_PROJECT_VEC=1: a warp's two 16-byte stores per cell then cover 512
+    // contiguous bytes of each interleaved buffer (full sectors), whereas four cells per thread leave every
+    // store instruction scattered over 32 half-written sectors.
+    static const bool want_vec = getenv("PFS_PROJECT_VEC") && getenv("PFS_PROJECT_VEC")[0] == '1';
+    const bool v4 = want_vec && vec4_ok(w, u, v, p_n, p_prev, div);
     dim3 block(BX, BY), grid = stencil_grid(w, h, v4 ? 4 : 1, 1);
     float4 *q4 = reinterpret_cast<float4 *>(out_q), *p4 = reinterpret_cast<float4 *>(out_p);
     if (v4)

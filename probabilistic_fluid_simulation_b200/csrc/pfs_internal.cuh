@@ -63,10 +63,33 @@ struct PhaseScope {
 // exact-arithmetic device helpers (each cites the reference expression it reproduces)
 // ---------------------------------------------------------------------------------------------
 
-// fluid.cpp:48-49,105-106: fmod(fmod(x, ext) + ext, ext) on floats.  CUDA fmodf is exact (0 ulp).
+// fluid.cpp:48-49,105-106: fmod(fmod(x, ext) + ext, ext) on floats.  CUDA fmodf is exact (0 ulp) but
+// costs tens of instructions, and both calls are trivial for almost every cell:
+//   fmod(x, ext) = x            for 0 <= x < ext (also for x = -0, which stays -0),
+//   fmod(t, ext) = t            for 0 <= t < ext,
+//   fmod(t, ext) = t - ext      for ext <= t < 2*ext, and that subtraction is exact (Sterbenz' lemma),
+// so only cells whose departure point left the domain call fmodf.  Same bits in every case.
 __device__ __forceinline__ float wrap_coord(float x, float ext)
 {
-    return fmodf(__fadd_rn(fmodf(x, ext), ext), ext);
+    const float r = (x >= 0.0f && x < ext) ? x : fmodf(x, ext);
+    const float t = __fadd_rn(r, ext);
+    if (t >= ext && t < __fadd_rn(ext, ext)) return __fsub_rn(t, ext);
+    if (t >= 0.0f && t < ext) return t;
+    return fmodf(t, ext);
+}
+
+// a / ext, correctly rounded, for an extent with reciprocal rext = __frcp_rn(ext): the 3-instruction FMA
+// division whose exactness is established in sweeps_packed.cu (div_const_fast2) and
+// tests/exact_div_check.c; numerators outside its safe range (zero, tiny, huge, non-finite) take __fdiv_rn.
+__device__ __forceinline__ float div_extent(float a, float ext, float rext)
+{
+    const float aa = fabsf(a);
+    if (aa >= 0x1p-96f && aa <= 0x1p96f) {
+        const float q0 = __fmul_rn(a, rext);
+        const float e = __fmaf_rn(-ext, q0, a);
+        return __fmaf_rn(e, rext, q0);
+    }
+    return __fdiv_rn(a, ext);
 }
 
 // fluid.cpp:19-21 with alpha = 1, beta = 4 (fluid.cpp:215-216,255): (((pL+pR)+pT)+pB + 1.0f*b)/4.0f.

@@ -221,8 +221,8 @@ __global__ void __launch_bounds__(256)
     const float4 *own = source_row(S, j, overflow, 1);
     if (!own) return;
     const float2 uv = __ldg(reinterpret_cast<const float2 *>(own + i));
-    float xp = __fsub_rn((float)i, __fdiv_rn(__fmul_rn(dt, uv.x), fw));
-    float yp = __fsub_rn((float)j, __fdiv_rn(__fmul_rn(dt, uv.y), fh));
+    float xp = __fsub_rn((float)i, div_extent(__fmul_rn(dt, uv.x), fw, __frcp_rn(fw)));
+    float yp = __fsub_rn((float)j, div_extent(__fmul_rn(dt, uv.y), fh, __frcp_rn(fh)));
     xp = wrap_coord(xp, fw);
     yp = wrap_coord(yp, fh);
     const Bilinear b = make_bilinear(xp, yp, w, gh);
@@ -256,8 +256,8 @@ __global__ void __launch_bounds__(256)
         return;
     }
     const float2 uv = __ldg(reinterpret_cast<const float2 *>(vp + ((size_t)vj * vw + vi) * 4));
-    float xp = __fsub_rn((float)i, __fdiv_rn(__fmul_rn(dt_over_viw, uv.x), fiw));
-    float yp = __fsub_rn((float)j, __fdiv_rn(__fmul_rn(dt_over_vih, uv.y), fih));
+    float xp = __fsub_rn((float)i, div_extent(__fmul_rn(dt_over_viw, uv.x), fiw, __frcp_rn(fiw)));
+    float yp = __fsub_rn((float)j, div_extent(__fmul_rn(dt_over_vih, uv.y), fih, __frcp_rn(fih)));
     xp = wrap_coord(xp, fiw);
     yp = wrap_coord(yp, fih);
     const Bilinear b = make_bilinear(xp, yp, iw, ih);

@@ -29,3 +29,13 @@ def test_worst_case_enumeration(tmp_path):
     assert int(last[3]) > 10_000_000 and int(last[5]) == 0, out
 
 
+
+
+def test_fast_periodic_wrap_equals_double_fmod(tmp_path):
+    """wrap_coord() in pfs_internal.cuh skips fmodf where the result is known in closed form (Sterbenz);
+    tests/wrap_check.c compares it with fmod(fmod(x, W) + W, W) on 52 M values incl. every edge case."""
+    exe = tmp_path / "wrap_check"
+    subprocess.run(["gcc", "-O2", "-ffp-contract=off", "-o", str(exe), os.path.join(HERE, "wrap_check.c"), "-lm"], check=True)
+    out = subprocess.run([str(exe)], check=True, capture_output=True, text=True, timeout=600).stdout
+    words = out.strip().splitlines()[-1].split()
+    assert int(words[3]) > 50_000_000 and int(words[5]) == 0, out
