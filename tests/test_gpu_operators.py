@@ -234,3 +234,41 @@ def test_step_is_cuda_graph_capturable():
     assert_bit_equal(to_host(gv.data), to_host(ev.data), "graph vp")
     assert_bit_equal(to_host(gt.data), to_host(et.data), "graph vtmp")
     assert_bit_equal(to_host(gi.data), to_host(ei.data), "graph image")
+
+
+def test_step_graph_cache_survives_resizes_and_shutdown():
+    """The library captures the 2nd identical step call into a CUDA graph and replays it afterwards.  Alternate
+    between grids (forcing a scratch reallocation in between), reuse buffers, shut the library down in the
+    middle -- every step must still equal the oracle's."""
+    from probabilistic_fluid_simulation_b200 import _cabi
+    shapes = [(64, 96), (160, 256), (64, 96), (32, 512)]
+    states = {}
+    for rnd in range(3):
+        for idx, (h, w) in enumerate(shapes):
+            key = (idx, h, w)
+            if key not in states:
+                vp, vt = rand_field(h, w, 100 + idx, 0.8), rand_field(h, w, 200 + idx, 0.5)
+                states[key] = [vp, vt, pfs.vp_field(to_dev(vp)), pfs.vp_field(to_dev(vt))]
+            vp, vt, fv, ft = states[key]
+            for _ in range(4):                       # eager, capture, replay, replay
+                pfs.simulate_fluid_step(fv, ft, 0.9, 0.01, 6, 8)
+                vp, vt = oracle.Oracle(6, 8).simulate_fluid_step(vp, vt, 0.9, 0.01)
+            states[key][0], states[key][1] = vp, vt
+            assert_bit_equal(to_host(fv.data), vp, f"vp round {rnd} shape {h}x{w}")
+            assert_bit_equal(to_host(ft.data), vt, f"vtmp round {rnd} shape {h}x{w}")
+        if rnd == 1:
+            import torch
+            torch.cuda.synchronize()
+            assert _cabi.lib().pfs_shutdown() == 0   # drops scratch, graphs, streams; the next call rebuilds them
+
+
+def test_changing_parameters_never_replays_a_stale_graph():
+    h, w = 48, 64
+    vp, vt = rand_field(h, w, 301, 0.8), rand_field(h, w, 302, 0.5)
+    fv, ft = pfs.vp_field(to_dev(vp)), pfs.vp_field(to_dev(vt))
+    for dt, visc, nd, npr in [(0.5, 0.01, 4, 4)] * 3 + [(0.7, 0.01, 4, 4)] * 3 + [(0.7, 0.02, 4, 4)] * 3 + [(0.7, 0.02, 6, 4)] * 3 + \
+                             [(0.7, 0.02, 6, 2)] * 3 + [(0.5, 0.01, 4, 4)] * 3:
+        pfs.simulate_fluid_step(fv, ft, dt, visc, nd, npr)
+        vp, vt = oracle.Oracle(nd, npr).simulate_fluid_step(vp, vt, dt, visc)
+        assert_bit_equal(to_host(fv.data), vp, f"vp dt={dt} visc={visc} nd={nd} np={npr}")
+        assert_bit_equal(to_host(ft.data), vt, "vtmp")
