@@ -141,10 +141,20 @@ __device__ __forceinline__ float2 div_const_fast2(float2 a, float2 negb, float2 
     return fma2(e, y, q0);
 }
 
-template <int T, bool EXACT, int MINB>
+__device__ __forceinline__ void cp_async8(void *smem, const void *gmem)
+{
+    unsigned s = (unsigned)__cvta_generic_to_shared(smem);
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 8;\n" ::"r"(s), "l"(gmem) : "memory");
+}
+
+// NC = cells per lane (4: 128-column strips, 16*T registers of state; 2: 64-column strips, 8*T registers,
+// i.e. twice the resident warps at a 7 % wider relative halo -- which one is faster is measured, not assumed:
+// profiles/r01_tuning.md).
+template <int T, bool EXACT, int MINB, int NC>
 __global__ void __launch_bounds__(WARPS_PER_CTA * 32, MINB) diffuse_packed_kernel(const PackedParams P)
 {
-    __shared__ float4 ring[WARPS_PER_CTA][RING_SLOTS][2][32];
+    static_assert(NC == 4 || NC == 2, "4 or 2 cells per lane");
+    __shared__ __align__(16) float ring[WARPS_PER_CTA][RING_SLOTS][2][32 * NC];
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int item = blockIdx.x * WARPS_PER_CTA + warp;
@@ -164,7 +174,7 @@ __global__ void __launch_bounds__(WARPS_PER_CTA * 32, MINB) diffuse_packed_kerne
     const int w = P.w, h = P.h;
 
     const int x0 = strip * P.strip_out;
-    const int xc = x0 - P.halo_cols + 4 * lane;           // unwrapped first column of this lane
+    const int xc = x0 - P.halo_cols + NC * lane;          // unwrapped first column of this lane
     int xw = xc % w;
     if (xw < 0) xw += w;
     const bool store_lane = (xc >= x0) && (xc < x0 + P.strip_out) && (xc < w);
@@ -180,15 +190,21 @@ __global__ void __launch_bounds__(WARPS_PER_CTA * 32, MINB) diffuse_packed_kerne
     const int wrap_at = P.wrap ? h : 0x7fffffff;
     const int n_steps = L + 2 * T;
 
-    float4 *my = &ring[warp][0][0][lane];
-    constexpr int SLOT_STRIDE = 2 * 32;                   // float4 units per ring slot
+    float *my = &ring[warp][0][0][lane * NC];
+    constexpr int PLANE_STRIDE = 32 * NC;                 // floats between the u and the v row of a slot
+    constexpr int SLOT_STRIDE = 2 * PLANE_STRIDE;
 
     auto prefetch = [&](int s) {
         if (s < n_steps) {
-            float4 *dst = my + (s & (RING_SLOTS - 1)) * SLOT_STRIDE;
+            float *dst = my + (s & (RING_SLOTS - 1)) * SLOT_STRIDE;
             const size_t off = (size_t)ld_row * w + xw;
-            cp_async16(dst, P.in_u + off);
-            cp_async16(dst + 32, P.in_v + off);
+            if constexpr (NC == 4) {
+                cp_async16(dst, P.in_u + off);
+                cp_async16(dst + PLANE_STRIDE, P.in_v + off);
+            } else {
+                cp_async8(dst, P.in_u + off);
+                cp_async8(dst + PLANE_STRIDE, P.in_v + off);
+            }
             ld_row = (ld_row + 1 == wrap_at) ? 0 : ld_row + 1;
         }
         cp_async_commit();
@@ -196,13 +212,13 @@ __global__ void __launch_bounds__(WARPS_PER_CTA * 32, MINB) diffuse_packed_kerne
 #pragma unroll
     for (int s = 0; s < PREFETCH; s++) prefetch(s);
 
-    // S[l][k][c]: level l, k alternates with the step parity, c = cell 0..3; .x = u, .y = v.
+    // S[l][k][c]: level l, k alternates with the step parity, c = cell; .x = u, .y = v.
     // Initialised to 1 (not 0) so that warm-up garbage never looks like a zero numerator.
-    float2 S[T][2][4];
+    float2 S[T][2][NC];
 #pragma unroll
     for (int l = 0; l < T; l++)
 #pragma unroll
-        for (int c = 0; c < 4; c++) S[l][0][c] = S[l][1][c] = make_float2(1.f, 1.f);
+        for (int c = 0; c < NC; c++) S[l][0][c] = S[l][1][c] = make_float2(1.f, 1.f);
 
     const float2 alpha2 = make_float2(P.alpha, P.alpha);
     const float2 nz2 = make_float2(P.neg_zero, P.neg_zero);
@@ -221,43 +237,51 @@ __global__ void __launch_bounds__(WARPS_PER_CTA * 32, MINB) diffuse_packed_kerne
             const int s = sb + u;
             prefetch(s + PREFETCH);
             cp_async_wait<PREFETCH>();
-            const float4 *slot = my + (s & (RING_SLOTS - 1)) * SLOT_STRIDE;
-            const float4 ru = slot[0], rv = slot[32];
-            float2 fresh[4] = {make_float2(ru.x, rv.x), make_float2(ru.y, rv.y), make_float2(ru.z, rv.z),
-                               make_float2(ru.w, rv.w)};
+            const float *slot = my + (s & (RING_SLOTS - 1)) * SLOT_STRIDE;
+            float2 fresh[NC];
+            if constexpr (NC == 4) {
+                const float4 ru = *reinterpret_cast<const float4 *>(slot);
+                const float4 rv = *reinterpret_cast<const float4 *>(slot + PLANE_STRIDE);
+                fresh[0] = make_float2(ru.x, rv.x); fresh[1] = make_float2(ru.y, rv.y);
+                fresh[2] = make_float2(ru.z, rv.z); fresh[3] = make_float2(ru.w, rv.w);
+            } else {
+                const float2 ru = *reinterpret_cast<const float2 *>(slot);
+                const float2 rv = *reinterpret_cast<const float2 *>(slot + PLANE_STRIDE);
+                fresh[0] = make_float2(ru.x, rv.x); fresh[1] = make_float2(ru.y, rv.y);
+            }
             if constexpr (!EXACT) {
 #pragma unroll
-                for (int c = 0; c < 4; c++) in_max = max3abs(in_max, fresh[c].x, fresh[c].y);
+                for (int c = 0; c < NC; c++) in_max = max3abs(in_max, fresh[c].x, fresh[c].y);
             }
             const int older = u;
             // Software pipeline over the levels: the part of level l+1 that only needs rows stored in
             // earlier steps -- the alpha products of its centre and top rows, the lane shuffles and
             // (aL + aR) + aT -- is issued before the tail of level l, which depends on the row level l-1
             // has just produced.  Two independent instruction streams per warp instead of one.
-            float2 part[4], part_next[4];
-            auto prefix = [&](int l, float2(&dst)[4]) {
-                float2 aC[4], aT[4];
+            float2 part[NC], part_next[NC];
+            auto prefix = [&](int l, float2(&dst)[NC]) {
+                float2 aC[NC], aT[NC];
 #pragma unroll
-                for (int c = 0; c < 4; c++) {
+                for (int c = 0; c < NC; c++) {
                     aC[c] = mulc2(S[l - 1][older ^ 1][c], alpha2, nz2);   // alpha * centre row (s-l)
                     aT[c] = mulc2(S[l - 1][older][c], alpha2, nz2);       // alpha * top row (s-l-1)
                 }
-                const float2 aLft = shfl_up2(aC[3]);                      // alpha * (x-1) of cell 0
-                const float2 aRgt = shfl_down2(aC[0]);                    // alpha * (x+1) of cell 3
+                const float2 aLft = shfl_up2(aC[NC - 1]);                 // alpha * (x-1) of cell 0
+                const float2 aRgt = shfl_down2(aC[0]);                    // alpha * (x+1) of the last cell
 #pragma unroll
-                for (int c = 0; c < 4; c++) {
+                for (int c = 0; c < NC; c++) {
                     const float2 lft = (c == 0) ? aLft : aC[c - 1];
-                    const float2 rgt = (c == 3) ? aRgt : aC[c + 1];
+                    const float2 rgt = (c == NC - 1) ? aRgt : aC[c + 1];
                     dst[c] = add2(add2(lft, rgt), aT[c]);                 // (aL + aR) + aT, fluid.cpp:175-182
                 }
             };
             prefix(1, part);
 #pragma unroll
             for (int l = 1; l <= T; l++) {
-                float2 o[4];
+                float2 o[NC];
                 if (l < T) prefix(l + 1, part_next);
 #pragma unroll
-                for (int c = 0; c < 4; c++) {
+                for (int c = 0; c < NC; c++) {
                     const float2 aB = mulc2(fresh[c], alpha2, nz2);       // alpha * bottom row (s-l+1)
                     // ... + aB) + 1.0f*u_n
                     const float2 num = add2(add2(part[c], aB), S[l - 1][older ^ 1][c]);
@@ -269,7 +293,7 @@ __global__ void __launch_bounds__(WARPS_PER_CTA * 32, MINB) diffuse_packed_kerne
                     }
                 }
 #pragma unroll
-                for (int c = 0; c < 4; c++) {
+                for (int c = 0; c < NC; c++) {
                     S[l - 1][older][c] = fresh[c];
                     fresh[c] = o[c];
                     part[c] = part_next[c];
@@ -277,10 +301,15 @@ __global__ void __launch_bounds__(WARPS_PER_CTA * 32, MINB) diffuse_packed_kerne
             }
             const int orow = s - 2 * T;
             if (store_lane && orow >= 0 && orow < L) {
-                *reinterpret_cast<float4 *>(out_u + (size_t)orow * w) =
-                    make_float4(fresh[0].x, fresh[1].x, fresh[2].x, fresh[3].x);
-                *reinterpret_cast<float4 *>(out_v + (size_t)orow * w) =
-                    make_float4(fresh[0].y, fresh[1].y, fresh[2].y, fresh[3].y);
+                if constexpr (NC == 4) {
+                    *reinterpret_cast<float4 *>(out_u + (size_t)orow * w) =
+                        make_float4(fresh[0].x, fresh[1].x, fresh[2].x, fresh[3].x);
+                    *reinterpret_cast<float4 *>(out_v + (size_t)orow * w) =
+                        make_float4(fresh[0].y, fresh[1].y, fresh[2].y, fresh[3].y);
+                } else {
+                    *reinterpret_cast<float2 *>(out_u + (size_t)orow * w) = make_float2(fresh[0].x, fresh[1].x);
+                    *reinterpret_cast<float2 *>(out_v + (size_t)orow * w) = make_float2(fresh[0].y, fresh[1].y);
+                }
             }
         }
     }
@@ -443,41 +472,40 @@ int launch_pressure_packed_t(const PressurePackedParams &P, cudaStream_t s)
     return PFS_OK;
 }
 
-template <int T, int MINB>
+template <int T, int MINB, int NC>
 int launch_packed_mb(const PackedParams &P, cudaStream_t s)
 {
     const int total = P.n_strips * P.n_chunks;
     const unsigned blocks = (unsigned)((total + WARPS_PER_CTA - 1) / WARPS_PER_CTA);
-    PFS_LAUNCH((diffuse_packed_kernel<T, false, MINB>), blocks, WARPS_PER_CTA * 32, 0, s, P);
-    PFS_LAUNCH((diffuse_packed_kernel<T, true, MINB>), blocks, WARPS_PER_CTA * 32, 0, s, P);
+    PFS_LAUNCH((diffuse_packed_kernel<T, false, MINB, NC>), blocks, WARPS_PER_CTA * 32, 0, s, P);
+    PFS_LAUNCH((diffuse_packed_kernel<T, true, MINB, NC>), blocks, WARPS_PER_CTA * 32, 0, s, P);
     --g_passes;     // the repair launch belongs to the same pass
     return PFS_OK;
 }
 
-// resident CTAs per SM the kernel is compiled for (register cap 65536 / (128 * MINB)): depth <= 4 fits
-// three CTAs (12 warps/SM) without spilling, deeper passes get two (8 warps/SM, up to 255 registers)
-constexpr int packed_minb(int t) { return t > 4 ? 2 : 3; }
+// resident CTAs per SM the kernel is compiled for (register cap 65536 / (128 * MINB)).  4 cells per lane:
+// depth <= 4 fits three CTAs (12 warps/SM) without spilling, deeper passes get two (8 warps/SM, up to 255
+// registers).  2 cells per lane: four CTAs (16 warps/SM, 128 registers).
+constexpr int packed_minb(int t, int nc) { return nc == 2 ? 4 : (t > 4 ? 2 : 3); }
 
 template <int T>
-int launch_packed(const PackedParams &P, int minb, cudaStream_t s)
+int launch_packed(const PackedParams &P, int cells, cudaStream_t s)
 {
-    if constexpr (T == 5 || T == 6) {
-        if (minb == 3) return launch_packed_mb<T, 3>(P, s);
-    }
-    return launch_packed_mb<T, packed_minb(T)>(P, s);
+    if (cells == 2) return launch_packed_mb<T, packed_minb(T, 2), 2>(P, s);
+    return launch_packed_mb<T, packed_minb(T, 4), 4>(P, s);
 }
 
-int launch_packed_depth(int t, const PackedParams &P, int minb, cudaStream_t s)
+int launch_packed_depth(int t, const PackedParams &P, int cells, cudaStream_t s)
 {
     switch (t) {
-    case 1: return launch_packed<1>(P, minb, s);
-    case 2: return launch_packed<2>(P, minb, s);
-    case 3: return launch_packed<3>(P, minb, s);
-    case 4: return launch_packed<4>(P, minb, s);
-    case 5: return launch_packed<5>(P, minb, s);
-    case 6: return launch_packed<6>(P, minb, s);
-    case 7: return launch_packed<7>(P, minb, s);
-    case 8: return launch_packed<8>(P, minb, s);
+    case 1: return launch_packed<1>(P, cells, s);
+    case 2: return launch_packed<2>(P, cells, s);
+    case 3: return launch_packed<3>(P, cells, s);
+    case 4: return launch_packed<4>(P, cells, s);
+    case 5: return launch_packed<5>(P, cells, s);
+    case 6: return launch_packed<6>(P, cells, s);
+    case 7: return launch_packed<7>(P, cells, s);
+    case 8: return launch_packed<8>(P, cells, s);
     default: set_error("packed diffusion: unsupported depth %d", t); return PFS_EINVAL;
     }
 }
@@ -578,13 +606,13 @@ int launch_diffuse_packed(float *a0, float *a1, float *b0, float *b1, const Swee
         PackedParams P;
         P.in_u = cur0; P.in_v = cur1; P.out_u = oth0; P.out_v = oth1;
         P.w = p.w; P.h = p.h; P.y_base = p.y_base; P.wrap = p.wrap;
-        P.halo_cols = 4 * ((t + 3) / 4);
-        P.strip_out = 128 - 2 * P.halo_cols;
+        static const int env_cells = env_int("PFS_DIFFUSE_CELLS", 0);
+        const int cells = (env_cells == 2) ? 2 : 4;                         // cells per lane
+        P.halo_cols = cells * ((t + cells - 1) / cells);
+        P.strip_out = 32 * cells - 2 * P.halo_cols;
         P.n_strips = (p.w + P.strip_out - 1) / P.strip_out;
-        // chunk height: one resident wave of warps if the grid allows it, never shorter than 32 rows
-        // (2T halo rows are streamed per chunk) and never taller than 256
-        static const int env_minb = env_int("PFS_DIFFUSE_MINB", 0);
-        const int minb = (env_minb == 3 && (t == 5 || t == 6)) ? 3 : packed_minb(t);
+        // chunk height: one resident wave of warps if the grid allows it (pick_chunk_rows)
+        const int minb = packed_minb(t, cells);
         const int warps_per_sm = env_warps > 0 ? env_warps : 4 * minb;
         const long long slots = 148LL * warps_per_sm;
         P.chunk_rows = pick_chunk_rows(p.h, P.n_strips, slots, env_rows);
@@ -594,7 +622,7 @@ int launch_diffuse_packed(float *a0, float *a1, float *b0, float *b1, const Swee
         P.guard_hi_in = 0x1p60f;
         P.neg_zero = -0.0f;
         PFS_TRY(get_flags((size_t)P.n_strips * P.n_chunks, &P.flags));
-        PFS_TRY(launch_packed_depth(t, P, minb, s));
+        PFS_TRY(launch_packed_depth(t, P, cells, s));
         float *t0 = cur0, *t1 = cur1;
         cur0 = oth0; cur1 = oth1; oth0 = t0; oth1 = t1;
         hops++;
