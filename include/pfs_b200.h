@@ -184,6 +184,12 @@ int pfs_slab_advect_color_step(pfs_slab *const *slabs, int n_local, float **imag
 /* Synchronises and reports an internal halo overflow (a bug, never expected). */
 int pfs_slab_check(pfs_slab *const *slabs, int n_local);
 
+/* ---- frame packing: the float -> byte half of write_png_from_array (includes/utils.hpp:129-131) -------- */
+/* out[i] = (png_byte)(image[i] * 255.0) for all ix*iy*iz floats -- the reference's DOUBLE multiply and
+ * truncation, done on the device so that a frame costs ix*iy*4 bytes of PCIe traffic instead of 16 bytes per
+ * pixel (the reference copies the float image back every frame, main.cpp:231).  `out` is a device buffer. */
+int pfs_image_to_rgba8(const float *image, unsigned char *out, int ix, int iy, int iz, void *stream);
+
 /* ---- step diagnostics (not in the reference: it runs a fixed sweep count, no convergence test) ---- */
 /* From the two post-state buffers of pfs_simulate_fluid_step (*vp = [u, v, p_{N-1}, div], *tmp = [.., p_N, ..]):
  * out = { ||div||_2, ||p_N - p_{N-1}||_2 (the last Jacobi update, a residual proxy), ||(u,v)||_2, max(|u|,|v|) }.

@@ -64,6 +64,7 @@ SIGNATURES = {
     "pfs_slab_simulate_fluid_step": (_int, [_pp, _int, _pp, _pp, _f32, _f32, _int, _int, _pp]),
     "pfs_slab_advect_color_step": (_int, [_pp, _int, _pp, _pp, _pp, _f32, _pp]),
     "pfs_slab_check": (_int, [_pp, _int]),
+    "pfs_image_to_rgba8": (_int, [_vp, _vp, _int, _int, _int, _vp]),
     "pfs_step_norms": (_int, [_vp, _vp, _int, _int, _int, ctypes.POINTER(ctypes.c_double), _vp]),
     "pfs_slab_step_norms": (_int, [_pp, _int, _pp, _pp, ctypes.POINTER(ctypes.c_double), _pp]),
     "pfs_phase_timing_enable": (_int, [_int]),

@@ -397,6 +397,25 @@ __global__ void norms_final_kernel(const double *partials, int nblocks, double *
     out[0] = t0; out[1] = t1; out[2] = t2; out[3] = t3;
 }
 
+// ---------------------------------------------------------------------------------------------
+// Frame packing (includes/utils.hpp:129-131): byte = (png_byte)(x * 255.0) -- a DOUBLE multiply and a
+// truncation, exactly as the reference's write_png_from_array does on the host.  One pixel (4 channels) per
+// thread, one 4-byte store.  Values outside [0, 256/255) are undefined behaviour in the reference's cast; here
+// they saturate.
+// ---------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) pack_rgba8_kernel(const float4 *__restrict__ image, uchar4 *__restrict__ out, size_t n)
+{
+    const size_t i = (size_t)blockIdx.x * 256 + threadIdx.x;
+    if (i >= n) return;
+    const float4 c = __ldg(image + i);
+    auto q = [](float x) -> unsigned char {
+        const double v = (double)x * 255.0;
+        const int t = (int)v;                       // truncation toward zero
+        return (unsigned char)(t < 0 ? 0 : (t > 255 ? 255 : t));
+    };
+    out[i] = make_uchar4(q(c.x), q(c.y), q(c.z), q(c.w));
+}
+
 inline bool vec4_ok(int w, const void *a, const void *b = nullptr, const void *c = nullptr, const void *d = nullptr,
                     const void *e = nullptr, const void *f = nullptr)
 {
@@ -494,6 +513,14 @@ int launch_subtract_gradient_aos(const float *vp_aos, float *out_aos, float dt, 
     dim3 block(64, 4), grid((w + 63) / 64, (h + 3) / 4);
     PFS_LAUNCH(subtract_gradient_aos_kernel, grid, block, 0, s, reinterpret_cast<const float4 *>(vp_aos), out_aos, dt,
                w, h);
+    return PFS_OK;
+}
+
+int launch_pack_rgba8(const float *image_aos, unsigned char *out, size_t pixels, cudaStream_t s)
+{
+    const unsigned blocks = (unsigned)((pixels + 255) / 256);
+    PFS_LAUNCH(pack_rgba8_kernel, blocks, 256, 0, s, reinterpret_cast<const float4 *>(image_aos),
+               reinterpret_cast<uchar4 *>(out), pixels);
     return PFS_OK;
 }
 

@@ -692,6 +692,18 @@ extern "C" int pfs_add_forces_stochastic(float *vp, float sigma, uint64_t seed, 
     return launch_stochastic_force(vp, vp + 1, 4, sigma, seed, step, vx, vy, 0, 0, (cudaStream_t)stream);
 }
 
+extern "C" int pfs_image_to_rgba8(const float *image, unsigned char *out, int ix, int iy, int iz, void *stream)
+{
+    const char *fn = "pfs_image_to_rgba8";
+    PFS_TRY(check_dims(fn, ix, iy, iz));
+    PFS_TRY(check_ptr(fn, "image", image));
+    if (!out || (reinterpret_cast<uintptr_t>(out) & 3u)) {
+        set_error("%s: out must be a non-null, 4-byte aligned device buffer", fn);
+        return PFS_EINVAL;
+    }
+    return launch_pack_rgba8(image, out, (size_t)ix * iy, (cudaStream_t)stream);
+}
+
 extern "C" int pfs_step_norms(const float *vp, const float *tmp, int vx, int vy, int vz, double out[4], void *stream)
 {
     const char *fn = "pfs_step_norms";

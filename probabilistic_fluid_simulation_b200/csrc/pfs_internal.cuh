@@ -221,6 +221,9 @@ int launch_project_pack(const float *u, const float *v, const float *p_n, const 
 // subtractPressureGradient as a stand-alone operator on interleaved buffers (writes ch0,1 of out).
 int launch_subtract_gradient_aos(const float *vp_aos, float *out_aos, float dt, int w, int h, cudaStream_t s);
 
+// Interleaved float image -> RGBA8 bytes with the reference writer's conversion (utils.hpp:129-131).
+int launch_pack_rgba8(const float *image_aos, unsigned char *out, size_t pixels, cudaStream_t s);
+
 // Step diagnostics from the two post-state buffers (kernels_basic.cu): out4 = {sum div^2, sum (p_N - p_{N-1})^2,
 // sum (u^2 + v^2), max(|u|,|v|)} in device memory; `partials` holds 4 doubles per block (<= max_blocks blocks).
 int launch_step_norms(const float *vp_aos, const float *tmp_aos, size_t cells, double *partials, int max_blocks,

@@ -246,6 +246,18 @@ def timestep_host(vp: vp_field, vtmp: vp_field, image: vp_field, itmp: vp_field,
     _commit_host(list(zip(fs[2:], structs[2:])))
 
 
+def image_to_rgba8(image: vp_field):
+    """Device-side (png_byte)(x * 255.0) of an image (utils.hpp:129-131) -> uint8 CUDA tensor [H, W, 4]."""
+    import torch
+    L = _cabi.lib()
+    _check_buf(image, "image")
+    _require_device("image_to_rgba8", image)
+    out = torch.empty((image.y, image.x, 4), dtype=torch.uint8, device=image.data.device)
+    with _dev_guard(image.data):
+        check(L.pfs_image_to_rgba8(image.data.data_ptr(), out.data_ptr(), image.x, image.y, image.z, _stream_of(image.data)))
+    return out
+
+
 def step_norms(vp: vp_field, tmp: vp_field) -> dict:
     """Diagnostics of the step that produced (vp, tmp): L2 norm of the divergence, of the last Jacobi update
     p_N - p_{N-1}, of the projected velocity, and the maximum speed component (pfs_step_norms)."""

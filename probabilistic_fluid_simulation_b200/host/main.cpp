@@ -6,8 +6,9 @@
 // same frames <output_dir>/<i>.png, timing mode when no output_dir is given (:110-113).  It drives
 // the fluid.hpp entry points of the CUDA build (simulate_fluid_step / advect_color_step on device
 // buffers, main.cpp:222,225), which fluid_shim.cpp forwards to libpfs_b200.so.
-// Two deliberate differences from the reference's CUDA driver, both needed to reproduce what its CPU
-// build computes: the temporary velocity buffer IS uploaded (main.cpp:203-210 never initialises
+// Frames are converted to bytes on the device (pfs_image_to_rgba8, the reference's (png_byte)(x*255.0)) and
+// only those bytes cross PCIe.  Two deliberate differences from the reference's CUDA driver, both needed to
+// reproduce what its CPU build computes: the temporary velocity buffer IS uploaded (main.cpp:203-210 never initialises
 // d_vtmp although channel 2 of it is the first pressure guess), and the clock stops after the
 // device is idle (main.cpp:247 stops it before cudaDeviceSynchronize, :252-255).
 #include <chrono>
@@ -20,6 +21,7 @@
 #include <cuda_runtime_api.h>
 
 #define USE_CUDA
+#include "../../include/pfs_b200.h"
 #include "fluid.hpp"
 #include "png_io.hpp"
 
@@ -96,6 +98,14 @@ int main(int argc, char *argv[])
     if (!vtmp.data) return 1;
     for (size_t i = 0; i < vel_floats; i++) vtmp.data[i] = ((i % 4) == 3) ? 1.0f : -1.0f;
 
+    // frames leave the device as bytes: (png_byte)(x*255.0) is applied by pfs_image_to_rgba8 (utils.hpp:129-131)
+    const size_t frame_bytes = img_floats;
+    unsigned char *d_frame = nullptr, *h_frame = nullptr;
+    if (flags == 0) {
+        if (!cuda_ok(cudaMalloc((void **)&d_frame, frame_bytes), "cudaMalloc frame") ||
+            !cuda_ok(cudaMallocHost((void **)&h_frame, frame_bytes), "cudaMallocHost frame"))
+            return 1;
+    }
     float *d_image = nullptr, *d_vp = nullptr, *d_itmp = nullptr, *d_vtmp = nullptr;
     if (!cuda_ok(cudaMalloc((void **)&d_image, input_bytes), "cudaMalloc") ||
         !cuda_ok(cudaMalloc((void **)&d_vp, velocity_bytes), "cudaMalloc") ||
@@ -115,13 +125,16 @@ int main(int argc, char *argv[])
         simulate_fluid_step(&d_vp, &d_vtmp, delta_t, viscosity, vp.x, vp.y, vp.z);
         advect_color_step(&d_image, &d_itmp, &d_vp, delta_t, image.x, image.y, image.z, vp.x, vp.y, vp.z);
         if (flags == 0) {
-            cudaDeviceSynchronize();
-            if (!cuda_ok(cudaMemcpy(image.data, d_image, input_bytes, cudaMemcpyDeviceToHost), "D2H image")) return 1;
+            if (pfs_image_to_rgba8(d_image, d_frame, image.x, image.y, image.z, nullptr) != PFS_OK) {
+                std::cerr << pfs_last_error() << std::endl;
+                return 1;
+            }
+            if (!cuda_ok(cudaMemcpy(h_frame, d_frame, frame_bytes, cudaMemcpyDeviceToHost), "D2H frame")) return 1;
             std::string outpath = std::string(argv[6]);
             if (!outpath.empty() && outpath.back() != '/') outpath += "/";
             outpath += std::to_string(i) + ".png";
             std::cout << "[" << i << "] Writing to : " << outpath << std::endl;
-            pngio::write_png_from_array(&input_image, outpath.c_str(), image.data);
+            pngio::write_png_from_bytes(&input_image, outpath.c_str(), h_frame);
         }
     }
     cudaDeviceSynchronize();
@@ -137,5 +150,7 @@ int main(int argc, char *argv[])
     cudaFree(d_vp);
     cudaFree(d_itmp);
     cudaFree(d_vtmp);
+    if (d_frame) cudaFree(d_frame);
+    if (h_frame) cudaFreeHost(h_frame);
     return 0;
 }

@@ -103,4 +103,10 @@ inline int write_png_from_array(png_image *image, const char *fn, const float *x
     return p.write_to_file(image, fn, 0, buffer.data(), 0, nullptr) ? 0 : 1;
 }
 
+// Same file as write_png_from_array would produce, from bytes already converted on the device.
+inline int write_png_from_bytes(png_image *image, const char *fn, const unsigned char *rgba)
+{
+    return api().write_to_file(image, fn, 0, rgba, 0, nullptr) ? 0 : 1;
+}
+
 }  // namespace pngio

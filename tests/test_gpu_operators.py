@@ -272,3 +272,22 @@ def test_changing_parameters_never_replays_a_stale_graph():
         vp, vt = oracle.Oracle(nd, npr).simulate_fluid_step(vp, vt, dt, visc)
         assert_bit_equal(to_host(fv.data), vp, f"vp dt={dt} visc={visc} nd={nd} np={npr}")
         assert_bit_equal(to_host(ft.data), vt, "vtmp")
+
+
+def test_image_to_rgba8_matches_reference_writer():
+    """(png_byte)(x * 255.0), utils.hpp:129-131: double multiply + truncation, every k/255 boundary included."""
+    import torch
+    rng = np.random.default_rng(91)
+    img = rng.random((67, 129, 4)).astype(np.float32)
+    img.reshape(-1)[:256] = fixtures_bytes_as_floats()
+    img.reshape(-1)[256:512] = np.nextafter(fixtures_bytes_as_floats(), np.float32(0))     # one ulp below k/255
+    img[0, 0, 3] = np.float32(0.9999998)                                                   # SURVEY.md 4.4: alpha 254
+    got = pfs.image_to_rgba8(pfs.vp_field(to_dev(img))).cpu().numpy()
+    want = oracle.unit_float_to_bytes(img)
+    assert np.array_equal(got, want)
+    assert got[0, 0, 3] == 254
+
+
+def fixtures_bytes_as_floats():
+    from probabilistic_fluid_simulation_b200 import fixtures
+    return fixtures.bytes_to_unit_float(np.arange(256, dtype=np.uint8))
