@@ -51,9 +51,13 @@ int check_launch(const char *kernel, const char *file, int line)
 // per-device scratch: seven planes (u,v x2, p x2, divergence) sized for the largest grid seen,
 // plus staging buffers of the host API.
 // ---------------------------------------------------------------------------------------------
+// planes 0-3: (u,v) ping-pong, 4-5: pressure ping-pong, 6: divergence, 7-8: (u,v) of diffusion iterate n-1,
+// 9: pressure iterate n-1 (the iterates the reference leaves in its other buffer)
+constexpr size_t N_PLANES = 10;
+
 struct DeviceScratch {
     size_t plane_cells = 0;
-    float *planes = nullptr;          // 7 * plane_cells floats, one allocation
+    float *planes = nullptr;          // N_PLANES * plane_cells floats, one allocation
     float *stage[4] = {nullptr, nullptr, nullptr, nullptr};   // host-API device copies: vp, tmp, image, itmp
     size_t stage_floats[4] = {0, 0, 0, 0};
     cudaStream_t streams[2] = {nullptr, nullptr};             // host-API streams
@@ -105,7 +109,7 @@ static int get_scratch(size_t cells, DeviceScratch **out)
             sc.planes = nullptr;
             sc.plane_cells = 0;
         }
-        PFS_CUDA(cudaMalloc((void **)&sc.planes, 7 * need * sizeof(float)));
+        PFS_CUDA(cudaMalloc((void **)&sc.planes, N_PLANES * need * sizeof(float)));
         sc.plane_cells = need;
     }
     *out = &sc;
@@ -208,28 +212,39 @@ struct PlanePair {
     float *c0, *c1;   // c1 unused for pressure
 };
 
-static int run_sweeps(SweepOp op, PlanePair a, PlanePair b, const float *rhs, const SweepParams &p, int n,
-                      PlanePair *last, PlanePair *prev, cudaStream_t s)
+static int run_sweeps(SweepOp op, PlanePair a, PlanePair b, PlanePair extra, const float *rhs, const SweepParams &p,
+                      int n, PlanePair *last, PlanePair *prev, cudaStream_t s)
 {
-    int lead = n - 1;
-    int flips = 0;   // number of a<->b ping-pong hops the lead sweeps took (one per launch)
+    const int depth = g_fuse_depth;
+    const bool fused = (depth != 1) && fused_sweeps_supported(p.w, p.h);
+    // The packed (f32x2) pressure kernel is bit-exact but register-bound (255 registers, 8 warps/SM) and
+    // measured no faster than the scalar fused kernel at 4096^2 (0.91 vs 0.89 ms per 100 sweeps,
+    // profiles/r01_tuning.md), so it is opt-in: PFS_PRESSURE_KERNEL=packed.
+    static const bool packed_pressure = getenv("PFS_PRESSURE_KERNEL") && !strcmp(getenv("PFS_PRESSURE_KERNEL"), "packed");
+    int flips = 0;   // number of a<->b ping-pong hops taken (one per launch)
+    if (fused && !(op == SWEEP_PRESSURE && packed_pressure)) {
+        // All n sweeps in fused passes; the pass that reaches sweep n also stores iterate n-1 (into `extra`),
+        // so no separate last sweep -- and no extra trip through HBM -- is needed to have both.
+        int prev_written = 0;
+        if (op == SWEEP_DIFFUSE && packed_diffuse_supported(p))
+            PFS_TRY(launch_diffuse_packed(a.c0, a.c1, b.c0, b.c1, p, n, depth, &flips, s, extra.c0, extra.c1, &prev_written));
+        else
+            PFS_TRY(launch_sweeps_fused(op, a.c0, a.c1, b.c0, b.c1, rhs, p, n, depth, &flips, s, extra.c0, extra.c1,
+                                        &prev_written));
+        *last = (flips & 1) ? b : a;
+        *prev = prev_written ? extra : ((flips & 1) ? a : b);     // else: the set the last single sweep read
+        return PFS_OK;
+    }
+    // n-1 sweeps, then exactly one into the other set: iterates n-1 and n both exist afterwards
+    const int lead = n - 1;
     if (lead > 0) {
-        int depth = g_fuse_depth;
-        bool fused = (depth != 1) && fused_sweeps_supported(p.w, p.h);
-        // The packed (f32x2) pressure kernel is bit-exact but register-bound (255 registers, 8 warps/SM) and
-        // measured no faster than the scalar fused kernel at 4096^2 (0.91 vs 0.89 ms per 100 sweeps,
-        // profiles/r01_tuning.md), so it is opt-in: PFS_PRESSURE_KERNEL=packed.
-        static const bool scalar_pressure = !(getenv("PFS_PRESSURE_KERNEL") && !strcmp(getenv("PFS_PRESSURE_KERNEL"), "packed"));
-        if (fused && op == SWEEP_DIFFUSE && packed_diffuse_supported(p))
-            PFS_TRY(launch_diffuse_packed(a.c0, a.c1, b.c0, b.c1, p, lead, depth, &flips, s));
-        else if (fused && op == SWEEP_PRESSURE && !scalar_pressure && packed_pressure_supported(p))
+        if (fused && op == SWEEP_PRESSURE && packed_pressure_supported(p))
             PFS_TRY(launch_pressure_packed(a.c0, b.c0, rhs, p, lead, depth, &flips, s));
         else if (fused)
             PFS_TRY(launch_sweeps_fused(op, a.c0, a.c1, b.c0, b.c1, rhs, p, lead, depth, &flips, s));
         else
             PFS_TRY(launch_sweeps_basic(op, a.c0, a.c1, b.c0, b.c1, rhs, p, lead, &flips, s));
     }
-    // iterate n-1 is in b if the lead sweeps took an odd number of hops, else in a
     PlanePair cur = (flips & 1) ? b : a, oth = (flips & 1) ? a : b;
     int one = 0;
     PFS_TRY(launch_sweeps_basic(op, cur.c0, cur.c1, oth.c0, oth.c1, rhs, p, 1, &one, s));
@@ -388,7 +403,8 @@ extern "C" int pfs_diffuse(float **vp, float **vp_out, float viscosity, float dt
     float *in0 = *vp, *out0 = *vp_out;
     PlanePair a{sc->plane(0), sc->plane(1)}, b{sc->plane(2), sc->plane(3)}, last, prev;
     PFS_TRY(launch_unpack(in0, a.c0, a.c1, nullptr, nullptr, vx, vy, s));
-    PFS_TRY(run_sweeps(SWEEP_DIFFUSE, a, b, nullptr, diffuse_params(vx, vy, viscosity, dt), n_sweeps, &last, &prev, s));
+    PFS_TRY(run_sweeps(SWEEP_DIFFUSE, a, b, PlanePair{sc->plane(7), sc->plane(8)}, nullptr,
+                       diffuse_params(vx, vy, viscosity, dt), n_sweeps, &last, &prev, s));
     // Sweep k writes the original vp_out buffer when k is odd and the original vp buffer when k is
     // even (fluid.cpp:188-194).  Only channels 0,1 are ever written.
     float *buf_last = (n_sweeps & 1) ? out0 : in0;
@@ -421,7 +437,7 @@ extern "C" int pfs_compute_pressure(float **vp, float **vp_out, float dt, int vx
     PFS_TRY(launch_unpack(in0, u, v, nullptr, nullptr, vx, vy, s));
     PFS_TRY(launch_divergence(u, v, div, in0, a.c0, dt, vx, vy, s));
     SweepParams p{vx, vy, 1.0f, 4.0f};
-    PFS_TRY(run_sweeps(SWEEP_PRESSURE, a, b, div, p, n_sweeps, &last, &prev, s));
+    PFS_TRY(run_sweeps(SWEEP_PRESSURE, a, b, PlanePair{sc->plane(9), nullptr}, div, p, n_sweeps, &last, &prev, s));
     float *buf_last = (n_sweeps & 1) ? out0 : in0;
     float *buf_prev = (n_sweeps & 1) ? in0 : out0;
     // channel 3 of both buffers <- divergence (fluid.cpp:235-236); channel 2 <- the iterate each
@@ -478,8 +494,8 @@ static int enqueue_fluid_step(DeviceScratch *sc, float *X, float *Y, float dt, f
     // diffuse(tmp -> vp)  (fluid.cpp:300)
     {
         PhaseScope ph(PFS_PHASE_DIFFUSE, s);
-        PFS_TRY(run_sweeps(SWEEP_DIFFUSE, ua, ub, nullptr, diffuse_params(vx, vy, viscosity, dt), n_diffuse, &d_last,
-                           &d_prev, s));
+        PFS_TRY(run_sweeps(SWEEP_DIFFUSE, ua, ub, PlanePair{sc->plane(7), sc->plane(8)}, nullptr,
+                           diffuse_params(vx, vy, viscosity, dt), n_diffuse, &d_last, &d_prev, s));
     }
     // After diffuse the struct `vp` points at the buffer written last: sweep k writes X for odd k,
     // Y for even k (sweep 1 writes vp_out = the original vp buffer X).
@@ -500,7 +516,7 @@ static int enqueue_fluid_step(DeviceScratch *sc, float *X, float *Y, float dt, f
     {
         PhaseScope ph(PFS_PHASE_PRESSURE, s);
         SweepParams pp{vx, vy, 1.0f, 4.0f};
-        PFS_TRY(run_sweeps(SWEEP_PRESSURE, pa, pb, div, pp, n_pressure, &p_last, &p_prev, s));
+        PFS_TRY(run_sweeps(SWEEP_PRESSURE, pa, pb, PlanePair{sc->plane(9), nullptr}, div, pp, n_pressure, &p_last, &p_prev, s));
     }
     // Pressure sweep k writes Bo for odd k, Bv for even k; struct `tmp` ends on the buffer with p_N.
     float *Bp = (n_pressure & 1) ? Bo : Bv;

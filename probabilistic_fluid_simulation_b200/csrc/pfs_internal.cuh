@@ -190,15 +190,20 @@ int launch_sweeps_basic(SweepOp op, float *a0, float *a1, float *b0, float *b1, 
 
 // Temporally blocked version: up to `depth` sweeps fused per launch.  Same contract and bit-identical
 // results.  Returns PFS_EINVAL if the shape is not supported (caller then uses the basic path).
+// prev0/prev1 (optional): the pass that reaches sweep n also stores iterate n-1 there (the reference keeps it
+// in its other buffer); *prev_written says whether it did (not when the last hop is a single plain sweep --
+// iterate n-1 is then simply the plane set that sweep read).
 int launch_sweeps_fused(SweepOp op, float *a0, float *a1, float *b0, float *b1, const float *rhs,
-                        const SweepParams &p, int n, int depth, int *flips, cudaStream_t s);
+                        const SweepParams &p, int n, int depth, int *flips, cudaStream_t s, float *prev0 = nullptr,
+                        float *prev1 = nullptr, int *prev_written = nullptr);
 bool fused_sweeps_supported(int w, int h);
 int pick_chunk_rows(int h, int columns_of_items, long long slots, int forced_rows);   // sweeps_packed.cu
 
 // Packed-FP32 (f32x2) temporally blocked diffusion: u and v advanced together (sweeps_packed.cu).
 bool packed_diffuse_supported(const SweepParams &p);
 int launch_diffuse_packed(float *a0, float *a1, float *b0, float *b1, const SweepParams &p, int n, int depth,
-                          int *flips, cudaStream_t s);
+                          int *flips, cudaStream_t s, float *prev0 = nullptr, float *prev1 = nullptr,
+                          int *prev_written = nullptr);
 void packed_release_device_buffers();
 int default_diffuse_depth();      // sweeps fused per launch when the caller does not say (PFS_DIFFUSE_DEPTH)
 // Packed-FP32 temporally blocked pressure sweeps: two strips of the plane per warp (sweeps_packed.cu).

@@ -894,7 +894,6 @@ extern "C" int pfs_slab_simulate_fluid_step(pfs_slab *const *slabs, int n_local,
         };
         while (left > 0) {
             int t = std::min(left, depth);
-            if (t > 1 && !packed) t &= ~1;          // the scalar fused kernel takes even depths
             if (t < 1) t = 1;
             PFS_TRY(one_pass(t));
             left -= t;

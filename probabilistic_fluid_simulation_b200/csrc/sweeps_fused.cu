@@ -36,6 +36,7 @@ constexpr int PREFETCH = RING_SLOTS - 2;  // rows in flight ahead of the consume
 struct FusedParams {
     const float *in0, *in1;     // plane(s) of the current iterate (in1: diffusion's second plane)
     float *out0, *out1;         // plane(s) receiving iterate +T
+    float *prev0, *prev1;       // optional: plane(s) receiving iterate +T-1 as well (null = not wanted)
     const float *rhs;           // divergence plane (pressure) or null
     int w, h;
     int strip_out;              // columns stored per strip = 128 - 2*HL
@@ -203,6 +204,8 @@ __global__ void __launch_bounds__(WARPS_PER_CTA * 32, MINB) fused_sweeps_kernel(
     }
 
     float *out_ptr = out + (size_t)(P.y_base + y0) * w + xc;   // row y0 of this lane's columns (store lanes only)
+    float *prev = plane ? P.prev1 : P.prev0;                   // the reference keeps iterate n-1 in its other buffer
+    float *prev_ptr = prev ? prev + (size_t)(P.y_base + y0) * w + xc : nullptr;
 
     for (int sb = 0; sb < n_steps; sb += U) {
 #pragma unroll
@@ -218,6 +221,13 @@ __global__ void __launch_bounds__(WARPS_PER_CTA * 32, MINB) fused_sweeps_kernel(
 #pragma unroll
             for (int l = 1; l <= T; l++) {
                 // level l, row s-l, from level l-1 rows s-l-1 (top), s-l (centre), s-l+1 (fresh)
+                if (l == T && prev_ptr != nullptr) {
+                    // `fresh` is row s-(T-1) of level T-1 = output row y0 + (s - 2T + 1) of the previous iterate;
+                    // its valid columns include every column this lane stores
+                    const int prow = s - 2 * T + 1;
+                    if (store_lane && prow >= 0 && prow < L)
+                        *reinterpret_cast<float4 *>(prev_ptr + (size_t)prow * w) = fresh;
+                }
                 const float4 top = S[l - 1][older];
                 const float4 cen = S[l - 1][older ^ 1];
                 const float left = __shfl_up_sync(0xffffffffu, cen.w, 1);
@@ -252,8 +262,11 @@ int launch_depth(int depth, const FusedParams &P, cudaStream_t s)
 {
     switch (depth) {
     case 2: return launch_one<OP, 2>(P, s);
+    case 3: return launch_one<OP, 3>(P, s);
     case 4: return launch_one<OP, 4>(P, s);
+    case 5: return launch_one<OP, 5>(P, s);
     case 6: return launch_one<OP, 6>(P, s);
+    case 7: return launch_one<OP, 7>(P, s);
     case 8: return launch_one<OP, 8>(P, s);
     default: set_error("fused sweeps: unsupported depth %d", depth); return PFS_EINVAL;
     }
@@ -272,8 +285,10 @@ bool fused_sweeps_supported(int w, int h) { return (w % 4 == 0) && w >= 4 && h >
 constexpr int MAX_FUSE_DEPTH = 8;
 
 int launch_sweeps_fused(SweepOp op, float *a0, float *a1, float *b0, float *b1, const float *rhs,
-                        const SweepParams &p, int n, int depth, int *flips, cudaStream_t s)
+                        const SweepParams &p, int n, int depth, int *flips, cudaStream_t s, float *prev0, float *prev1,
+                        int *prev_written)
 {
+    if (prev_written) *prev_written = 0;
     if (!fused_sweeps_supported(p.w, p.h)) {
         set_error("fused sweeps need a width that is a multiple of 4 (got %d)", p.w);
         return PFS_EINVAL;
@@ -282,19 +297,22 @@ int launch_sweeps_fused(SweepOp op, float *a0, float *a1, float *b0, float *b1, 
     static const int env_rows = env_int("PFS_CHUNK_ROWS", 0);
     if (depth <= 0) depth = env_depth > 0 ? env_depth : MAX_FUSE_DEPTH;
     if (depth > MAX_FUSE_DEPTH) depth = MAX_FUSE_DEPTH;
-    depth &= ~1;                                   // even depths only; an odd remainder is one basic sweep
     int hops = 0;
     float *cur0 = a0, *cur1 = a1, *oth0 = b0, *oth1 = b1;
     int left = n;
     while (left > 0) {
-        int t = (left >= depth) ? depth : (left & ~1);
-        if (depth < 2 || t < 2) {                  // odd remainder (or depth 1): one plain sweep
+        int t = (left >= depth) ? depth : left;
+        if (depth < 2 || t < 2) {                  // a single remaining sweep (or depth 1): one plain sweep
             int one = 0;
             PFS_TRY(launch_sweeps_basic(op, cur0, cur1, oth0, oth1, rhs, p, 1, &one, s));
             t = 1;
         } else {
             FusedParams P;
             P.in0 = cur0; P.in1 = cur1; P.out0 = oth0; P.out1 = oth1; P.rhs = rhs;
+            const bool last_pass = (left - t == 0) && prev0 != nullptr;
+            P.prev0 = last_pass ? prev0 : nullptr;
+            P.prev1 = last_pass ? prev1 : nullptr;
+            if (last_pass && prev_written) *prev_written = 1;
             P.w = p.w; P.h = p.h; P.y_base = p.y_base; P.wrap = p.wrap;
             P.halo_cols = 4 * ((t + 3) / 4);
             P.strip_out = 128 - 2 * P.halo_cols;

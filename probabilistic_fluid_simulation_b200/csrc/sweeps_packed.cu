@@ -40,6 +40,7 @@ constexpr int PREFETCH = RING_SLOTS - 2;
 struct PackedParams {
     const float *in_u, *in_v;
     float *out_u, *out_v;
+    float *prev_u, *prev_v;     // optional: planes receiving iterate +T-1 as well (null = not wanted)
     int *flags;                 // one int per work item (main kernel raises, repair kernel consumes)
     int w, h;
     int strip_out, halo_cols;
@@ -230,6 +231,8 @@ __global__ void __launch_bounds__(WARPS_PER_CTA * 32, MINB) diffuse_packed_kerne
 
     float *out_u = P.out_u + (size_t)(P.y_base + y0) * w + xc;
     float *out_v = P.out_v + (size_t)(P.y_base + y0) * w + xc;
+    float *prev_u = P.prev_u ? P.prev_u + (size_t)(P.y_base + y0) * w + xc : nullptr;
+    float *prev_v = P.prev_v ? P.prev_v + (size_t)(P.y_base + y0) * w + xc : nullptr;
 
     for (int sb = 0; sb < n_steps; sb += 2) {
 #pragma unroll
@@ -279,6 +282,22 @@ __global__ void __launch_bounds__(WARPS_PER_CTA * 32, MINB) diffuse_packed_kerne
 #pragma unroll
             for (int l = 1; l <= T; l++) {
                 float2 o[NC];
+                if (l == T && prev_u != nullptr) {
+                    // `fresh` is row s-(T-1) of level T-1: the previous iterate, which the reference keeps in its
+                    // other buffer (fluid.cpp:188-194); every column this lane stores is valid at that level too
+                    const int prow = s - 2 * T + 1;
+                    if (store_lane && prow >= 0 && prow < L) {
+                        if constexpr (NC == 4) {
+                            *reinterpret_cast<float4 *>(prev_u + (size_t)prow * w) =
+                                make_float4(fresh[0].x, fresh[1].x, fresh[2].x, fresh[3].x);
+                            *reinterpret_cast<float4 *>(prev_v + (size_t)prow * w) =
+                                make_float4(fresh[0].y, fresh[1].y, fresh[2].y, fresh[3].y);
+                        } else {
+                            *reinterpret_cast<float2 *>(prev_u + (size_t)prow * w) = make_float2(fresh[0].x, fresh[1].x);
+                            *reinterpret_cast<float2 *>(prev_v + (size_t)prow * w) = make_float2(fresh[0].y, fresh[1].y);
+                        }
+                    }
+                }
                 if (l < T) prefix(l + 1, part_next);
 #pragma unroll
                 for (int c = 0; c < NC; c++) {
@@ -592,8 +611,9 @@ int default_diffuse_depth()
 
 // n diffusion sweeps, up to `depth` per launch, ping-ponging (a0,a1) <-> (b0,b1).
 int launch_diffuse_packed(float *a0, float *a1, float *b0, float *b1, const SweepParams &p, int n, int depth,
-                          int *flips, cudaStream_t s)
+                          int *flips, cudaStream_t s, float *prev0, float *prev1, int *prev_written)
 {
+    if (prev_written) *prev_written = 0;
     static const int env_rows = env_int("PFS_DIFFUSE_ROWS", 0);
     static const int env_warps = env_int("PFS_DIFFUSE_WARPS_PER_SM", 0);
     if (depth <= 0) depth = default_diffuse_depth();
@@ -605,6 +625,10 @@ int launch_diffuse_packed(float *a0, float *a1, float *b0, float *b1, const Swee
         const int t = left < depth ? left : depth;
         PackedParams P;
         P.in_u = cur0; P.in_v = cur1; P.out_u = oth0; P.out_v = oth1;
+        const bool last_pass = (left - t == 0) && prev0 != nullptr && t >= 2;
+        P.prev_u = last_pass ? prev0 : nullptr;
+        P.prev_v = last_pass ? prev1 : nullptr;
+        if (last_pass && prev_written) *prev_written = 1;
         P.w = p.w; P.h = p.h; P.y_base = p.y_base; P.wrap = p.wrap;
         static const int env_cells = env_int("PFS_DIFFUSE_CELLS", 0);
         const int cells = (env_cells == 2) ? 2 : 4;                         // cells per lane

@@ -1,12 +1,14 @@
 #!/bin/bash
 set -u
 TAG=${1:-exp}; OUT=gpurun_out/$TAG; mkdir -p "$OUT"; : > "$OUT/summary.txt"
-echo "== new tests" | tee -a "$OUT/summary.txt"
-timeout 900 python -m pytest tests/test_gpu_operators.py tests/test_gpu_driver.py -x -q -m gpu > "$OUT/pytest.log" 2>&1
-echo "pytest exit $?" | tee -a "$OUT/summary.txt"; tail -3 "$OUT/pytest.log" | tee -a "$OUT/summary.txt"
-echo "== ncu launch list of bench.py (2 timed steps, eager launches)" | tee -a "$OUT/summary.txt"
-PFS_STEP_GRAPH=0 timeout 900 ncu --clock-control none --metrics gpu__time_duration.sum -c 600 --csv --log-file "$OUT/bench_launches.csv" python bench.py --steps 2 --warmup 3 --no-e2e --no-cpu > "$OUT/bench_under_ncu.json" 2> "$OUT/bench_under_ncu.err"
-echo "ncu exit $?" | tee -a "$OUT/summary.txt"; wc -l "$OUT/bench_launches.csv" | tee -a "$OUT/summary.txt"
-echo "== 16384^2 on one GPU" | tee -a "$OUT/summary.txt"
-timeout 900 python scripts/strong_16384.py 16384 100 4 > "$OUT/strong_16384.json" 2> "$OUT/strong_16384.err"
-echo "exit $?" | tee -a "$OUT/summary.txt"; cat "$OUT/strong_16384.json" | tee -a "$OUT/summary.txt"; tail -3 "$OUT/strong_16384.err" | tee -a "$OUT/summary.txt"
+timeout 1200 python -m pytest tests -x -q -m gpu > "$OUT/pytest.log" 2>&1
+echo "pytest exit $?" | tee -a "$OUT/summary.txt"; tail -4 "$OUT/pytest.log" | tee -a "$OUT/summary.txt"
+run() {
+  name=$1; extra=$2; shift; shift
+  echo "== $name" | tee -a "$OUT/summary.txt"
+  env "$@" timeout 600 python bench.py --no-e2e --no-cpu $extra > "$OUT/bench_$name.json" 2> "$OUT/bench_$name.err"
+  python -c "import json;d=json.load(open('$OUT/bench_$name.json'));print('ms/step %.4f'%d['ms_per_step'], 'eager %.4f'%d['phase_region']['ms_per_step_eager_with_phase_events'], {k: round(v,4) for k,v in d['phases_ms'].items()}, d['gpu_launches'])" | tee -a "$OUT/summary.txt"
+  tail -2 "$OUT/bench_$name.err" | tee -a "$OUT/summary.txt"
+}
+run default "--steps 50 --warmup 5" X=1
+run cfg2 "--width 1024 --height 1024 --iters 50 --steps 400 --warmup 20" X=1
