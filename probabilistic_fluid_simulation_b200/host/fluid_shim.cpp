@@ -5,6 +5,7 @@
 // Plain g++ + the CUDA runtime headers only; no nvcc needed (as for the reference's main.cpp).
 #include <cstdio>
 #include <cstdlib>
+#include <vector>
 
 #include <cuda_runtime_api.h>
 
@@ -22,8 +23,33 @@ void die_on(int status, const char *where)
 
 #ifdef USE_CUDA
 
+namespace {
+// The reference's CUDA driver never initialises its temporary velocity buffer (main.cpp:203-210 upload only
+// image and vp), although fluid.cpp's semantics read channel 2 of it as the first pressure guess, which the CPU
+// build sets to (-1,-1,-1,+1) per cell (main.cpp:188-195).  With PFS_SHIM_INIT_TMP=1 the first call of the
+// process writes that pattern into *tmp, so the UNMODIFIED main.cpp -DUSE_CUDA linked against this library
+// reproduces the frames of the CPU build.  Off by default: a driver that uploads vtmp itself (host/main.cpp)
+// must not have it overwritten.
+void init_tmp_once(float *tmp, int vx, int vy, int vz)
+{
+    static bool done = false;
+    if (done) return;
+    done = true;
+    const char *e = std::getenv("PFS_SHIM_INIT_TMP");
+    if (!e || e[0] != '1' || vz != 4) return;
+    const size_t n = (size_t)vx * vy * vz;
+    std::vector<float> h(n);
+    for (size_t i = 0; i < n; i++) h[i] = ((i % 4) == 3) ? 1.0f : -1.0f;
+    if (cudaMemcpy(tmp, h.data(), n * sizeof(float), cudaMemcpyHostToDevice) != cudaSuccess) {
+        std::fprintf(stderr, "fluid.hpp shim: cannot initialise the temporary velocity buffer\n");
+        std::abort();
+    }
+}
+}  // namespace
+
 void simulate_fluid_step(float **vp, float **tmp, float dt, float viscosity, int vx, int vy, int vz)
 {
+    init_tmp_once(*tmp, vx, vy, vz);
     die_on(pfs_simulate_fluid_step(vp, tmp, dt, viscosity, vx, vy, vz, NUM_JACOBI_ITERS, NUM_JACOBI_ITERS, nullptr),
            "simulate_fluid_step");
 }

@@ -6,8 +6,9 @@
 // same frames <output_dir>/<i>.png, timing mode when no output_dir is given (:110-113).  It drives
 // the fluid.hpp entry points of the CUDA build (simulate_fluid_step / advect_color_step on device
 // buffers, main.cpp:222,225), which fluid_shim.cpp forwards to libpfs_b200.so.
-// Frames are converted to bytes on the device (pfs_image_to_rgba8, the reference's (png_byte)(x*255.0)) and
-// only those bytes cross PCIe.  Two deliberate differences from the reference's CUDA driver, both needed to
+// Frames are converted to bytes on the device (pfs_image_to_rgba8, the reference's (png_byte)(x*255.0)), only those
+// bytes cross PCIe (on a second stream), and the PNGs are encoded by worker threads while the next steps run
+// (frame_writer.hpp; PFS_FRAME_WRITERS=0 gives the serial copy-and-encode of the reference).  Two deliberate differences from the reference's CUDA driver, both needed to
 // reproduce what its CPU build computes: the temporary velocity buffer IS uploaded (main.cpp:203-210 never initialises
 // d_vtmp although channel 2 of it is the first pressure guess), and the clock stops after the
 // device is idle (main.cpp:247 stops it before cudaDeviceSynchronize, :252-255).
@@ -24,6 +25,7 @@
 #include "../../include/pfs_b200.h"
 #include "fluid.hpp"
 #include "png_io.hpp"
+#include "frame_writer.hpp"
 
 #define NUM_CHANNELS (4)
 #define VP_RANGE (2.0)
@@ -101,7 +103,17 @@ int main(int argc, char *argv[])
     // frames leave the device as bytes: (png_byte)(x*255.0) is applied by pfs_image_to_rgba8 (utils.hpp:129-131)
     const size_t frame_bytes = img_floats;
     unsigned char *d_frame = nullptr, *h_frame = nullptr;
-    if (flags == 0) {
+    int n_writers = 4;
+    if (const char *e = getenv("PFS_FRAME_WRITERS")) n_writers = atoi(e);
+    if (n_writers > 64) n_writers = 64;
+    FrameWriter *writer = nullptr;
+    if (flags == 0 && n_writers > 0) {
+        writer = new FrameWriter(input_image, image.x, image.y, image.z, n_writers + 2, n_writers);
+        if (!writer->ok()) {
+            std::cerr << "cannot set up the frame writer" << std::endl;
+            return 1;
+        }
+    } else if (flags == 0) {
         if (!cuda_ok(cudaMalloc((void **)&d_frame, frame_bytes), "cudaMalloc frame") ||
             !cuda_ok(cudaMallocHost((void **)&h_frame, frame_bytes), "cudaMallocHost frame"))
             return 1;
@@ -125,24 +137,36 @@ int main(int argc, char *argv[])
         simulate_fluid_step(&d_vp, &d_vtmp, delta_t, viscosity, vp.x, vp.y, vp.z);
         advect_color_step(&d_image, &d_itmp, &d_vp, delta_t, image.x, image.y, image.z, vp.x, vp.y, vp.z);
         if (flags == 0) {
+            std::string outpath = std::string(argv[6]);
+            if (!outpath.empty() && outpath.back() != '/') outpath += "/";
+            outpath += std::to_string(i) + ".png";
+            std::cout << "[" << i << "] Writing to : " << outpath << std::endl;
+            if (writer) {
+                if (!writer->submit(d_image, outpath)) {
+                    std::cerr << writer->error() << std::endl;
+                    return 1;
+                }
+                continue;
+            }
             if (pfs_image_to_rgba8(d_image, d_frame, image.x, image.y, image.z, nullptr) != PFS_OK) {
                 std::cerr << pfs_last_error() << std::endl;
                 return 1;
             }
             if (!cuda_ok(cudaMemcpy(h_frame, d_frame, frame_bytes, cudaMemcpyDeviceToHost), "D2H frame")) return 1;
-            std::string outpath = std::string(argv[6]);
-            if (!outpath.empty() && outpath.back() != '/') outpath += "/";
-            outpath += std::to_string(i) + ".png";
-            std::cout << "[" << i << "] Writing to : " << outpath << std::endl;
             pngio::write_png_from_bytes(&input_image, outpath.c_str(), h_frame);
         }
     }
     cudaDeviceSynchronize();
+    if (writer && !writer->finish()) {   // every frame is on disk before the clock stops
+        std::cerr << writer->error() << std::endl;
+        return 1;
+    }
     auto time_end = std::chrono::high_resolution_clock::now();
     std::cout << n_timesteps << " timesteps took "
               << std::chrono::duration_cast<std::chrono::microseconds>(time_end - time_start).count() << " us."
               << std::endl;
 
+    delete writer;
     cudaFreeHost(image.data);
     cudaFreeHost(vp.data);
     cudaFreeHost(vtmp.data);

@@ -59,3 +59,36 @@ def test_driver_timing_mode_and_errors(pngs):
     assert r.returncode == 1 and "Timesteps must be greater than 0." in r.stderr
     r = subprocess.run([EXE, "3", "0.1", "0.001", "/nonexistent.png", "b"], capture_output=True, text=True)
     assert r.returncode == 1 and "Something went wrong reading the input image..." in r.stderr
+
+
+# ---- the committed frames of the reference's own program (tests/golden/driver_frames.json) --------------------------
+import driver_cases as dc  # noqa: E402
+
+
+@pytest.mark.parametrize("name", sorted(dc.CASES))
+def test_b200_driver_matches_reference_program(name, tmp_path):
+    lines, crcs, out = dc.run_driver(dc.B200, name, str(tmp_path))
+    gold = dc.load_driver_golden()["cases"][name]
+    assert crcs == gold["frames_crc32"]
+    assert lines[0] == gold["stdout_head"]
+    want = dc.expected_lines(name, out, pngio.read_rgba8(str(tmp_path / "vel.png")).shape)
+    assert lines[:len(want)] == want
+
+
+@pytest.mark.skipif(not os.path.exists(dc.REF_MAIN_B200), reason="oracle/_ref/fluidsim_cuda_b200 not built")
+@pytest.mark.parametrize("name", sorted(dc.CASES))
+def test_unmodified_reference_main_on_b200_backend(name, tmp_path):
+    """src/main.cpp -DUSE_CUDA of the reference, unmodified, linked against libfluid_b200.so instead of fluid.cu
+    (INTEGRATION.md 3.1).  PFS_SHIM_INIT_TMP=1 supplies the initial vtmp the reference's CUDA driver forgets to upload."""
+    lines, crcs, out = dc.run_driver(dc.REF_MAIN_B200, name, str(tmp_path), env={"PFS_SHIM_INIT_TMP": "1"})
+    gold = dc.load_driver_golden()["cases"][name]
+    assert crcs == gold["frames_crc32"]
+    assert lines[0] == gold["stdout_head"]
+
+
+@pytest.mark.parametrize("writers", ["0", "1", "3"])
+def test_b200_driver_frame_writer_modes(writers, tmp_path):
+    """Serial copy-and-encode (0) and the threaded frame ring (host/frame_writer.hpp) write the same files."""
+    name = "voronoi256_tulips"
+    lines, crcs, out = dc.run_driver(dc.B200, name, str(tmp_path), env={"PFS_FRAME_WRITERS": writers})
+    assert crcs == dc.load_driver_golden()["cases"][name]["frames_crc32"]
