@@ -196,6 +196,18 @@ int pfs_image_to_rgba8(const float *image, unsigned char *out, int ix, int iy, i
  * Warp-shuffle + fixed-order block reduction in double; synchronises `stream`.  The slab variant all-reduces
  * over the ring (NCCL) and returns the norms of the whole grid on every rank. */
 int pfs_step_norms(const float *vp, const float *tmp, int vx, int vy, int vz, double out[4], void *stream);
+
+/* ---- pressure solve with a run-time sweep count (not in the reference: computePressure always runs
+ *      NUM_JACOBI_ITERS sweeps with no residual test, fluid.cpp:239-266) ---- */
+/* As pfs_compute_pressure, but the number of sweeps N is chosen while running: sweeps go in batches of
+ * `check_every` (>= 2; each batch is fused passes), and after each batch rms(p_N - p_{N-1}) =
+ * ||p_N - p_{N-1}||_2 / sqrt(vx*vy) is read back; the solve stops at the first batch where it is <= tol, or at
+ * max_sweeps.  The buffers then hold EXACTLY what pfs_compute_pressure(n_sweeps = *sweeps_out) leaves in them
+ * (same bits, same pointer exchange), so a run can be replayed with the fixed-count entry point.
+ * *update_rms_out = the last rms.  Synchronises `stream` once per batch; cannot be captured into a graph. */
+int pfs_compute_pressure_adaptive(float **vp, float **vp_out, float dt, int vx, int vy, int vz, float tol,
+                                  int max_sweeps, int check_every, int *sweeps_out, double *update_rms_out,
+                                  void *stream);
 int pfs_slab_step_norms(pfs_slab *const *slabs, int n_local, float *const *vp, float *const *tmp, double out[4],
                         void *const *streams);
 

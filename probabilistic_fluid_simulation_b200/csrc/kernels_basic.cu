@@ -386,15 +386,62 @@ __global__ void __launch_bounds__(256)
     }
 }
 
+// Same reduction for two SoA planes: [0] sum (a-b)^2, [1] 0, [2] sum a^2, [3] max |a-b|
+// (a = iterate N, b = iterate N-1 of the pressure solve; used by pfs_compute_pressure_adaptive).
+__global__ void __launch_bounds__(256)
+    plane_diff_partial_kernel(const float *__restrict__ a, const float *__restrict__ b, size_t n, double *partials)
+{
+    double s0 = 0.0, s2 = 0.0;
+    float m = 0.f;
+    for (size_t i = (size_t)blockIdx.x * 256 + threadIdx.x; i < n; i += (size_t)gridDim.x * 256) {
+        const float x = __ldg(a + i), y = __ldg(b + i);
+        const double r = (double)x - (double)y;
+        s0 += r * r;
+        s2 += (double)x * (double)x;
+        m = fmaxf(m, fabsf(__fsub_rn(x, y)));
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        s0 += __shfl_xor_sync(0xffffffffu, s0, o);
+        s2 += __shfl_xor_sync(0xffffffffu, s2, o);
+        m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, o));
+    }
+    __shared__ double sh[8][3];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    if (lane == 0) {
+        sh[warp][0] = s0; sh[warp][1] = s2; sh[warp][2] = (double)m;
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        double t0 = 0, t2 = 0, t3 = 0;
+        for (int q = 0; q < 8; q++) {
+            t0 += sh[q][0]; t2 += sh[q][1]; t3 = fmax(t3, sh[q][2]);
+        }
+        double *o = partials + 4 * (size_t)blockIdx.x;
+        o[0] = t0; o[1] = 0.0; o[2] = t2; o[3] = t3;
+    }
+}
+
+// One warp folds the per-block partials: lane l takes partials l, l+32, ... in that order, then a shuffle tree.
+// The order depends only on nblocks, so the result does not depend on scheduling.
 __global__ void norms_final_kernel(const double *partials, int nblocks, double *out)
 {
-    if (threadIdx.x != 0 || blockIdx.x != 0) return;
+    if (blockIdx.x != 0 || threadIdx.x >= 32) return;
     double t0 = 0, t1 = 0, t2 = 0, t3 = 0;
-    for (int q = 0; q < nblocks; q++) {
+    for (int q = threadIdx.x; q < nblocks; q += 32) {
         t0 += partials[4 * q + 0]; t1 += partials[4 * q + 1]; t2 += partials[4 * q + 2];
         t3 = fmax(t3, partials[4 * q + 3]);
     }
-    out[0] = t0; out[1] = t1; out[2] = t2; out[3] = t3;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        t0 += __shfl_xor_sync(0xffffffffu, t0, o);
+        t1 += __shfl_xor_sync(0xffffffffu, t1, o);
+        t2 += __shfl_xor_sync(0xffffffffu, t2, o);
+        t3 = fmax(t3, __shfl_xor_sync(0xffffffffu, t3, o));
+    }
+    if (threadIdx.x == 0) {
+        out[0] = t0; out[1] = t1; out[2] = t2; out[3] = t3;
+    }
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -521,6 +568,16 @@ int launch_pack_rgba8(const float *image_aos, unsigned char *out, size_t pixels,
     const unsigned blocks = (unsigned)((pixels + 255) / 256);
     PFS_LAUNCH(pack_rgba8_kernel, blocks, 256, 0, s, reinterpret_cast<const float4 *>(image_aos),
                reinterpret_cast<uchar4 *>(out), pixels);
+    return PFS_OK;
+}
+
+int launch_plane_diff_norms(const float *a, const float *b, size_t cells, double *partials, int max_blocks, double *out4,
+                            cudaStream_t s)
+{
+    int blocks = (int)std::min<size_t>((size_t)max_blocks, (cells + 255) / 256);
+    if (blocks < 1) blocks = 1;
+    PFS_LAUNCH(plane_diff_partial_kernel, blocks, 256, 0, s, a, b, cells, partials);
+    PFS_LAUNCH(norms_final_kernel, 1, 32, 0, s, partials, blocks, out4);
     return PFS_OK;
 }
 

@@ -62,6 +62,8 @@ struct DeviceScratch {
     size_t stage_floats[4] = {0, 0, 0, 0};
     cudaStream_t streams[2] = {nullptr, nullptr};             // host-API streams
     cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};
+    double *norm_dev = nullptr;       // reduction partials + 4 results (pfs_compute_pressure_adaptive)
+    double *norm_host = nullptr;      // pinned, 4 doubles
     float *plane(int k) const { return planes + (size_t)k * plane_cells; }
 };
 
@@ -78,6 +80,8 @@ static void free_scratch(DeviceScratch &sc)
         if (sc.streams[i]) cudaStreamDestroy(sc.streams[i]);
     for (int i = 0; i < 4; i++)
         if (sc.ev[i]) cudaEventDestroy(sc.ev[i]);
+    if (sc.norm_dev) cudaFree(sc.norm_dev);
+    if (sc.norm_host) cudaFreeHost(sc.norm_host);
     sc = DeviceScratch();
 }
 
@@ -446,6 +450,83 @@ extern "C" int pfs_compute_pressure(float **vp, float **vp_out, float dt, int vx
     PFS_TRY(launch_pack(buf_prev, nullptr, nullptr, (n_sweeps >= 2) ? prev.c0 : nullptr, div, vx, vy, s));
     *vp_out = buf_last;
     *vp = buf_prev;
+    return PFS_OK;
+}
+
+// Run-time choice of the sweep count (the reference fixes it, fluid.cpp:239).  Batches of
+// `check_every` sweeps; after each, rms(p_N - p_{N-1}) from the two iterates the fused pass leaves behind.
+extern "C" int pfs_compute_pressure_adaptive(float **vp, float **vp_out, float dt, int vx, int vy, int vz, float tol,
+                                             int max_sweeps, int check_every, int *sweeps_out, double *update_rms_out,
+                                             void *stream)
+{
+    const char *fn = "pfs_compute_pressure_adaptive";
+    PFS_TRY(check_dims(fn, vx, vy, vz));
+    PFS_TRY(check_sweeps(fn, max_sweeps));
+    if (!vp || !vp_out) {
+        set_error("%s: vp / vp_out handle is null", fn);
+        return PFS_EINVAL;
+    }
+    if (check_every < 2 || !(tol >= 0.0f)) {
+        set_error("%s: check_every must be >= 2 and tol >= 0 (got %d, %g)", fn, check_every, (double)tol);
+        return PFS_EINVAL;
+    }
+    PFS_TRY(check_ptr(fn, "*vp", *vp));
+    PFS_TRY(check_ptr(fn, "*vp_out", *vp_out));
+    cudaStream_t s = (cudaStream_t)stream;
+    cudaStreamCaptureStatus cap = cudaStreamCaptureStatusNone;
+    PFS_CUDA(cudaStreamIsCapturing(s, &cap));
+    if (cap != cudaStreamCaptureStatusNone) {
+        set_error("%s: reads a norm back after every batch, cannot be captured into a graph", fn);
+        return PFS_EINVAL;
+    }
+    DeviceScratch *sc;
+    const size_t cells = (size_t)vx * vy;
+    PFS_TRY(get_scratch(cells, &sc));
+    float *in0 = *vp, *out0 = *vp_out;
+    float *u = sc->plane(0), *v = sc->plane(1), *div = sc->plane(6);
+    PlanePair cur{sc->plane(4), nullptr}, oth{sc->plane(5), nullptr}, last = cur, prev = oth;
+    const PlanePair extra{sc->plane(9), nullptr};
+    PFS_TRY(launch_unpack(in0, u, v, nullptr, nullptr, vx, vy, s));
+    PFS_TRY(launch_divergence(u, v, div, in0, cur.c0, dt, vx, vy, s));
+    SweepParams p{vx, vy, 1.0f, 4.0f};
+    constexpr int kBlocks = 1184;
+    if (!sc->norm_dev) PFS_CUDA(cudaMalloc((void **)&sc->norm_dev, (4 * (size_t)kBlocks + 4) * sizeof(double)));
+    if (!sc->norm_host) PFS_CUDA(cudaMallocHost((void **)&sc->norm_host, 4 * sizeof(double)));
+    double *scratch = sc->norm_dev, *host = sc->norm_host;
+    int done = 0, rc = PFS_OK;
+    double rms = 0.0;
+    while (done < max_sweeps) {
+        int n = std::min(check_every, max_sweeps - done);
+        if (max_sweeps - done - n == 1) n += 1;             // never leave a batch of one sweep (it keeps no p_{N-1})
+        rc = run_sweeps(SWEEP_PRESSURE, cur, oth, extra, div, p, n, &last, &prev, s);
+        if (rc != PFS_OK) break;
+        done += n;
+        rc = launch_plane_diff_norms(last.c0, prev.c0, cells, scratch, kBlocks, scratch + 4 * (size_t)kBlocks, s);
+        if (rc != PFS_OK) break;
+        cudaError_t e = cudaMemcpyAsync(host, scratch + 4 * (size_t)kBlocks, 4 * sizeof(double), cudaMemcpyDeviceToHost, s);
+        if (e == cudaSuccess) e = cudaStreamSynchronize(s);
+        if (e != cudaSuccess) {
+            rc = cuda_fail(e, fn, __FILE__, __LINE__);
+            break;
+        }
+        rms = sqrt(host[0] / (double)cells);
+        if (rms <= (double)tol) break;
+        if (done < max_sweeps) {
+            // next batch starts from iterate `done`; the other plane of the ping-pong pair is free again
+            // (p_{done-1} is only needed if this was the final batch)
+            oth = (last.c0 == sc->plane(4)) ? PlanePair{sc->plane(5), nullptr} : PlanePair{sc->plane(4), nullptr};
+            cur = last;
+        }
+    }
+    if (rc != PFS_OK) return rc;
+    float *buf_last = (done & 1) ? out0 : in0;
+    float *buf_prev = (done & 1) ? in0 : out0;
+    PFS_TRY(launch_pack(buf_last, nullptr, nullptr, last.c0, div, vx, vy, s));
+    PFS_TRY(launch_pack(buf_prev, nullptr, nullptr, prev.c0, div, vx, vy, s));
+    *vp_out = buf_last;
+    *vp = buf_prev;
+    if (sweeps_out) *sweeps_out = done;
+    if (update_rms_out) *update_rms_out = rms;
     return PFS_OK;
 }
 

@@ -231,6 +231,8 @@ int launch_pack_rgba8(const float *image_aos, unsigned char *out, size_t pixels,
 
 // Step diagnostics from the two post-state buffers (kernels_basic.cu): out4 = {sum div^2, sum (p_N - p_{N-1})^2,
 // sum (u^2 + v^2), max(|u|,|v|)} in device memory; `partials` holds 4 doubles per block (<= max_blocks blocks).
+int launch_plane_diff_norms(const float *a, const float *b, size_t cells, double *partials, int max_blocks, double *out4,
+                            cudaStream_t s);
 int launch_step_norms(const float *vp_aos, const float *tmp_aos, size_t cells, double *partials, int max_blocks,
                       double *out4, cudaStream_t s);
 

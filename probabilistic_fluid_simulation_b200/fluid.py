@@ -154,6 +154,23 @@ def computePressure(vp: vp_field, vp_out: vp_field, dt: float, n_sweeps: int = N
     h.commit()
 
 
+def computePressureAdaptive(vp: vp_field, vp_out: vp_field, dt: float, tol: float, max_sweeps: int,  # noqa: N802
+                            check_every: int = 16) -> tuple[int, float]:
+    """computePressure with the sweep count chosen at run time (pfs_compute_pressure_adaptive; not in the reference,
+    which fixes NUM_JACOBI_ITERS).  -> (sweeps done, rms of the last update).  The buffers hold exactly what
+    computePressure(n_sweeps=sweeps done) would have left."""
+    L = _cabi.lib()
+    _check_buf(vp, "vp"); _check_buf(vp_out, "vp_out")
+    _require_device("computePressureAdaptive", vp, vp_out)
+    h = _Handles(vp, vp_out)
+    n, rms = ctypes.c_int(0), ctypes.c_double(0.0)
+    with _dev_guard(vp.data):
+        check(L.pfs_compute_pressure_adaptive(h.ref(0), h.ref(1), dt, vp.x, vp.y, vp.z, tol, max_sweeps, check_every,
+                                              ctypes.byref(n), ctypes.byref(rms), _stream_of(vp.data)))
+    h.commit()
+    return n.value, rms.value
+
+
 def subtractPressureGradient(vp: vp_field, vp_out: vp_field, dt: float) -> None:  # noqa: N802
     L = _cabi.lib()
     _check_buf(vp, "vp"); _check_buf(vp_out, "vp_out")

@@ -103,7 +103,9 @@ int main(int argc, char *argv[])
     // frames leave the device as bytes: (png_byte)(x*255.0) is applied by pfs_image_to_rgba8 (utils.hpp:129-131)
     const size_t frame_bytes = img_floats;
     unsigned char *d_frame = nullptr, *h_frame = nullptr;
-    int n_writers = 4;
+    int n_writers = (int)(std::thread::hardware_concurrency() / 2);   // PNG encoding is the slow part of a frame
+    if (n_writers < 1) n_writers = 1;
+    if (n_writers > 8) n_writers = 8;
     if (const char *e = getenv("PFS_FRAME_WRITERS")) n_writers = atoi(e);
     if (n_writers > 64) n_writers = 64;
     FrameWriter *writer = nullptr;

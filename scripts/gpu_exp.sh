@@ -1,14 +1,9 @@
 #!/bin/bash
 set -u
 TAG=${1:-exp}; OUT=gpurun_out/$TAG; mkdir -p "$OUT"; : > "$OUT/summary.txt"
-timeout 1200 python -m pytest tests -x -q -m gpu > "$OUT/pytest.log" 2>&1
-echo "pytest exit $?" | tee -a "$OUT/summary.txt"; tail -4 "$OUT/pytest.log" | tee -a "$OUT/summary.txt"
-run() {
-  name=$1; extra=$2; shift; shift
-  echo "== $name" | tee -a "$OUT/summary.txt"
-  env "$@" timeout 600 python bench.py --no-e2e --no-cpu $extra > "$OUT/bench_$name.json" 2> "$OUT/bench_$name.err"
-  python -c "import json;d=json.load(open('$OUT/bench_$name.json'));print('ms/step %.4f'%d['ms_per_step'], 'eager %.4f'%d['phase_region']['ms_per_step_eager_with_phase_events'], {k: round(v,4) for k,v in d['phases_ms'].items()}, d['gpu_launches'])" | tee -a "$OUT/summary.txt"
-  tail -2 "$OUT/bench_$name.err" | tee -a "$OUT/summary.txt"
-}
-run default "--steps 50 --warmup 5" X=1
-run cfg2 "--width 1024 --height 1024 --iters 50 --steps 400 --warmup 20" X=1
+timeout 1500 python -m pytest tests -x -q -m gpu > "$OUT/pytest.log" 2>&1
+echo "pytest exit $?" | tee -a "$OUT/summary.txt"; tail -6 "$OUT/pytest.log" | tee -a "$OUT/summary.txt"
+timeout 600 python scripts/adaptive_report.py > "$OUT/adaptive.json" 2> "$OUT/adaptive.err"; echo "adaptive exit $?" | tee -a "$OUT/summary.txt"
+timeout 600 python scripts/frame_mode_timing.py 1024 24 > "$OUT/frames_1024.json" 2> "$OUT/frames.err"; echo "frames exit $?" | tee -a "$OUT/summary.txt"
+timeout 600 python scripts/frame_mode_timing.py 4096 8 > "$OUT/frames_4096.json" 2>> "$OUT/frames.err"; echo "frames4096 exit $?" | tee -a "$OUT/summary.txt"
+nproc | tee -a "$OUT/summary.txt"
