@@ -35,6 +35,7 @@ namespace pfs {
 
 constexpr int MAX_HALO = 32;   // halo rows per side: one exchange feeds MAX_HALO / depth fused passes
 constexpr int MIN_HALO = 8;    // >= the deepest fused pass
+constexpr int N_SLAB_PLANES = 10;   // u,v x2 | p x2 | div | iterate n-1 of the last pass: u,v | p
 
 // ---------------------------------------------------------------------------------------------
 // NCCL through dlopen
@@ -135,7 +136,7 @@ struct pfs_slab {
     int device = 0;
     int halo = pfs::MIN_HALO;             // halo rows per side of every plane (multiple of 8, <= the thinnest band)
     size_t plane_floats = 0;
-    float *planes = nullptr;              // 7 planes of (rows + 2*halo) x gw
+    float *planes = nullptr;              // N_SLAB_PLANES planes of (rows + 2*halo) x gw
     // gather sources of advect / advect_color: D halo rows received from each ring neighbour (interleaved
     // cells, [above | below]); or -- when D exceeds a band -- a copy of the whole field (all-gather)
     float4 *vhalo = nullptr, *ihalo = nullptr;
@@ -585,8 +586,8 @@ extern "C" int pfs_slab_create(pfs_slab **out, int rank, int nranks, int gw, int
     auto fail = [&](cudaError_t ce, const char *what) {
         st = cuda_fail(ce, what, __FILE__, __LINE__);
     };
-    if ((e = cudaMalloc((void **)&s->planes, 7 * s->plane_floats * sizeof(float))) != cudaSuccess) fail(e, "cudaMalloc planes");
-    if (st == PFS_OK && (e = cudaMemset(s->planes, 0, 7 * s->plane_floats * sizeof(float))) != cudaSuccess) fail(e, "cudaMemset");
+    if ((e = cudaMalloc((void **)&s->planes, pfs::N_SLAB_PLANES * s->plane_floats * sizeof(float))) != cudaSuccess) fail(e, "cudaMalloc planes");
+    if (st == PFS_OK && (e = cudaMemset(s->planes, 0, pfs::N_SLAB_PLANES * s->plane_floats * sizeof(float))) != cudaSuccess) fail(e, "cudaMemset");
     if (st == PFS_OK && (e = cudaMalloc((void **)&s->d_scalars, 4 * sizeof(float))) != cudaSuccess) fail(e, "cudaMalloc scalars");
     if (st == PFS_OK && (e = cudaMemset(s->d_scalars, 0, 4 * sizeof(float))) != cudaSuccess) fail(e, "cudaMemset");
     if (st == PFS_OK && (e = cudaMallocHost((void **)&s->h_scalars, 4 * sizeof(float))) != cudaSuccess) fail(e, "cudaMallocHost");
@@ -838,15 +839,16 @@ extern "C" int pfs_slab_simulate_fluid_step(pfs_slab *const *slabs, int n_local,
         }
     }
 
-    // n sweeps starting from iterate 0 in planes (pa0, pa1): n-1 in fused passes, then one sweep into the
-    // other set.  `valid` tracks how many halo rows of the current iterate are correct on every slab: an
-    // exchange makes it `halo`; a pass of depth t needs t of them and -- by also recomputing the e = valid-t
-    // rows just outside the band -- leaves e valid rows on its result.
+    // n sweeps starting from iterate 0 in planes (pa0, pa1), all in fused passes; the pass that reaches sweep n also
+    // stores iterate n-1 into planes (px0, px1) (as pfs_api.cu's run_sweeps does), so both iterates the reference
+    // leaves behind exist afterwards.  `valid` tracks how many halo rows of the current iterate are correct on
+    // every slab: an exchange makes it `halo`; a pass of depth t needs t of them and -- by also recomputing the
+    // e = valid-t rows just outside the band -- leaves e valid rows on its result.
     const int halo = L[0]->halo;
-    auto run_sweeps = [&](SweepOp op, int pa0, int pa1, int pb0, int pb1, const SweepParams &proto, int count,
-                          int *last_is_b, int *valid_out) -> int {
+    auto run_sweeps = [&](SweepOp op, int pa0, int pa1, int pb0, int pb1, int px0, int px1, const SweepParams &proto,
+                          int count, int *last0, int *last1, int *prev0, int *prev1, int *valid_out) -> int {
         int cur0 = pa0, cur1 = pa1, oth0 = pb0, oth1 = pb1;
-        int left = count - 1;
+        int left = count;
         int valid = 0;
         const bool vec = (gw % 4 == 0);
         SweepParams p0 = proto;
@@ -854,7 +856,8 @@ extern "C" int pfs_slab_simulate_fluid_step(pfs_slab *const *slabs, int n_local,
         const int user_depth = pfs_get_fuse_depth();
         int depth = user_depth > 0 ? std::min(user_depth, MIN_HALO) : (packed ? default_diffuse_depth() : MIN_HALO);
         if (!vec) depth = 1;
-        auto one_pass = [&](int t) -> int {
+        bool prev_in_extra = false;
+        auto one_pass = [&](int t, bool final_pass) -> int {
             if (valid < t) {
                 std::vector<std::vector<float *>> pl(n);
                 for (int k = 0; k < n; k++) {
@@ -873,19 +876,22 @@ extern "C" int pfs_slab_simulate_fluid_step(pfs_slab *const *slabs, int n_local,
                 p.h = s->rows + 2 * e;
                 p.y_base = halo - e;
                 p.wrap = 0;
-                int flips = 0;
+                int flips = 0, wrote = 0;
                 float *a0 = s->plane(cur0), *a1 = s->plane(cur1), *b0 = s->plane(oth0), *b1 = s->plane(oth1);
+                float *x0 = (final_pass && t >= 2) ? s->plane(px0) : nullptr;
+                float *x1 = (final_pass && t >= 2) ? s->plane(px1) : nullptr;
                 const float *rhs = (op == SWEEP_PRESSURE) ? s->plane(6) : nullptr;
                 if (t == 1)
                     PFS_TRY(launch_sweeps_basic(op, a0, a1, b0, b1, rhs, p, 1, &flips, s->stream));
                 else if (packed)
-                    PFS_TRY(launch_diffuse_packed(a0, a1, b0, b1, p, t, t, &flips, s->stream));
+                    PFS_TRY(launch_diffuse_packed(a0, a1, b0, b1, p, t, t, &flips, s->stream, x0, x1, &wrote));
                 else
-                    PFS_TRY(launch_sweeps_fused(op, a0, a1, b0, b1, rhs, p, t, t, &flips, s->stream));
-                if (flips != 1) {
-                    set_error("slab sweeps: a pass of depth %d took %d hops", t, flips);
+                    PFS_TRY(launch_sweeps_fused(op, a0, a1, b0, b1, rhs, p, t, t, &flips, s->stream, x0, x1, &wrote));
+                if (flips != 1 || (x0 != nullptr && !wrote)) {
+                    set_error("slab sweeps: a pass of depth %d took %d hops (previous iterate stored: %d)", t, flips, wrote);
                     return PFS_ESTATE;
                 }
+                if (x0 != nullptr) prev_in_extra = true;
             }
             valid = e;
             std::swap(cur0, oth0);
@@ -895,11 +901,14 @@ extern "C" int pfs_slab_simulate_fluid_step(pfs_slab *const *slabs, int n_local,
         while (left > 0) {
             int t = std::min(left, depth);
             if (t < 1) t = 1;
-            PFS_TRY(one_pass(t));
+            if (left - t == 1 && t >= 3) t -= 1;        // never end on a lone single sweep: it could not store iterate n-1
+            PFS_TRY(one_pass(t, left - t == 0));
             left -= t;
         }
-        PFS_TRY(one_pass(1));
-        *last_is_b = (cur0 == pb0) ? 1 : 0;
+        *last0 = cur0;
+        *last1 = cur1;
+        *prev0 = prev_in_extra ? px0 : oth0;            // else: the set the last (single) sweep read
+        *prev1 = prev_in_extra ? px1 : oth1;
         *valid_out = valid;
         return PFS_OK;
     };
@@ -909,12 +918,11 @@ extern "C" int pfs_slab_simulate_fluid_step(pfs_slab *const *slabs, int n_local,
     dp.h = L[0]->rows;
     dp.alpha = viscosity * dt;
     dp.beta = (float)(1.0 + 4.0 * (double)dp.alpha);
-    int d_last_is_b = 0, d_valid = 0;
+    int d_valid = 0;
+    int dl0 = 0, dl1 = 1, dp0 = 2, dp1 = 3;                              // iterate n_d, iterate n_d - 1
     next_phase(PFS_PHASE_DIFFUSE);
-    PFS_TRY(run_sweeps(SWEEP_DIFFUSE, 0, 1, 2, 3, dp, n_diffuse, &d_last_is_b, &d_valid));
+    PFS_TRY(run_sweeps(SWEEP_DIFFUSE, 0, 1, 2, 3, 7, 8, dp, n_diffuse, &dl0, &dl1, &dp0, &dp1, &d_valid));
     next_phase(PFS_PHASE_DIVERGENCE);
-    const int dl0 = d_last_is_b ? 2 : 0, dl1 = d_last_is_b ? 3 : 1;      // iterate n_d
-    const int dp0 = d_last_is_b ? 0 : 2, dp1 = d_last_is_b ? 1 : 3;      // iterate n_d - 1
 
     // pointer choreography (pfs_simulate_fluid_step)
     std::vector<float *> Bv(n), Bo(n), Bp(n), Bq(n);
@@ -944,11 +952,11 @@ extern "C" int pfs_slab_simulate_fluid_step(pfs_slab *const *slabs, int n_local,
     pp.h = L[0]->rows;
     pp.alpha = 1.0f;
     pp.beta = 4.0f;
-    int p_last_is_b = 0, p_valid = 0;
+    int p_valid = 0;
+    int pl_last = 4, pl_prev = 5, unused0 = 0, unused1 = 0;
     next_phase(PFS_PHASE_PRESSURE);
-    PFS_TRY(run_sweeps(SWEEP_PRESSURE, 4, 4, 5, 5, pp, n_pressure, &p_last_is_b, &p_valid));
+    PFS_TRY(run_sweeps(SWEEP_PRESSURE, 4, 4, 5, 5, 9, 9, pp, n_pressure, &pl_last, &unused0, &pl_prev, &unused1, &p_valid));
     next_phase(PFS_PHASE_PROJECT);
-    const int pl_last = p_last_is_b ? 5 : 4, pl_prev = p_last_is_b ? 4 : 5;
 
     // ---- gradient subtraction + write-back (needs one halo row of p_N) ----
     {
