@@ -1,8 +1,11 @@
 #!/bin/bash
+# N=2: the NCCL slab test + the N=2 bench line
 set -u
 TAG=${1:-exp}; OUT=gpurun_out/$TAG; mkdir -p "$OUT"; : > "$OUT/summary.txt"
-timeout 1500 python -m pytest tests -x -q -m gpu > "$OUT/pytest.log" 2>&1
-echo "pytest exit $?" | tee -a "$OUT/summary.txt"; tail -6 "$OUT/pytest.log" | tee -a "$OUT/summary.txt"
-timeout 600 python scripts/adaptive_report.py > "$OUT/adaptive.json" 2> "$OUT/adaptive.err"; echo "adaptive exit $?" | tee -a "$OUT/summary.txt"
-timeout 600 python bench.py --no-e2e --no-cpu --width 16384 --height 2048 --steps 20 --warmup 3 > "$OUT/bench_16384x2048.json" 2> "$OUT/bench_16384x2048.err"; echo "bench slab-shaped exit $?" | tee -a "$OUT/summary.txt"
-timeout 900 python bench.py > "$OUT/bench_default.json" 2> "$OUT/bench_default.err"; echo "bench default exit $?" | tee -a "$OUT/summary.txt"
+timeout 900 python -m pytest tests/test_gpu_slabs.py -x -q -m gpu > "$OUT/pytest_slabs.log" 2>&1
+echo "pytest slabs exit $?" | tee -a "$OUT/summary.txt"; tail -4 "$OUT/pytest_slabs.log" | tee -a "$OUT/summary.txt"
+n=2
+timeout 1200 python -m torch.distributed.run --nnodes=1 --nproc-per-node $n --master-addr 127.0.0.1 --master-port 29511 bench.py --gpus $n --steps 10 --warmup 3 > "$OUT/bench_n$n.json" 2> "$OUT/bench_n$n.err"
+echo "bench exit $?" | tee -a "$OUT/summary.txt"
+python -c "import json;d=json.load(open('$OUT/bench_n$n.json'));print('ms/step',d['ms_per_step'],'value',d['value'],'e2e',d['e2e'] and d['e2e']['ms_per_step'], d['phases_ms_rank0'], d['clocks'])" | tee -a "$OUT/summary.txt"
+grep -v "OMP_NUM_THREADS\|^\*\*\*\|NCCL version" "$OUT/bench_n$n.err" | tail -3 | tee -a "$OUT/summary.txt"
