@@ -174,6 +174,10 @@ int pfs_slab_rows(const pfs_slab *s, int *row0, int *rows, int *irow0, int *irow
 int pfs_slab_connect_local(pfs_slab *const *slabs, int n);         /* all n ranks, in rank order */
 int pfs_slab_nccl_unique_id(char id[128]);                          /* rank 0; ship the bytes to every rank */
 int pfs_slab_connect_nccl(pfs_slab *s, const char id[128]);         /* collective over all ranks */
+/* Which transport carries this slab's halo rows: "p2p" (rows stored straight into the ring neighbours' memory
+ * through CUDA IPC mappings, set up by pfs_slab_connect_nccl when every rank can map its neighbours;
+ * PFS_SLAB_TRANSPORT=nccl turns it off), "nccl" (send/recv), "local" (slabs of one process), "unconnected". */
+const char *pfs_slab_transport(const pfs_slab *s);
 /* simulate_fluid_step / advect_color_step (fluid.hpp:107,116) on the bands.  slabs/vp/tmp/streams are
  * arrays over the LOCAL slabs (all ranks for the in-process transport, exactly one under NCCL); vp[k] and
  * tmp[k] are exchanged exactly as pfs_simulate_fluid_step exchanges *vp and *tmp. */

@@ -68,6 +68,7 @@ SIGNATURES = {
     "pfs_step_norms": (_int, [_vp, _vp, _int, _int, _int, ctypes.POINTER(ctypes.c_double), _vp]),
     "pfs_compute_pressure_adaptive": (_int, [_pp, _pp, _f32, _int, _int, _int, _f32, _int, _int, ctypes.POINTER(_int),
                                              ctypes.POINTER(ctypes.c_double), _vp]),
+    "pfs_slab_transport": (ctypes.c_char_p, [_vp]),
     "pfs_slab_step_norms": (_int, [_pp, _int, _pp, _pp, ctypes.POINTER(ctypes.c_double), _pp]),
     "pfs_phase_timing_enable": (_int, [_int]),
     "pfs_phase_times": (_int, [ctypes.POINTER(_f32), ctypes.POINTER(ctypes.c_uint64), _int]),

@@ -36,6 +36,8 @@ namespace pfs {
 constexpr int MAX_HALO = 32;   // halo rows per side: one exchange feeds MAX_HALO / depth fused passes
 constexpr int MIN_HALO = 8;    // >= the deepest fused pass
 constexpr int N_SLAB_PLANES = 10;   // u,v x2 | p x2 | div | iterate n-1 of the last pass: u,v | p
+constexpr int P2P_GATHER_ROWS = 64; // capacity (rows per side) of the peer-written gather halos; deeper gathers go through NCCL
+constexpr int P2P_FLAG_INTS = 16;
 
 // ---------------------------------------------------------------------------------------------
 // NCCL through dlopen
@@ -50,6 +52,7 @@ struct NcclApi {
     ncclResult_t (*Recv)(void *, size_t, ncclDataType_t, int, ncclComm_t, cudaStream_t) = nullptr;
     ncclResult_t (*AllReduce)(const void *, void *, size_t, ncclDataType_t, ncclRedOp_t, ncclComm_t, cudaStream_t) = nullptr;
     ncclResult_t (*Broadcast)(const void *, void *, size_t, ncclDataType_t, int, ncclComm_t, cudaStream_t) = nullptr;
+    ncclResult_t (*AllGather)(const void *, void *, size_t, ncclDataType_t, ncclComm_t, cudaStream_t) = nullptr;   // optional
     const char *(*GetErrorString)(ncclResult_t) = nullptr;
     bool loaded = false;
 };
@@ -77,6 +80,7 @@ static NcclApi &nccl()
     PFS_NCCL_SYM(Recv, "ncclRecv");
     PFS_NCCL_SYM(AllReduce, "ncclAllReduce");
     PFS_NCCL_SYM(Broadcast, "ncclBroadcast");
+    PFS_NCCL_SYM(AllGather, "ncclAllGather");
     PFS_NCCL_SYM(GetErrorString, "ncclGetErrorString");
 #undef PFS_NCCL_SYM
     a.loaded = a.GetUniqueId && a.CommInitRank && a.CommDestroy && a.GroupStart && a.GroupEnd && a.Send && a.Recv &&
@@ -146,6 +150,20 @@ struct pfs_slab {
     float *d_scalars = nullptr;           // [0] max|v| (advect), [1] max|v| (advect_color), [2] overflow flag (as int)
     float *h_scalars = nullptr;           // pinned mirror
     ncclComm_t comm = nullptr;
+    // peer transport (one process per GPU, CUDA IPC): the ring neighbours' planes / gather halos / flags mapped here
+    struct PeerLink {
+        float *planes = nullptr;
+        float4 *vhalo = nullptr, *ihalo = nullptr;
+        int *flags = nullptr;
+        size_t plane_floats = 0;
+        int rows = 0, irows = 0;
+    };
+    bool p2p = false;
+    PeerLink link_up, link_down;
+    int *flags = nullptr;                 // [0] ready<-up [1] ready<-down [2] pushed<-up [3] pushed<-down [4] CTA counter
+    float4 *vhalo_p2p = nullptr, *ihalo_p2p = nullptr;   // [above: P2P_GATHER_ROWS rows | below: same], written by the neighbours
+    int xseq = 0;                         // exchanges done over the peer transport (the same on every rank)
+    std::vector<void *> ipc_opened;
     std::vector<pfs_slab *> group;        // in-process transport: all ranks, indexed by rank (empty under NCCL)
     cudaStream_t stream = nullptr;        // stream of the call in flight
     cudaEvent_t ev_ready = nullptr, ev_done = nullptr;
@@ -273,6 +291,103 @@ __global__ void __launch_bounds__(256)
     out[(size_t)jl * iw + i] = o;
 }
 
+// ---- peer transport: halo rows stored straight into the ring neighbours' memory -------------------------------
+// One launch per exchange.  Flags live in each rank's own memory and are written by its neighbours (system-scope
+// release stores through the IPC mapping); `seq` counts exchanges and is the same on every rank.
+//   1. tell both neighbours "my edge rows for exchange seq are final and my halos may be overwritten"
+//   2. wait for the same word from both, then store my top rows into the upper neighbour's bottom halo and my
+//      bottom rows into the lower neighbour's top halo (16-byte stores over NVLink, whole grid)
+//   3. the last CTA to finish fences, tells both neighbours "pushed", and waits until both have pushed to me,
+//      so when the kernel retires this rank's halos are complete.
+// A wait that lasts longer than 20 s gives up and raises the slab's error flag (pfs_slab_check) instead of hanging.
+struct PushSeg {
+    const float4 *src_up, *src_down;
+    float4 *dst_up, *dst_down;
+    unsigned long long n16;
+};
+struct PushArgs {
+    PushSeg seg[3];
+    int nseg;
+    int *mine, *up, *down, *error_flag;
+    int seq;
+};
+
+__device__ __forceinline__ void st_release_sys(int *p, int v)
+{
+    asm volatile("st.release.sys.global.s32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
+__device__ __forceinline__ int ld_acquire_sys(const int *p)
+{
+    int v;
+    asm volatile("ld.acquire.sys.global.s32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+    return v;
+}
+__device__ __forceinline__ unsigned long long global_ns()
+{
+    unsigned long long t;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+    return t;
+}
+__device__ __forceinline__ void wait_flag(const int *p, int seq, int *error_flag)
+{
+    const unsigned long long t0 = global_ns();
+    while (ld_acquire_sys(p) < seq) {
+        if (global_ns() - t0 > 20000000000ull) {
+            atomicExch(error_flag, 9);
+            return;
+        }
+    }
+}
+
+__global__ void __launch_bounds__(256) halo_push_kernel(const PushArgs A)
+{
+    if (threadIdx.x == 0) {
+        if (blockIdx.x == 0) {
+            st_release_sys(A.up + 1, A.seq);
+            st_release_sys(A.down + 0, A.seq);
+        }
+        wait_flag(A.mine + 0, A.seq, A.error_flag);
+        wait_flag(A.mine + 1, A.seq, A.error_flag);
+    }
+    __syncthreads();
+    const size_t tid = (size_t)blockIdx.x * 256 + threadIdx.x, nth = (size_t)gridDim.x * 256;
+    for (int q = 0; q < A.nseg; q++) {
+        const PushSeg g = A.seg[q];
+        for (size_t i = tid; i < g.n16; i += nth) {
+            g.dst_up[i] = g.src_up[i];
+            g.dst_down[i] = g.src_down[i];
+        }
+    }
+    __threadfence_system();
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        const int done = atomicAdd(A.mine + 4, 1);
+        if (done == (int)gridDim.x - 1) {
+            atomicExch(A.mine + 4, 0);
+            __threadfence_system();
+            st_release_sys(A.up + 3, A.seq);
+            st_release_sys(A.down + 2, A.seq);
+            wait_flag(A.mine + 2, A.seq, A.error_flag);
+            wait_flag(A.mine + 3, A.seq, A.error_flag);
+        }
+    }
+}
+
+int launch_halo_push(pfs_slab *s, PushArgs &A)
+{
+    unsigned long long total = 0;
+    for (int q = 0; q < A.nseg; q++) total += A.seg[q].n16;
+    int blocks = (int)std::min<unsigned long long>(128, (total + 255) / 256);
+    if (blocks < 1) blocks = 1;
+    A.mine = s->flags;
+    A.up = s->link_up.flags;
+    A.down = s->link_down.flags;
+    A.error_flag = reinterpret_cast<int *>(s->d_scalars + 2);
+    A.seq = ++s->xseq;
+    PFS_LAUNCH(halo_push_kernel, blocks, 256, 0, s->stream, A);
+    return PFS_OK;
+}
+
 // ---- transport ----------------------------------------------------------------------------------
 // One exchange = for every local slab a list of segments; a segment sends `bytes` from send_up to the
 // upper neighbour's recv_from_down and from send_down to the lower neighbour's recv_from_up.
@@ -341,6 +456,25 @@ int ring_exchange(const std::vector<pfs_slab *> &local, const std::vector<std::v
 // halo exchange of `t` rows of the given planes (same plane indices on every slab)
 int exchange_planes(const std::vector<pfs_slab *> &local, const std::vector<std::vector<float *>> &planes, int t)
 {
+    if (local.size() == 1 && local[0]->p2p && local[0]->gw % 4 == 0 && planes[0].size() <= 3) {
+        pfs_slab *s = local[0];
+        Guard g(s->device);
+        PushArgs A;
+        A.nseg = 0;
+        const size_t gw = (size_t)s->gw;
+        for (float *p : planes[0]) {
+            const size_t k = (size_t)(p - s->planes) / s->plane_floats;           // plane index: same on every rank
+            PushSeg &sg = A.seg[A.nseg++];
+            sg.src_up = reinterpret_cast<const float4 *>(p + (size_t)s->halo * gw);
+            sg.src_down = reinterpret_cast<const float4 *>(p + (size_t)(s->halo + s->rows - t) * gw);
+            sg.dst_up = reinterpret_cast<float4 *>(s->link_up.planes + k * s->link_up.plane_floats +
+                                                   (size_t)(s->halo + s->link_up.rows) * gw);
+            sg.dst_down = reinterpret_cast<float4 *>(s->link_down.planes + k * s->link_down.plane_floats +
+                                                     (size_t)(s->halo - t) * gw);
+            sg.n16 = (unsigned long long)t * gw / 4;
+        }
+        return launch_halo_push(s, A);
+    }
     std::vector<std::vector<Segment>> segs(local.size());
     for (size_t k = 0; k < local.size(); k++) {
         pfs_slab *s = local[k];
@@ -411,6 +545,25 @@ int build_row_sources(const std::vector<pfs_slab *> &local, const FieldBands &F,
     const size_t n = local.size();
     const size_t row = (size_t)F.width * sizeof(float4);
     out->resize(n);
+    if (!whole && n == 1 && local[0]->p2p && D <= P2P_GATHER_ROWS && (F.image ? local[0]->ihalo_p2p : local[0]->vhalo_p2p)) {
+        // peer transport: my top D rows become the upper neighbour's "below" rows, my bottom D rows the lower
+        // neighbour's "above" rows; both land in the fixed-capacity halos that were IPC-mapped at connect time
+        pfs_slab *s = local[0];
+        Guard g(s->device);
+        const size_t cap = (size_t)P2P_GATHER_ROWS * F.width;
+        float4 *mine = F.image ? s->ihalo_p2p : s->vhalo_p2p;
+        float4 *up = F.image ? s->link_up.ihalo : s->link_up.vhalo;
+        float4 *down = F.image ? s->link_down.ihalo : s->link_down.vhalo;
+        PushArgs A;
+        A.nseg = 1;
+        A.seg[0].src_up = F.band[0];
+        A.seg[0].src_down = F.band[0] + (size_t)(F.count[0] - D) * F.width;
+        A.seg[0].dst_up = up + cap;                 // its rows [band_n, band_n + D)
+        A.seg[0].dst_down = down;                   // its rows [-D, 0)
+        A.seg[0].n16 = (unsigned long long)D * F.width;
+        (*out)[0] = RowSource{F.band[0], mine, mine + cap, F.first[0], F.count[0], D, F.total, F.width};
+        return launch_halo_push(s, A);
+    }
     if (!whole) {
         std::vector<std::vector<Segment>> segs(n);
         for (size_t k = 0; k < n; k++) {
@@ -602,11 +755,18 @@ extern "C" int pfs_slab_create(pfs_slab **out, int rank, int nranks, int gw, int
     return PFS_OK;
 }
 
+namespace pfs {
+namespace {
+void p2p_release(pfs_slab *s);
+}
+}  // namespace pfs
+
 extern "C" int pfs_slab_destroy(pfs_slab *s)
 {
     if (!s) return PFS_OK;
     Guard g(s->device);
     cudaDeviceSynchronize();
+    p2p_release(s);
     if (s->comm && nccl().loaded) nccl().CommDestroy(s->comm);
     if (s->planes) cudaFree(s->planes);
     if (s->vhalo) cudaFree(s->vhalo);
@@ -664,6 +824,150 @@ extern "C" int pfs_slab_nccl_unique_id(char id[128])
     return PFS_OK;
 }
 
+namespace pfs {
+namespace {
+
+// What a rank publishes to the ring when the peer transport is set up (all-gathered through NCCL).
+struct PeerInfo {
+    cudaIpcMemHandle_t planes, flags, vhalo, ihalo;
+    unsigned long long plane_floats;
+    int rows, irows, device, has_image;
+};
+
+void p2p_release(pfs_slab *s)
+{
+    for (void *p : s->ipc_opened) cudaIpcCloseMemHandle(p);
+    s->ipc_opened.clear();
+    if (s->flags) cudaFree(s->flags);
+    if (s->vhalo_p2p) cudaFree(s->vhalo_p2p);
+    if (s->ihalo_p2p) cudaFree(s->ihalo_p2p);
+    s->flags = nullptr;
+    s->vhalo_p2p = s->ihalo_p2p = nullptr;
+    s->link_up = s->link_down = pfs_slab::PeerLink();
+    s->p2p = false;
+    (void)cudaGetLastError();
+}
+
+// Collective over the ring (called from pfs_slab_connect_nccl).  Every rank shares its planes, its gather halos
+// and its flag words through CUDA IPC and maps its two neighbours'.  If any rank fails at any point the whole ring
+// stays on NCCL send/recv (the decision is all-reduced), so this never turns a working setup into an error.
+int p2p_setup(pfs_slab *s)
+{
+    if (s->nranks < 2 || !nccl().AllGather) return PFS_OK;
+    if (const char *e = getenv("PFS_SLAB_TRANSPORT"))
+        if (!strcmp(e, "nccl")) return PFS_OK;
+    cudaStream_t st = nullptr;
+    int ok = 1;
+    PeerInfo mine;
+    memset(&mine, 0, sizeof(mine));
+    const size_t vbytes = 2 * (size_t)P2P_GATHER_ROWS * s->gw * sizeof(float4);
+    const size_t ibytes = 2 * (size_t)P2P_GATHER_ROWS * s->iw * sizeof(float4);
+    if (cudaMalloc((void **)&s->flags, P2P_FLAG_INTS * sizeof(int)) != cudaSuccess ||
+        cudaMemset(s->flags, 0, P2P_FLAG_INTS * sizeof(int)) != cudaSuccess ||
+        cudaMalloc((void **)&s->vhalo_p2p, vbytes) != cudaSuccess ||
+        (s->iw > 0 && cudaMalloc((void **)&s->ihalo_p2p, ibytes) != cudaSuccess))
+        ok = 0;
+    if (ok && (cudaIpcGetMemHandle(&mine.planes, s->planes) != cudaSuccess ||
+               cudaIpcGetMemHandle(&mine.flags, s->flags) != cudaSuccess ||
+               cudaIpcGetMemHandle(&mine.vhalo, s->vhalo_p2p) != cudaSuccess ||
+               (s->ihalo_p2p && cudaIpcGetMemHandle(&mine.ihalo, s->ihalo_p2p) != cudaSuccess)))
+        ok = 0;
+    (void)cudaGetLastError();
+    // stamp the first word of every shared buffer, so that a neighbour can verify that the pointer it gets from
+    // cudaIpcOpenMemHandle really is the start of that buffer (removed again once every rank has checked)
+    const float fstamp = 1000.f + (float)s->rank;
+    const int istamp = 1000 + s->rank;
+    if (ok && (cudaMemcpy(s->planes, &fstamp, sizeof(float), cudaMemcpyHostToDevice) != cudaSuccess ||
+               cudaMemcpy(s->vhalo_p2p, &fstamp, sizeof(float), cudaMemcpyHostToDevice) != cudaSuccess ||
+               (s->ihalo_p2p && cudaMemcpy(s->ihalo_p2p, &fstamp, sizeof(float), cudaMemcpyHostToDevice) != cudaSuccess) ||
+               cudaMemcpy(s->flags + 8, &istamp, sizeof(int), cudaMemcpyHostToDevice) != cudaSuccess))
+        ok = 0;
+    mine.plane_floats = s->plane_floats;
+    mine.rows = s->rows;
+    mine.irows = s->irows;
+    mine.device = s->device;
+    mine.has_image = s->ihalo_p2p ? 1 : 0;
+
+    // all-gather the records (in place), then the "everything worked here" bit
+    std::vector<PeerInfo> all(s->nranks);
+    char *d_all = nullptr;
+    PFS_CUDA(cudaMalloc((void **)&d_all, s->nranks * sizeof(PeerInfo)));
+    PFS_CUDA(cudaMemcpy(d_all + (size_t)s->rank * sizeof(PeerInfo), &mine, sizeof(PeerInfo), cudaMemcpyHostToDevice));
+    ncclResult_t nr = nccl().AllGather(d_all + (size_t)s->rank * sizeof(PeerInfo), d_all, sizeof(PeerInfo), ncclUint8, s->comm, st);
+    cudaError_t ce = cudaStreamSynchronize(st);
+    if (nr == ncclSuccess && ce == cudaSuccess)
+        ce = cudaMemcpy(all.data(), d_all, s->nranks * sizeof(PeerInfo), cudaMemcpyDeviceToHost);
+    cudaFree(d_all);
+    if (nr != ncclSuccess || ce != cudaSuccess) {
+        p2p_release(s);
+        set_error("peer transport: exchanging IPC handles failed");
+        return PFS_ECUDA;          // the communicator itself is broken: every rank sees this
+    }
+    auto open_link = [&](int r, pfs_slab::PeerLink *L) {
+        const PeerInfo &pi = all[r];
+        void *p = nullptr;
+        if (cudaIpcOpenMemHandle(&p, pi.planes, cudaIpcMemLazyEnablePeerAccess) != cudaSuccess) return false;
+        s->ipc_opened.push_back(p);
+        L->planes = (float *)p;
+        if (cudaIpcOpenMemHandle(&p, pi.flags, cudaIpcMemLazyEnablePeerAccess) != cudaSuccess) return false;
+        s->ipc_opened.push_back(p);
+        L->flags = (int *)p;
+        if (cudaIpcOpenMemHandle(&p, pi.vhalo, cudaIpcMemLazyEnablePeerAccess) != cudaSuccess) return false;
+        s->ipc_opened.push_back(p);
+        L->vhalo = (float4 *)p;
+        if (pi.has_image) {
+            if (cudaIpcOpenMemHandle(&p, pi.ihalo, cudaIpcMemLazyEnablePeerAccess) != cudaSuccess) return false;
+            s->ipc_opened.push_back(p);
+            L->ihalo = (float4 *)p;
+        }
+        L->plane_floats = (size_t)pi.plane_floats;
+        L->rows = pi.rows;
+        L->irows = pi.irows;
+        float f[3] = {0.f, 0.f, 1000.f + (float)r};
+        int i = 0;
+        if (cudaMemcpy(&f[0], L->planes, sizeof(float), cudaMemcpyDeviceToHost) != cudaSuccess ||
+            cudaMemcpy(&f[1], L->vhalo, sizeof(float), cudaMemcpyDeviceToHost) != cudaSuccess ||
+            (L->ihalo && cudaMemcpy(&f[2], L->ihalo, sizeof(float), cudaMemcpyDeviceToHost) != cudaSuccess) ||
+            cudaMemcpy(&i, L->flags + 8, sizeof(int), cudaMemcpyDeviceToHost) != cudaSuccess)
+            return false;
+        const float want = 1000.f + (float)r;
+        return f[0] == want && f[1] == want && f[2] == want && i == 1000 + r;
+    };
+    if (ok) {
+        for (int r = 0; r < s->nranks; r++)
+            if (all[r].device == s->device && r != s->rank) ok = 0;      // two ranks on one GPU: nothing to gain, keep NCCL
+    }
+    if (ok && !open_link(s->up(), &s->link_up)) ok = 0;
+    if (ok) {
+        if (s->down() == s->up())
+            s->link_down = s->link_up;                  // two ranks: both neighbours are the same peer, map it once
+        else if (!open_link(s->down(), &s->link_down))
+            ok = 0;
+    }
+    (void)cudaGetLastError();
+    // unanimous?
+    float *d_ok = s->d_scalars + 3;
+    const float mine_ok = ok ? 1.f : 0.f;
+    float all_ok = 0.f;
+    PFS_CUDA(cudaMemcpy(d_ok, &mine_ok, sizeof(float), cudaMemcpyHostToDevice));
+    PFS_NCCL(nccl().AllReduce(d_ok, d_ok, 1, ncclFloat, ncclMin, s->comm, st));
+    PFS_CUDA(cudaStreamSynchronize(st));
+    PFS_CUDA(cudaMemcpy(&all_ok, d_ok, sizeof(float), cudaMemcpyDeviceToHost));
+    if (all_ok != 1.f) {
+        p2p_release(s);
+        PFS_CUDA(cudaMemset(s->planes, 0, sizeof(float)));
+        return PFS_OK;
+    }
+    PFS_CUDA(cudaMemset(s->planes, 0, sizeof(float)));
+    PFS_CUDA(cudaMemset(s->flags + 8, 0, sizeof(int)));
+    s->p2p = true;
+    s->xseq = 0;
+    return PFS_OK;
+}
+
+}  // namespace
+}  // namespace pfs
+
 extern "C" int pfs_slab_connect_nccl(pfs_slab *s, const char id[128])
 {
     if (!s || !id) {
@@ -679,7 +983,14 @@ extern "C" int pfs_slab_connect_nccl(pfs_slab *s, const char id[128])
     memcpy(u.internal, id, 128);
     PFS_NCCL(nccl().CommInitRank(&s->comm, s->nranks, u, s->rank));
     s->group.clear();
-    return PFS_OK;
+    return p2p_setup(s);
+}
+
+extern "C" const char *pfs_slab_transport(const pfs_slab *s)
+{
+    if (!s) return "none";
+    if (s->comm) return s->p2p ? "p2p" : "nccl";
+    return s->group.empty() ? "unconnected" : "local";
 }
 
 extern "C" int pfs_slab_check(pfs_slab *const *slabs, int n_local)

@@ -144,6 +144,11 @@ class SlabRank(_SlabBase):
         if self.nranks > 1:
             check(_cabi.lib().pfs_slab_connect_nccl(self._h, ctypes.create_string_buffer(unique_id, 128)))
 
+    @property
+    def transport(self) -> str:
+        """"p2p" (halo rows stored into the neighbours' memory over NVLink), "nccl" (send/recv) or "unconnected"."""
+        return _cabi.lib().pfs_slab_transport(self._h).decode()
+
     def _stream(self, t):
         import torch
         return _ptr_array([torch.cuda.current_stream(t.device).cuda_stream])

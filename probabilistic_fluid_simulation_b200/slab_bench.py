@@ -46,6 +46,13 @@ def sum_over_ranks(x: float, device="cuda") -> float:
 
 
 # ---- the bench arm ---------------------------------------------------------------------------------
+TRANSPORT_TEXT = {
+    "p2p": "halo rows stored straight into the ring neighbours' memory (CUDA IPC mappings over NVLink, one kernel per "
+           "exchange with flag handshakes); NCCL only for the all-reduce of the displacement bound (one process per GPU)",
+    "nccl": "NCCL send/recv of halo rows between ring neighbours (one process per GPU)",
+}
+
+
 def run(args, bench) -> None:
     import numpy as np
     import torch
@@ -174,7 +181,7 @@ def run(args, bench) -> None:
                                                 "achieved_gbs": step_bytes / (ms_step * 1e-3) / 1e9,
                                                 "frac": step_bytes / (ms_step * 1e-3) / 1e9 / peak},
                 "cell_steps_per_s": cells_global / (ms_step * 1e-3), "phases_ms_rank0": per_phase, "kernels": kernels,
-                "transport": "NCCL send/recv of halo rows between ring neighbours (one process per GPU)",
+                "transport": TRANSPORT_TEXT.get(slab.transport, slab.transport),
                 "rows_per_gpu": slab.rows}
         print(json.dumps(line), flush=True)
     dist.barrier()

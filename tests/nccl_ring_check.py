@@ -16,11 +16,24 @@ from probabilistic_fluid_simulation_b200 import fixtures, vp_field  # noqa: E402
 from probabilistic_fluid_simulation_b200.slab import SlabRank  # noqa: E402
 
 
+# (grid h, w, image h, w, dt, steps): the second case has bands of different heights and a 25-row gather halo, the
+# third a gather deeper than the peer transport's fixed halos (it must fall back to send/recv for that exchange),
+# the fourth a displacement larger than a band (whole-field path)
+CASES = [(128, 256, 192, 256, 2.0, 3), (131, 64, 131, 64, 3000.0, 2), (400, 32, 400, 32, 32000.0, 2),
+         (96, 64, 96, 64, 20000.0, 1)]
+
+
 def main():
     rank, world = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"])
     torch.cuda.set_device(int(os.environ.get("LOCAL_RANK", rank)))
     dist.init_process_group("nccl")
-    h, w, ih, iw = 128, 256, 192, 256
+    for case in CASES:
+        run_case(rank, world, *case)
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def run_case(rank, world, h, w, ih, iw, dt, steps):
     vel = fixtures.smooth_velocity_bytes(h, w)
     img = fixtures.random_image_bytes(ih, iw, 11)
     vp, vtmp, image, itmp = fixtures.make_state(vel, img)
@@ -30,10 +43,12 @@ def main():
         uid.copy_(torch.frombuffer(bytearray(SlabRank.unique_id()), dtype=torch.uint8))
     dist.broadcast(uid, 0)
     slab.connect(bytes(uid.cpu().numpy().tobytes()))
+    if rank == 0:
+        print("transport", slab.transport, flush=True)
     r0, rows, i0, irows = slab.row0, slab.rows, slab.irow0, slab.irows
     fv, ft = vp_field(torch.from_numpy(vp[r0:r0 + rows].copy()).cuda()), vp_field(torch.from_numpy(vtmp[r0:r0 + rows].copy()).cuda())
     fi, fm = vp_field(torch.from_numpy(image[i0:i0 + irows].copy()).cuda()), vp_field(torch.from_numpy(itmp[i0:i0 + irows].copy()).cuda())
-    dt, visc, nd, npr, steps = 2.0, 0.002, 30, 30, 3
+    visc, nd, npr = 0.002, 30, 30
     for _ in range(steps):
         slab.simulate_fluid_step(fv, ft, dt, visc, nd, npr)
         slab.advect_color_step(fi, fm, fv, dt)
@@ -51,13 +66,12 @@ def main():
         assert abs(norms["div_l2"] - np.sqrt((d * d).sum())) <= 1e-11 * np.sqrt((d * d).sum())
         assert abs(norms["pressure_update_l2"] - np.sqrt((r * r).sum())) <= 1e-11 * np.sqrt((r * r).sum())
         assert norms["speed_max"] == float(max(np.abs(want[0][..., 0]).max(), np.abs(want[0][..., 1]).max()))
-        print("NCCL ring matches oracle")
+        print(f"ring matches oracle {h}x{w}", flush=True)
     all_norms = [None] * world
     dist.all_gather_object(all_norms, norms)
     assert all(n == all_norms[0] for n in all_norms), all_norms
     dist.barrier()
     slab.close()
-    dist.destroy_process_group()
 
 
 if __name__ == "__main__":

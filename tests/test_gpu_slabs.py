@@ -89,13 +89,20 @@ def test_ring_wide_grid_fused_depth():
         assert_bit_equal(g, wv, name)
 
 
-def test_nccl_two_ranks(tmp_path):
+@pytest.mark.parametrize("transport", ["p2p", "nccl"])
+def test_two_processes_two_gpus(tmp_path, transport):
+    """One process per GPU.  "p2p": halo rows stored into the neighbour's memory through CUDA IPC mappings (the default
+    when every rank can map its neighbours); "nccl": send/recv.  Both must reproduce the oracle bit for bit."""
     import torch
     if torch.cuda.device_count() < 2:
         pytest.skip("needs two GPUs")
-    out = tmp_path / "nccl.json"
+    env = dict(os.environ)
+    env.pop("PFS_SLAB_TRANSPORT", None)
+    if transport == "nccl":
+        env["PFS_SLAB_TRANSPORT"] = "nccl"
     cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node=2", "--master-addr", "127.0.0.1",
-           "--master-port", "29541", os.path.join(ROOT, "tests", "nccl_ring_check.py"), str(out)]
-    r = subprocess.run(cmd, capture_output=True, text=True, timeout=600, cwd=ROOT)
+           "--master-port", "29541" if transport == "p2p" else "29543", os.path.join(ROOT, "tests", "nccl_ring_check.py")]
+    r = subprocess.run(cmd, capture_output=True, text=True, timeout=600, cwd=ROOT, env=env)
     assert r.returncode == 0, r.stdout[-3000:] + r.stderr[-3000:]
-    assert "NCCL ring matches oracle" in r.stdout
+    assert r.stdout.count("ring matches oracle") == 4, r.stdout[-3000:]
+    assert r.stdout.count(f"transport {transport}") == 4, r.stdout[-3000:]
