@@ -147,7 +147,8 @@ struct pfs_slab {
     size_t vhalo_rows = 0, ihalo_rows = 0;         // capacity in rows (both sides together)
     float4 *vwhole = nullptr, *iwhole = nullptr;
     size_t vwhole_rows = 0, iwhole_rows = 0;
-    float *d_scalars = nullptr;           // [0] max|v| (advect), [1] max|v| (advect_color), [2] overflow flag (as int)
+    float *d_scalars = nullptr;           // [0] max|v| (advect), [1] max|v| (advect_color), [2] overflow flag (as int),
+                                          // [3] setup scratch, [4] max|v| and [5] overflow (as float) of a speculative advect
     float *h_scalars = nullptr;           // pinned mirror
     ncclComm_t comm = nullptr;
     // peer transport (one process per GPU, CUDA IPC): the ring neighbours' planes / gather halos / flags mapped here
@@ -166,7 +167,9 @@ struct pfs_slab {
     std::vector<void *> ipc_opened;
     std::vector<pfs_slab *> group;        // in-process transport: all ranks, indexed by rank (empty under NCCL)
     cudaStream_t stream = nullptr;        // stream of the call in flight
-    cudaEvent_t ev_ready = nullptr, ev_done = nullptr;
+    cudaEvent_t ev_ready = nullptr, ev_done = nullptr, ev_meas = nullptr, ev_fork = nullptr;
+    cudaStream_t side = nullptr;          // carries the all-reduce + read-back of a speculative advect's (max|v|, flag)
+    float vbound = -1.f;                  // max|v| of the field the last fluid step started from (< 0: not known yet)
     float *plane(int k) const { return planes + (size_t)k * plane_floats; }
     int up() const { return (rank + nranks - 1) % nranks; }
     int down() const { return (rank + 1) % nranks; }
@@ -190,6 +193,8 @@ struct Guard {   // cudaSetDevice for the scope of one slab's work
 };
 
 // ---- small kernels of the slab path -----------------------------------------------------------
+__global__ void flag_to_float_kernel(const int *flag, float *out) { *out = (*flag != 0) ? 1.f : 0.f; }
+
 __global__ void __launch_bounds__(256) max_abs_v_kernel(const float4 *__restrict__ vp, size_t n, float *out)
 {
     float m = 0.f;
@@ -231,15 +236,30 @@ __device__ __forceinline__ const float4 *source_row(const RowSource &S, int grow
 // grid from the interleaved field (u,v in the first 8 bytes of a cell, as in the single-GPU kernel).
 __global__ void __launch_bounds__(256)
     advect_slab_kernel(const RowSource S, float *__restrict__ u_out, float *__restrict__ v_out, float dt, int w, int gh,
-                       int row0, int rows, int y_base, int *overflow)
+                       int row0, int rows, int y_base, int *overflow, float *vmax_out)
 {
     const int i = blockIdx.x * 64 + threadIdx.x, jl = blockIdx.y * 4 + threadIdx.y;
-    if (i >= w || jl >= rows) return;
+    const bool live = (i < w && jl < rows);
     const int j = row0 + jl;
     const float fw = (float)w, fh = (float)gh;
-    const float4 *own = source_row(S, j, overflow, 1);
+    const float4 *own = live ? source_row(S, j, overflow, 1) : nullptr;
+    const float2 uv = own ? __ldg(reinterpret_cast<const float2 *>(own + i)) : make_float2(0.f, 0.f);
+    if (vmax_out != nullptr) {
+        // by-product: max|v| of the field being advected (what bounds the row displacement), NaN -> +inf.
+        // One atomic per warp, and only when the warp would raise the current value.
+        float m = fabsf(uv.y);
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+            const float t = __shfl_xor_sync(0xffffffffu, m, o);
+            m = (t > m || t != t) ? t : m;
+        }
+        if (((threadIdx.y * 64 + threadIdx.x) & 31) == 0) {
+            if (m != m) m = __int_as_float(0x7f800000);
+            if (m > *reinterpret_cast<volatile float *>(vmax_out))
+                atomicMax(reinterpret_cast<int *>(vmax_out), __float_as_int(m));
+        }
+    }
     if (!own) return;
-    const float2 uv = __ldg(reinterpret_cast<const float2 *>(own + i));
     float xp = __fsub_rn((float)i, div_extent(__fmul_rn(dt, uv.x), fw, __frcp_rn(fw)));
     float yp = __fsub_rn((float)j, div_extent(__fmul_rn(dt, uv.y), fh, __frcp_rn(fh)));
     xp = wrap_coord(xp, fw);
@@ -741,11 +761,14 @@ extern "C" int pfs_slab_create(pfs_slab **out, int rank, int nranks, int gw, int
     };
     if ((e = cudaMalloc((void **)&s->planes, pfs::N_SLAB_PLANES * s->plane_floats * sizeof(float))) != cudaSuccess) fail(e, "cudaMalloc planes");
     if (st == PFS_OK && (e = cudaMemset(s->planes, 0, pfs::N_SLAB_PLANES * s->plane_floats * sizeof(float))) != cudaSuccess) fail(e, "cudaMemset");
-    if (st == PFS_OK && (e = cudaMalloc((void **)&s->d_scalars, 4 * sizeof(float))) != cudaSuccess) fail(e, "cudaMalloc scalars");
-    if (st == PFS_OK && (e = cudaMemset(s->d_scalars, 0, 4 * sizeof(float))) != cudaSuccess) fail(e, "cudaMemset");
-    if (st == PFS_OK && (e = cudaMallocHost((void **)&s->h_scalars, 4 * sizeof(float))) != cudaSuccess) fail(e, "cudaMallocHost");
+    if (st == PFS_OK && (e = cudaMalloc((void **)&s->d_scalars, 8 * sizeof(float))) != cudaSuccess) fail(e, "cudaMalloc scalars");
+    if (st == PFS_OK && (e = cudaMemset(s->d_scalars, 0, 8 * sizeof(float))) != cudaSuccess) fail(e, "cudaMemset");
+    if (st == PFS_OK && (e = cudaMallocHost((void **)&s->h_scalars, 8 * sizeof(float))) != cudaSuccess) fail(e, "cudaMallocHost");
     if (st == PFS_OK && (e = cudaEventCreateWithFlags(&s->ev_ready, cudaEventDisableTiming)) != cudaSuccess) fail(e, "event");
     if (st == PFS_OK && (e = cudaEventCreateWithFlags(&s->ev_done, cudaEventDisableTiming)) != cudaSuccess) fail(e, "event");
+    if (st == PFS_OK && (e = cudaEventCreateWithFlags(&s->ev_meas, cudaEventDisableTiming)) != cudaSuccess) fail(e, "event");
+    if (st == PFS_OK && (e = cudaEventCreateWithFlags(&s->ev_fork, cudaEventDisableTiming)) != cudaSuccess) fail(e, "event");
+    if (st == PFS_OK && (e = cudaStreamCreateWithFlags(&s->side, cudaStreamNonBlocking)) != cudaSuccess) fail(e, "stream");
     if (st != PFS_OK) {
         pfs_slab_destroy(s);
         return st;
@@ -777,6 +800,9 @@ extern "C" int pfs_slab_destroy(pfs_slab *s)
     if (s->h_scalars) cudaFreeHost(s->h_scalars);
     if (s->ev_ready) cudaEventDestroy(s->ev_ready);
     if (s->ev_done) cudaEventDestroy(s->ev_done);
+    if (s->ev_meas) cudaEventDestroy(s->ev_meas);
+    if (s->ev_fork) cudaEventDestroy(s->ev_fork);
+    if (s->side) cudaStreamDestroy(s->side);
     (void)cudaGetLastError();
     delete s;
     return PFS_OK;
@@ -1075,8 +1101,13 @@ extern "C" int pfs_slab_step_norms(pfs_slab *const *slabs, int n_local, float *c
 // simulate_fluid_step on slabs.  vp[k] / tmp[k]: the k-th local slab's band of the interleaved buffers
 // (rows x gw x 4 floats, device memory of that slab's device).  Pointer exchange as pfs_simulate_fluid_step.
 // ---------------------------------------------------------------------------------------------
-extern "C" int pfs_slab_simulate_fluid_step(pfs_slab *const *slabs, int n_local, float **vp, float **tmp, float dt,
-                                            float viscosity, int n_diffuse, int n_pressure, void *const *streams)
+// `exact_bound`: take the gather depth of the velocity advection from a max|v| reduction that the host waits for
+// (one synchronisation at the start of the step).  Otherwise the depth is a guess from the previous step's maximum
+// (x2, +4 rows), the advect kernel raises a flag if a departure row is missing, and the flag is read back much later --
+// just before the only kernel that overwrites the caller's buffers -- when it has long been written.  A raised flag
+// (never seen outside the tests that provoke it) discards the step's scratch results and reruns it with the exact bound.
+static int slab_fluid_step(pfs_slab *const *slabs, int n_local, float **vp, float **tmp, float dt, float viscosity,
+                           int n_diffuse, int n_pressure, void *const *streams, bool exact_bound)
 {
     const char *fn = "pfs_slab_simulate_fluid_step";
     std::vector<pfs_slab *> L;
@@ -1112,26 +1143,42 @@ extern "C" int pfs_slab_simulate_fluid_step(pfs_slab *const *slabs, int n_local,
     };
 
     // ---- advect: displacement bound -> halo depth D of the (u,v) gather source ----
-    for (int k = 0; k < n; k++) {
-        pfs_slab *s = L[k];
-        Guard g(s->device);
-        PFS_CUDA(cudaMemsetAsync(s->d_scalars, 0, sizeof(float), s->stream));
-        const size_t cells = (size_t)s->rows * gw;
-        PFS_LAUNCH(max_abs_v_kernel, 592, 256, 0, s->stream, reinterpret_cast<const float4 *>(vp[k]), cells, s->d_scalars);
-    }
-    float vmax = 0.f;
-    PFS_TRY(global_max(L, 0, &vmax));
-    // |dt*v/H| in cells, with slack for the float roundings of the kernel's own expression; +2 for the
-    // bilinear neighbour and the wrap
-    const double disp = std::fabs((double)dt) * (double)vmax / (double)gh;
     int min_rows = gh;
     for (int r = 0; r < L[0]->nranks; r++) {
         int f, c;
         band(gh, L[0]->nranks, r, &f, &c);
         min_rows = std::min(min_rows, c);
     }
-    const bool whole = !(disp * 1.001 + 3.0 < (double)min_rows);
-    const int D = whole ? 0 : (int)std::ceil(disp * 1.001) + 2;
+    static const bool spec_env = !(getenv("PFS_SLAB_SPECULATE") && !strcmp(getenv("PFS_SLAB_SPECULATE"), "0"));
+    bool speculate = spec_env && !exact_bound && L[0]->vbound >= 0.f;
+    bool whole = false;
+    int D = 0;
+    if (speculate) {
+        // |dt*v/H| in rows from the last known maximum, doubled, +4 (bilinear neighbour, wrap, roundings, growth)
+        const double guess = 2.0 * std::fabs((double)dt) * (double)L[0]->vbound / (double)gh;
+        if (guess * 1.001 + 5.0 < (double)min_rows)
+            D = std::max(8, (int)std::ceil(guess * 1.001) + 4);
+        else
+            speculate = false;                       // large displacements: measure first
+        if (D + 3 >= min_rows) speculate = false;
+    }
+    if (!speculate) {
+        for (int k = 0; k < n; k++) {
+            pfs_slab *s = L[k];
+            Guard g(s->device);
+            PFS_CUDA(cudaMemsetAsync(s->d_scalars, 0, sizeof(float), s->stream));
+            const size_t cells = (size_t)s->rows * gw;
+            PFS_LAUNCH(max_abs_v_kernel, 592, 256, 0, s->stream, reinterpret_cast<const float4 *>(vp[k]), cells, s->d_scalars);
+        }
+        float vmax = 0.f;
+        PFS_TRY(global_max(L, 0, &vmax));
+        for (int k = 0; k < n; k++) L[k]->vbound = vmax;
+        // |dt*v/H| in cells, with slack for the float roundings of the kernel's own expression; +2 for the
+        // bilinear neighbour and the wrap
+        const double disp = std::fabs((double)dt) * (double)vmax / (double)gh;
+        whole = !(disp * 1.001 + 3.0 < (double)min_rows);
+        D = whole ? 0 : (int)std::ceil(disp * 1.001) + 2;
+    }
     {
         FieldBands F{gw, gh, {}, {}, {}, false};
         for (int k = 0; k < n; k++) {
@@ -1144,9 +1191,22 @@ extern "C" int pfs_slab_simulate_fluid_step(pfs_slab *const *slabs, int n_local,
         for (int k = 0; k < n; k++) {
             pfs_slab *s = L[k];
             Guard g(s->device);
+            if (speculate) PFS_CUDA(cudaMemsetAsync(s->d_scalars + 4, 0, 2 * sizeof(float), s->stream));
             dim3 block(64, 4), grid((gw + 63) / 64, (s->rows + 3) / 4);
             PFS_LAUNCH(advect_slab_kernel, grid, block, 0, s->stream, src[k], s->plane(0), s->plane(1), dt, gw, gh,
-                       s->row0, s->rows, s->halo, reinterpret_cast<int *>(s->d_scalars + 2));
+                       s->row0, s->rows, s->halo, reinterpret_cast<int *>(s->d_scalars + 2),
+                       speculate ? s->d_scalars + 4 : nullptr);
+            if (speculate) {
+                // (max|v| of this step's input, "a departure row was missing") -> every rank, then the host; nobody waits yet
+                // (on a side stream: the sweeps that follow do not depend on it)
+                PFS_LAUNCH(flag_to_float_kernel, 1, 1, 0, s->stream, reinterpret_cast<const int *>(s->d_scalars + 2), s->d_scalars + 5);
+                PFS_CUDA(cudaEventRecord(s->ev_fork, s->stream));
+                PFS_CUDA(cudaStreamWaitEvent(s->side, s->ev_fork, 0));
+                if (s->comm != nullptr)
+                    PFS_NCCL(nccl().AllReduce(s->d_scalars + 4, s->d_scalars + 4, 2, ncclFloat, ncclMax, s->comm, s->side));
+                PFS_CUDA(cudaMemcpyAsync(s->h_scalars + 4, s->d_scalars + 4, 2 * sizeof(float), cudaMemcpyDeviceToHost, s->side));
+                PFS_CUDA(cudaEventRecord(s->ev_meas, s->side));
+            }
         }
     }
 
@@ -1269,6 +1329,31 @@ extern "C" int pfs_slab_simulate_fluid_step(pfs_slab *const *slabs, int n_local,
     PFS_TRY(run_sweeps(SWEEP_PRESSURE, 4, 4, 5, 5, 9, 9, pp, n_pressure, &pl_last, &unused0, &pl_prev, &unused1, &p_valid));
     next_phase(PFS_PHASE_PROJECT);
 
+    // ---- late check of a speculative advect: everything so far only wrote scratch planes ----
+    if (speculate) {
+        float vmax = 0.f;
+        bool missed = false;
+        for (int k = 0; k < n; k++) {
+            pfs_slab *s = L[k];
+            Guard g(s->device);
+            PFS_CUDA(cudaEventSynchronize(s->ev_meas));          // recorded right after advect: long done by now
+            const float v = s->h_scalars[4];
+            vmax = (v != v) ? INFINITY : std::max(vmax, v);
+            missed = missed || (s->h_scalars[5] != 0.f);
+        }
+        for (int k = 0; k < n; k++) L[k]->vbound = vmax;
+        if (missed) {
+            for (int k = 0; k < n; k++) {
+                pfs_slab *s = L[k];
+                Guard g(s->device);
+                PFS_CUDA(cudaMemsetAsync(s->d_scalars + 2, 0, sizeof(int), s->stream));
+            }
+            delete ph;
+            ph = nullptr;
+            return slab_fluid_step(slabs, n_local, vp, tmp, dt, viscosity, n_diffuse, n_pressure, streams, true);
+        }
+    }
+
     // ---- gradient subtraction + write-back (needs one halo row of p_N) ----
     {
         std::vector<std::vector<float *>> pl(n);
@@ -1288,6 +1373,12 @@ extern "C" int pfs_slab_simulate_fluid_step(pfs_slab *const *slabs, int n_local,
         tmp[k] = Bp[k];
     }
     return PFS_OK;
+}
+
+extern "C" int pfs_slab_simulate_fluid_step(pfs_slab *const *slabs, int n_local, float **vp, float **tmp, float dt,
+                                            float viscosity, int n_diffuse, int n_pressure, void *const *streams)
+{
+    return slab_fluid_step(slabs, n_local, vp, tmp, dt, viscosity, n_diffuse, n_pressure, streams, false);
 }
 
 // ---------------------------------------------------------------------------------------------

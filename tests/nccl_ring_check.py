@@ -29,8 +29,53 @@ def main():
     dist.init_process_group("nccl")
     for case in CASES:
         run_case(rank, world, *case)
+    run_jump_case(rank, world)
     dist.barrier()
     dist.destroy_process_group()
+
+
+def connect(rank, world, w, h, iw, ih):
+    slab = SlabRank(rank, world, w, h, iw, ih)
+    uid = torch.zeros(128, dtype=torch.uint8, device="cuda")
+    if rank == 0:
+        uid.copy_(torch.frombuffer(bytearray(SlabRank.unique_id()), dtype=torch.uint8))
+    dist.broadcast(uid, 0)
+    slab.connect(bytes(uid.cpu().numpy().tobytes()))
+    return slab
+
+
+def run_jump_case(rank, world):
+    """The caller replaces the velocities by ones 100x larger between two steps: the guessed gather depth of the third
+    step is too shallow, the step must rerun itself with the measured bound (tests/test_gpu_slabs.py has the
+    single-process twin of this case)."""
+    h, w = 256, 64
+    vp, vtmp, _, _ = fixtures.make_state(fixtures.smooth_velocity_bytes(h, w), fixtures.random_image_bytes(8, 8, 1))
+    big = vp[..., :2].copy()
+    vp[..., :2] *= np.float32(0.01)
+    dt, visc, nd, npr = 4000.0, 0.001, 4, 4
+    slab = connect(rank, world, w, h, 0, 0)
+    r0, rows = slab.row0, slab.rows
+    fv, ft = vp_field(torch.from_numpy(vp[r0:r0 + rows].copy()).cuda()), vp_field(torch.from_numpy(vtmp[r0:r0 + rows].copy()).cuda())
+    slab.simulate_fluid_step(fv, ft, dt, visc, nd, npr)
+    slab.simulate_fluid_step(fv, ft, dt, visc, nd, npr)
+    fv.data[..., :2] = torch.from_numpy(big[r0:r0 + rows].copy()).cuda()
+    slab.simulate_fluid_step(fv, ft, dt, visc, nd, npr)
+    slab.check()
+    parts = [None] * world
+    dist.all_gather_object(parts, (fv.data.cpu().numpy(), ft.data.cpu().numpy()))
+    if rank == 0:
+        orc = oracle.Oracle(nd, npr)
+        wv, wt = orc.simulate_fluid_step(vp, vtmp, dt, visc)
+        wv, wt = orc.simulate_fluid_step(wv, wt, dt, visc)
+        wv = wv.copy()
+        wv[..., :2] = big
+        wv, wt = orc.simulate_fluid_step(wv, wt, dt, visc)
+        got = [np.concatenate([p[k] for p in parts], axis=0) for k in range(2)]
+        assert np.array_equal(got[0].view(np.uint32), wv.view(np.uint32)), "vp after the jump"
+        assert np.array_equal(got[1].view(np.uint32), wt.view(np.uint32)), "vtmp after the jump"
+        print("jump case matches oracle", flush=True)
+    dist.barrier()
+    slab.close()
 
 
 def run_case(rank, world, h, w, ih, iw, dt, steps):

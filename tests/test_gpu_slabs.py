@@ -89,6 +89,45 @@ def test_ring_wide_grid_fused_depth():
         assert_bit_equal(g, wv, name)
 
 
+@pytest.mark.parametrize("nranks", [2, 4])
+def test_ring_speculative_gather_depth_reruns_when_the_field_jumps(nranks):
+    """From the second step on, the gather depth of the velocity advection is a guess from the previous step's max|v|
+    and a device flag says whether it was enough.  Here the caller replaces the velocities between two steps by ones
+    100x larger (the API allows that: it is what addForces is for), so the guess is too shallow: the step must notice,
+    rerun itself with the exact bound and still match the oracle bit for bit."""
+    from probabilistic_fluid_simulation_b200 import _cabi
+    h, w = 256, 64
+    vp, vtmp, image, itmp = _state(h, w, h, w, 13)
+    big = vp[..., :2].copy()
+    vp[..., :2] *= np.float32(0.01)
+    dt, visc, nd, npr = 4000.0, 0.001, 4, 4
+    orc = oracle.Oracle(nd, npr)
+    ring = SlabRing(nranks, w, h, w, h)
+    bv, bt = ring.split(vp), ring.split(vtmp)
+    L = _cabi.lib()
+    c0 = L.pfs_kernel_launch_count()
+    ring.simulate_fluid_step(bv, bt, dt, visc, nd, npr)           # measured bound (first step)
+    c1 = L.pfs_kernel_launch_count()
+    ring.simulate_fluid_step(bv, bt, dt, visc, nd, npr)           # guessed bound, sufficient
+    c2 = L.pfs_kernel_launch_count()
+    want_v, want_t = orc.simulate_fluid_step(vp, vtmp, dt, visc)
+    want_v, want_t = orc.simulate_fluid_step(want_v, want_t, dt, visc)
+    assert_bit_equal(ring.gather(bv), want_v, "vp after two steps")
+    hv = ring.gather(bv)
+    hv[..., :2] = big                                               # the field jumps
+    want_v = want_v.copy()
+    want_v[..., :2] = big
+    bv = ring.split(hv)
+    ring.simulate_fluid_step(bv, bt, dt, visc, nd, npr)           # guessed bound too shallow -> rerun
+    c3 = L.pfs_kernel_launch_count()
+    want_v, want_t = orc.simulate_fluid_step(want_v, want_t, dt, visc)
+    assert_bit_equal(ring.gather(bv), want_v, "vp after the jump")
+    assert_bit_equal(ring.gather(bt), want_t, "vtmp after the jump")
+    ring.check()
+    ring.close()
+    assert (c3 - c2) > 1.5 * (c2 - c1), (c1 - c0, c2 - c1, c3 - c2)   # the third step really ran twice
+
+
 @pytest.mark.parametrize("transport", ["p2p", "nccl"])
 def test_two_processes_two_gpus(tmp_path, transport):
     """One process per GPU.  "p2p": halo rows stored into the neighbour's memory through CUDA IPC mappings (the default
@@ -105,4 +144,5 @@ def test_two_processes_two_gpus(tmp_path, transport):
     r = subprocess.run(cmd, capture_output=True, text=True, timeout=600, cwd=ROOT, env=env)
     assert r.returncode == 0, r.stdout[-3000:] + r.stderr[-3000:]
     assert r.stdout.count("ring matches oracle") == 4, r.stdout[-3000:]
+    assert "jump case matches oracle" in r.stdout, r.stdout[-3000:]
     assert r.stdout.count(f"transport {transport}") == 4, r.stdout[-3000:]
