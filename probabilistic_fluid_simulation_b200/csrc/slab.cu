@@ -8,7 +8,8 @@
 // kernels are the single-GPU kernels with the row map (y_base = halo, wrap = 0).
 //
 // What moves between neighbours each timestep (rows are W*4 bytes per plane):
-//   advect        D rows of (u,v) each way, D = ceil(max|dt*v/H|) + 2 from an all-reduce(max)
+//   advect        D rows of (u,v) each way, D = ceil(max|dt*v/H|) + 2 from an all-reduce(max) on the first step,
+//                 guessed from the previous step and verified by a device flag afterwards (rerun if too shallow)
 //   diffusion     `halo` (32) rows x 2 planes; a pass of depth t then also recomputes the halo-t rows next to
 //                 the band (an "extended interior"), so the next passes find valid halos without another
 //                 exchange: one exchange per 32/t passes, ~1.5 % redundant rows on a 2048-row band
@@ -18,9 +19,11 @@
 //   advect_color  D_i rows of the image each way
 // Results are bit-identical to the single-GPU path (same per-cell arithmetic, global indices).
 //
-// Transports: NCCL send/recv between one process per GPU (resolved with dlopen, so the single-GPU
-// library has no NCCL dependency), or direct copies between slabs that live in one process (any
-// devices; used by the tests to run R slabs on one GPU and by single-process multi-GPU callers).
+// Transports, one process per GPU: peer stores into the neighbours' planes through CUDA IPC mappings (one kernel
+// per exchange, flag handshakes; set up over an NCCL communicator, which also carries the all-reduces), or NCCL
+// send/recv when a rank cannot map its neighbours (NCCL is resolved with dlopen, so the single-GPU library has no
+// NCCL dependency).  Slabs that live in one process use direct copies (any devices; used by the tests to run
+// R slabs on one GPU and by single-process multi-GPU callers).
 #include <dlfcn.h>
 #include <nccl.h>   // types and enums only; every function is resolved at run time
 #include <stdlib.h>
