@@ -34,6 +34,10 @@ int pick_chunk_rows(int h, int columns_of_items, long long slots, int forced_row
 namespace {
 
 constexpr int WARPS_PER_CTA = 4;
+#ifndef PFS_CARRY_MAX_DEPTH
+#define PFS_CARRY_MAX_DEPTH 6
+#endif
+constexpr int CARRY_MAX_DEPTH = PFS_CARRY_MAX_DEPTH;
 constexpr int RING_SLOTS = 4;
 constexpr int PREFETCH = RING_SLOTS - 2;
 
@@ -220,6 +224,15 @@ __global__ void __launch_bounds__(WARPS_PER_CTA * 32, MINB) diffuse_packed_kerne
     for (int l = 0; l < T; l++)
 #pragma unroll
         for (int c = 0; c < NC; c++) S[l][0][c] = S[l][1][c] = make_float2(1.f, 1.f);
+    // Shallow passes have registers to spare for a third row per level: the alpha product of the centre row, formed
+    // when that row arrived as the bottom row.  Then every row is multiplied by alpha exactly once per level
+    // (the reference multiplies it four times, once per neighbour that reads it -- same value each time).
+    constexpr bool CARRY = (NC == 4 && T <= CARRY_MAX_DEPTH);
+    float2 A[CARRY ? T : 1][NC];
+#pragma unroll
+    for (int l = 0; l < (CARRY ? T : 1); l++)
+#pragma unroll
+        for (int c = 0; c < NC; c++) A[l][c] = make_float2(1.f, 1.f);
 
     const float2 alpha2 = make_float2(P.alpha, P.alpha);
     const float2 nz2 = make_float2(P.neg_zero, P.neg_zero);
@@ -261,24 +274,24 @@ __global__ void __launch_bounds__(WARPS_PER_CTA * 32, MINB) diffuse_packed_kerne
             // earlier steps -- the alpha products of its centre and top rows, the lane shuffles and
             // (aL + aR) + aT -- is issued before the tail of level l, which depends on the row level l-1
             // has just produced.  Two independent instruction streams per warp instead of one.
-            float2 part[NC], part_next[NC];
-            auto prefix = [&](int l, float2(&dst)[NC]) {
-                float2 aC[NC], aT[NC];
+            // State per level: slot [older^1] holds the centre row (s-l) as VALUES, slot [older] the top row
+            // (s-l-1) already MULTIPLIED by alpha -- it is the product formed when that row was the centre row one
+            // step ago, so the reference's alpha*T costs nothing here (the raw values of the top row are not needed).
+            float2 part[NC], part_next[NC], aCen[NC], aCen_next[NC];
+            auto prefix = [&](int l, float2(&dst)[NC], float2(&aC)[NC]) {
 #pragma unroll
-                for (int c = 0; c < NC; c++) {
-                    aC[c] = mulc2(S[l - 1][older ^ 1][c], alpha2, nz2);   // alpha * centre row (s-l)
-                    aT[c] = mulc2(S[l - 1][older][c], alpha2, nz2);       // alpha * top row (s-l-1)
-                }
+                for (int c = 0; c < NC; c++)        // alpha * centre row: carried from the step that produced it, or formed now
+                    aC[c] = CARRY ? A[CARRY ? l - 1 : 0][c] : mulc2(S[l - 1][older ^ 1][c], alpha2, nz2);
                 const float2 aLft = shfl_up2(aC[NC - 1]);                 // alpha * (x-1) of cell 0
                 const float2 aRgt = shfl_down2(aC[0]);                    // alpha * (x+1) of the last cell
 #pragma unroll
                 for (int c = 0; c < NC; c++) {
                     const float2 lft = (c == 0) ? aLft : aC[c - 1];
                     const float2 rgt = (c == NC - 1) ? aRgt : aC[c + 1];
-                    dst[c] = add2(add2(lft, rgt), aT[c]);                 // (aL + aR) + aT, fluid.cpp:175-182
+                    dst[c] = add2(add2(lft, rgt), S[l - 1][older][c]);    // (aL + aR) + aT, fluid.cpp:175-182
                 }
             };
-            prefix(1, part);
+            prefix(1, part, aCen);
 #pragma unroll
             for (int l = 1; l <= T; l++) {
                 float2 o[NC];
@@ -298,10 +311,12 @@ __global__ void __launch_bounds__(WARPS_PER_CTA * 32, MINB) diffuse_packed_kerne
                         }
                     }
                 }
-                if (l < T) prefix(l + 1, part_next);
+                if (l < T) prefix(l + 1, part_next, aCen_next);
+                float2 aBot[NC];
 #pragma unroll
                 for (int c = 0; c < NC; c++) {
                     const float2 aB = mulc2(fresh[c], alpha2, nz2);       // alpha * bottom row (s-l+1)
+                    aBot[c] = aB;
                     // ... + aB) + 1.0f*u_n
                     const float2 num = add2(add2(part[c], aB), S[l - 1][older ^ 1][c]);
                     if constexpr (EXACT) {
@@ -313,9 +328,12 @@ __global__ void __launch_bounds__(WARPS_PER_CTA * 32, MINB) diffuse_packed_kerne
                 }
 #pragma unroll
                 for (int c = 0; c < NC; c++) {
-                    S[l - 1][older][c] = fresh[c];
+                    S[l - 1][older ^ 1][c] = aCen[c];     // the centre row becomes the top row: keep its alpha product
+                    S[l - 1][older][c] = fresh[c];        // the bottom row becomes the centre row: keep its values
+                    if constexpr (CARRY) A[l - 1][c] = aBot[c];   // ... and its alpha product
                     fresh[c] = o[c];
                     part[c] = part_next[c];
+                    aCen[c] = aCen_next[c];
                 }
             }
             const int orow = s - 2 * T;
