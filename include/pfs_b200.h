@@ -73,6 +73,12 @@ int pfs_shutdown(void);
  * bit-identical for every value. */
 int pfs_set_fuse_depth(int max_sweeps_per_launch);
 int pfs_get_fuse_depth(void);
+/* Diagnostic, host arithmetic only (works without a GPU): how many instructions the fused diffusion passes spend on the
+ * division by beta = (float)(1.0 + 4.0*(double)(viscosity*dt)) of fluid.cpp:144-145,182 -- 2 if the two-instruction
+ * constant division was verified for this beta (all 2^23 numerator significands tried against the true quotient),
+ * else 3 (the FMA-corrected reciprocal multiply, proven for every divisor), 0 if the parameters take the scalar
+ * kernels.  Every variant returns the correctly rounded quotient; the choice never changes a result bit. */
+int pfs_diffuse_division_ops(float viscosity, float dt);
 
 /* Pinned host memory (the reference's CUDA build reads PNGs into cudaMallocHost memory,
  * includes/utils.hpp:69-76). */

@@ -38,6 +38,7 @@ SIGNATURES = {
     "pfs_shutdown": (_int, []),
     "pfs_set_fuse_depth": (_int, [_int]),
     "pfs_get_fuse_depth": (_int, []),
+    "pfs_diffuse_division_ops": (_int, [_f32, _f32]),
     "pfs_host_alloc": (_int, [_pp, ctypes.c_size_t]),
     "pfs_host_free": (_int, [_vp]),
     "pfs_simulate_fluid_step": (_int, [_pp, _pp, _f32, _f32, _int, _int, _int, _int, _int, _vp]),

@@ -322,6 +322,13 @@ extern "C" int pfs_set_fuse_depth(int d)
 
 extern "C" int pfs_get_fuse_depth(void) { return g_fuse_depth; }
 
+extern "C" int pfs_diffuse_division_ops(float viscosity, float dt)
+{
+    SweepParams p = diffuse_params(4, 1, viscosity, dt);
+    if (!packed_diffuse_supported(p)) return 0;
+    return packed_division_ops(p.beta);
+}
+
 extern "C" int pfs_host_alloc(void **ptr, size_t bytes)
 {
     if (!ptr) {

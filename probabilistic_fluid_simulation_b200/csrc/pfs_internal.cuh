@@ -205,7 +205,8 @@ int launch_diffuse_packed(float *a0, float *a1, float *b0, float *b1, const Swee
                           int *flips, cudaStream_t s, float *prev0 = nullptr, float *prev1 = nullptr,
                           int *prev_written = nullptr);
 void packed_release_device_buffers();
-int default_diffuse_depth();      // sweeps fused per launch when the caller does not say (PFS_DIFFUSE_DEPTH)
+int default_diffuse_depth();
+int packed_division_ops(float beta);      // sweeps fused per launch when the caller does not say (PFS_DIFFUSE_DEPTH)
 // Packed-FP32 temporally blocked pressure sweeps: two strips of the plane per warp (sweeps_packed.cu).
 bool packed_pressure_supported(const SweepParams &p);
 int launch_pressure_packed(float *a, float *b, const float *rhs, const SweepParams &p, int n, int depth, int *flips,

@@ -19,10 +19,17 @@
 //     items with __fdiv_rn.  Real velocity fields never raise the flag; exact-zero regions do, and
 //     stay correct.
 // Results are bit-identical to the one-sweep kernel and to fluid.cpp for every T.
+#include <math.h>
+#include <stdint.h>
 #include <stdlib.h>
+#include <string.h>
 
 #include <map>
 #include <mutex>
+#include <thread>
+#include <vector>
+#include <algorithm>
+#include <cmath>
 #include <utility>
 
 #include "pfs_internal.cuh"
@@ -51,6 +58,8 @@ struct PackedParams {
     int n_strips, n_chunks, chunk_rows;
     int y_base, wrap;           // row map of the planes (SweepParams)
     float alpha, beta, rbeta;
+    float zh, zl;               // 2-instruction division (div_const_two2): RN(1/beta) and RN(1/beta - zh); used iff div2
+    int div2;
     float guard_lo, guard_hi_in;   // |numerator| >= guard_lo and |input| <= guard_hi_in keep the FMA division exact
     float neg_zero;             // -0.0f, deliberately a RUN-TIME value: see mulc2()
 };
@@ -146,6 +155,16 @@ __device__ __forceinline__ float2 div_const_fast2(float2 a, float2 negb, float2 
     return fma2(e, y, q0);
 }
 
+// Two-instruction variant (Brisebarre & Muller, "Correctly rounded multiplication by arbitrary precision constants"):
+// with C = 1/b split as zh = RN(C), zl = RN(C - zh),  q = RN(a*zh + RN(a*zl)).  For most divisors this is RN(a/b)
+// for EVERY a, for some it is wrong for a few a -- so it is only used for a divisor after div2_constants() (below, host)
+// has tried all 2^23 significands of a against the true quotient; scaling a by a power of two scales every
+// intermediate exactly as long as a*zl stays normal, which the guard on |numerator| ensures.
+__device__ __forceinline__ float2 div_const_two2(float2 a, float2 zh, float2 zl)
+{
+    return fma2(a, zh, mul2(a, zl));
+}
+
 __device__ __forceinline__ void cp_async8(void *smem, const void *gmem)
 {
     unsigned s = (unsigned)__cvta_generic_to_shared(smem);
@@ -155,7 +174,7 @@ __device__ __forceinline__ void cp_async8(void *smem, const void *gmem)
 // NC = cells per lane (4: 128-column strips, 16*T registers of state; 2: 64-column strips, 8*T registers,
 // i.e. twice the resident warps at a 7 % wider relative halo -- which one is faster is measured, not assumed:
 // profiles/r01_tuning.md).
-template <int T, bool EXACT, int MINB, int NC>
+template <int T, bool EXACT, int MINB, int NC, bool DIV2 = false>
 __global__ void __launch_bounds__(WARPS_PER_CTA * 32, MINB) diffuse_packed_kernel(const PackedParams P)
 {
     static_assert(NC == 4 || NC == 2, "4 or 2 cells per lane");
@@ -238,6 +257,7 @@ __global__ void __launch_bounds__(WARPS_PER_CTA * 32, MINB) diffuse_packed_kerne
     const float2 nz2 = make_float2(P.neg_zero, P.neg_zero);
     const float2 negb2 = make_float2(-P.beta, -P.beta);
     const float2 y2 = make_float2(P.rbeta, P.rbeta);
+    const float2 zh2 = make_float2(P.zh, P.zh), zl2 = make_float2(P.zl, P.zl);
     const float beta = P.beta;
     float num_min = __int_as_float(0x7f800000);           // +inf
     float in_max = 0.f;
@@ -322,7 +342,7 @@ __global__ void __launch_bounds__(WARPS_PER_CTA * 32, MINB) diffuse_packed_kerne
                     if constexpr (EXACT) {
                         o[c] = make_float2(__fdiv_rn(num.x, beta), __fdiv_rn(num.y, beta));
                     } else {
-                        o[c] = div_const_fast2(num, negb2, y2);
+                        o[c] = DIV2 ? div_const_two2(num, zh2, zl2) : div_const_fast2(num, negb2, y2);
                         num_min = min3abs(num_min, num.x, num.y);
                     }
                 }
@@ -514,7 +534,10 @@ int launch_packed_mb(const PackedParams &P, cudaStream_t s)
 {
     const int total = P.n_strips * P.n_chunks;
     const unsigned blocks = (unsigned)((total + WARPS_PER_CTA - 1) / WARPS_PER_CTA);
-    PFS_LAUNCH((diffuse_packed_kernel<T, false, MINB, NC>), blocks, WARPS_PER_CTA * 32, 0, s, P);
+    if (NC == 4 && P.div2)
+        PFS_LAUNCH((diffuse_packed_kernel<T, false, MINB, NC, (NC == 4)>), blocks, WARPS_PER_CTA * 32, 0, s, P);
+    else
+        PFS_LAUNCH((diffuse_packed_kernel<T, false, MINB, NC>), blocks, WARPS_PER_CTA * 32, 0, s, P);
     PFS_LAUNCH((diffuse_packed_kernel<T, true, MINB, NC>), blocks, WARPS_PER_CTA * 32, 0, s, P);
     --g_passes;     // the repair launch belongs to the same pass
     return PFS_OK;
@@ -585,6 +608,54 @@ int env_int(const char *name, int dflt)
 
 }  // namespace
 
+// ---------------------------------------------------------------------------------------------
+// Is the two-instruction division (div_const_two2) correctly rounded for EVERY numerator with this divisor?
+// Tried, not assumed: all 2^23 significands of a in [1,2) against RN(a/b) (formed in double and rounded once more:
+// innocuous for a quotient of two 24-bit numbers since 53 >= 2*24+2).  ~10 ms on 8 host threads, once per divisor value.
+// ---------------------------------------------------------------------------------------------
+struct Div2Entry {
+    bool ok;
+    float zh, zl;
+};
+std::mutex g_div2_mutex;
+std::map<uint32_t, Div2Entry> g_div2;
+
+Div2Entry div2_constants(float beta)
+{
+    uint32_t key;
+    memcpy(&key, &beta, sizeof(key));
+    std::lock_guard<std::mutex> lock(g_div2_mutex);
+    auto it = g_div2.find(key);
+    if (it != g_div2.end()) return it->second;
+    Div2Entry e;
+    const double C = 1.0 / (double)beta;
+    e.zh = (float)C;
+    e.zl = (float)(C - (double)e.zh);
+    constexpr int NT = 8;
+    bool good[NT];
+    std::vector<std::thread> th;
+    for (int t = 0; t < NT; t++) {
+        th.emplace_back([&, t] {
+            bool ok = true;
+            const uint32_t lo = (uint32_t)t << 20, hi = lo + (1u << 20);
+            for (uint32_t m = lo; m < hi && ok; m++) {
+                const uint32_t bits = 0x3f800000u | m;
+                float a;
+                memcpy(&a, &bits, sizeof(a));
+                volatile float prod = a * e.zl;                       // rounded to binary32 on its own
+                const float q = fmaf(a, e.zh, prod);
+                ok = (q == (float)((double)a / (double)beta));
+            }
+            good[t] = ok;
+        });
+    }
+    for (auto &x : th) x.join();
+    e.ok = true;
+    for (int t = 0; t < NT; t++) e.ok = e.ok && good[t];
+    g_div2[key] = e;
+    return e;
+}
+
 // Rows per work item: every warp streams rows + 2T input rows for `rows` output rows, so chunks should be
 // tall; but there should also be about one resident wave of warps (`slots`), and all chunks should be the
 // same height (a short last chunk costs a whole extra wave).  -> as few chunks as fill the machine once,
@@ -619,6 +690,13 @@ bool packed_diffuse_supported(const SweepParams &p)
     // alpha >= 0 makes every sweep a convex combination (|values| never exceed the input maximum),
     // which is what lets the guard bound numerators by checking inputs only.
     return (p.w % 4 == 0) && p.w >= 4 && p.h >= 1 && p.alpha >= 0.f && p.beta >= 1.f && p.beta <= 0x1p20f;
+}
+
+// 2 or 3: instructions of the constant division the fused passes use for this divisor (diagnostic; host arithmetic only)
+int packed_division_ops(float beta)
+{
+    static const bool div2_env = !(getenv("PFS_DIFFUSE_DIV2") && getenv("PFS_DIFFUSE_DIV2")[0] == '0');
+    return (div2_env && div2_constants(beta).ok) ? 2 : 3;
 }
 
 int default_diffuse_depth()
@@ -661,6 +739,13 @@ int launch_diffuse_packed(float *a0, float *a1, float *b0, float *b1, const Swee
         P.n_chunks = (p.h + P.chunk_rows - 1) / P.chunk_rows;
         P.alpha = p.alpha; P.beta = p.beta; P.rbeta = 1.0f / p.beta;
         P.guard_lo = 0x1p-96f;
+        static const bool div2_env = !(getenv("PFS_DIFFUSE_DIV2") && getenv("PFS_DIFFUSE_DIV2")[0] == '0');
+        const Div2Entry d2 = (div2_env && cells == 4) ? div2_constants(p.beta) : Div2Entry{false, 0.f, 0.f};
+        P.div2 = d2.ok ? 1 : 0;
+        P.zh = d2.zh;
+        P.zl = d2.zl;
+        if (d2.ok && d2.zl != 0.f)       // numerator * zl must stay a normal number (scale invariance of the proof)
+            P.guard_lo = std::max(P.guard_lo, 0x1p-124f / std::fabs(d2.zl));
         P.guard_hi_in = 0x1p60f;
         P.neg_zero = -0.0f;
         PFS_TRY(get_flags((size_t)P.n_strips * P.n_chunks, &P.flags));

@@ -56,6 +56,24 @@ def test_diffuse_parameter_range(visc, dt):
     assert_bit_equal(to_host(fb.data), rb, "diffuse vp_out")
 
 
+@pytest.mark.parametrize("beta_bits", ["3ff4291f", "406b65c7", "40d1684b", "3f800d1b", "3fb33333", "40000000"])
+def test_diffuse_with_either_constant_division(beta_bits):
+    """Divisors for which the fused passes use the verified two-instruction division (the last three) and divisors
+    for which that form would be wrong for one numerator, so the three-instruction one is used (the first three;
+    tests/test_exact_division.py checks the decision itself)."""
+    from test_exact_division import DIV2_WRONG, _beta_to_params
+    from probabilistic_fluid_simulation_b200 import _cabi
+    visc, dt = _beta_to_params(beta_bits)
+    assert _cabi.lib().pfs_diffuse_division_ops(visc, dt) == (3 if beta_bits in DIV2_WRONG else 2)
+    h, w = 72, 256
+    a, b = rand_field(h, w, 41), rand_field(h, w, 42)
+    fa, fb = pfs.vp_field(to_dev(a)), pfs.vp_field(to_dev(b))
+    pfs.diffuse(fa, fb, visc, dt, 25)
+    ra, rb = oracle.Oracle().diffuse(a, b, visc, dt, 25)
+    assert_bit_equal(to_host(fa.data), ra, "diffuse vp")
+    assert_bit_equal(to_host(fb.data), rb, "diffuse vp_out")
+
+
 @pytest.mark.parametrize("n", [1, 2, 3, 4, 7, 30, 31])
 @pytest.mark.parametrize("shape", [(16, 16), (29, 37), (48, 40), (130, 260), (64, 4), (3, 5)])
 def test_compute_pressure(n, shape):
