@@ -115,14 +115,22 @@ __device__ __forceinline__ float max3abs(float m, float a, float b)
     asm("max.f32 %0, %1, %2, %3;" : "=f"(d) : "f"(m), "f"(fabsf(a)), "f"(fabsf(b)));
     return d;
 }
-__device__ __forceinline__ float2 shfl_up2(float2 v)
+// Lane shuffles with immediate operands (inline PTX): the intrinsic form made ptxas keep the lane delta and clamp in
+// registers and funnel every shuffle through one fixed source/destination register pair, i.e. two MOVs per SHFL.
+__device__ __forceinline__ float shfl_up1(float v)
 {
-    return make_float2(__shfl_up_sync(0xffffffffu, v.x, 1), __shfl_up_sync(0xffffffffu, v.y, 1));
+    float d;
+    asm volatile("shfl.sync.up.b32 %0, %1, 1, 0, 0xffffffff;" : "=f"(d) : "f"(v));
+    return d;
 }
-__device__ __forceinline__ float2 shfl_down2(float2 v)
+__device__ __forceinline__ float shfl_down1(float v)
 {
-    return make_float2(__shfl_down_sync(0xffffffffu, v.x, 1), __shfl_down_sync(0xffffffffu, v.y, 1));
+    float d;
+    asm volatile("shfl.sync.down.b32 %0, %1, 1, 31, 0xffffffff;" : "=f"(d) : "f"(v));
+    return d;
 }
+__device__ __forceinline__ float2 shfl_up2(float2 v) { return make_float2(shfl_up1(v.x), shfl_up1(v.y)); }
+__device__ __forceinline__ float2 shfl_down2(float2 v) { return make_float2(shfl_down1(v.x), shfl_down1(v.y)); }
 
 __device__ __forceinline__ void cp_async16(void *smem, const void *gmem)
 {
@@ -243,9 +251,10 @@ __global__ void __launch_bounds__(WARPS_PER_CTA * 32, MINB) diffuse_packed_kerne
     for (int l = 0; l < T; l++)
 #pragma unroll
         for (int c = 0; c < NC; c++) S[l][0][c] = S[l][1][c] = make_float2(1.f, 1.f);
-    // Shallow passes have registers to spare for a third row per level: the alpha product of the centre row, formed
-    // when that row arrived as the bottom row.  Then every row is multiplied by alpha exactly once per level
-    // (the reference multiplies it four times, once per neighbour that reads it -- same value each time).
+    // Passes up to CARRY_MAX_DEPTH have registers to spare for a third row per level, so that the alpha product of a
+    // row, formed when the row arrives as the bottom row, is kept while the row is the centre and then the top row:
+    // every value is multiplied by alpha exactly once per level (the reference multiplies it four times, once per
+    // neighbour that reads it -- same value each time).  See the state layout at the prefix lambda below.
     constexpr bool CARRY = (NC == 4 && T <= CARRY_MAX_DEPTH);
     float2 A[CARRY ? T : 1][NC];
 #pragma unroll
@@ -294,14 +303,16 @@ __global__ void __launch_bounds__(WARPS_PER_CTA * 32, MINB) diffuse_packed_kerne
             // earlier steps -- the alpha products of its centre and top rows, the lane shuffles and
             // (aL + aR) + aT -- is issued before the tail of level l, which depends on the row level l-1
             // has just produced.  Two independent instruction streams per warp instead of one.
-            // State per level: slot [older^1] holds the centre row (s-l) as VALUES, slot [older] the top row
-            // (s-l-1) already MULTIPLIED by alpha -- it is the product formed when that row was the centre row one
-            // step ago, so the reference's alpha*T costs nothing here (the raw values of the top row are not needed).
+            // State per level.  Without CARRY: slot [older^1] holds the centre row (s-l) as VALUES, slot [older] the top
+            // row (s-l-1) already MULTIPLIED by alpha (the product formed when that row was the centre row one step
+            // ago).  With CARRY both slots hold alpha products -- [older^1] the centre row's, [older] the top row's --
+            // and A[] holds the centre row's values; the top slot is dead after the prefix, so the product of the
+            // incoming bottom row is written straight into it and the slots just swap roles with the step parity.
             float2 part[NC], part_next[NC], aCen[NC], aCen_next[NC];
             auto prefix = [&](int l, float2(&dst)[NC], float2(&aC)[NC]) {
 #pragma unroll
                 for (int c = 0; c < NC; c++)        // alpha * centre row: carried from the step that produced it, or formed now
-                    aC[c] = CARRY ? A[CARRY ? l - 1 : 0][c] : mulc2(S[l - 1][older ^ 1][c], alpha2, nz2);
+                    aC[c] = CARRY ? S[l - 1][older ^ 1][c] : mulc2(S[l - 1][older ^ 1][c], alpha2, nz2);
                 const float2 aLft = shfl_up2(aC[NC - 1]);                 // alpha * (x-1) of cell 0
                 const float2 aRgt = shfl_down2(aC[0]);                    // alpha * (x+1) of the last cell
 #pragma unroll
@@ -338,7 +349,7 @@ __global__ void __launch_bounds__(WARPS_PER_CTA * 32, MINB) diffuse_packed_kerne
                     const float2 aB = mulc2(fresh[c], alpha2, nz2);       // alpha * bottom row (s-l+1)
                     aBot[c] = aB;
                     // ... + aB) + 1.0f*u_n
-                    const float2 num = add2(add2(part[c], aB), S[l - 1][older ^ 1][c]);
+                    const float2 num = add2(add2(part[c], aB), CARRY ? A[CARRY ? l - 1 : 0][c] : S[l - 1][older ^ 1][c]);
                     if constexpr (EXACT) {
                         o[c] = make_float2(__fdiv_rn(num.x, beta), __fdiv_rn(num.y, beta));
                     } else {
@@ -348,12 +359,16 @@ __global__ void __launch_bounds__(WARPS_PER_CTA * 32, MINB) diffuse_packed_kerne
                 }
 #pragma unroll
                 for (int c = 0; c < NC; c++) {
-                    S[l - 1][older ^ 1][c] = aCen[c];     // the centre row becomes the top row: keep its alpha product
-                    S[l - 1][older][c] = fresh[c];        // the bottom row becomes the centre row: keep its values
-                    if constexpr (CARRY) A[l - 1][c] = aBot[c];   // ... and its alpha product
+                    if constexpr (CARRY) {
+                        S[l - 1][older][c] = aBot[c];         // the dead top slot takes the new centre row's alpha product
+                        A[l - 1][c] = fresh[c];               // ... and A its values
+                    } else {
+                        S[l - 1][older ^ 1][c] = aCen[c];     // the centre row becomes the top row: keep its alpha product
+                        S[l - 1][older][c] = fresh[c];        // the bottom row becomes the centre row: keep its values
+                        aCen[c] = aCen_next[c];
+                    }
                     fresh[c] = o[c];
                     part[c] = part_next[c];
-                    aCen[c] = aCen_next[c];
                 }
             }
             const int orow = s - 2 * T;

@@ -1,8 +1,8 @@
 #!/bin/bash
 set -u
 TAG=${1:-exp}; OUT=gpurun_out/$TAG; mkdir -p "$OUT"; : > "$OUT/summary.txt"
-timeout 1500 python -m pytest tests -x -q -m gpu > "$OUT/pytest.log" 2>&1
-echo "pytest exit $?" | tee -a "$OUT/summary.txt"; tail -6 "$OUT/pytest.log" | tee -a "$OUT/summary.txt"
+timeout 900 python -m pytest tests/test_gpu_operators.py tests/test_gpu_fullsize.py tests/test_gpu_golden.py tests/test_gpu_adaptive_pressure.py -x -q -m gpu > "$OUT/pytest.log" 2>&1
+echo "pytest exit $?" | tee -a "$OUT/summary.txt"; tail -4 "$OUT/pytest.log" | tee -a "$OUT/summary.txt"
 run() {
   name=$1; extra=$2; shift; shift
   echo "== $name" | tee -a "$OUT/summary.txt"
@@ -11,7 +11,6 @@ run() {
   tail -2 "$OUT/bench_$name.err" | tee -a "$OUT/summary.txt"
 }
 run default "--steps 50 --warmup 5" X=1
-run div3 "--steps 50 --warmup 5" PFS_DIFFUSE_DIV2=0
-run d5 "--steps 50 --warmup 5" PFS_DIFFUSE_DEPTH=5
-run d7 "--steps 50 --warmup 5" PFS_DIFFUSE_DEPTH=7
+run p7 "--steps 50 --warmup 5" PFS_FUSE_DEPTH=7 PFS_DIFFUSE_DEPTH=6
+run p6 "--steps 50 --warmup 5" PFS_FUSE_DEPTH=6 PFS_DIFFUSE_DEPTH=6
 run cfg2 "--width 1024 --height 1024 --iters 50 --steps 400 --warmup 20" X=1
