@@ -45,8 +45,13 @@ constexpr int WARPS_PER_CTA = 4;
 #define PFS_CARRY_MAX_DEPTH 6
 #endif
 constexpr int CARRY_MAX_DEPTH = PFS_CARRY_MAX_DEPTH;
-constexpr int RING_SLOTS = 4;
-constexpr int PREFETCH = RING_SLOTS - 2;
+#ifndef PFS_RING_SLOTS
+#define PFS_RING_SLOTS 4
+#endif
+constexpr int RING_SLOTS = PFS_RING_SLOTS;   // cp.async ring depth per warp (rows), a power of two
+constexpr int PREFETCH = RING_SLOTS - 2;      // rows in flight ahead of the consumer
+constexpr int PRING_SLOTS = 4;                // the (opt-in) packed pressure kernel keeps its 4-slot ring (64 B x 32 lanes per slot)
+constexpr int PPREFETCH = PRING_SLOTS - 2;
 
 struct PackedParams {
     const float *in_u, *in_v;
@@ -421,7 +426,7 @@ template <int T, int MINB>
 __global__ void __launch_bounds__(WARPS_PER_CTA * 32, MINB) pressure_packed_kernel(const PressurePackedParams P)
 {
     constexpr int U = PressureUnroll<T>::value;
-    __shared__ float4 ring[WARPS_PER_CTA][RING_SLOTS][4][32];   // per slot: p(A), p(B), div(A), div(B)
+    __shared__ float4 ring[WARPS_PER_CTA][PRING_SLOTS][4][32];   // per slot: p(A), p(B), div(A), div(B)
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int item = blockIdx.x * WARPS_PER_CTA + warp;
@@ -457,7 +462,7 @@ __global__ void __launch_bounds__(WARPS_PER_CTA * 32, MINB) pressure_packed_kern
 
     auto prefetch = [&](int s) {
         if (s < n_steps) {
-            float4 *dst = my + (s & (RING_SLOTS - 1)) * SLOT_STRIDE;
+            float4 *dst = my + (s & (PRING_SLOTS - 1)) * SLOT_STRIDE;
             const size_t row = (size_t)ld_row * w;
             cp_async16(dst, P.in + row + xwA);
             cp_async16(dst + 32, P.in + row + xwB);
@@ -468,7 +473,7 @@ __global__ void __launch_bounds__(WARPS_PER_CTA * 32, MINB) pressure_packed_kern
         cp_async_commit();
     };
 #pragma unroll
-    for (int s = 0; s < PREFETCH; s++) prefetch(s);
+    for (int s = 0; s < PPREFETCH; s++) prefetch(s);
 
     float2 S[T][2][4];      // pressure rows: level, parity slot, cell; .x = strip A, .y = strip B
     float2 Q[T][4];         // divergence rows s-T .. s-1; row r lives in Q[r mod T]
@@ -489,9 +494,9 @@ __global__ void __launch_bounds__(WARPS_PER_CTA * 32, MINB) pressure_packed_kern
 #pragma unroll
         for (int u = 0; u < U; u++) {
             const int s = sb + u;
-            prefetch(s + PREFETCH);
-            cp_async_wait<PREFETCH>();
-            const float4 *slot = my + (s & (RING_SLOTS - 1)) * SLOT_STRIDE;
+            prefetch(s + PPREFETCH);
+            cp_async_wait<PPREFETCH>();
+            const float4 *slot = my + (s & (PRING_SLOTS - 1)) * SLOT_STRIDE;
             const float4 pa = slot[0], pb = slot[32], qa = slot[64], qb = slot[96];
             float2 fresh[4] = {make_float2(pa.x, pb.x), make_float2(pa.y, pb.y), make_float2(pa.z, pb.z),
                                make_float2(pa.w, pb.w)};

@@ -1,10 +1,17 @@
 #!/bin/bash
-# two GPUs: the whole GPU suite (incl. the two-process transports), then the N=2 bench line
 set -u
 TAG=${1:-exp}; OUT=gpurun_out/$TAG; mkdir -p "$OUT"; : > "$OUT/summary.txt"
-timeout 1500 python -m pytest tests -x -q -m gpu > "$OUT/pytest.log" 2>&1
-echo "pytest exit $?" | tee -a "$OUT/summary.txt"; tail -5 "$OUT/pytest.log" | tee -a "$OUT/summary.txt"
-n=2
-timeout 600 python -m torch.distributed.run --nnodes=1 --nproc-per-node $n --master-addr 127.0.0.1 --master-port 29511 bench.py --gpus $n --steps 10 --warmup 3 > "$OUT/bench_n$n.json" 2> "$OUT/bench_n$n.err"
-echo "bench exit $?" | tee -a "$OUT/summary.txt"
-python -c "import json;d=json.load(open('$OUT/bench_n$n.json'));print('ms/step',d['ms_per_step'],'value',d['value'],'e2e',d['e2e'] and d['e2e']['ms_per_step'], d['phases_ms_rank0'], d['transport'][:30])" | tee -a "$OUT/summary.txt"
+LIB=probabilistic_fluid_simulation_b200/lib/libpfs_b200.so
+run() {
+  name=$1; extra=$2; shift; shift
+  echo "== $name" | tee -a "$OUT/summary.txt"
+  env "$@" timeout 600 python bench.py --no-e2e --no-cpu $extra > "$OUT/bench_$name.json" 2> "$OUT/bench_$name.err"
+  python -c "import json;d=json.load(open('$OUT/bench_$name.json'));print('ms/step %.4f'%d['ms_per_step'], 'eager %.4f'%d['phase_region']['ms_per_step_eager_with_phase_events'], {k: round(v,4) for k,v in d['phases_ms'].items()}, d['gpu_launches'])" | tee -a "$OUT/summary.txt"
+  tail -2 "$OUT/bench_$name.err" | tee -a "$OUT/summary.txt"
+}
+cp scratch_libs/libpfs_r8.so $LIB
+timeout 600 python -m pytest tests/test_gpu_operators.py tests/test_gpu_fullsize.py -x -q -m gpu > "$OUT/pytest_r8.log" 2>&1; echo "pytest r8 exit $?" | tee -a "$OUT/summary.txt"; tail -2 "$OUT/pytest_r8.log" | tee -a "$OUT/summary.txt"
+run r8 "--steps 50 --warmup 5" X=1
+run r8_cfg2 "--width 1024 --height 1024 --iters 50 --steps 400 --warmup 20" X=1
+cp scratch_libs/libpfs_r4.so $LIB
+run r4 "--steps 50 --warmup 5" X=1
