@@ -24,3 +24,5 @@ run default "" X=1
 run default_nograph "--no-e2e --no-cpu" PFS_STEP_GRAPH=0
 run cfg2 "--width 1024 --height 1024 --iters 50 --steps 400 --warmup 20 --no-e2e --no-cpu" X=1
 run n30_2048 "--width 2048 --height 2048 --iters 30 --steps 200 --warmup 10 --no-e2e --no-cpu" X=1
+echo "== bench --impl reference" | tee -a "$OUT/summary.txt"
+timeout 600 python bench.py --impl reference --steps 2 --warmup 1 > "$OUT/bench_reference_arm.json" 2> "$OUT/bench_reference_arm.err"; echo "exit $?" | tee -a "$OUT/summary.txt"; cut -c1-300 "$OUT/bench_reference_arm.json" | tee -a "$OUT/summary.txt"
