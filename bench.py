@@ -53,57 +53,106 @@ def measured_peak_gbs():
 
 
 class ClockSampler:
-    """nvidia-smi clocks / throttle reasons sampled every 50 ms during the timed region."""
+    """SM clock and throttle reasons of one GPU sampled DURING the timed region: NVML polled every 5 ms from a
+    thread (time-stamped on this host's clock, so samples can be matched to the region exactly); if NVML cannot
+    be loaded, `nvidia-smi -lms 50` through a pipe (coarser: its output arrives in bursts)."""
 
     Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
          "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
          "clocks_event_reasons.sw_power_cap")
+    NAMES = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+    # nvmlClocksThrottleReason* / nvmlClocksEventReason* bits (nvml.h)
+    BITS = {"hw_slowdown": 0x8, "hw_thermal_slowdown": 0x40, "sw_thermal_slowdown": 0x20, "sw_power_cap": 0x4}
 
-    def __init__(self, index: int):
+    def __init__(self, index: int, period_s: float = 0.005):
         self.index = index
-        self.rows = []
+        self.period = period_s
+        self.rows = []          # (t, sm_mhz, sm_max_mhz, set(reasons))
         self.proc = None
+        self.thread = None
+        self.source = None
+        self._stop = threading.Event()
+
+    # ---- NVML ----
+    def _nvml_handle(self):
+        import pynvml
+        pynvml.nvmlInit()
+        try:                                    # CUDA ordinal -> NVML device through the UUID (CUDA_VISIBLE_DEVICES-proof)
+            uuid = str(torch.cuda.get_device_properties(self.index).uuid)
+            return pynvml, pynvml.nvmlDeviceGetHandleByUUID(("GPU-" + uuid).encode())
+        except Exception:
+            return pynvml, pynvml.nvmlDeviceGetHandleByIndex(self.index)
+
+    def _poll_nvml(self, nv, h):
+        try:
+            mx = float(nv.nvmlDeviceGetMaxClockInfo(h, nv.NVML_CLOCK_SM))
+        except Exception:
+            mx = None
+        get_reasons = getattr(nv, "nvmlDeviceGetCurrentClocksEventReasons", None) or \
+            nv.nvmlDeviceGetCurrentClocksThrottleReasons
+        while not self._stop.is_set():
+            try:
+                sm = float(nv.nvmlDeviceGetClockInfo(h, nv.NVML_CLOCK_SM))
+                mask = int(get_reasons(h))
+                t = time.perf_counter()
+                self.rows.append((t, sm, mx, {n for n, b in self.BITS.items() if mask & b}))
+            except Exception:
+                pass
+            self._stop.wait(self.period)
+
+    # ---- nvidia-smi fallback ----
+    def _read_smi(self):
+        for line in self.proc.stdout:
+            r = [x.strip() for x in line.split(",")]
+            try:
+                reasons = {n for n, v in zip(self.NAMES, r[3:7]) if v.lower().startswith("active")}
+                self.rows.append((time.perf_counter(), float(r[0]), float(r[1]), reasons))
+            except Exception:
+                continue
 
     def start(self):
+        try:
+            nv, h = self._nvml_handle()
+            nv.nvmlDeviceGetClockInfo(h, nv.NVML_CLOCK_SM)
+            self.thread = threading.Thread(target=self._poll_nvml, args=(nv, h), daemon=True)
+            self.thread.start()
+            self.source = f"nvml, every {self.period * 1e3:.0f} ms"
+            return
+        except Exception:
+            pass
         try:
             self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), f"--query-gpu={self.Q}",
                                           "--format=csv,noheader,nounits", "-lms", "50"],
                                          stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
-            self.thread = threading.Thread(target=self._read, daemon=True)
+            self.thread = threading.Thread(target=self._read_smi, daemon=True)
             self.thread.start()
+            self.source = "nvidia-smi -lms 50"
         except Exception:
             self.proc = None
 
-    def _read(self):
-        for line in self.proc.stdout:
-            self.rows.append((time.perf_counter(), [x.strip() for x in line.split(",")]))
-
     def stop(self, t0=None, t1=None):
-        if not self.proc:
-            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
-        time.sleep(0.25)
-        self.proc.terminate()
-        try:
-            self.proc.wait(timeout=5)
-        except Exception:
-            self.proc.kill()
-        sm, mx, reasons = [], [], set()
-        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        inside = [r for (t, r) in self.rows if t0 is None or (t0 <= t <= t1 + 0.06)]
+        if self.source is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvml and nvidia-smi unavailable"]}
+        if self.proc:
+            time.sleep(0.25)
+            self.proc.terminate()
+            try:
+                self.proc.wait(timeout=5)
+            except Exception:
+                self.proc.kill()
+        else:
+            self._stop.set()
+            self.thread.join(timeout=2)
+        slack = 0.06 if self.proc else 0.0
+        inside = [r for r in self.rows if t0 is None or (t0 <= r[0] <= t1 + slack)]
         window = "timed region"
         if not inside:                       # region shorter than the sampling period
-            inside, window = [r for (_, r) in self.rows], "whole run (timed region shorter than one sample)"
-        for r in inside:
-            try:
-                sm.append(float(r[0])); mx.append(float(r[1]))
-                for n, v in zip(names, r[3:7]):
-                    if v.lower().startswith("active"):
-                        reasons.add(n)
-            except Exception:
-                continue
-        sm.sort()
+            inside, window = list(self.rows), "whole run (timed region shorter than one sample)"
+        sm = sorted(r[1] for r in inside)
+        mx = [r[2] for r in inside if r[2] is not None]
+        reasons = set().union(*[r[3] for r in inside]) if inside else set()
         return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": max(mx) if mx else None,
-                "reasons": sorted(reasons), "samples": len(sm), "window": window}
+                "reasons": sorted(reasons), "samples": len(sm), "window": window, "source": self.source}
 
 
 def make_inputs(h: int, w: int, rows=None):
@@ -265,7 +314,7 @@ def run_single_gpu(args):
     #  so the per-phase / per-kernel figures come from a second region right after, see below)
     sampler = ClockSampler(0)
     sampler.start()
-    time.sleep(0.12)          # let nvidia-smi deliver its first sample before the (short) timed region
+    time.sleep(0.05)          # the sampler is running before the (short) timed region starts
     l0 = pfs.kernel_launch_count()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     torch.cuda.synchronize()
