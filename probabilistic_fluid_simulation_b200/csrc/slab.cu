@@ -249,17 +249,31 @@ __global__ void __launch_bounds__(256)
     const float2 uv = own ? __ldg(reinterpret_cast<const float2 *>(own + i)) : make_float2(0.f, 0.f);
     if (vmax_out != nullptr) {
         // by-product: max|v| of the field being advected (what bounds the row displacement), NaN -> +inf.
-        // One atomic per warp, and only when the warp would raise the current value.
+        // Reduced over the whole CTA first (every thread gets here, dead ones with 0): ONE look at the running
+        // maximum per CTA, and an atomic only when the CTA would raise it -- a look per warp was a million loads of
+        // one address per step, all served by the same L2 slice.
+        __shared__ float warp_max[8];
         float m = fabsf(uv.y);
 #pragma unroll
         for (int o = 16; o > 0; o >>= 1) {
             const float t = __shfl_xor_sync(0xffffffffu, m, o);
             m = (t > m || t != t) ? t : m;
         }
-        if (((threadIdx.y * 64 + threadIdx.x) & 31) == 0) {
-            if (m != m) m = __int_as_float(0x7f800000);
-            if (m > *reinterpret_cast<volatile float *>(vmax_out))
-                atomicMax(reinterpret_cast<int *>(vmax_out), __float_as_int(m));
+        const int tid = threadIdx.y * 64 + threadIdx.x;
+        if ((tid & 31) == 0) warp_max[tid >> 5] = m;
+        __syncthreads();
+        if (tid < 32) {
+            m = (tid < 8) ? warp_max[tid] : 0.f;
+#pragma unroll
+            for (int o = 4; o > 0; o >>= 1) {
+                const float t = __shfl_xor_sync(0xffffffffu, m, o);
+                m = (t > m || t != t) ? t : m;
+            }
+            if (tid == 0) {
+                if (m != m) m = __int_as_float(0x7f800000);
+                if (m > *reinterpret_cast<volatile float *>(vmax_out))
+                    atomicMax(reinterpret_cast<int *>(vmax_out), __float_as_int(m));
+            }
         }
     }
     if (!own) return;
