@@ -40,6 +40,8 @@ int pick_chunk_rows(int h, int columns_of_items, long long slots, int forced_row
 
 namespace {
 
+int env_int(const char *name, int dflt);
+
 constexpr int WARPS_PER_CTA = 4;
 #ifndef PFS_CARRY_MAX_DEPTH
 #define PFS_CARRY_MAX_DEPTH 6
@@ -187,10 +189,16 @@ __device__ __forceinline__ void cp_async8(void *smem, const void *gmem)
 // NC = cells per lane (4: 128-column strips, 16*T registers of state; 2: 64-column strips, 8*T registers,
 // i.e. twice the resident warps at a 7 % wider relative halo -- which one is faster is measured, not assumed:
 // profiles/r01_tuning.md).
-template <int T, bool EXACT, int MINB, int NC, bool DIV2 = false>
+// UNR = stream steps per trip of the main loop (even: the row slots alternate with the step parity).  Steps past the
+// last one are harmless -- their prefetch is skipped and every store is masked by its row range -- so the trip count is
+// simply rounded up.  2 is the shipped value; 4 is an opt-in (PFS_DIFFUSE_UNROLL=4) that lets ptxas drop a third of the
+// register moves at the loop back-edge (13.4 instead of 14.4 instructions per update, scripts/sass_loop_stats.py) at
+// twice the loop body (20 KB); not measured on a GPU yet.
+template <int T, bool EXACT, int MINB, int NC, bool DIV2 = false, int UNR = 2>
 __global__ void __launch_bounds__(WARPS_PER_CTA * 32, MINB) diffuse_packed_kernel(const PackedParams P)
 {
     static_assert(NC == 4 || NC == 2, "4 or 2 cells per lane");
+    static_assert(UNR >= 2 && UNR % 2 == 0, "the unroll factor must be even");
     __shared__ __align__(16) float ring[WARPS_PER_CTA][RING_SLOTS][2][32 * NC];
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -281,10 +289,11 @@ __global__ void __launch_bounds__(WARPS_PER_CTA * 32, MINB) diffuse_packed_kerne
     float *prev_u = P.prev_u ? P.prev_u + (size_t)(P.y_base + y0) * w + xc : nullptr;
     float *prev_v = P.prev_v ? P.prev_v + (size_t)(P.y_base + y0) * w + xc : nullptr;
 
-    for (int sb = 0; sb < n_steps; sb += 2) {
+    for (int sb = 0; sb < n_steps; sb += UNR) {
 #pragma unroll
-        for (int u = 0; u < 2; u++) {
-            const int s = sb + u;
+        for (int uu = 0; uu < UNR; uu++) {
+            const int u = uu & 1;
+            const int s = sb + uu;
             prefetch(s + PREFETCH);
             cp_async_wait<PREFETCH>();
             const float *slot = my + (s & (RING_SLOTS - 1)) * SLOT_STRIDE;
@@ -554,7 +563,11 @@ int launch_packed_mb(const PackedParams &P, cudaStream_t s)
 {
     const int total = P.n_strips * P.n_chunks;
     const unsigned blocks = (unsigned)((total + WARPS_PER_CTA - 1) / WARPS_PER_CTA);
-    if (NC == 4 && P.div2)
+    static const int unroll = env_int("PFS_DIFFUSE_UNROLL", 2);
+    if (NC == 4 && P.div2 && unroll == 4)
+        PFS_LAUNCH((diffuse_packed_kernel<T, false, MINB, NC, (NC == 4), (NC == 4 ? 4 : 2)>), blocks, WARPS_PER_CTA * 32, 0,
+                   s, P);
+    else if (NC == 4 && P.div2)
         PFS_LAUNCH((diffuse_packed_kernel<T, false, MINB, NC, (NC == 4)>), blocks, WARPS_PER_CTA * 32, 0, s, P);
     else
         PFS_LAUNCH((diffuse_packed_kernel<T, false, MINB, NC>), blocks, WARPS_PER_CTA * 32, 0, s, P);
