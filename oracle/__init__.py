@@ -3,10 +3,12 @@
 Only ``tests/``, ``__graft_entry__.smoke()`` and the ``cpu_baseline`` / ``--impl reference`` legs of
 ``bench.py`` may import this package.  The product (``probabilistic_fluid_simulation_b200``) never does.
 
-Two back ends with the same Python surface:
+Two back ends with the same Python surface, and the input boundary:
 
 * :class:`Oracle` -- ``oracle/liboracle.so``, the plain-C restatement in ``fluid_oracle.c`` (run-time
   sweep counts).
+* ``oracle.png_decode`` -- the reference's PNG reader (libpng simplified API, 8-bit RGBA) restated without libpng
+  (``png_restate.c``, also in ``liboracle.so``); pinned against the real libpng by tests/test_png_restatement.py.
 * :class:`Reference` -- ``oracle/_ref/libfluid_ref_<N>.so``, the UNMODIFIED reference
   ``/root/reference/src/fluid.cpp`` compiled by ``oracle/Makefile`` through ``ref_wrap.cpp``
   (compile-time sweep count N, one library per N).
