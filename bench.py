@@ -76,6 +76,7 @@ class ClockSampler:
     # ---- NVML ----
     def _nvml_handle(self):
         import pynvml
+        import torch
         pynvml.nvmlInit()
         try:                                    # CUDA ordinal -> NVML device through the UUID (CUDA_VISIBLE_DEVICES-proof)
             uuid = str(torch.cuda.get_device_properties(self.index).uuid)
@@ -244,6 +245,76 @@ def run_reference_arm(args):
             "e2e": {"value": rate, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "gpu_launches": 0}
     print(json.dumps(line), flush=True)
+
+
+# --------------------------------------------------------------------------------------------
+# multi-GPU arm: parity of the ring the timed steps run on (outside the timed region)
+# --------------------------------------------------------------------------------------------
+def ring_parity_check(rank: int, world: int, make_slab):
+    """Runs small whole-grid cases through the SAME one-process-per-GPU ring as the timed workload (same SlabRank
+    class, same transport) and compares every band, bit for bit, with the CPU oracle run on the whole grid by rank 0
+    (reference semantics: fluid.cpp:298-320).  `make_slab(w, h, iw, ih)` returns a connected SlabRank.
+    Grid 1024 x (64 * ranks), image 1536 x (96 * ranks) (image/grid ratio 1.5: the look-up factor of fluid.cpp:82-83 is
+    inexact in binary32), 7 + 10 sweeps, 3 steps; two time steps: one whose departure rows reach ~20 rows into the
+    neighbouring bands (peer-written gather halos) and one whose departure rows lie beyond the neighbouring bands
+    (whole-field gather).  -> the "parity" object of the JSON line (identical on every rank)."""
+    import numpy as np
+    import torch
+    import torch.distributed as dist
+
+    import probabilistic_fluid_simulation_b200 as pfs
+    from probabilistic_fluid_simulation_b200 import fixtures
+
+    w, h, iw, ih = 1024, 64 * world, 1536, 96 * world
+    nd, npr, steps, visc = 7, 10, 3, 0.002
+    vel = fixtures.smooth_velocity_bytes(h, w)
+    noise = fixtures.hash_bytes(h, w, 2, 77).astype(np.int16) % 13 - 6
+    vel[..., :2] = np.clip(vel[..., :2].astype(np.int16) + noise, 0, 255).astype(np.uint8)
+    img = fixtures.hash_bytes(ih, iw, 4, 78)
+    state = fixtures.make_state(vel, img)
+    cases = []
+    ok_all = True
+    transport = None
+    for label, dt in (("gather reaches into the neighbouring bands", 20.0 * h), ("gather beyond the neighbouring bands", 150.0 * h)):
+        slab = make_slab(w, h, iw, ih)
+        transport = slab.transport
+        r0, rows, i0, irows = slab.row0, slab.rows, slab.irow0, slab.irows
+        vp, vtmp, image, itmp = (x.copy() for x in state)
+        fv, ft = (pfs.vp_field(torch.from_numpy(x[r0:r0 + rows].copy()).cuda()) for x in (vp, vtmp))
+        fi, fm = (pfs.vp_field(torch.from_numpy(x[i0:i0 + irows].copy()).cuda()) for x in (image, itmp))
+        for _ in range(steps):
+            slab.simulate_fluid_step(fv, ft, dt, visc, nd, npr)
+            slab.advect_color_step(fi, fm, fv, dt)
+        slab.check()
+        mine = {"rank": rank, "rows": (r0, rows), "irows": (i0, irows),
+                "vp": fv.data.cpu().numpy(), "vtmp": ft.data.cpu().numpy(), "image": fi.data.cpu().numpy()}
+        parts = [None] * world
+        dist.all_gather_object(parts, mine)
+        verdict = [True, {}]
+        if rank == 0:
+            import oracle          # the checker: never on the timed or shipped path
+            want = oracle.Oracle(nd, npr).run_steps(*(x.copy() for x in state), np.float32(dt), np.float32(visc), steps)
+            bad = []
+            for part in parts:
+                a, n = part["rows"]
+                b, m = part["irows"]
+                for name, wfield, sl in (("vp", want[0], slice(a, a + n)), ("vtmp", want[1], slice(a, a + n)),
+                                         ("image", want[2], slice(b, b + m))):
+                    if not np.array_equal(part[name].view(np.uint32), np.ascontiguousarray(wfield[sl]).view(np.uint32)):
+                        bad.append(f"rank {part['rank']} {name}")
+            got_vp = np.concatenate([p_["vp"] for p_ in sorted(parts, key=lambda q: q["rank"])], axis=0)
+            verdict = [not bad, {"mismatches": bad, "fnv1a_vp_whole_grid": oracle.field_hashes(got_vp),
+                                 "fnv1a_vp_oracle": oracle.field_hashes(want[0])}]
+        box = [verdict]
+        dist.broadcast_object_list(box, src=0)
+        ok, detail = box[0]
+        ok_all = ok_all and ok
+        cases.append({"case": label, "dt": dt, "bit_identical": ok, **detail})
+        dist.barrier()
+        slab.close()
+    return {"ranks": world, "transport": transport, "bit_identical": ok_all, "checker": "oracle.Oracle (C restatement of "
+            "fluid.cpp, pinned against the compiled reference) on the whole grid, rank 0", "grid": [w, h], "image": [iw, ih],
+            "sweeps": [nd, npr], "steps": steps, "cases": cases}
 
 
 # --------------------------------------------------------------------------------------------
@@ -457,6 +528,8 @@ def main():
                     help="replay the timed steps from a CUDA graph of two captured timesteps (small, launch-bound grids)")
     ap.add_argument("--no-e2e", action="store_true", help="skip the host-buffer end-to-end leg (tuning runs)")
     ap.add_argument("--no-cpu", action="store_true", help="skip the CPU baseline leg (tuning runs)")
+    ap.add_argument("--no-parity", action="store_true",
+                    help="multi-GPU arm: skip the oracle check of the ring that precedes the timed region (tuning runs)")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 0)
     if args.impl == "reference":

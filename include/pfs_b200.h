@@ -43,6 +43,10 @@ extern "C" {
 
 #define PFS_B200_VERSION 100 /* major*100 + minor */
 
+/* Largest supported height of a grid or image (rows are the y dimension of the kernels' launch grids: 65535 blocks of
+ * 4 rows).  Wider-than-tall shapes up to the reference's 2^28-cell index limit (fluid.cpp:15-17) are unaffected. */
+#define PFS_MAX_ROWS 262140
+
 typedef enum pfs_status {
     PFS_OK = 0,
     PFS_EINVAL = 1,      /* bad argument (null pointer, non-positive size, channels != 4, ...) */

@@ -38,6 +38,27 @@ int cuda_fail(cudaError_t e, const char *what, const char *file, int line)
     return PFS_ECUDA;
 }
 
+int sm_count()
+{
+    static std::mutex m;
+    static std::map<int, int> cache;
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess) {
+        (void)cudaGetLastError();
+        return 148;
+    }
+    std::lock_guard<std::mutex> lock(m);
+    auto it = cache.find(dev);
+    if (it != cache.end()) return it->second;
+    int n = 0;
+    if (cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || n < 1) {
+        (void)cudaGetLastError();
+        n = 148;
+    }
+    cache[dev] = n;
+    return n;
+}
+
 int check_launch(const char *kernel, const char *file, int line)
 {
     cudaError_t e = cudaGetLastError();
@@ -129,10 +150,11 @@ struct PhaseSpan {
     unsigned long long launches;
 };
 static bool g_phase_timing = false;
+static std::mutex g_phase_mutex;                 // guards g_spans and g_event_pool (worker threads may step too)
 static std::vector<PhaseSpan> g_spans;
 static std::vector<cudaEvent_t> g_event_pool;
 
-static cudaEvent_t take_event()
+static cudaEvent_t take_event()                  // g_phase_mutex held
 {
     if (!g_event_pool.empty()) {
         cudaEvent_t e = g_event_pool.back();
@@ -147,7 +169,10 @@ static cudaEvent_t take_event()
 PhaseScope::PhaseScope(int phase_, cudaStream_t s_) : phase(phase_), s(s_)
 {
     if (!g_phase_timing) return;
-    a = take_event();
+    {
+        std::lock_guard<std::mutex> lock(g_phase_mutex);
+        a = take_event();
+    }
     l0 = g_passes;
     cudaEventRecord(a, s);
 }
@@ -155,6 +180,7 @@ PhaseScope::PhaseScope(int phase_, cudaStream_t s_) : phase(phase_), s(s_)
 PhaseScope::~PhaseScope()
 {
     if (!a) return;
+    std::lock_guard<std::mutex> lock(g_phase_mutex);
     cudaEvent_t b = take_event();
     cudaEventRecord(b, s);
     g_spans.push_back({phase, a, b, g_passes - l0});
@@ -176,6 +202,11 @@ static int check_dims(const char *fn, int x, int y, int z)
     if ((size_t)x * (size_t)y > ((size_t)1 << 28)) {
         // the reference's int indexing (fluid.cpp:15-17) tops out at 2^30 floats = 2^28 cells
         set_error("%s: %d x %d exceeds 2^28 cells (the reference's int32 index limit)", fn, x, y);
+        return PFS_EINVAL;
+    }
+    if (y > PFS_MAX_ROWS) {
+        // rows are the y dimension of the launch grids (4 rows per block, 65535 blocks)
+        set_error("%s: height %d exceeds the supported maximum of %d rows", fn, y, PFS_MAX_ROWS);
         return PFS_EINVAL;
     }
     return PFS_OK;
@@ -298,6 +329,7 @@ extern "C" int pfs_shutdown(void)
     }
     g_scratch.clear();
     packed_release_device_buffers();
+    std::lock_guard<std::mutex> plock(g_phase_mutex);
     for (auto &sp : g_spans) {
         cudaEventDestroy(sp.a);
         cudaEventDestroy(sp.b);
@@ -358,6 +390,7 @@ extern "C" int pfs_phase_times(float ms_out[PFS_NUM_PHASES], uint64_t launches_o
         if (ms_out) ms_out[i] = 0.f;
         if (launches_out) launches_out[i] = 0;
     }
+    std::lock_guard<std::mutex> lock(g_phase_mutex);
     for (auto &sp : g_spans) {
         PFS_CUDA(cudaEventSynchronize(sp.b));
         float ms = 0.f;
@@ -643,6 +676,8 @@ struct CachedStep {
     cudaGraphExec_t exec = nullptr;
     unsigned long long launches = 0, passes = 0;
 };
+static std::mutex g_graph_mutex;                 // guards the cache, g_prev_key and the capture streams: a second host thread
+                                                 // stepping another field must not see a half-built entry (capture included)
 static std::vector<CachedStep> g_step_graphs;
 static StepKey g_prev_key;
 static std::map<int, cudaStream_t> g_capture_streams;
@@ -714,6 +749,7 @@ static int simulate_fluid_step_impl(const char *fn, float **vp, float **tmp, flo
         }
     }
     if (use_graph) {
+        std::lock_guard<std::mutex> glock(g_graph_mutex);
         StepKey key;
         PFS_CUDA(cudaGetDevice(&key.dev));
         key.X = X; key.Y = Y; key.planes = sc->planes; key.plane_cells = sc->plane_cells;

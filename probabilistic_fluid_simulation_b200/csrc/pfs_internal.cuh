@@ -34,6 +34,10 @@ int cuda_fail(cudaError_t e, const char *what, const char *file, int line);
         if (s__ != PFS_OK) return s__;      \
     } while (0)
 
+// Multiprocessors of the current device (cached per device; 148 on a full B200, fewer on MIG slices and other bins).
+// The fused passes size their chunks to one resident wave of warps, so the count has to be the device's own.
+int sm_count();
+
 extern unsigned long long g_launches;   // kernels launched by this library (host counter)
 extern unsigned long long g_passes;     // same, minus the guard-repair launches (what pfs_phase_times reports)
 int check_launch(const char *kernel, const char *file, int line);

@@ -25,7 +25,7 @@
 // NCCL dependency).  Slabs that live in one process use direct copies (any devices; used by the tests to run
 // R slabs on one GPU and by single-process multi-GPU callers).
 #include <dlfcn.h>
-#include <nccl.h>   // types and enums only; every function is resolved at run time
+#include <string.h>
 #include <stdlib.h>
 
 #include <algorithm>
@@ -43,8 +43,19 @@ constexpr int P2P_GATHER_ROWS = 64; // capacity (rows per side) of the peer-writ
 constexpr int P2P_FLAG_INTS = 16;
 
 // ---------------------------------------------------------------------------------------------
-// NCCL through dlopen
+// NCCL through dlopen.  The handful of types and enum values the calls below need are declared here (they are part of
+// NCCL's stable ABI, nccl.h 2.x), so that the library builds on a box without NCCL headers; every function is resolved
+// at run time and the single-GPU paths never touch any of it.
 // ---------------------------------------------------------------------------------------------
+typedef struct ncclComm *ncclComm_t;
+typedef struct { char internal[128]; } ncclUniqueId;          // NCCL_UNIQUE_ID_BYTES
+typedef int ncclResult_t;
+constexpr ncclResult_t ncclSuccess = 0;
+typedef int ncclDataType_t;
+constexpr ncclDataType_t ncclUint8 = 1, ncclFloat = 7, ncclDouble = 8;
+typedef int ncclRedOp_t;
+constexpr ncclRedOp_t ncclSum = 0, ncclMax = 2, ncclMin = 3;
+
 struct NcclApi {
     ncclResult_t (*GetUniqueId)(ncclUniqueId *) = nullptr;
     ncclResult_t (*CommInitRank)(ncclComm_t *, int, ncclUniqueId, int) = nullptr;
@@ -150,10 +161,12 @@ struct pfs_slab {
     size_t vhalo_rows = 0, ihalo_rows = 0;         // capacity in rows (both sides together)
     float4 *vwhole = nullptr, *iwhole = nullptr;
     size_t vwhole_rows = 0, iwhole_rows = 0;
-    float *d_scalars = nullptr;           // [0] max|v| (advect), [1] max|v| (advect_color), [2] overflow flag (as int),
-                                          // [3] setup scratch, [4] max|v| and [5] overflow (as float) of a speculative advect
+    float *d_scalars = nullptr;           // [0] max|v| (advect), [1] max|v| (advect_color), [2] sticky error word (as int: gather
+                                          // overflow under an exact bound 1/2/3, peer-transport timeout 9; read by pfs_slab_check),
+                                          // [3] setup scratch, [4] max|v| and [5] "a departure row was missing" (as float) of a
+                                          // speculative advect, [6] the same flag as the kernel raises it (int; reset every step)
     float *h_scalars = nullptr;           // pinned mirror
-    ncclComm_t comm = nullptr;
+    pfs::ncclComm_t comm = nullptr;
     // peer transport (one process per GPU, CUDA IPC): the ring neighbours' planes / gather halos / flags mapped here
     struct PeerLink {
         float *planes = nullptr;
@@ -747,6 +760,10 @@ extern "C" int pfs_slab_create(pfs_slab **out, int rank, int nranks, int gw, int
         set_error("%s: grid exceeds 2^28 cells (the reference's int32 index limit)", fn);
         return PFS_EINVAL;
     }
+    if (gh > PFS_MAX_ROWS || ih > PFS_MAX_ROWS) {
+        set_error("%s: height exceeds the supported maximum of %d rows", fn, PFS_MAX_ROWS);
+        return PFS_EINVAL;
+    }
     if (gh / nranks < MIN_HALO) {
         set_error("%s: every slab needs at least %d rows (grid height %d over %d ranks)", fn, MIN_HALO, gh, nranks);
         return PFS_EINVAL;
@@ -1208,15 +1225,15 @@ static int slab_fluid_step(pfs_slab *const *slabs, int n_local, float **vp, floa
         for (int k = 0; k < n; k++) {
             pfs_slab *s = L[k];
             Guard g(s->device);
-            if (speculate) PFS_CUDA(cudaMemsetAsync(s->d_scalars + 4, 0, 2 * sizeof(float), s->stream));
+            if (speculate) PFS_CUDA(cudaMemsetAsync(s->d_scalars + 4, 0, 3 * sizeof(float), s->stream));
             dim3 block(64, 4), grid((gw + 63) / 64, (s->rows + 3) / 4);
             PFS_LAUNCH(advect_slab_kernel, grid, block, 0, s->stream, src[k], s->plane(0), s->plane(1), dt, gw, gh,
-                       s->row0, s->rows, s->halo, reinterpret_cast<int *>(s->d_scalars + 2),
+                       s->row0, s->rows, s->halo, reinterpret_cast<int *>(s->d_scalars + (speculate ? 6 : 2)),
                        speculate ? s->d_scalars + 4 : nullptr);
             if (speculate) {
                 // (max|v| of this step's input, "a departure row was missing") -> every rank, then the host; nobody waits yet
                 // (on a side stream: the sweeps that follow do not depend on it)
-                PFS_LAUNCH(flag_to_float_kernel, 1, 1, 0, s->stream, reinterpret_cast<const int *>(s->d_scalars + 2), s->d_scalars + 5);
+                PFS_LAUNCH(flag_to_float_kernel, 1, 1, 0, s->stream, reinterpret_cast<const int *>(s->d_scalars + 6), s->d_scalars + 5);
                 PFS_CUDA(cudaEventRecord(s->ev_fork, s->stream));
                 PFS_CUDA(cudaStreamWaitEvent(s->side, s->ev_fork, 0));
                 if (s->comm != nullptr)
@@ -1360,11 +1377,8 @@ static int slab_fluid_step(pfs_slab *const *slabs, int n_local, float **vp, floa
         }
         for (int k = 0; k < n; k++) L[k]->vbound = vmax;
         if (missed) {
-            for (int k = 0; k < n; k++) {
-                pfs_slab *s = L[k];
-                Guard g(s->device);
-                PFS_CUDA(cudaMemsetAsync(s->d_scalars + 2, 0, sizeof(int), s->stream));
-            }
+            // the miss was recorded in its own word ([6]); the sticky error word ([2]: gather overflow of an exact bound,
+            // peer-transport timeout) is never touched here, so pfs_slab_check still sees whatever it holds
             delete ph;
             ph = nullptr;
             return slab_fluid_step(slabs, n_local, vp, tmp, dt, viscosity, n_diffuse, n_pressure, streams, true);

@@ -325,7 +325,7 @@ int launch_sweeps_fused(SweepOp op, float *a0, float *a1, float *b0, float *b1, 
             P.n_strips = (p.w + P.strip_out - 1) / P.strip_out;
             P.n_planes = (op == SWEEP_DIFFUSE) ? 2 : 1;
             // chunk height: enough chunks to fill the machine, tall enough to amortise the 2T halo rows
-            const long long slots = 148LL * 12;    // resident warps at 12 warps per SM (168 registers)
+            const long long slots = (long long)sm_count() * 12;    // resident warps at 12 warps per SM (168 registers)
             const int rows = pick_chunk_rows(p.h, P.n_strips * P.n_planes, slots, env_rows);
             P.chunk_rows = rows;
             P.n_chunks = (p.h + rows - 1) / rows;

@@ -767,7 +767,7 @@ int launch_diffuse_packed(float *a0, float *a1, float *b0, float *b1, const Swee
         // chunk height: one resident wave of warps if the grid allows it (pick_chunk_rows)
         const int minb = packed_minb(t, cells);
         const int warps_per_sm = env_warps > 0 ? env_warps : 4 * minb;
-        const long long slots = 148LL * warps_per_sm;
+        const long long slots = (long long)sm_count() * warps_per_sm;
         P.chunk_rows = pick_chunk_rows(p.h, P.n_strips, slots, env_rows);
         P.n_chunks = (p.h + P.chunk_rows - 1) / P.chunk_rows;
         P.alpha = p.alpha; P.beta = p.beta; P.rbeta = 1.0f / p.beta;
@@ -823,7 +823,7 @@ int launch_pressure_packed(float *a, float *b, const float *rhs, const SweepPara
             P.n_strips = (p.w + P.strip_out - 1) / P.strip_out;
             P.n_pairs = (P.n_strips + 1) / 2;
             const int warps_per_sm = env_warps > 0 ? env_warps : 8;
-            const long long slots = 148LL * warps_per_sm;
+            const long long slots = (long long)sm_count() * warps_per_sm;
             P.chunk_rows = pick_chunk_rows(p.h, P.n_pairs, slots, env_rows);
             P.n_chunks = (p.h + P.chunk_rows - 1) / P.chunk_rows;
             P.neg_zero = -0.0f;

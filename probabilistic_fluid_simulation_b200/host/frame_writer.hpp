@@ -11,6 +11,7 @@
 #pragma once
 
 #include <condition_variable>
+#include <cstdio>
 #include <deque>
 #include <mutex>
 #include <string>
@@ -80,7 +81,8 @@ public:
         return true;
     }
 
-    // Wait until every submitted frame is on disk and stop the workers.  false if any frame failed.
+    // Wait until every submitted frame is on disk (or was reported as unwritable) and stop the workers.
+    // false only if a CUDA call failed.
     bool finish()
     {
         {
@@ -110,6 +112,15 @@ private:
         return false;
     }
 
+    // A frame that cannot be written (missing output directory, full disk) is not fatal: the reference ignores the
+    // return value of write_png_from_array (main.cpp:68), finishes the run and exits 0.  Same here, plus a line on stderr.
+    void warn_unwritten(const std::string &path)
+    {
+        std::lock_guard<std::mutex> lk(m_);
+        ++unwritten_;
+        std::fprintf(stderr, "warning: cannot write %s\n", path.c_str());
+    }
+
     void work()
     {
         for (;;) {
@@ -125,7 +136,7 @@ private:
             if (cudaEventSynchronize(s->copied) != cudaSuccess)
                 fail("frame copy failed");
             else if (pngio::write_png_from_bytes(&header, s->path.c_str(), s->host) != 0)
-                fail(("cannot write " + s->path).c_str());
+                warn_unwritten(s->path);
             {
                 std::lock_guard<std::mutex> lk(m_);
                 free_.push_back(s);
@@ -138,6 +149,7 @@ private:
     int w_, h_, c_;
     size_t bytes_;
     bool ok_ = false, failed_ = false, stopping_ = false;
+    int unwritten_ = 0;
     std::string error_;
     cudaStream_t copy_stream_ = nullptr;
     std::vector<Slot> slots_;

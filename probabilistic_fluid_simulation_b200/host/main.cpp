@@ -155,7 +155,8 @@ int main(int argc, char *argv[])
                 return 1;
             }
             if (!cuda_ok(cudaMemcpy(h_frame, d_frame, frame_bytes, cudaMemcpyDeviceToHost), "D2H frame")) return 1;
-            pngio::write_png_from_bytes(&input_image, outpath.c_str(), h_frame);
+            if (pngio::write_png_from_bytes(&input_image, outpath.c_str(), h_frame) != 0)
+                std::fprintf(stderr, "warning: cannot write %s\n", outpath.c_str());   // as the reference: not fatal (main.cpp:68)
         }
     }
     cudaDeviceSynchronize();

@@ -44,14 +44,15 @@ inline const Api &api()
     if (const char *e = getenv("PFS_LIBPNG")) cands.push_back(e);
     cands.push_back("libpng16.so.16");
     cands.push_back("libpng16.so");
-    for (const char *pat : {"/opt/prime-rl/.venv/lib/python3*/site-packages/pillow.libs/libpng16*.so*",
-                            "/usr/lib/python3*/site-packages/pillow.libs/libpng16*.so*",
-                            "/usr/local/lib/python3*/site-packages/pillow.libs/libpng16*.so*"}) {
+#ifdef PFS_LIBPNG_HINT
+    // a glob pattern found by the build (host/Makefile looks for the libpng bundled with Pillow when the system has none)
+    {
         glob_t g;
-        if (glob(pat, 0, nullptr, &g) == 0)
+        if (glob(PFS_LIBPNG_HINT, 0, nullptr, &g) == 0)
             for (size_t i = 0; i < g.gl_pathc; i++) cands.push_back(g.gl_pathv[i]);
         globfree(&g);
     }
+#endif
     for (const auto &c : cands) {
         void *h = dlopen(c.c_str(), RTLD_NOW | RTLD_LOCAL);
         if (!h) continue;

@@ -75,11 +75,18 @@ def run(args, bench) -> None:
     sys.stdout.flush()
     saved_stdout = os.dup(1)
     os.dup2(2, 1)
+    def make_slab(gw, gh, iw, ih):
+        sl = SlabRank(rank, world, gw, gh, iw, ih)
+        sl.connect(broadcast_bytes(SlabRank.unique_id() if rank == 0 else None, 128))
+        return sl
+
+    parity = None
     try:
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
-        slab = SlabRank(rank, world, w, h, w, h)
-        uid = broadcast_bytes(SlabRank.unique_id() if rank == 0 else None, 128)
-        slab.connect(uid)
+        if not getattr(args, "no_parity", False):
+            # the ring is verified against the CPU oracle before anything is timed (bench.ring_parity_check)
+            parity = bench.ring_parity_check(rank, world, make_slab)
+        slab = make_slab(w, h, w, h)
         dist.barrier()
         torch.cuda.synchronize()
     finally:
@@ -182,8 +189,10 @@ def run(args, bench) -> None:
                                                 "frac": step_bytes / (ms_step * 1e-3) / 1e9 / peak},
                 "cell_steps_per_s": cells_global / (ms_step * 1e-3), "phases_ms_rank0": per_phase, "kernels": kernels,
                 "transport": TRANSPORT_TEXT.get(slab.transport, slab.transport),
-                "rows_per_gpu": slab.rows}
+                "rows_per_gpu": slab.rows, "parity": parity}
         print(json.dumps(line), flush=True)
     dist.barrier()
     slab.close()
     dist.destroy_process_group()
+    if parity is not None and not parity["bit_identical"]:
+        raise SystemExit(3)          # a ring that does not reproduce the oracle must not look like a result

@@ -13,6 +13,23 @@ def pytest_configure(config):
     config.addinivalue_line("markers", "gpu: needs a CUDA device (run on the B200 box with -m gpu)")
 
 
+def pytest_collection_modifyitems(config, items):
+    """On a machine without a CUDA device the `gpu` tests are skipped (with the reason shown) instead of failing in
+    torch's CUDA initialisation; on the GPU box they run and a missing libpfs_b200.so is an error, never a skip."""
+    gpu_items = [it for it in items if it.get_closest_marker("gpu")]
+    if not gpu_items:
+        return
+    try:
+        import torch
+        have = torch.cuda.is_available()
+    except Exception:
+        have = False
+    if not have:
+        skip = pytest.mark.skip(reason="no CUDA device visible (the product path has no CPU fallback)")
+        for it in gpu_items:
+            it.add_marker(skip)
+
+
 @pytest.fixture(scope="session", autouse=True)
 def _built_oracle():
     """The C restatement is test infrastructure: build it once per session if it is not there."""

@@ -1,4 +1,4 @@
-"""torchrun worker for tests/test_gpu_slabs.py::test_nccl_two_ranks: one process per GPU, NCCL halo
+"""torchrun worker for tests/test_gpu_slabs.py::test_ring_of_processes: one process per GPU, NCCL halo
 exchange, result gathered on rank 0 and compared with the CPU oracle bit for bit."""
 import os
 import sys

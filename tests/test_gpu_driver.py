@@ -92,3 +92,21 @@ def test_b200_driver_frame_writer_modes(writers, tmp_path):
     name = "voronoi256_tulips"
     lines, crcs, out = dc.run_driver(dc.B200, name, str(tmp_path), env={"PFS_FRAME_WRITERS": writers})
     assert crcs == dc.load_driver_golden()["cases"][name]["frames_crc32"]
+
+
+@pytest.mark.parametrize("writers", ["0", "2"])
+def test_b200_driver_unwritable_output_dir_is_not_fatal(writers, pngs, tmp_path):
+    """The reference ignores the return value of write_png_from_array (main.cpp:68): a run whose frames cannot be written
+    still prints every "Writing to" line and the timing line and exits 0.  Both writer modes of the B200 driver do the
+    same, plus one warning per frame on stderr."""
+    d, _, _ = pngs
+    env = dict(os.environ)
+    env["PFS_FRAME_WRITERS"] = writers
+    missing = tmp_path / "does" / "not" / "exist"
+    r = subprocess.run([EXE, "3", "0.5", "0.001", str(d / "img.png"), str(d / "vel.png"), str(missing)],
+                       capture_output=True, text=True, timeout=300, env=env)
+    assert r.returncode == 0, (r.stdout, r.stderr)
+    lines = r.stdout.strip().splitlines()
+    assert [ln for ln in lines if "Writing to" in ln] == [f"[{i}] Writing to : {missing}/{i}.png" for i in range(3)]
+    assert lines[-1].startswith("3 timesteps took ") and lines[-1].endswith(" us.")
+    assert r.stderr.count("warning: cannot write") == 3, r.stderr

@@ -1,7 +1,7 @@
 """GPU parity, part 4: the row-slab (multi-GPU) path.  R slabs of one periodic grid, driven inside one
 process on ONE GPU (direct-copy transport), must reproduce the CPU oracle bit for bit -- the same check
 as the single-GPU path, so it also proves slab result == single-GPU result.  The NCCL transport is
-exercised by test_nccl_two_ranks when two GPUs are visible."""
+exercised by test_ring_of_processes (2, 4 and 8 processes, one GPU each) when that many GPUs are visible."""
 import os
 import subprocess
 import sys
@@ -129,19 +129,23 @@ def test_ring_speculative_gather_depth_reruns_when_the_field_jumps(nranks):
 
 
 @pytest.mark.parametrize("transport", ["p2p", "nccl"])
-def test_two_processes_two_gpus(tmp_path, transport):
-    """One process per GPU.  "p2p": halo rows stored into the neighbour's memory through CUDA IPC mappings (the default
-    when every rank can map its neighbours); "nccl": send/recv.  Both must reproduce the oracle bit for bit."""
+@pytest.mark.parametrize("world", [2, 4, 8])
+def test_ring_of_processes(tmp_path, world, transport):
+    """One process per GPU, `world` of them.  "p2p": halo rows stored into the neighbours' memory through CUDA IPC mappings
+    (the default when every rank can map its neighbours); "nccl": send/recv.  Both must reproduce the oracle bit for bit
+    (tests/nccl_ring_check.py: bands of different heights, a 25-row gather, a gather deeper than the peer halos, the
+    whole-field path, the rerun after a field jump).  Skipped only when fewer than `world` GPUs are visible."""
     import torch
-    if torch.cuda.device_count() < 2:
-        pytest.skip("needs two GPUs")
+    if torch.cuda.device_count() < world:
+        pytest.skip(f"needs {world} GPUs, {torch.cuda.device_count()} visible")
     env = dict(os.environ)
     env.pop("PFS_SLAB_TRANSPORT", None)
     if transport == "nccl":
         env["PFS_SLAB_TRANSPORT"] = "nccl"
-    cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node=2", "--master-addr", "127.0.0.1",
-           "--master-port", "29541" if transport == "p2p" else "29543", os.path.join(ROOT, "tests", "nccl_ring_check.py")]
-    r = subprocess.run(cmd, capture_output=True, text=True, timeout=600, cwd=ROOT, env=env)
+    port = 29541 + 2 * world + (0 if transport == "p2p" else 1)
+    cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", f"--nproc-per-node={world}", "--master-addr",
+           "127.0.0.1", "--master-port", str(port), os.path.join(ROOT, "tests", "nccl_ring_check.py")]
+    r = subprocess.run(cmd, capture_output=True, text=True, timeout=900, cwd=ROOT, env=env)
     assert r.returncode == 0, r.stdout[-3000:] + r.stderr[-3000:]
     assert r.stdout.count("ring matches oracle") == 4, r.stdout[-3000:]
     assert "jump case matches oracle" in r.stdout, r.stdout[-3000:]
