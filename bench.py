@@ -355,9 +355,22 @@ def run_single_gpu(args):
     vp, vtmp, image, itmp = make_inputs(h, w)
     fv, ft, fi, fm = (pfs.vp_field(torch.from_numpy(x).cuda()) for x in (vp, vtmp, image, itmp))
 
+    # The timed workload runs on a persistent-state context (pfs_ctx_*): the fields are resident in HBM in the library's
+    # planar layout, one pfs_ctx_step per timestep = simulate_fluid_step + advect_color_step (main.cpp:236-239).  The
+    # stateless entry points (caller-owned interleaved buffers re-read and re-written every step) are timed beside it.
+    ctx = None
+    if args.graph:
+        args.stateless = True          # an outer graph of two steps needs the caller-owned buffers of the stateless calls
+    if not args.stateless:
+        ctx = pfs.FluidContext(w, h, w, h)
+        ctx.upload(fv.data, ft.data, fi.data)
+
     def step():
-        pfs.simulate_fluid_step(fv, ft, DT, VISC, n, n)
-        pfs.advect_color_step(fi, fm, fv, DT)
+        if ctx is not None:
+            ctx.step(1, DT, VISC, n, n)
+        else:
+            pfs.simulate_fluid_step(fv, ft, DT, VISC, n, n)
+            pfs.advect_color_step(fi, fm, fv, DT)
 
     for _ in range(args.warmup):
         step()
@@ -465,6 +478,26 @@ def run_single_gpu(args):
     whole_step = {"alg_bytes": step_bytes, "achieved_gbs": step_bytes / (ms_step * 1e-3) / 1e9,
                   "frac": step_bytes / (ms_step * 1e-3) / 1e9 / peak}
 
+    # ---- the stateless entry points on the same workload (what a caller that keeps its own interleaved buffers gets) ----
+    stateless = None
+    if ctx is not None:
+        def sl_step():
+            pfs.simulate_fluid_step(fv, ft, DT, VISC, n, n)
+            pfs.advect_color_step(fi, fm, fv, DT)
+        for _ in range(3):
+            sl_step()
+        sl_steps = max(2, min(args.steps, 20))
+        s0, s1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        torch.cuda.synchronize()
+        s0.record()
+        for _ in range(sl_steps):
+            sl_step()
+        s1.record()
+        torch.cuda.synchronize()
+        sl_ms = s0.elapsed_time(s1) / sl_steps
+        stateless = {"ms_per_step": sl_ms, "value": cells * n / (sl_ms * 1e-3), "unit": UNIT, "steps": sl_steps,
+                     "api": "pfs_simulate_fluid_step + pfs_advect_color_step on caller-owned interleaved device buffers"}
+
     # ---- end to end: host buffers in pinned memory, H2D + kernels + D2H inside the timed region ----
     e2e = None
     if not args.no_e2e:
@@ -507,9 +540,12 @@ def run_single_gpu(args):
             "pressure_solve": {"ms": per_phase["pressure"], "cell_updates_per_s": cells * n / (per_phase["pressure"] * 1e-3)},
             "cell_steps_per_s": cells / (ms_step * 1e-3), "phases_ms": per_phase, "kernels": kernels,
             "fuse_depth": depth, "fluid_cu_baseline": refcu,
+            "api": ("pfs_ctx_step on a persistent-state context (fields resident in HBM in the planar layout)" if ctx is not None
+                    else "pfs_simulate_fluid_step + pfs_advect_color_step (stateless, --stateless)"),
+            "stateless_entry_points": stateless,
             "launch_mode": ("torch CUDA graph of two timesteps (--graph)" if graph is not None else
-                            "library step graph: the 2nd identical pfs_simulate_fluid_step call is captured, later "
-                            "calls replay it (PFS_STEP_GRAPH=0 disables)"),
+                            "library step graphs: a step whose plane roles were seen before replays a captured CUDA graph "
+                            "(PFS_STEP_GRAPH=0 disables)"),
             "phase_region": {"steps": phase_steps, "ms_per_step_eager_with_phase_events": ms_step_eager}}
     print(json.dumps(line), flush=True)
 
@@ -526,8 +562,12 @@ def main():
     ap.add_argument("--fuse-depth", type=int, default=None)
     ap.add_argument("--graph", action="store_true",
                     help="replay the timed steps from a CUDA graph of two captured timesteps (small, launch-bound grids)")
+    ap.add_argument("--stateless", action="store_true",
+                    help="time the stateless entry points (caller-owned interleaved buffers) instead of a persistent context")
     ap.add_argument("--no-e2e", action="store_true", help="skip the host-buffer end-to-end leg (tuning runs)")
     ap.add_argument("--no-cpu", action="store_true", help="skip the CPU baseline leg (tuning runs)")
+    ap.add_argument("--no-unit", action="store_true",
+                    help="multi-GPU arm: skip the 1-GPU measurement of the per-GPU band shape (the weak-scaling unit)")
     ap.add_argument("--no-parity", action="store_true",
                     help="multi-GPU arm: skip the oracle check of the ring that precedes the timed region (tuning runs)")
     args = ap.parse_args()

@@ -41,7 +41,7 @@
 extern "C" {
 #endif
 
-#define PFS_B200_VERSION 100 /* major*100 + minor */
+#define PFS_B200_VERSION 200 /* major*100 + minor */
 
 /* Largest supported height of a grid or image (rows are the y dimension of the kernels' launch grids: 65535 blocks of
  * 4 rows).  Wider-than-tall shapes up to the reference's 2^28-cell index limit (fluid.cpp:15-17) are unaffected. */
@@ -123,8 +123,10 @@ int pfs_advect(const float *vp, float *vp_out, float dt, int vx, int vy, int vz,
  * between the two buffers; *vp_out ends on the buffer written last, *vp on the other. */
 int pfs_diffuse(float **vp, float **vp_out, float viscosity, float dt,
                 int vx, int vy, int vz, int n_sweeps, void *stream);
-/* addForces (fluid.hpp:70, fluid.cpp:198-208): the reference body is empty and its call site is
- * commented out (fluid.cpp:302).  Kept as a validated no-op so the operator surface is complete. */
+/* addForces (fluid.hpp:70, fluid.cpp:198-208): the reference body is an empty loop over every cell and channel and its
+ * call site is commented out (fluid.cpp:302).  forces == NULL reproduces that (a validated no-op).  With a force field
+ * (device buffer shaped like vp) the velocity channels take it: vp[..,0:2] += forces[..,0:2]; see
+ * pfs_simulate_fluid_step_forced for the definition and its parity status. */
 int pfs_add_forces(float *vp, const float *forces, int vx, int vy, int vz, void *stream);
 /* computePressure (fluid.hpp:81, fluid.cpp:210-267): divergence of *vp ch0,1 into ch3 of BOTH
  * buffers, then n_sweeps Jacobi sweeps on ch2 starting from *vp ch2; pointer rule as pfs_diffuse. */
@@ -136,6 +138,45 @@ int pfs_subtract_pressure_gradient(const float *vp, float *vp_out, float dt,
 /* advect_color (fluid.hpp:45, fluid.cpp:72-127): itmp <- image advected through vp ch0,1. */
 int pfs_advect_color(const float *image, float *itmp, const float *vp, float dt,
                      int ix, int iy, int iz, int vx, int vy, int vz, void *stream);
+
+/* ---- external force at the addForces slot --------------------------------------------------- */
+/* pfs_simulate_fluid_step with addForces(vp, forces) (fluid.hpp:62-71) applied where fluid.cpp:302 would call it
+ * (after diffuse, before computePressure): `forces` is a device buffer shaped like the velocity field (vx*vy*4 floats,
+ * "force values for each pixel in the grid"); channels 0,1 are added to (u, v) of the field struct `vp` points at after
+ * diffuse, one rounded addition each, channels 2,3 are ignored.  forces == NULL is pfs_simulate_fluid_step.  The
+ * reference's addForces body is an empty loop (fluid.cpp:198-208), so reference parity of the force term is UNPINNED BY
+ * CONSTRUCTION; oracle/fluid_oracle.c restates this definition and the GPU path is checked against it bit for bit.
+ * The addition is fused into the store of the last diffusion pass (no extra trip through memory). */
+int pfs_simulate_fluid_step_forced(float **vp, float **tmp, float dt, float viscosity, int vx, int vy, int vz,
+                                   int n_diffuse, int n_pressure, const float *forces, void *stream);
+
+/* ---- persistent-state contexts (pfs_ctx_create / upload / step / download / destroy) ---------- */
+/* The stateless calls above re-read and re-write the caller's interleaved buffers every step (the caller may have
+ * changed them in between).  A context owns the state instead, in the planar layout the kernels use, so a step moves
+ * only what the algorithm needs; the interleaved form exists only in upload and download.  What n steps leave behind is
+ * bit for bit what n calls of pfs_simulate_fluid_step + pfs_advect_color_step leave in the caller's buffers (same
+ * pointer choreography for every sweep-count parity).  The reference driver's loop (main.cpp:219-246) maps onto it as:
+ * upload once, pfs_ctx_step per timestep, pfs_ctx_image / pfs_image_to_rgba8 per frame, download at the end.
+ * One context per field; a context is bound to the device that was current at creation; calls on one context are
+ * serialised internally.  Repeated steps with the same parameters replay CUDA graphs (PFS_STEP_GRAPH=0 disables). */
+typedef struct pfs_ctx pfs_ctx;
+int pfs_ctx_create(pfs_ctx **out, int vx, int vy, int ix, int iy);      /* ix = iy = 0: no image */
+int pfs_ctx_destroy(pfs_ctx *c);
+/* Device pointers to interleaved buffers (vx*vy*4 / ix*iy*4 floats); NULL = leave that buffer's state as it is (the
+ * first upload needs all of them).  `tmp` is the reference's vtmp: its channel 2 is the first pressure guess. */
+int pfs_ctx_upload(pfs_ctx *c, const float *vp, const float *tmp, const float *image, void *stream);
+int pfs_ctx_download(pfs_ctx *c, float *vp, float *tmp, float *image, void *stream);   /* NULL = skip */
+/* simulate_fluid_step / advect_color_step (fluid.hpp:107,116) on the context's state. */
+int pfs_ctx_simulate_fluid_step(pfs_ctx *c, float dt, float viscosity, int n_diffuse, int n_pressure, void *stream);
+int pfs_ctx_simulate_fluid_step_forced(pfs_ctx *c, float dt, float viscosity, int n_diffuse, int n_pressure,
+                                       const float *forces, void *stream);
+int pfs_ctx_simulate_fluid_step_stochastic(pfs_ctx *c, float dt, float viscosity, int n_diffuse, int n_pressure,
+                                           float sigma, uint64_t seed, uint32_t step, void *stream);
+int pfs_ctx_advect_color_step(pfs_ctx *c, float dt, void *stream);
+/* n_steps iterations of the driver loop: simulate_fluid_step + advect_color_step (the latter only with an image). */
+int pfs_ctx_step(pfs_ctx *c, int n_steps, float dt, float viscosity, int n_diffuse, int n_pressure, void *stream);
+/* Device pointer of the current image (interleaved RGBA floats), e.g. for pfs_image_to_rgba8; valid until the next step. */
+int pfs_ctx_image(pfs_ctx *c, const float **image_dev);
 
 /* ---- opt-in stochastic forcing at the addForces slot (NOT in the reference) ------------------- */
 /* The reference's addForces is an empty stub whose call is commented out (fluid.cpp:198-208, :302) and the
@@ -195,6 +236,10 @@ int pfs_slab_simulate_fluid_step(pfs_slab *const *slabs, int n_local, float **vp
                                  float viscosity, int n_diffuse, int n_pressure, void *const *streams);
 int pfs_slab_advect_color_step(pfs_slab *const *slabs, int n_local, float **image, float **itmp,
                                float *const *vp, float dt, void *const *streams);
+/* pfs_simulate_fluid_step_forced on the bands: forces[k] = the k-th local slab's band of the force field. */
+int pfs_slab_simulate_fluid_step_forced(pfs_slab *const *slabs, int n_local, float **vp, float **tmp, float dt,
+                                        float viscosity, int n_diffuse, int n_pressure, const float *const *forces,
+                                        void *const *streams);
 /* Synchronises and reports an internal halo overflow (a bug, never expected). */
 int pfs_slab_check(pfs_slab *const *slabs, int n_local);
 

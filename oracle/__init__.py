@@ -99,6 +99,10 @@ class Oracle:
             lib.oracle_simulate_fluid_step_stochastic.argtypes = [F, F, f32, f32, ctypes.c_int, ctypes.c_int, f32,
                                                                   ctypes.c_uint64, ctypes.c_uint32]
             lib.oracle_simulate_fluid_step_stochastic.restype = None
+            lib.oracle_add_forces.argtypes = [F, ctypes.POINTER(f32)]
+            lib.oracle_add_forces.restype = None
+            lib.oracle_simulate_fluid_step_forced.argtypes = [F, F, f32, f32, ctypes.c_int, ctypes.c_int, ctypes.POINTER(f32)]
+            lib.oracle_simulate_fluid_step_forced.restype = None
             lib.oracle_philox4x32_10.argtypes = [ctypes.POINTER(ctypes.c_uint32)] * 3
             lib.oracle_philox4x32_10.restype = None
             lib.oracle_channel_hash.argtypes = [ctypes.POINTER(f32), ctypes.c_size_t, ctypes.c_int, ctypes.c_int]
@@ -167,6 +171,19 @@ class Oracle:
         p = _Pair(vp, tmp)
         self.L.oracle_simulate_fluid_step_stochastic(p.fa, p.fb, dt, viscosity, self.n_diffuse, self.n_pressure, sigma,
                                                      seed, step)
+        return p.resolve()
+
+    # --- external force at the addForces slot (the reference body is empty: parity unpinned by construction) ---
+    def add_forces(self, vp, forces):
+        assert forces.dtype == np.float32 and forces.shape == vp.shape and forces.flags["C_CONTIGUOUS"]
+        self.L.oracle_add_forces(_as_field(vp), forces.ctypes.data_as(ctypes.POINTER(ctypes.c_float)))
+        return vp
+
+    def simulate_fluid_step_forced(self, vp, tmp, dt, viscosity, forces):
+        assert forces.dtype == np.float32 and forces.shape == vp.shape and forces.flags["C_CONTIGUOUS"]
+        p = _Pair(vp, tmp)
+        self.L.oracle_simulate_fluid_step_forced(p.fa, p.fb, dt, viscosity, self.n_diffuse, self.n_pressure,
+                                                 forces.ctypes.data_as(ctypes.POINTER(ctypes.c_float)))
         return p.resolve()
 
     def run_steps(self, vp, vtmp, image, itmp, dt, viscosity, n_steps):

@@ -372,3 +372,36 @@ void oracle_simulate_fluid_step_stochastic(pfs_oracle_field *vp, pfs_oracle_fiel
     oracle_compute_pressure(vp, tmp, dt, n_pressure);
     oracle_subtract_pressure_gradient(tmp, vp, dt);
 }
+
+/* ---------------------------------------------------------------------------------------------
+ * External force at the addForces slot.  fluid.cpp:198-208 declares addForces(vp_field *vp, float *forces) with an
+ * EMPTY triple loop over (x, y, z) ("TODO: Perform force addition") and fluid.cpp:302 leaves its call commented out,
+ * so there is nothing in the reference to restate: PARITY OF THIS TERM IS UNPINNED BY CONSTRUCTION.  What is restated
+ * here is the definition the B200 library gives the loop body (include/pfs_b200.h, pfs_add_forces): `forces` is shaped
+ * like vp ("force values for each pixel in the grid", fluid.hpp:62-66), the velocity channels take it with one
+ * rounded addition each, the pressure and divergence channels are left alone.  forces == NULL is the reference.
+ * --------------------------------------------------------------------------------------------- */
+void oracle_add_forces(pfs_oracle_field *vp, const float *forces)
+{
+    if (!forces) return;
+    const int w = vp->x, h = vp->y, c = vp->z;
+    for (int x = 0; x < w; x++) {
+        for (int y = 0; y < h; y++) {
+            for (int z = 0; z < c && z < 2; z++) {
+                const int idx = as_idx(x, y, z, w, c);
+                vp->data[idx] = vp->data[idx] + forces[idx];
+            }
+        }
+    }
+}
+
+/* simulate_fluid_step with addForces(vp, forces) where fluid.cpp:302 has it commented out. */
+void oracle_simulate_fluid_step_forced(pfs_oracle_field *vp, pfs_oracle_field *tmp, float dt, float viscosity,
+                                       int n_diffuse, int n_pressure, const float *forces)
+{
+    oracle_advect(vp, tmp, dt);
+    oracle_diffuse(tmp, vp, viscosity, dt, n_diffuse);
+    oracle_add_forces(vp, forces);
+    oracle_compute_pressure(vp, tmp, dt, n_pressure);
+    oracle_subtract_pressure_gradient(tmp, vp, dt);
+}

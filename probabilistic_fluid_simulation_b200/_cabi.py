@@ -52,6 +52,17 @@ SIGNATURES = {
     "pfs_add_forces_stochastic": (_int, [_vp, _f32, ctypes.c_uint64, ctypes.c_uint32, _int, _int, _int, _vp]),
     "pfs_simulate_fluid_step_stochastic": (_int, [_pp, _pp, _f32, _f32, _int, _int, _int, _int, _int, _f32,
                                                    ctypes.c_uint64, ctypes.c_uint32, _vp]),
+    "pfs_simulate_fluid_step_forced": (_int, [_pp, _pp, _f32, _f32, _int, _int, _int, _int, _int, _vp, _vp]),
+    "pfs_ctx_create": (_int, [_pp, _int, _int, _int, _int]),
+    "pfs_ctx_destroy": (_int, [_vp]),
+    "pfs_ctx_upload": (_int, [_vp, _vp, _vp, _vp, _vp]),
+    "pfs_ctx_download": (_int, [_vp, _vp, _vp, _vp, _vp]),
+    "pfs_ctx_simulate_fluid_step": (_int, [_vp, _f32, _f32, _int, _int, _vp]),
+    "pfs_ctx_simulate_fluid_step_forced": (_int, [_vp, _f32, _f32, _int, _int, _vp, _vp]),
+    "pfs_ctx_simulate_fluid_step_stochastic": (_int, [_vp, _f32, _f32, _int, _int, _f32, ctypes.c_uint64, ctypes.c_uint32, _vp]),
+    "pfs_ctx_advect_color_step": (_int, [_vp, _f32, _vp]),
+    "pfs_ctx_step": (_int, [_vp, _int, _f32, _f32, _int, _int, _vp]),
+    "pfs_ctx_image": (_int, [_vp, _pp]),
     "pfs_simulate_fluid_step_host": (_int, [_F, _F, _f32, _f32, _int, _int]),
     "pfs_advect_color_step_host": (_int, [_F, _F, _F, _f32]),
     "pfs_timestep_host": (_int, [_F, _F, _F, _F, _f32, _f32, _int, _int]),
@@ -64,6 +75,7 @@ SIGNATURES = {
     "pfs_slab_connect_nccl": (_int, [_vp, ctypes.c_char_p]),
     "pfs_slab_simulate_fluid_step": (_int, [_pp, _int, _pp, _pp, _f32, _f32, _int, _int, _pp]),
     "pfs_slab_advect_color_step": (_int, [_pp, _int, _pp, _pp, _pp, _f32, _pp]),
+    "pfs_slab_simulate_fluid_step_forced": (_int, [_pp, _int, _pp, _pp, _f32, _f32, _int, _int, _pp, _pp]),
     "pfs_slab_check": (_int, [_pp, _int]),
     "pfs_image_to_rgba8": (_int, [_vp, _vp, _int, _int, _int, _vp]),
     "pfs_step_norms": (_int, [_vp, _vp, _int, _int, _int, ctypes.POINTER(ctypes.c_double), _vp]),

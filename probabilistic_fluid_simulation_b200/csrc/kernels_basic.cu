@@ -2,8 +2,9 @@
 // advect_color, interleaved<->planar movers) and the one-sweep-per-launch Jacobi kernel that is the
 // reference point / remainder path for the temporally blocked sweeps in sweeps_fused.cu.
 //
-// All kernels are HBM-streaming: planar fp32, float4 per thread along x when W % 4 == 0 (V = 4),
-// scalar otherwise (V = 1).  Periodic wrap is resolved by index (no halo copies on one GPU).
+// All kernels are HBM-streaming: scalar planes (pressure, divergence) and (u,v) planes (velocity, 8 bytes per cell),
+// float4 per thread along x when W % 4 == 0 (V = 4), scalar otherwise (V = 1).  Periodic wrap is resolved by index
+// (no halo copies on one GPU).
 #include <math.h>
 #include <stdlib.h>
 
@@ -73,36 +74,55 @@ inline dim3 stencil_grid(int w, int h, int v, int planes)
 }
 
 // ---------------------------------------------------------------------------------------------
-// one Jacobi sweep (fluid.cpp:154-186 diffusion, :239-258 pressure)
+// one Jacobi sweep of the pressure (fluid.cpp:239-258) on a scalar plane
 // ---------------------------------------------------------------------------------------------
-template <int OP, int V>
+template <int V>
 __global__ void __launch_bounds__(BX *BY)
-    sweep_kernel(const float *__restrict__ in0, const float *__restrict__ in1, float *__restrict__ out0,
-                 float *__restrict__ out1, const float *__restrict__ rhs, int w, int h, float alpha, float beta,
-                 int y_base, int wrap)
+    pressure_sweep_kernel(const float *__restrict__ in, float *__restrict__ out, const float *__restrict__ rhs, int w, int h,
+                          int y_base, int wrap)
 {
     StencilPos s = stencil_pos<V>(w, h, y_base, wrap);
     if (!s.valid) return;
-    const float *in = blockIdx.z ? in1 : in0;
-    float *out = blockIdx.z ? out1 : out0;
     const float *rc = in + (size_t)s.rj * w;
-    float c[V], t[V], b[V], o[V];
+    float c[V], t[V], b[V], o[V], q[V];
     load_vec<V>(rc + s.x, c);
     load_vec<V>(in + (size_t)s.jm * w + s.x, t);
     load_vec<V>(in + (size_t)s.jp * w + s.x, b);
     float l = __ldg(rc + s.xm), r = __ldg(rc + s.xp);
-    float q[V];
-    if constexpr (OP == SWEEP_PRESSURE) load_vec<V>(rhs + (size_t)s.rj * w + s.x, q);
+    load_vec<V>(rhs + (size_t)s.rj * w + s.x, q);
 #pragma unroll
     for (int k = 0; k < V; k++) {
         float left = (k == 0) ? l : c[k - 1];
         float right = (k == V - 1) ? r : c[k + 1];
-        if constexpr (OP == SWEEP_PRESSURE)
-            o[k] = pressure_update(left, right, t[k], b[k], q[k]);
-        else
-            o[k] = diffuse_update(left, right, t[k], b[k], c[k], alpha, beta);
+        o[k] = pressure_update(left, right, t[k], b[k], q[k]);
     }
     store_vec<V>(out + (size_t)s.rj * w + s.x, o);
+}
+
+// ---------------------------------------------------------------------------------------------
+// one smoothing sweep of the velocity (fluid.cpp:154-186) on a (u,v) plane: one cell (8 bytes) per thread.
+// Reference point of the packed fused passes, and the path of widths that are not a multiple of four and of
+// coefficients outside the packed kernel's range (negative viscosity, huge alpha).
+// ---------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256)
+    diffuse_sweep_kernel(const float2 *__restrict__ in, float2 *__restrict__ out, int w, int h, float alpha, float beta,
+                         int y_base, int wrap)
+{
+    const int i = blockIdx.x * 64 + threadIdx.x, j = blockIdx.y * 4 + threadIdx.y;
+    if (i >= w || j >= h) return;
+    const int im = (i == 0) ? w - 1 : i - 1, ip = (i + 1 >= w) ? 0 : i + 1;     // fluid.cpp:159-160
+    int jm = j - 1, jp = j + 1;
+    if (wrap) {
+        if (jm < 0) jm = h - 1;                                                  // fluid.cpp:161
+        if (jp >= h) jp = 0;                                                     // fluid.cpp:162
+    }
+    const float2 *rc = in + (size_t)(y_base + j) * w;
+    const float2 c = __ldg(rc + i), l = __ldg(rc + im), r = __ldg(rc + ip);
+    const float2 t = __ldg(in + (size_t)(y_base + jm) * w + i), b = __ldg(in + (size_t)(y_base + jp) * w + i);
+    float2 o;
+    o.x = diffuse_update(l.x, r.x, t.x, b.x, c.x, alpha, beta);
+    o.y = diffuse_update(l.y, r.y, t.y, b.y, c.y, alpha, beta);
+    out[(size_t)(y_base + j) * w + i] = o;
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -110,18 +130,27 @@ __global__ void __launch_bounds__(BX *BY)
 // ---------------------------------------------------------------------------------------------
 template <int V>
 __global__ void __launch_bounds__(BX *BY)
-    divergence_kernel(const float *__restrict__ u, const float *__restrict__ v, float *__restrict__ div,
-                      const float *__restrict__ p0_src, float *__restrict__ p0, float gamma, int w, int h,
-                      int y_base, int wrap)
+    divergence_kernel(const float2 *__restrict__ uv, float *__restrict__ div, const float *__restrict__ p0_src,
+                      float *__restrict__ p0, float gamma, int w, int h, int y_base, int wrap)
 {
     StencilPos s = stencil_pos<V>(w, h, y_base, wrap);
     if (!s.valid) return;
-    const float *ur = u + (size_t)s.rj * w;
+    const float2 *rc = uv + (size_t)s.rj * w, *rt = uv + (size_t)s.jm * w, *rb = uv + (size_t)s.jp * w;
     float uc[V], vt[V], vb[V], o[V];
-    load_vec<V>(ur + s.x, uc);
-    load_vec<V>(v + (size_t)s.jm * w + s.x, vt);
-    load_vec<V>(v + (size_t)s.jp * w + s.x, vb);
-    float ul = __ldg(ur + s.xm), urr = __ldg(ur + s.xp);
+    if constexpr (V == 4) {
+        // four cells = two 16-byte loads per row; u comes from the centre row, v from the rows above and below
+        const float4 c0 = __ldg(reinterpret_cast<const float4 *>(rc + s.x)), c1 = __ldg(reinterpret_cast<const float4 *>(rc + s.x + 2));
+        const float4 t0 = __ldg(reinterpret_cast<const float4 *>(rt + s.x)), t1 = __ldg(reinterpret_cast<const float4 *>(rt + s.x + 2));
+        const float4 b0 = __ldg(reinterpret_cast<const float4 *>(rb + s.x)), b1 = __ldg(reinterpret_cast<const float4 *>(rb + s.x + 2));
+        uc[0] = c0.x; uc[1] = c0.z; uc[2] = c1.x; uc[3] = c1.z;
+        vt[0] = t0.y; vt[1] = t0.w; vt[2] = t1.y; vt[3] = t1.w;
+        vb[0] = b0.y; vb[1] = b0.w; vb[2] = b1.y; vb[3] = b1.w;
+    } else {
+        uc[0] = __ldg(rc + s.x).x;
+        vt[0] = __ldg(rt + s.x).y;
+        vb[0] = __ldg(rb + s.x).y;
+    }
+    const float ul = __ldg(rc + s.xm).x, urr = __ldg(rc + s.xp).x;
 #pragma unroll
     for (int k = 0; k < V; k++) {
         float left = (k == 0) ? ul : uc[k - 1];
@@ -142,35 +171,89 @@ __global__ void __launch_bounds__(BX *BY)
 // subtract pressure gradient (fluid.cpp:273-294) fused with the write-back of both interleaved
 // post-state buffers (full 16-byte cells, so no read-modify-write of the caller's buffers).
 // ---------------------------------------------------------------------------------------------
-template <int V>
 __global__ void __launch_bounds__(BX *BY)
-    project_pack_kernel(const float *__restrict__ u, const float *__restrict__ v, const float *__restrict__ pn,
-                        const float *__restrict__ pprev, const float *__restrict__ div,
-                        float4 *__restrict__ out_q, float4 *__restrict__ out_p, float dt, int w, int h,
-                        int y_base, int wrap)
+    project_pack_kernel(const float2 *__restrict__ uv, const float *__restrict__ pn, const float *__restrict__ pprev,
+                        const float *__restrict__ div, float4 *__restrict__ out_q, float4 *__restrict__ out_p, float dt,
+                        int w, int h, int y_base, int wrap)
 {
-    StencilPos s = stencil_pos<V>(w, h, y_base, wrap);
+    // One cell per thread: a warp's two 16-byte stores per cell then cover 512 contiguous bytes of each interleaved
+    // buffer (full sectors); four cells per thread would leave every store instruction scattered over 32 half-written sectors.
+    StencilPos s = stencil_pos<1>(w, h, y_base, wrap);
     if (!s.valid) return;
     const float *pr = pn + (size_t)s.rj * w;
-    float pc[V], pt[V], pb[V], uu[V], vv[V], pp[V], dd[V];
-    size_t off = (size_t)s.rj * w + s.x;                 // planes (with halo rows)
-    const size_t cell = (size_t)s.j * w + s.x;           // interleaved buffers (no halo rows)
-    load_vec<V>(pr + s.x, pc);
-    load_vec<V>(pn + (size_t)s.jm * w + s.x, pt);
-    load_vec<V>(pn + (size_t)s.jp * w + s.x, pb);
-    float pl = __ldg(pr + s.xm), prr = __ldg(pr + s.xp);
-    load_vec<V>(u + off, uu);
-    load_vec<V>(v + off, vv);
-    load_vec<V>(pprev + off, pp);
-    load_vec<V>(div + off, dd);
+    const size_t off = (size_t)s.rj * w + s.x;                 // planes (with halo rows)
+    const size_t cell = (size_t)s.j * w + s.x;                 // interleaved buffers (no halo rows)
+    const float pc = __ldg(pr + s.x), pl = __ldg(pr + s.xm), prr = __ldg(pr + s.xp);
+    const float pt = __ldg(pn + (size_t)s.jm * w + s.x), pb = __ldg(pn + (size_t)s.jp * w + s.x);
+    const float2 v = __ldg(uv + off);
+    const float pp = __ldg(pprev + off), dd = __ldg(div + off);
+    const float un = project_component(v.x, prr, pl, dt);
+    const float vn = project_component(v.y, pb, pt, dt);
+    out_q[cell] = make_float4(un, vn, pp, dd);
+    out_p[cell] = make_float4(v.x, v.y, pc, dd);
+}
+
+// The same subtraction with the result kept in a (u,v) plane (persistent-state contexts): two cells per thread, one
+// 16-byte load and store of the velocity.  vmax (optional): running maximum of |v| of the projected field -- what bounds
+// the row displacement of the gathers that follow (advect_color of this step, advect of the next); NaN counts as +inf.
+template <int V>
+__global__ void __launch_bounds__(BX *BY)
+    project_uv_kernel(const float2 *__restrict__ uv, const float *__restrict__ pn, float2 *__restrict__ uv_out, float dt,
+                      int w, int h, int y_base, int wrap, float *vmax)
+{
+    StencilPos s = stencil_pos<V>(w, h, y_base, wrap);
+    float m = 0.f;
+    if (s.valid) {
+        const float *pr = pn + (size_t)s.rj * w;
+        float pc[V], pt[V], pb[V];
+        load_vec<V>(pr + s.x, pc);
+        load_vec<V>(pn + (size_t)s.jm * w + s.x, pt);
+        load_vec<V>(pn + (size_t)s.jp * w + s.x, pb);
+        const float pl = __ldg(pr + s.xm), prr = __ldg(pr + s.xp);
+        const float2 *src = uv + (size_t)s.rj * w + s.x;
+        float2 *dst = uv_out + (size_t)s.rj * w + s.x;
+        float2 v[V], o[V];
+        if constexpr (V == 4) {
+            const float4 a = __ldg(reinterpret_cast<const float4 *>(src)), b = __ldg(reinterpret_cast<const float4 *>(src + 2));
+            v[0] = make_float2(a.x, a.y); v[1] = make_float2(a.z, a.w); v[2] = make_float2(b.x, b.y); v[3] = make_float2(b.z, b.w);
+        } else {
+            v[0] = __ldg(src);
+        }
 #pragma unroll
-    for (int k = 0; k < V; k++) {
-        float left = (k == 0) ? pl : pc[k - 1];
-        float right = (k == V - 1) ? prr : pc[k + 1];
-        float un = project_component(uu[k], right, left, dt);
-        float vn = project_component(vv[k], pb[k], pt[k], dt);
-        out_q[cell + k] = make_float4(un, vn, pp[k], dd[k]);
-        out_p[cell + k] = make_float4(uu[k], vv[k], pc[k], dd[k]);
+        for (int k = 0; k < V; k++) {
+            const float left = (k == 0) ? pl : pc[k - 1];
+            const float right = (k == V - 1) ? prr : pc[k + 1];
+            o[k].x = project_component(v[k].x, right, left, dt);
+            o[k].y = project_component(v[k].y, pb[k], pt[k], dt);
+            const float av = fabsf(o[k].y);
+            m = (av > m || av != av) ? av : m;
+        }
+        if constexpr (V == 4) {
+            *reinterpret_cast<float4 *>(dst) = make_float4(o[0].x, o[0].y, o[1].x, o[1].y);
+            *reinterpret_cast<float4 *>(dst + 2) = make_float4(o[2].x, o[2].y, o[3].x, o[3].y);
+        } else {
+            *dst = o[0];
+        }
+    }
+    if (vmax != nullptr) {                      // every thread of the block gets here
+        __shared__ float warp_max[BX * BY / 32];
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+            const float t = __shfl_xor_sync(0xffffffffu, m, o);
+            m = (t > m || t != t) ? t : m;
+        }
+        const int tid = threadIdx.y * BX + threadIdx.x;
+        if ((tid & 31) == 0) warp_max[tid >> 5] = m;
+        __syncthreads();
+        if (tid == 0) {
+            for (int q = 1; q < BX * BY / 32; q++) {
+                const float t = warp_max[q];
+                m = (t > m || t != t) ? t : m;
+            }
+            if (m != m) m = __int_as_float(0x7f800000);
+            if (m > *reinterpret_cast<volatile float *>(vmax))
+                atomicMax(reinterpret_cast<int *>(vmax), __float_as_int(m));    // non-negative floats order like their bits
+        }
     }
 }
 
@@ -193,45 +276,40 @@ __global__ void __launch_bounds__(256)
 }
 
 // ---------------------------------------------------------------------------------------------
-// advect (fluid.cpp:24-70): back-trace, periodic wrap, bilinear gather of (u, v) from the
-// interleaved field.  One 8-byte load fetches both components of a corner; neighbouring threads'
+// advect (fluid.cpp:24-70): back-trace, periodic wrap, bilinear gather of (u, v) from the interleaved field or from
+// a (u,v) plane.  One 8-byte load fetches both components of a corner; neighbouring threads'
 // corners share 32-byte sectors, so the gather runs out of L1 for coherent flows.
 // ---------------------------------------------------------------------------------------------
-template <bool TO_PLANES>
+template <int SS, int DS>     // floats per source / destination cell: 4 = interleaved [u,v,p,div], 2 = (u,v) plane
 __global__ void __launch_bounds__(256)
-    advect_kernel(const float *__restrict__ vp, float *__restrict__ u_out, float *__restrict__ v_out,
-                  float *__restrict__ aos_out, float dt, int w, int h)
+    advect_kernel(const float *__restrict__ src, float *__restrict__ dst, float dt, int w, int h)
 {
     int i = blockIdx.x * 64 + threadIdx.x, j = blockIdx.y * 4 + threadIdx.y;
     if (i >= w || j >= h) return;
     const float fw = (float)w, fh = (float)h;
     size_t cell = (size_t)j * w + i;
-    float2 uv = __ldg(reinterpret_cast<const float2 *>(vp + cell * 4));
+    float2 uv = __ldg(reinterpret_cast<const float2 *>(src + cell * SS));
     // fluid.cpp:39,41: (float)i - dt*u/fwidth  ==  i - ((dt*u)/fwidth)
     float xp = __fsub_rn((float)i, div_extent(__fmul_rn(dt, uv.x), fw, __frcp_rn(fw)));
     float yp = __fsub_rn((float)j, div_extent(__fmul_rn(dt, uv.y), fh, __frcp_rn(fh)));
     xp = wrap_coord(xp, fw);
     yp = wrap_coord(yp, fh);
     Bilinear b = make_bilinear(xp, yp, w, h);
-    const float *r0 = vp + (size_t)b.j0 * w * 4, *r1 = vp + (size_t)b.j1 * w * 4;
-    float2 f00 = __ldg(reinterpret_cast<const float2 *>(r0 + (size_t)b.i0 * 4));
-    float2 f10 = __ldg(reinterpret_cast<const float2 *>(r0 + (size_t)b.i1 * 4));
-    float2 f01 = __ldg(reinterpret_cast<const float2 *>(r1 + (size_t)b.i0 * 4));
-    float2 f11 = __ldg(reinterpret_cast<const float2 *>(r1 + (size_t)b.i1 * 4));
+    const float *r0 = src + (size_t)b.j0 * w * SS, *r1 = src + (size_t)b.j1 * w * SS;
+    float2 f00 = __ldg(reinterpret_cast<const float2 *>(r0 + (size_t)b.i0 * SS));
+    float2 f10 = __ldg(reinterpret_cast<const float2 *>(r0 + (size_t)b.i1 * SS));
+    float2 f01 = __ldg(reinterpret_cast<const float2 *>(r1 + (size_t)b.i0 * SS));
+    float2 f11 = __ldg(reinterpret_cast<const float2 *>(r1 + (size_t)b.i1 * SS));
     float un = bilerp(b, f00.x, f10.x, f01.x, f11.x);
     float vn = bilerp(b, f00.y, f10.y, f01.y, f11.y);
-    if constexpr (TO_PLANES) {
-        u_out[cell] = un;
-        v_out[cell] = vn;
-    } else {
-        *reinterpret_cast<float2 *>(aos_out + cell * 4) = make_float2(un, vn);
-    }
+    *reinterpret_cast<float2 *>(dst + cell * DS) = make_float2(un, vn);
 }
 
 // ---------------------------------------------------------------------------------------------
 // advect_color (fluid.cpp:72-127): one thread per pixel, velocity point-sampled at
 // ((int)(i*viw), (int)(j*vih)), four float4 texel gathers, one coalesced float4 store.
 // ---------------------------------------------------------------------------------------------
+template <int VS>     // floats per velocity cell: 4 = interleaved buffer, 2 = (u,v) plane
 __global__ void __launch_bounds__(256)
     advect_color_kernel(const float4 *__restrict__ image, float4 *__restrict__ out, const float *__restrict__ vp,
                         float dt_over_viw, float dt_over_vih, float viw, float vih, int iw, int ih, int vw)
@@ -241,7 +319,7 @@ __global__ void __launch_bounds__(256)
     const float fiw = (float)iw, fih = (float)ih;
     int vi = (int)__fmul_rn((float)i, viw);   // fluid.cpp:89
     int vj = (int)__fmul_rn((float)j, vih);   // fluid.cpp:90
-    float2 uv = __ldg(reinterpret_cast<const float2 *>(vp + ((size_t)vj * vw + vi) * 4));
+    float2 uv = __ldg(reinterpret_cast<const float2 *>(vp + ((size_t)vj * vw + vi) * VS));
     // fluid.cpp:97-98: (float)i - (dt/viw) * u / fiwidth
     float xp = __fsub_rn((float)i, div_extent(__fmul_rn(dt_over_viw, uv.x), fiw, __frcp_rn(fiw)));
     float yp = __fsub_rn((float)j, div_extent(__fmul_rn(dt_over_vih, uv.y), fih, __frcp_rn(fih)));
@@ -262,38 +340,46 @@ __global__ void __launch_bounds__(256)
 // interleaved <-> planar movers (operator API; the fused step never needs a separate pass)
 // ---------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(256)
-    unpack_kernel(const float4 *__restrict__ aos, float *c0, float *c1, float *c2, float *c3, size_t n)
+    unpack_kernel(const float4 *__restrict__ aos, float2 *uv, float *p, float *div, size_t n)
 {
     size_t i = (size_t)blockIdx.x * 256 + threadIdx.x;
     if (i >= n) return;
     float4 v = __ldg(aos + i);
-    if (c0) c0[i] = v.x;
-    if (c1) c1[i] = v.y;
-    if (c2) c2[i] = v.z;
-    if (c3) c3[i] = v.w;
+    if (uv) uv[i] = make_float2(v.x, v.y);
+    if (p) p[i] = v.z;
+    if (div) div[i] = v.w;
 }
 
 __global__ void __launch_bounds__(256)
-    pack_kernel(float *__restrict__ aos, const float *c0, const float *c1, const float *c2, const float *c3, size_t n)
+    pack_kernel(float *__restrict__ aos, const float2 *uv, const float *p, const float *div, size_t n)
 {
     size_t i = (size_t)blockIdx.x * 256 + threadIdx.x;
     if (i >= n) return;
-    if (c0 && c1 && c2 && c3) {
-        reinterpret_cast<float4 *>(aos)[i] = make_float4(c0[i], c1[i], c2[i], c3[i]);
+    if (uv && p && div) {
+        const float2 v = uv[i];
+        reinterpret_cast<float4 *>(aos)[i] = make_float4(v.x, v.y, p[i], div[i]);
         return;
     }
-    if (c0 && c1) {
-        *reinterpret_cast<float2 *>(aos + i * 4) = make_float2(c0[i], c1[i]);
+    if (uv) *reinterpret_cast<float2 *>(aos + i * 4) = uv[i];
+    if (p && div) {
+        *reinterpret_cast<float2 *>(aos + i * 4 + 2) = make_float2(p[i], div[i]);
     } else {
-        if (c0) aos[i * 4 + 0] = c0[i];
-        if (c1) aos[i * 4 + 1] = c1[i];
+        if (p) aos[i * 4 + 2] = p[i];
+        if (div) aos[i * 4 + 3] = div[i];
     }
-    if (c2 && c3) {
-        *reinterpret_cast<float2 *>(aos + i * 4 + 2) = make_float2(c2[i], c3[i]);
-    } else {
-        if (c2) aos[i * 4 + 2] = c2[i];
-        if (c3) aos[i * 4 + 3] = c3[i];
-    }
+}
+
+// addForces slot (fluid.cpp:198-208; the reference body is an empty loop over every cell and channel): the velocity
+// channels take the force, dst[cell] (u,v) += force[cell] channels 0,1, one rounded addition each.
+template <int DS>
+__global__ void __launch_bounds__(256) add_forces_kernel(float *__restrict__ dst, const float4 *__restrict__ force, size_t n)
+{
+    size_t i = (size_t)blockIdx.x * 256 + threadIdx.x;
+    if (i >= n) return;
+    const float4 f = __ldg(force + i);
+    float2 *d = reinterpret_cast<float2 *>(dst + i * DS);
+    const float2 v = *d;
+    *d = make_float2(__fadd_rn(v.x, f.x), __fadd_rn(v.y, f.y));
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -475,83 +561,114 @@ inline bool vec4_ok(int w, const void *a, const void *b = nullptr, const void *c
 // ---------------------------------------------------------------------------------------------
 // host wrappers
 // ---------------------------------------------------------------------------------------------
-int launch_unpack(const float *aos, float *c0, float *c1, float *c2, float *c3, int w, int h, cudaStream_t s)
+int launch_unpack(const float *aos, float *uv, float *p, float *div, int w, int h, cudaStream_t s)
 {
     size_t n = (size_t)w * h;
     unsigned blocks = (unsigned)((n + 255) / 256);
-    PFS_LAUNCH(unpack_kernel, blocks, 256, 0, s, reinterpret_cast<const float4 *>(aos), c0, c1, c2, c3, n);
+    PFS_LAUNCH(unpack_kernel, blocks, 256, 0, s, reinterpret_cast<const float4 *>(aos), reinterpret_cast<float2 *>(uv), p,
+               div, n);
     return PFS_OK;
 }
 
-int launch_pack(float *aos, const float *c0, const float *c1, const float *c2, const float *c3, int w, int h,
-                cudaStream_t s)
+int launch_pack(float *aos, const float *uv, const float *p, const float *div, int w, int h, cudaStream_t s)
 {
     size_t n = (size_t)w * h;
     unsigned blocks = (unsigned)((n + 255) / 256);
-    PFS_LAUNCH(pack_kernel, blocks, 256, 0, s, aos, c0, c1, c2, c3, n);
+    PFS_LAUNCH(pack_kernel, blocks, 256, 0, s, aos, reinterpret_cast<const float2 *>(uv), p, div, n);
     return PFS_OK;
 }
 
-int launch_advect(const float *vp_aos, float *u_out, float *v_out, float *aos_out, float dt, int w, int h,
-                  cudaStream_t s)
+int launch_add_forces(float *dst, int dst_stride, const float *force_aos, int w, int rows, cudaStream_t s)
+{
+    const size_t n = (size_t)w * rows;
+    if (n == 0) return PFS_OK;
+    const unsigned blocks = (unsigned)((n + 255) / 256);
+    const float4 *f = reinterpret_cast<const float4 *>(force_aos);
+    if (dst_stride == 2)
+        PFS_LAUNCH(add_forces_kernel<2>, blocks, 256, 0, s, dst, f, n);
+    else
+        PFS_LAUNCH(add_forces_kernel<4>, blocks, 256, 0, s, dst, f, n);
+    return PFS_OK;
+}
+
+int launch_advect(const float *src, int src_stride, float *dst, int dst_stride, float dt, int w, int h, cudaStream_t s)
 {
     dim3 block(64, 4), grid((w + 63) / 64, (h + 3) / 4);
-    if (aos_out == nullptr)
-        PFS_LAUNCH(advect_kernel<true>, grid, block, 0, s, vp_aos, u_out, v_out, aos_out, dt, w, h);
-    else
-        PFS_LAUNCH(advect_kernel<false>, grid, block, 0, s, vp_aos, u_out, v_out, aos_out, dt, w, h);
+    if (src_stride == 4 && dst_stride == 2)
+        PFS_LAUNCH((advect_kernel<4, 2>), grid, block, 0, s, src, dst, dt, w, h);
+    else if (src_stride == 2 && dst_stride == 2)
+        PFS_LAUNCH((advect_kernel<2, 2>), grid, block, 0, s, src, dst, dt, w, h);
+    else if (src_stride == 4 && dst_stride == 4)
+        PFS_LAUNCH((advect_kernel<4, 4>), grid, block, 0, s, src, dst, dt, w, h);
+    else {
+        set_error("advect: unsupported cell strides %d -> %d", src_stride, dst_stride);
+        return PFS_EINVAL;
+    }
     return PFS_OK;
 }
 
-int launch_sweeps_basic(SweepOp op, float *a0, float *a1, float *b0, float *b1, const float *rhs,
-                        const SweepParams &p, int n, int *flips, cudaStream_t s)
+int launch_pressure_basic(float *a, float *b, const float *rhs, const SweepParams &p, int n, int *flips, cudaStream_t s)
 {
-    const int planes = (op == SWEEP_DIFFUSE) ? 2 : 1;
-    const bool v4 = vec4_ok(p.w, a0, a1, b0, b1, rhs);
-    dim3 block(BX, BY), grid = stencil_grid(p.w, p.h, v4 ? 4 : 1, planes);
-    using SweepFn = void (*)(const float *, const float *, float *, float *, const float *, int, int, float, float, int,
-                             int);
-    SweepFn fn;
-    if (op == SWEEP_PRESSURE)
-        fn = v4 ? sweep_kernel<SWEEP_PRESSURE, 4> : sweep_kernel<SWEEP_PRESSURE, 1>;
-    else
-        fn = v4 ? sweep_kernel<SWEEP_DIFFUSE, 4> : sweep_kernel<SWEEP_DIFFUSE, 1>;
+    const bool v4 = vec4_ok(p.w, a, b, rhs);
+    dim3 block(BX, BY), grid = stencil_grid(p.w, p.h, v4 ? 4 : 1, 1);
     for (int it = 0; it < n; it++) {
-        const float *i0 = (it & 1) ? b0 : a0, *i1 = (it & 1) ? b1 : a1;
-        float *o0 = (it & 1) ? a0 : b0, *o1 = (it & 1) ? a1 : b1;
-        PFS_LAUNCH(fn, grid, block, 0, s, i0, i1, o0, o1, rhs, p.w, p.h, p.alpha, p.beta, p.y_base, p.wrap);
+        const float *in = (it & 1) ? b : a;
+        float *out = (it & 1) ? a : b;
+        if (v4)
+            PFS_LAUNCH(pressure_sweep_kernel<4>, grid, block, 0, s, in, out, rhs, p.w, p.h, p.y_base, p.wrap);
+        else
+            PFS_LAUNCH(pressure_sweep_kernel<1>, grid, block, 0, s, in, out, rhs, p.w, p.h, p.y_base, p.wrap);
     }
     *flips = n;
     return PFS_OK;
 }
 
-int launch_divergence(const float *u, const float *v, float *div, const float *p0_src_aos, float *p0, float dt,
-                      int w, int h, cudaStream_t s, int y_base, int wrap)
+int launch_diffuse_basic(float *a_uv, float *b_uv, const SweepParams &p, int n, int *flips, cudaStream_t s)
 {
-    const float gamma = (float)(-1.0 / (double)dt);   // fluid.cpp:218
-    const bool v4 = vec4_ok(w, u, v, div, p0);
-    dim3 block(BX, BY), grid = stencil_grid(w, h, v4 ? 4 : 1, 1);
-    if (v4)
-        PFS_LAUNCH(divergence_kernel<4>, grid, block, 0, s, u, v, div, p0_src_aos, p0, gamma, w, h, y_base, wrap);
-    else
-        PFS_LAUNCH(divergence_kernel<1>, grid, block, 0, s, u, v, div, p0_src_aos, p0, gamma, w, h, y_base, wrap);
+    dim3 block(64, 4), grid((p.w + 63) / 64, (p.h + 3) / 4);
+    for (int it = 0; it < n; it++) {
+        const float2 *in = reinterpret_cast<const float2 *>((it & 1) ? b_uv : a_uv);
+        float2 *out = reinterpret_cast<float2 *>((it & 1) ? a_uv : b_uv);
+        PFS_LAUNCH(diffuse_sweep_kernel, grid, block, 0, s, in, out, p.w, p.h, p.alpha, p.beta, p.y_base, p.wrap);
+    }
+    *flips = n;
     return PFS_OK;
 }
 
-int launch_project_pack(const float *u, const float *v, const float *p_n, const float *p_prev, const float *div,
-                        float *out_q, float *out_p, float dt, int w, int h, cudaStream_t s, int y_base, int wrap)
+int launch_divergence(const float *uv, float *div, const float *p0_src_aos, float *p0, float dt, int w, int h,
+                      cudaStream_t s, int y_base, int wrap)
 {
-    // One cell per thread unless PFS_PROJECT_VEC=1: a warp's two 16-byte stores per cell then cover 512
-    // contiguous bytes of each interleaved buffer (full sectors), whereas four cells per thread leave every
-    // store instruction scattered over 32 half-written sectors.
-    static const bool want_vec = getenv("PFS_PROJECT_VEC") && getenv("PFS_PROJECT_VEC")[0] == '1';
-    const bool v4 = want_vec && vec4_ok(w, u, v, p_n, p_prev, div);
+    const float gamma = (float)(-1.0 / (double)dt);   // fluid.cpp:218
+    const bool v4 = vec4_ok(w, uv, div, p0);
     dim3 block(BX, BY), grid = stencil_grid(w, h, v4 ? 4 : 1, 1);
-    float4 *q4 = reinterpret_cast<float4 *>(out_q), *p4 = reinterpret_cast<float4 *>(out_p);
+    const float2 *uv2 = reinterpret_cast<const float2 *>(uv);
     if (v4)
-        PFS_LAUNCH(project_pack_kernel<4>, grid, block, 0, s, u, v, p_n, p_prev, div, q4, p4, dt, w, h, y_base, wrap);
+        PFS_LAUNCH(divergence_kernel<4>, grid, block, 0, s, uv2, div, p0_src_aos, p0, gamma, w, h, y_base, wrap);
     else
-        PFS_LAUNCH(project_pack_kernel<1>, grid, block, 0, s, u, v, p_n, p_prev, div, q4, p4, dt, w, h, y_base, wrap);
+        PFS_LAUNCH(divergence_kernel<1>, grid, block, 0, s, uv2, div, p0_src_aos, p0, gamma, w, h, y_base, wrap);
+    return PFS_OK;
+}
+
+int launch_project_pack(const float *uv, const float *p_n, const float *p_prev, const float *div, float *out_q,
+                        float *out_p, float dt, int w, int h, cudaStream_t s, int y_base, int wrap)
+{
+    dim3 block(BX, BY), grid = stencil_grid(w, h, 1, 1);
+    PFS_LAUNCH(project_pack_kernel, grid, block, 0, s, reinterpret_cast<const float2 *>(uv), p_n, p_prev, div,
+               reinterpret_cast<float4 *>(out_q), reinterpret_cast<float4 *>(out_p), dt, w, h, y_base, wrap);
+    return PFS_OK;
+}
+
+int launch_project_uv(const float *uv, const float *p_n, float *uv_out, float dt, int w, int h, cudaStream_t s, int y_base,
+                      int wrap, float *vmax_out)
+{
+    const bool v4 = vec4_ok(w, uv, p_n, uv_out);
+    dim3 block(BX, BY), grid = stencil_grid(w, h, v4 ? 4 : 1, 1);
+    const float2 *in = reinterpret_cast<const float2 *>(uv);
+    float2 *out = reinterpret_cast<float2 *>(uv_out);
+    if (v4)
+        PFS_LAUNCH(project_uv_kernel<4>, grid, block, 0, s, in, p_n, out, dt, w, h, y_base, wrap, vmax_out);
+    else
+        PFS_LAUNCH(project_uv_kernel<1>, grid, block, 0, s, in, p_n, out, dt, w, h, y_base, wrap, vmax_out);
     return PFS_OK;
 }
 
@@ -604,8 +721,8 @@ int launch_stochastic_force(float *u, float *v, int stride, float sigma, unsigne
     return PFS_OK;
 }
 
-int launch_advect_color(const float *image, float *out, const float *vp_aos, float dt, int iw, int ih, int vw, int vh,
-                        cudaStream_t s)
+int launch_advect_color(const float *image, float *out, const float *vel, int vel_stride, float dt, int iw, int ih, int vw,
+                        int vh, cudaStream_t s)
 {
     // fluid.cpp:82-83 and the (dt/viw), (dt/vih) factors of :97-98, all binary32
     const float viw = (float)vw / (float)iw;
@@ -613,8 +730,12 @@ int launch_advect_color(const float *image, float *out, const float *vp_aos, flo
     const float dt_over_viw = dt / viw;
     const float dt_over_vih = dt / vih;
     dim3 block(64, 4), grid((iw + 63) / 64, (ih + 3) / 4);
-    PFS_LAUNCH(advect_color_kernel, grid, block, 0, s, reinterpret_cast<const float4 *>(image),
-               reinterpret_cast<float4 *>(out), vp_aos, dt_over_viw, dt_over_vih, viw, vih, iw, ih, vw);
+    const float4 *img = reinterpret_cast<const float4 *>(image);
+    float4 *o4 = reinterpret_cast<float4 *>(out);
+    if (vel_stride == 2)
+        PFS_LAUNCH(advect_color_kernel<2>, grid, block, 0, s, img, o4, vel, dt_over_viw, dt_over_vih, viw, vih, iw, ih, vw);
+    else
+        PFS_LAUNCH(advect_color_kernel<4>, grid, block, 0, s, img, o4, vel, dt_over_viw, dt_over_vih, viw, vih, iw, ih, vw);
     return PFS_OK;
 }
 

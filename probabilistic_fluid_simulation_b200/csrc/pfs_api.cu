@@ -72,8 +72,9 @@ int check_launch(const char *kernel, const char *file, int line)
 // per-device scratch: seven planes (u,v x2, p x2, divergence) sized for the largest grid seen,
 // plus staging buffers of the host API.
 // ---------------------------------------------------------------------------------------------
-// planes 0-3: (u,v) ping-pong, 4-5: pressure ping-pong, 6: divergence, 7-8: (u,v) of diffusion iterate n-1,
-// 9: pressure iterate n-1 (the iterates the reference leaves in its other buffer)
+// Scratch of the stateless entry points, in units of plane_cells floats: three (u,v) planes of two units each
+// (ping, pong, diffusion iterate n-1), three pressure planes (ping, pong, iterate n-1), the divergence.
+// (The iterates n-1 are what the reference leaves in its other buffer.)
 constexpr size_t N_PLANES = 10;
 
 struct DeviceScratch {
@@ -85,7 +86,9 @@ struct DeviceScratch {
     cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};
     double *norm_dev = nullptr;       // reduction partials + 4 results (pfs_compute_pressure_adaptive)
     double *norm_host = nullptr;      // pinned, 4 doubles
-    float *plane(int k) const { return planes + (size_t)k * plane_cells; }
+    float *uv(int k) const { return planes + (size_t)(2 * k) * plane_cells; }      // k = 0..2
+    float *p(int k) const { return planes + (size_t)(6 + k) * plane_cells; }       // k = 0..2
+    float *div() const { return planes + (size_t)9 * plane_cells; }
 };
 
 static std::mutex g_mutex;
@@ -150,6 +153,7 @@ struct PhaseSpan {
     unsigned long long launches;
 };
 static bool g_phase_timing = false;
+bool phase_timing_on() { return g_phase_timing; }
 static std::mutex g_phase_mutex;                 // guards g_spans and g_event_pool (worker threads may step too)
 static std::vector<PhaseSpan> g_spans;
 static std::vector<cudaEvent_t> g_event_pool;
@@ -189,7 +193,7 @@ PhaseScope::~PhaseScope()
 // ---------------------------------------------------------------------------------------------
 // argument checks
 // ---------------------------------------------------------------------------------------------
-static int check_dims(const char *fn, int x, int y, int z)
+int check_dims(const char *fn, int x, int y, int z)
 {
     if (x <= 0 || y <= 0) {
         set_error("%s: width and height must be positive (got %d x %d)", fn, x, y);
@@ -212,7 +216,7 @@ static int check_dims(const char *fn, int x, int y, int z)
     return PFS_OK;
 }
 
-static int check_ptr(const char *fn, const char *name, const void *p)
+int check_ptr(const char *fn, const char *name, const void *p)
 {
     if (p == nullptr) {
         set_error("%s: %s is null", fn, name);
@@ -225,7 +229,7 @@ static int check_ptr(const char *fn, const char *name, const void *p)
     return PFS_OK;
 }
 
-static int check_sweeps(const char *fn, int n)
+int check_sweeps(const char *fn, int n)
 {
     if (n < 1) {
         set_error("%s: sweep count must be >= 1 (got %d)", fn, n);
@@ -235,60 +239,46 @@ static int check_sweeps(const char *fn, int n)
 }
 
 // ---------------------------------------------------------------------------------------------
-// n Jacobi sweeps on planes with the reference's "n-1 swaps" semantics.
+// n sweeps on planes with the reference's "n-1 swaps" semantics.
 //
-// Start: iterate 0 in planes a*.  The reference loop writes sweep k to the "other" buffer and
-// swaps, so the caller needs BOTH iterate n (the result) and iterate n-1 (left behind in the other
-// buffer, fluid.cpp:188-194).  We run n-1 sweeps with as much temporal blocking as allowed, which
-// leaves iterate n-1 in one plane set, then exactly one sweep into the other set.
-// On return *last points at the planes of iterate n and *prev at those of iterate n-1.
+// Start: iterate 0 in plane a.  The reference loop writes sweep k to the "other" buffer and swaps, so the caller
+// needs BOTH iterate n (the result) and iterate n-1 (left behind in the other buffer, fluid.cpp:188-194, 260-265).
+// The fused pass that reaches sweep n also stores iterate n-1 (into `extra`), so no separate last sweep -- and no
+// extra trip through HBM -- is needed to have both.  On return *last is the plane of iterate n, *prev that of n-1.
 // ---------------------------------------------------------------------------------------------
-struct PlanePair {
-    float *c0, *c1;   // c1 unused for pressure
-};
+int fuse_depth() { return g_fuse_depth; }
 
-static int run_sweeps(SweepOp op, PlanePair a, PlanePair b, PlanePair extra, const float *rhs, const SweepParams &p,
-                      int n, PlanePair *last, PlanePair *prev, cudaStream_t s)
+int run_diffuse(float *a, float *b, float *extra, const SweepParams &p, int n, float **last, float **prev, cudaStream_t s,
+                const ForceField *force)
 {
-    const int depth = g_fuse_depth;
-    const bool fused = (depth != 1) && fused_sweeps_supported(p.w, p.h);
-    // The packed (f32x2) pressure kernel is bit-exact but register-bound (255 registers, 8 warps/SM) and
-    // measured no faster than the scalar fused kernel at 4096^2 (0.91 vs 0.89 ms per 100 sweeps,
-    // profiles/r01_tuning.md), so it is opt-in: PFS_PRESSURE_KERNEL=packed.
-    static const bool packed_pressure = getenv("PFS_PRESSURE_KERNEL") && !strcmp(getenv("PFS_PRESSURE_KERNEL"), "packed");
-    int flips = 0;   // number of a<->b ping-pong hops taken (one per launch)
-    if (fused && !(op == SWEEP_PRESSURE && packed_pressure)) {
-        // All n sweeps in fused passes; the pass that reaches sweep n also stores iterate n-1 (into `extra`),
-        // so no separate last sweep -- and no extra trip through HBM -- is needed to have both.
-        int prev_written = 0;
-        if (op == SWEEP_DIFFUSE && packed_diffuse_supported(p))
-            PFS_TRY(launch_diffuse_packed(a.c0, a.c1, b.c0, b.c1, p, n, depth, &flips, s, extra.c0, extra.c1, &prev_written));
-        else
-            PFS_TRY(launch_sweeps_fused(op, a.c0, a.c1, b.c0, b.c1, rhs, p, n, depth, &flips, s, extra.c0, extra.c1,
-                                        &prev_written));
-        *last = (flips & 1) ? b : a;
-        *prev = prev_written ? extra : ((flips & 1) ? a : b);     // else: the set the last single sweep read
-        return PFS_OK;
+    int flips = 0, prev_written = 0;
+    if (g_fuse_depth != 1 && packed_diffuse_supported(p)) {
+        PFS_TRY(launch_diffuse_packed(a, b, p, n, g_fuse_depth, &flips, s, extra, &prev_written, force));
+    } else {
+        PFS_TRY(launch_diffuse_basic(a, b, p, n, &flips, s));
+        if (force)
+            PFS_TRY(launch_add_forces(((flips & 1) ? b : a) + (size_t)(p.y_base + force->skip_rows) * 2 * p.w, 2, force->aos,
+                                      p.w, force->rows, s));
     }
-    // n-1 sweeps, then exactly one into the other set: iterates n-1 and n both exist afterwards
-    const int lead = n - 1;
-    if (lead > 0) {
-        if (fused && op == SWEEP_PRESSURE && packed_pressure_supported(p))
-            PFS_TRY(launch_pressure_packed(a.c0, b.c0, rhs, p, lead, depth, &flips, s));
-        else if (fused)
-            PFS_TRY(launch_sweeps_fused(op, a.c0, a.c1, b.c0, b.c1, rhs, p, lead, depth, &flips, s));
-        else
-            PFS_TRY(launch_sweeps_basic(op, a.c0, a.c1, b.c0, b.c1, rhs, p, lead, &flips, s));
-    }
-    PlanePair cur = (flips & 1) ? b : a, oth = (flips & 1) ? a : b;
-    int one = 0;
-    PFS_TRY(launch_sweeps_basic(op, cur.c0, cur.c1, oth.c0, oth.c1, rhs, p, 1, &one, s));
-    *last = oth;
-    *prev = cur;
+    *last = (flips & 1) ? b : a;
+    *prev = prev_written ? extra : ((flips & 1) ? a : b);     // else: the plane the last single sweep read
     return PFS_OK;
 }
 
-static SweepParams diffuse_params(int w, int h, float viscosity, float dt)
+int run_pressure(float *a, float *b, float *extra, const float *rhs, const SweepParams &p, int n, float **last,
+                 float **prev, cudaStream_t s)
+{
+    int flips = 0, prev_written = 0;
+    if (g_fuse_depth != 1 && fused_sweeps_supported(p.w, p.h))
+        PFS_TRY(launch_pressure_fused(a, b, rhs, p, n, g_fuse_depth, &flips, s, extra, &prev_written));
+    else
+        PFS_TRY(launch_pressure_basic(a, b, rhs, p, n, &flips, s));
+    *last = (flips & 1) ? b : a;
+    *prev = prev_written ? extra : ((flips & 1) ? a : b);
+    return PFS_OK;
+}
+
+SweepParams diffuse_params(int w, int h, float viscosity, float dt)
 {
     SweepParams p;
     p.w = w;
@@ -302,6 +292,8 @@ static SweepParams diffuse_params(int w, int h, float viscosity, float dt)
 
 using namespace pfs;
 
+static std::mutex g_graph_mutex;                        // guards the step-graph cache, g_prev_key and the capture streams: a second host
+                                                        // thread stepping another field must not see a half-built entry
 static void drop_step_graphs();                         // step-graph cache, defined with the step API below
 static void destroy_capture_streams();
 
@@ -317,8 +309,11 @@ extern "C" uint64_t pfs_kernel_launch_count(void) { return g_launches; }
 extern "C" int pfs_shutdown(void)
 {
     std::lock_guard<std::mutex> lock(g_mutex);
-    drop_step_graphs();
-    destroy_capture_streams();
+    {
+        std::lock_guard<std::mutex> glock(g_graph_mutex);
+        drop_step_graphs();
+        destroy_capture_streams();
+    }
     int cur = 0;
     bool have = (cudaGetDevice(&cur) == cudaSuccess);
     for (auto &kv : g_scratch) {
@@ -328,7 +323,6 @@ extern "C" int pfs_shutdown(void)
         }
     }
     g_scratch.clear();
-    packed_release_device_buffers();
     std::lock_guard<std::mutex> plock(g_phase_mutex);
     for (auto &sp : g_spans) {
         cudaEventDestroy(sp.a);
@@ -416,17 +410,22 @@ extern "C" int pfs_advect(const float *vp, float *vp_out, float dt, int vx, int 
     PFS_TRY(check_dims("pfs_advect", vx, vy, vz));
     PFS_TRY(check_ptr("pfs_advect", "vp", vp));
     PFS_TRY(check_ptr("pfs_advect", "vp_out", vp_out));
-    return launch_advect(vp, nullptr, nullptr, vp_out, dt, vx, vy, (cudaStream_t)stream);
+    return launch_advect(vp, 4, vp_out, 4, dt, vx, vy, (cudaStream_t)stream);
 }
 
 extern "C" int pfs_add_forces(float *vp, const float *forces, int vx, int vy, int vz, void *stream)
 {
-    // fluid.cpp:198-208: empty loop body; call site commented out (fluid.cpp:302).
-    (void)forces;
-    (void)stream;
-    PFS_TRY(check_dims("pfs_add_forces", vx, vy, vz));
-    PFS_TRY(check_ptr("pfs_add_forces", "vp", vp));
-    return PFS_OK;
+    // fluid.cpp:198-208: a loop over every cell and channel with an EMPTY body ("TODO: Perform force addition"); the
+    // call site is commented out (fluid.cpp:302).  forces == NULL keeps exactly that: nothing happens.  With a force
+    // field the loop gets the body its signature and comment announce (fluid.hpp:62-71, "force values for each pixel in
+    // the grid"): the velocity channels take the force, vp[..,0:2] += forces[..,0:2], one rounded addition each; the
+    // pressure and divergence channels are left alone.  Reference parity of that body is unpinned by construction.
+    const char *fn = "pfs_add_forces";
+    PFS_TRY(check_dims(fn, vx, vy, vz));
+    PFS_TRY(check_ptr(fn, "vp", vp));
+    if (forces == nullptr) return PFS_OK;
+    PFS_TRY(check_ptr(fn, "forces", forces));
+    return launch_add_forces(vp, 4, forces, vx, vy, (cudaStream_t)stream);
 }
 
 extern "C" int pfs_diffuse(float **vp, float **vp_out, float viscosity, float dt, int vx, int vy, int vz, int n_sweeps,
@@ -445,16 +444,16 @@ extern "C" int pfs_diffuse(float **vp, float **vp_out, float viscosity, float dt
     DeviceScratch *sc;
     PFS_TRY(get_scratch((size_t)vx * vy, &sc));
     float *in0 = *vp, *out0 = *vp_out;
-    PlanePair a{sc->plane(0), sc->plane(1)}, b{sc->plane(2), sc->plane(3)}, last, prev;
-    PFS_TRY(launch_unpack(in0, a.c0, a.c1, nullptr, nullptr, vx, vy, s));
-    PFS_TRY(run_sweeps(SWEEP_DIFFUSE, a, b, PlanePair{sc->plane(7), sc->plane(8)}, nullptr,
-                       diffuse_params(vx, vy, viscosity, dt), n_sweeps, &last, &prev, s));
+    float *last = nullptr, *prev = nullptr;
+    PFS_TRY(launch_unpack(in0, sc->uv(0), nullptr, nullptr, vx, vy, s));
+    PFS_TRY(run_diffuse(sc->uv(0), sc->uv(1), sc->uv(2), diffuse_params(vx, vy, viscosity, dt), n_sweeps, &last, &prev, s,
+                        nullptr));
     // Sweep k writes the original vp_out buffer when k is odd and the original vp buffer when k is
     // even (fluid.cpp:188-194).  Only channels 0,1 are ever written.
     float *buf_last = (n_sweeps & 1) ? out0 : in0;
     float *buf_prev = (n_sweeps & 1) ? in0 : out0;
-    PFS_TRY(launch_pack(buf_last, last.c0, last.c1, nullptr, nullptr, vx, vy, s));
-    if (n_sweeps >= 2) PFS_TRY(launch_pack(buf_prev, prev.c0, prev.c1, nullptr, nullptr, vx, vy, s));
+    PFS_TRY(launch_pack(buf_last, last, nullptr, nullptr, vx, vy, s));
+    if (n_sweeps >= 2) PFS_TRY(launch_pack(buf_prev, prev, nullptr, nullptr, vx, vy, s));
     *vp_out = buf_last;
     *vp = buf_prev;
     return PFS_OK;
@@ -476,18 +475,18 @@ extern "C" int pfs_compute_pressure(float **vp, float **vp_out, float dt, int vx
     DeviceScratch *sc;
     PFS_TRY(get_scratch((size_t)vx * vy, &sc));
     float *in0 = *vp, *out0 = *vp_out;
-    float *u = sc->plane(0), *v = sc->plane(1), *div = sc->plane(6);
-    PlanePair a{sc->plane(4), nullptr}, b{sc->plane(5), nullptr}, last, prev;
-    PFS_TRY(launch_unpack(in0, u, v, nullptr, nullptr, vx, vy, s));
-    PFS_TRY(launch_divergence(u, v, div, in0, a.c0, dt, vx, vy, s));
+    float *uv = sc->uv(0), *div = sc->div();
+    float *last = nullptr, *prev = nullptr;
+    PFS_TRY(launch_unpack(in0, uv, nullptr, nullptr, vx, vy, s));
+    PFS_TRY(launch_divergence(uv, div, in0, sc->p(0), dt, vx, vy, s));
     SweepParams p{vx, vy, 1.0f, 4.0f};
-    PFS_TRY(run_sweeps(SWEEP_PRESSURE, a, b, PlanePair{sc->plane(9), nullptr}, div, p, n_sweeps, &last, &prev, s));
+    PFS_TRY(run_pressure(sc->p(0), sc->p(1), sc->p(2), div, p, n_sweeps, &last, &prev, s));
     float *buf_last = (n_sweeps & 1) ? out0 : in0;
     float *buf_prev = (n_sweeps & 1) ? in0 : out0;
     // channel 3 of both buffers <- divergence (fluid.cpp:235-236); channel 2 <- the iterate each
     // buffer was last written with.  With one sweep the input buffer keeps its pressure.
-    PFS_TRY(launch_pack(buf_last, nullptr, nullptr, last.c0, div, vx, vy, s));
-    PFS_TRY(launch_pack(buf_prev, nullptr, nullptr, (n_sweeps >= 2) ? prev.c0 : nullptr, div, vx, vy, s));
+    PFS_TRY(launch_pack(buf_last, nullptr, last, div, vx, vy, s));
+    PFS_TRY(launch_pack(buf_prev, nullptr, (n_sweeps >= 2) ? prev : nullptr, div, vx, vy, s));
     *vp_out = buf_last;
     *vp = buf_prev;
     return PFS_OK;
@@ -523,11 +522,11 @@ extern "C" int pfs_compute_pressure_adaptive(float **vp, float **vp_out, float d
     const size_t cells = (size_t)vx * vy;
     PFS_TRY(get_scratch(cells, &sc));
     float *in0 = *vp, *out0 = *vp_out;
-    float *u = sc->plane(0), *v = sc->plane(1), *div = sc->plane(6);
-    PlanePair cur{sc->plane(4), nullptr}, oth{sc->plane(5), nullptr}, last = cur, prev = oth;
-    const PlanePair extra{sc->plane(9), nullptr};
-    PFS_TRY(launch_unpack(in0, u, v, nullptr, nullptr, vx, vy, s));
-    PFS_TRY(launch_divergence(u, v, div, in0, cur.c0, dt, vx, vy, s));
+    float *uv = sc->uv(0), *div = sc->div();
+    float *cur = sc->p(0), *oth = sc->p(1), *last = cur, *prev = oth;
+    float *const extra = sc->p(2);
+    PFS_TRY(launch_unpack(in0, uv, nullptr, nullptr, vx, vy, s));
+    PFS_TRY(launch_divergence(uv, div, in0, cur, dt, vx, vy, s));
     SweepParams p{vx, vy, 1.0f, 4.0f};
     constexpr int kBlocks = 1184;
     if (!sc->norm_dev) PFS_CUDA(cudaMalloc((void **)&sc->norm_dev, (4 * (size_t)kBlocks + 4) * sizeof(double)));
@@ -538,10 +537,10 @@ extern "C" int pfs_compute_pressure_adaptive(float **vp, float **vp_out, float d
     while (done < max_sweeps) {
         int n = std::min(check_every, max_sweeps - done);
         if (max_sweeps - done - n == 1) n += 1;             // never leave a batch of one sweep (it keeps no p_{N-1})
-        rc = run_sweeps(SWEEP_PRESSURE, cur, oth, extra, div, p, n, &last, &prev, s);
+        rc = run_pressure(cur, oth, extra, div, p, n, &last, &prev, s);
         if (rc != PFS_OK) break;
         done += n;
-        rc = launch_plane_diff_norms(last.c0, prev.c0, cells, scratch, kBlocks, scratch + 4 * (size_t)kBlocks, s);
+        rc = launch_plane_diff_norms(last, prev, cells, scratch, kBlocks, scratch + 4 * (size_t)kBlocks, s);
         if (rc != PFS_OK) break;
         cudaError_t e = cudaMemcpyAsync(host, scratch + 4 * (size_t)kBlocks, 4 * sizeof(double), cudaMemcpyDeviceToHost, s);
         if (e == cudaSuccess) e = cudaStreamSynchronize(s);
@@ -554,15 +553,15 @@ extern "C" int pfs_compute_pressure_adaptive(float **vp, float **vp_out, float d
         if (done < max_sweeps) {
             // next batch starts from iterate `done`; the other plane of the ping-pong pair is free again
             // (p_{done-1} is only needed if this was the final batch)
-            oth = (last.c0 == sc->plane(4)) ? PlanePair{sc->plane(5), nullptr} : PlanePair{sc->plane(4), nullptr};
+            oth = (last == sc->p(0)) ? sc->p(1) : sc->p(0);
             cur = last;
         }
     }
     if (rc != PFS_OK) return rc;
     float *buf_last = (done & 1) ? out0 : in0;
     float *buf_prev = (done & 1) ? in0 : out0;
-    PFS_TRY(launch_pack(buf_last, nullptr, nullptr, last.c0, div, vx, vy, s));
-    PFS_TRY(launch_pack(buf_prev, nullptr, nullptr, prev.c0, div, vx, vy, s));
+    PFS_TRY(launch_pack(buf_last, nullptr, last, div, vx, vy, s));
+    PFS_TRY(launch_pack(buf_prev, nullptr, prev, div, vx, vy, s));
     *vp_out = buf_last;
     *vp = buf_prev;
     if (sweeps_out) *sweeps_out = done;
@@ -589,7 +588,7 @@ extern "C" int pfs_advect_color(const float *image, float *itmp, const float *vp
     PFS_TRY(check_ptr(fn, "image", image));
     PFS_TRY(check_ptr(fn, "itmp", itmp));
     PFS_TRY(check_ptr(fn, "vp", vp));
-    return launch_advect_color(image, itmp, vp, dt, ix, iy, vx, vy, (cudaStream_t)stream);
+    return launch_advect_color(image, itmp, vp, 4, dt, ix, iy, vx, vy, (cudaStream_t)stream);
 }
 
 // =============================================================================================
@@ -601,53 +600,54 @@ extern "C" int pfs_advect_color(const float *image, float *itmp, const float *vp
 // advect and the diffusion sweeps already run on vp.
 static int enqueue_fluid_step(DeviceScratch *sc, float *X, float *Y, float dt, float viscosity, int vx, int vy,
                               int n_diffuse, int n_pressure, float sigma, unsigned long long seed, unsigned step,
-                              cudaStream_t s, cudaEvent_t wait_tmp)
+                              const float *forces, cudaStream_t s, cudaEvent_t wait_tmp)
 {
-    PlanePair ua{sc->plane(0), sc->plane(1)}, ub{sc->plane(2), sc->plane(3)}, d_last, d_prev;
-    PlanePair pa{sc->plane(4), nullptr}, pb{sc->plane(5), nullptr}, p_last, p_prev;
-    float *div = sc->plane(6);
+    float *d_last = nullptr, *d_prev = nullptr, *p_last = nullptr, *p_prev = nullptr;
+    float *div = sc->div();
 
-    // advect(vp -> tmp)  (fluid.cpp:299): X.uv gathered, result kept planar (iterate 0 of diffusion)
+    // advect(vp -> tmp)  (fluid.cpp:299): X.uv gathered, result kept in a (u,v) plane (iterate 0 of diffusion)
     {
         PhaseScope ph(PFS_PHASE_ADVECT, s);
-        PFS_TRY(launch_advect(X, ua.c0, ua.c1, nullptr, dt, vx, vy, s));
+        PFS_TRY(launch_advect(X, 4, sc->uv(0), 2, dt, vx, vy, s));
     }
-    // diffuse(tmp -> vp)  (fluid.cpp:300)
+    // diffuse(tmp -> vp)  (fluid.cpp:300); addForces slot (fluid.cpp:302, commented out in the reference): the external
+    // force, if any, goes to the field struct `vp` points at after diffuse, i.e. diffusion iterate n_diffuse -- added as
+    // the last fused pass stores it
     {
         PhaseScope ph(PFS_PHASE_DIFFUSE, s);
-        PFS_TRY(run_sweeps(SWEEP_DIFFUSE, ua, ub, PlanePair{sc->plane(7), sc->plane(8)}, nullptr,
-                           diffuse_params(vx, vy, viscosity, dt), n_diffuse, &d_last, &d_prev, s));
+        ForceField ff{forces, 0, vy};
+        PFS_TRY(run_diffuse(sc->uv(0), sc->uv(1), sc->uv(2), diffuse_params(vx, vy, viscosity, dt), n_diffuse, &d_last,
+                            &d_prev, s, forces ? &ff : nullptr));
     }
     // After diffuse the struct `vp` points at the buffer written last: sweep k writes X for odd k,
     // Y for even k (sweep 1 writes vp_out = the original vp buffer X).
     float *Bv = (n_diffuse & 1) ? X : Y;     // holds iterate n_diffuse in ch0,1; its ch2 is the warm start
     float *Bo = (n_diffuse & 1) ? Y : X;     // holds iterate n_diffuse-1 in ch0,1
-    // addForces slot (fluid.cpp:302, commented out in the reference): optional stochastic forcing of the
-    // field struct `vp` points at after diffuse, i.e. diffusion iterate n_diffuse
+    // optional stochastic forcing at the same slot
     if (sigma != 0.0f) {
         PhaseScope ph(PFS_PHASE_DIFFUSE, s);
-        PFS_TRY(launch_stochastic_force(d_last.c0, d_last.c1, 1, sigma, seed, step, vx, vy, 0, 0, s));
+        PFS_TRY(launch_stochastic_force(d_last, d_last + 1, 2, sigma, seed, step, vx, vy, 0, 0, s));
     }
     // computePressure(vp -> tmp)  (fluid.cpp:303): divergence of iterate n_diffuse, p_0 = Bv.ch2
     if (wait_tmp) PFS_CUDA(cudaStreamWaitEvent(s, wait_tmp, 0));
     {
         PhaseScope ph(PFS_PHASE_DIVERGENCE, s);
-        PFS_TRY(launch_divergence(d_last.c0, d_last.c1, div, Bv, pa.c0, dt, vx, vy, s));
+        PFS_TRY(launch_divergence(d_last, div, Bv, sc->p(0), dt, vx, vy, s));
     }
     {
         PhaseScope ph(PFS_PHASE_PRESSURE, s);
         SweepParams pp{vx, vy, 1.0f, 4.0f};
-        PFS_TRY(run_sweeps(SWEEP_PRESSURE, pa, pb, PlanePair{sc->plane(9), nullptr}, div, pp, n_pressure, &p_last, &p_prev, s));
+        PFS_TRY(run_pressure(sc->p(0), sc->p(1), sc->p(2), div, pp, n_pressure, &p_last, &p_prev, s));
     }
     // Pressure sweep k writes Bo for odd k, Bv for even k; struct `tmp` ends on the buffer with p_N.
     float *Bp = (n_pressure & 1) ? Bo : Bv;
     float *Bq = (n_pressure & 1) ? Bv : Bo;
     // subtractPressureGradient(tmp -> vp)  (fluid.cpp:304) reads ch0,1 of the buffer holding p_N,
     // which carries diffusion iterate n_diffuse if that buffer is Bv, else iterate n_diffuse-1.
-    const PlanePair &uv_p = (Bp == Bv) ? d_last : d_prev;
+    const float *uv_p = (Bp == Bv) ? d_last : d_prev;
     {
         PhaseScope ph(PFS_PHASE_PROJECT, s);
-        PFS_TRY(launch_project_pack(uv_p.c0, uv_p.c1, p_last.c0, p_prev.c0, div, Bq, Bp, dt, vx, vy, s));
+        PFS_TRY(launch_project_pack(uv_p, p_last, p_prev, div, Bq, Bp, dt, vx, vy, s));
     }
     return PFS_OK;
 }
@@ -661,13 +661,13 @@ static int enqueue_fluid_step(DeviceScratch *sc, float *X, float *Y, float dt, f
 // ---------------------------------------------------------------------------------------------
 struct StepKey {
     int dev = -1;
-    const float *X = nullptr, *Y = nullptr, *planes = nullptr;
+    const float *X = nullptr, *Y = nullptr, *planes = nullptr, *forces = nullptr;
     size_t plane_cells = 0;
     int vx = 0, vy = 0, nd = 0, np = 0, fuse = 0;
     unsigned dt_bits = 0, visc_bits = 0;
     bool operator==(const StepKey &o) const
     {
-        return dev == o.dev && X == o.X && Y == o.Y && planes == o.planes && plane_cells == o.plane_cells && vx == o.vx && vy == o.vy && nd == o.nd &&
+        return dev == o.dev && X == o.X && Y == o.Y && planes == o.planes && forces == o.forces && plane_cells == o.plane_cells && vx == o.vx && vy == o.vy && nd == o.nd &&
                np == o.np && fuse == o.fuse && dt_bits == o.dt_bits && visc_bits == o.visc_bits;
     }
 };
@@ -676,8 +676,6 @@ struct CachedStep {
     cudaGraphExec_t exec = nullptr;
     unsigned long long launches = 0, passes = 0;
 };
-static std::mutex g_graph_mutex;                 // guards the cache, g_prev_key and the capture streams: a second host thread
-                                                 // stepping another field must not see a half-built entry (capture included)
 static std::vector<CachedStep> g_step_graphs;
 static StepKey g_prev_key;
 static std::map<int, cudaStream_t> g_capture_streams;
@@ -716,7 +714,7 @@ static unsigned float_bits(float f)
 
 static int simulate_fluid_step_impl(const char *fn, float **vp, float **tmp, float dt, float viscosity, int vx, int vy,
                                     int vz, int n_diffuse, int n_pressure, float sigma, unsigned long long seed,
-                                    unsigned step, void *stream, cudaEvent_t wait_tmp = nullptr)
+                                    unsigned step, void *stream, cudaEvent_t wait_tmp = nullptr, const float *forces = nullptr)
 {
     PFS_TRY(check_dims(fn, vx, vy, vz));
     PFS_TRY(check_sweeps(fn, n_diffuse));
@@ -731,6 +729,7 @@ static int simulate_fluid_step_impl(const char *fn, float **vp, float **tmp, flo
         set_error("%s: vp and tmp must be distinct buffers", fn);
         return PFS_EINVAL;
     }
+    if (forces != nullptr) PFS_TRY(check_ptr(fn, "forces", forces));
     cudaStream_t s = (cudaStream_t)stream;
     DeviceScratch *sc;
     PFS_TRY(get_scratch((size_t)vx * vy, &sc));
@@ -752,7 +751,7 @@ static int simulate_fluid_step_impl(const char *fn, float **vp, float **tmp, flo
         std::lock_guard<std::mutex> glock(g_graph_mutex);
         StepKey key;
         PFS_CUDA(cudaGetDevice(&key.dev));
-        key.X = X; key.Y = Y; key.planes = sc->planes; key.plane_cells = sc->plane_cells;
+        key.X = X; key.Y = Y; key.planes = sc->planes; key.plane_cells = sc->plane_cells; key.forces = forces;
         key.vx = vx; key.vy = vy; key.nd = n_diffuse; key.np = n_pressure; key.fuse = g_fuse_depth;
         key.dt_bits = float_bits(dt); key.visc_bits = float_bits(viscosity);
         for (auto &c : g_step_graphs) {
@@ -778,7 +777,7 @@ static int simulate_fluid_step_impl(const char *fn, float **vp, float **tmp, flo
             bool ok = cudaStreamBeginCapture(cs, cudaStreamCaptureModeRelaxed) == cudaSuccess;
             if (ok) {
                 const int rc = enqueue_fluid_step(sc, X, Y, dt, viscosity, vx, vy, n_diffuse, n_pressure, 0.0f, 0ull, 0u,
-                                                  cs, nullptr);
+                                                  forces, cs, nullptr);
                 ok = (cudaStreamEndCapture(cs, &graph) == cudaSuccess) && rc == PFS_OK && graph != nullptr;
             }
             if (ok) ok = cudaGraphInstantiate(&exec, graph, 0) == cudaSuccess;
@@ -801,7 +800,7 @@ static int simulate_fluid_step_impl(const char *fn, float **vp, float **tmp, flo
         }
         g_prev_key = key;
     }
-    PFS_TRY(enqueue_fluid_step(sc, X, Y, dt, viscosity, vx, vy, n_diffuse, n_pressure, sigma, seed, step, s, wait_tmp));
+    PFS_TRY(enqueue_fluid_step(sc, X, Y, dt, viscosity, vx, vy, n_diffuse, n_pressure, sigma, seed, step, forces, s, wait_tmp));
     *vp = Bq;
     *tmp = Bp;
     return PFS_OK;
@@ -820,6 +819,13 @@ extern "C" int pfs_simulate_fluid_step_stochastic(float **vp, float **tmp, float
 {
     return simulate_fluid_step_impl("pfs_simulate_fluid_step_stochastic", vp, tmp, dt, viscosity, vx, vy, vz, n_diffuse,
                                     n_pressure, sigma, seed, step, stream);
+}
+
+extern "C" int pfs_simulate_fluid_step_forced(float **vp, float **tmp, float dt, float viscosity, int vx, int vy, int vz,
+                                              int n_diffuse, int n_pressure, const float *forces, void *stream)
+{
+    return simulate_fluid_step_impl("pfs_simulate_fluid_step_forced", vp, tmp, dt, viscosity, vx, vy, vz, n_diffuse,
+                                    n_pressure, 0.0f, 0ull, 0u, stream, nullptr, forces);
 }
 
 extern "C" int pfs_add_forces_stochastic(float *vp, float sigma, uint64_t seed, uint32_t step, int vx, int vy, int vz,

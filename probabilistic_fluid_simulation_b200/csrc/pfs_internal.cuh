@@ -161,10 +161,12 @@ __device__ __forceinline__ float bilerp(const Bilinear &b, float f00, float f10,
 }
 
 // ---------------------------------------------------------------------------------------------
-// host-side launch wrappers (kernels_basic.cu, sweeps_fused.cu)
+// host-side launch wrappers (kernels_basic.cu, sweeps_fused.cu, sweeps_packed.cu)
+//
+// Internal layout: the velocity lives in "(u,v) planes" -- row-major, (u, v) interleaved, 8 bytes per cell,
+// 2*w floats per row -- because the diffusion sweeps advance u and v together in packed-FP32 register pairs; pressure
+// and divergence are scalar planes of w floats per row.  The caller-visible buffers stay interleaved [u, v, p, div].
 // ---------------------------------------------------------------------------------------------
-
-enum SweepOp { SWEEP_PRESSURE = 0, SWEEP_DIFFUSE = 1 };
 
 struct SweepParams {
     int w, h;
@@ -176,57 +178,74 @@ struct SweepParams {
     int wrap = 1;
 };
 
-// interleaved (AoS) <-> planar (SoA) movers.  Null plane pointers are skipped.
-int launch_unpack(const float *aos, float *c0, float *c1, float *c2, float *c3, int w, int h, cudaStream_t s);
-int launch_pack(float *aos, const float *c0, const float *c1, const float *c2, const float *c3, int w, int h,
-                cudaStream_t s);
+// External force of the addForces slot (fluid.cpp:198-208, :302): an interleaved [rows][w][4] field like the velocity
+// buffers; channels 0,1 are added to (u, v), channels 2,3 are ignored.  Row 0 of the field is row `skip_rows` of the
+// plane rows a pass writes (a slab pass also recomputes rows outside its band, which get no force here).
+struct ForceField {
+    const float *aos;
+    int skip_rows, rows;
+};
 
-// advect (fluid.cpp:24-70).  Source is always the interleaved field; destination is either two
-// planes (u_out, v_out) or channels 0,1 of an interleaved buffer (aos_out), whichever is non-null.
-int launch_advect(const float *vp_aos, float *u_out, float *v_out, float *aos_out, float dt, int w, int h,
-                  cudaStream_t s);
+// ---- shared by the stateless entry points (pfs_api.cu), the persistent contexts (pfs_ctx.cu) and the slabs (slab.cu) ----
+int check_dims(const char *fn, int x, int y, int z);
+int check_ptr(const char *fn, const char *name, const void *p);
+int check_sweeps(const char *fn, int n);
+SweepParams diffuse_params(int w, int h, float viscosity, float dt);     // alpha, beta as fluid.cpp:144-145 forms them
+int fuse_depth();                                                         // pfs_set_fuse_depth (0 = default)
+bool phase_timing_on();
+// n sweeps from iterate 0 in plane a, ping-ponging a <-> b, iterate n-1 into `extra` when a fused pass can store it;
+// *last = plane of iterate n, *prev = plane of iterate n-1 (the one the reference leaves in its other buffer)
+int run_diffuse(float *a_uv, float *b_uv, float *extra_uv, const SweepParams &p, int n, float **last, float **prev,
+                cudaStream_t s, const ForceField *force);
+int run_pressure(float *a, float *b, float *extra, const float *rhs, const SweepParams &p, int n, float **last,
+                 float **prev, cudaStream_t s);
 
-// n sweeps of the 5-point update on planes, one sweep per launch, ping-ponging a<->b.
-// pressure: planes a0/b0 only, rhs = divergence plane.  diffuse: (a0,a1) <-> (b0,b1), rhs unused.
-// *flips receives the number of a<->b hops taken (= launches): the result is in b* if it is odd.
-int launch_sweeps_basic(SweepOp op, float *a0, float *a1, float *b0, float *b1, const float *rhs,
-                        const SweepParams &p, int n, int *flips, cudaStream_t s);
+// interleaved [u,v,p,div] <-> (u,v) plane + scalar planes.  Null pointers are skipped (channels left alone).
+int launch_unpack(const float *aos, float *uv, float *p, float *div, int w, int h, cudaStream_t s);
+int launch_pack(float *aos, const float *uv, const float *p, const float *div, int w, int h, cudaStream_t s);
 
-// Temporally blocked version: up to `depth` sweeps fused per launch.  Same contract and bit-identical
-// results.  Returns PFS_EINVAL if the shape is not supported (caller then uses the basic path).
-// prev0/prev1 (optional): the pass that reaches sweep n also stores iterate n-1 there (the reference keeps it
-// in its other buffer); *prev_written says whether it did (not when the last hop is a single plain sweep --
-// iterate n-1 is then simply the plane set that sweep read).
-int launch_sweeps_fused(SweepOp op, float *a0, float *a1, float *b0, float *b1, const float *rhs,
-                        const SweepParams &p, int n, int depth, int *flips, cudaStream_t s, float *prev0 = nullptr,
-                        float *prev1 = nullptr, int *prev_written = nullptr);
+// advect (fluid.cpp:24-70).  src: the field to advect AND to gather from, cells `src_stride` floats apart with (u,v) first
+// (4: an interleaved buffer, 2: a (u,v) plane); dst likewise (2: a (u,v) plane, 4: channels 0,1 of an interleaved buffer).
+int launch_advect(const float *src, int src_stride, float *dst, int dst_stride, float dt, int w, int h, cudaStream_t s);
+
+// n one-sweep launches, ping-ponging a <-> b; *flips = n.  Reference point and remainder path of the fused passes.
+int launch_pressure_basic(float *a, float *b, const float *rhs, const SweepParams &p, int n, int *flips, cudaStream_t s);
+int launch_diffuse_basic(float *a_uv, float *b_uv, const SweepParams &p, int n, int *flips, cudaStream_t s);
+
+// Temporally blocked pressure sweeps: up to `depth` sweeps fused per launch, bit-identical results.
+// *flips = a<->b hops taken (the result is in b if it is odd).  prev (optional): the pass that reaches sweep n also
+// stores iterate n-1 there (the reference keeps it in its other buffer); *prev_written says whether it did (not when the
+// last hop is a single plain sweep -- iterate n-1 is then simply the plane that sweep read).
+int launch_pressure_fused(float *a, float *b, const float *rhs, const SweepParams &p, int n, int depth, int *flips,
+                          cudaStream_t s, float *prev = nullptr, int *prev_written = nullptr);
 bool fused_sweeps_supported(int w, int h);
 int pick_chunk_rows(int h, int columns_of_items, long long slots, int forced_rows);   // sweeps_packed.cu
 
-// Packed-FP32 (f32x2) temporally blocked diffusion: u and v advanced together (sweeps_packed.cu).
+// Packed-FP32 (f32x2) temporally blocked diffusion on (u,v) planes (sweeps_packed.cu); same contract.  `force`: added to
+// iterate n as the last pass stores it.
 bool packed_diffuse_supported(const SweepParams &p);
-int launch_diffuse_packed(float *a0, float *a1, float *b0, float *b1, const SweepParams &p, int n, int depth,
-                          int *flips, cudaStream_t s, float *prev0 = nullptr, float *prev1 = nullptr,
-                          int *prev_written = nullptr);
-void packed_release_device_buffers();
-int default_diffuse_depth();
-int packed_division_ops(float beta);      // sweeps fused per launch when the caller does not say (PFS_DIFFUSE_DEPTH)
-// Packed-FP32 temporally blocked pressure sweeps: two strips of the plane per warp (sweeps_packed.cu).
-bool packed_pressure_supported(const SweepParams &p);
-int launch_pressure_packed(float *a, float *b, const float *rhs, const SweepParams &p, int n, int depth, int *flips,
-                           cudaStream_t s);
+int launch_diffuse_packed(float *a_uv, float *b_uv, const SweepParams &p, int n, int depth, int *flips, cudaStream_t s,
+                          float *prev_uv = nullptr, int *prev_written = nullptr, const ForceField *force = nullptr);
+int default_diffuse_depth();              // sweeps fused per launch when the caller does not say (PFS_DIFFUSE_DEPTH)
+int packed_division_ops(float beta);
 
-// divergence (fluid.cpp:221-237) of planes (u, v) into plane div; optionally also extracts
-// channel 2 of an interleaved buffer into plane p0 (the pressure warm start) in the same pass.
-int launch_divergence(const float *u, const float *v, float *div, const float *p0_src_aos, float *p0,
-                      float dt, int w, int h, cudaStream_t s, int y_base = 0, int wrap = 1);
+// dst[cell*stride + {0,1}] += force[cell*4 + {0,1}] over `rows` rows of w cells (both pointers at their first row).
+int launch_add_forces(float *dst, int dst_stride, const float *force_aos, int w, int rows, cudaStream_t s);
+
+// divergence (fluid.cpp:221-237) of a (u,v) plane into plane div; optionally also extracts channel 2 of an
+// interleaved buffer into plane p0 (the pressure warm start) in the same pass.
+int launch_divergence(const float *uv, float *div, const float *p0_src_aos, float *p0, float dt, int w, int h,
+                      cudaStream_t s, int y_base = 0, int wrap = 1);
 
 // End of simulate_fluid_step: subtract the gradient of p_n from (u, v) (fluid.cpp:269-296) and write
 // BOTH interleaved post-state buffers with full-cell stores:
 //   out_q = [u - gx, v - gy, p_prev, div]      out_p = [u, v, p_n, div]
-int launch_project_pack(const float *u, const float *v, const float *p_n, const float *p_prev,
-                        const float *div, float *out_q, float *out_p, float dt, int w, int h, cudaStream_t s,
-                        int y_base = 0, int wrap = 1);
+int launch_project_pack(const float *uv, const float *p_n, const float *p_prev, const float *div, float *out_q,
+                        float *out_p, float dt, int w, int h, cudaStream_t s, int y_base = 0, int wrap = 1);
+// The same subtraction for state that stays in planes (pfs_ctx): uv_out <- uv - grad(p_n)*dt/2.  uv_out has no halo rows
+// of its own concern: it is indexed like uv.  vmax_out (optional): atomic max of |v| of the result (bounds the next gathers).
+int launch_project_uv(const float *uv, const float *p_n, float *uv_out, float dt, int w, int h, cudaStream_t s,
+                      int y_base = 0, int wrap = 1, float *vmax_out = nullptr);
 
 // subtractPressureGradient as a stand-alone operator on interleaved buffers (writes ch0,1 of out).
 int launch_subtract_gradient_aos(const float *vp_aos, float *out_aos, float dt, int w, int h, cudaStream_t s);
@@ -241,12 +260,13 @@ int launch_plane_diff_norms(const float *a, const float *b, size_t cells, double
 int launch_step_norms(const float *vp_aos, const float *tmp_aos, size_t cells, double *partials, int max_blocks,
                       double *out4, cudaStream_t s);
 
-// Opt-in Gaussian forcing of (u, v) at the addForces slot (kernels_basic.cu).  stride 1 = planes, 4 = interleaved.
+// Opt-in Gaussian forcing of (u, v) at the addForces slot (kernels_basic.cu).  stride 2 = a (u,v) plane, 4 = interleaved.
 int launch_stochastic_force(float *u, float *v, int stride, float sigma, unsigned long long seed, unsigned step, int w,
                             int h, int row0, int y_base, cudaStream_t s);
 
-// advect_color (fluid.cpp:72-127) on interleaved buffers.
-int launch_advect_color(const float *image, float *out, const float *vp_aos, float dt, int iw, int ih, int vw,
+// advect_color (fluid.cpp:72-127) on interleaved image buffers; the velocity is point-sampled from cells `vel_stride`
+// floats apart (4: interleaved buffer, 2: (u,v) plane).
+int launch_advect_color(const float *image, float *out, const float *vel, int vel_stride, float dt, int iw, int ih, int vw,
                         int vh, cudaStream_t s);
 
 }  // namespace pfs

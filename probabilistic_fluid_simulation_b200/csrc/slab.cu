@@ -38,7 +38,9 @@ namespace pfs {
 
 constexpr int MAX_HALO = 32;   // halo rows per side: one exchange feeds MAX_HALO / depth fused passes
 constexpr int MIN_HALO = 8;    // >= the deepest fused pass
-constexpr int N_SLAB_PLANES = 10;   // u,v x2 | p x2 | div | iterate n-1 of the last pass: u,v | p
+constexpr int N_SLAB_PLANES = 10;   // units of plane_floats: (u,v) ping [0,1] | (u,v) pong [2,3] | p x2 [4][5] | div [6] |
+                                    // iterate n-1 of the last pass: (u,v) [7,8] | p [9].  A (u,v) plane is two units wide.
+constexpr int UV_A = 0, UV_B = 2, UV_X = 7, P_A = 4, P_B = 5, P_X = 9, DIV = 6;
 constexpr int P2P_GATHER_ROWS = 64; // capacity (rows per side) of the peer-written gather halos; deeper gathers go through NCCL
 constexpr int P2P_FLAG_INTS = 16;
 
@@ -251,7 +253,7 @@ __device__ __forceinline__ const float4 *source_row(const RowSource &S, int grow
 // advect (fluid.cpp:24-70) with GLOBAL indices: this rank produces rows [row0, row0+rows) of the gh-row
 // grid from the interleaved field (u,v in the first 8 bytes of a cell, as in the single-GPU kernel).
 __global__ void __launch_bounds__(256)
-    advect_slab_kernel(const RowSource S, float *__restrict__ u_out, float *__restrict__ v_out, float dt, int w, int gh,
+    advect_slab_kernel(const RowSource S, float2 *__restrict__ uv_out, float dt, int w, int gh,
                        int row0, int rows, int y_base, int *overflow, float *vmax_out)
 {
     const int i = blockIdx.x * 64 + threadIdx.x, jl = blockIdx.y * 4 + threadIdx.y;
@@ -301,9 +303,7 @@ __global__ void __launch_bounds__(256)
     const float2 f10 = __ldg(reinterpret_cast<const float2 *>(r0 + b.i1));
     const float2 f01 = __ldg(reinterpret_cast<const float2 *>(r1 + b.i0));
     const float2 f11 = __ldg(reinterpret_cast<const float2 *>(r1 + b.i1));
-    const size_t o = (size_t)(y_base + jl) * w + i;
-    u_out[o] = bilerp(b, f00.x, f10.x, f01.x, f11.x);
-    v_out[o] = bilerp(b, f00.y, f10.y, f01.y, f11.y);
+    uv_out[(size_t)(y_base + jl) * w + i] = make_float2(bilerp(b, f00.x, f10.x, f01.x, f11.x), bilerp(b, f00.y, f10.y, f01.y, f11.y));
 }
 
 // advect_color (fluid.cpp:72-127) with GLOBAL indices: image rows [irow0, irow0+irows) of the ih-row
@@ -503,32 +503,32 @@ int ring_exchange(const std::vector<pfs_slab *> &local, const std::vector<std::v
     return PFS_OK;
 }
 
-// halo exchange of `t` rows of the given planes (same plane indices on every slab)
-int exchange_planes(const std::vector<pfs_slab *> &local, const std::vector<std::vector<float *>> &planes, int t)
+// halo exchange of `t` rows of the given planes (same plane units on every slab); `rf` = floats per plane row
+// (gw for a scalar plane, 2*gw for a (u,v) plane)
+int exchange_planes(const std::vector<pfs_slab *> &local, const std::vector<std::vector<float *>> &planes, int t, size_t rf)
 {
     if (local.size() == 1 && local[0]->p2p && local[0]->gw % 4 == 0 && planes[0].size() <= 3) {
         pfs_slab *s = local[0];
         Guard g(s->device);
         PushArgs A;
         A.nseg = 0;
-        const size_t gw = (size_t)s->gw;
         for (float *p : planes[0]) {
-            const size_t k = (size_t)(p - s->planes) / s->plane_floats;           // plane index: same on every rank
+            const size_t k = (size_t)(p - s->planes) / s->plane_floats;           // plane unit: same on every rank
             PushSeg &sg = A.seg[A.nseg++];
-            sg.src_up = reinterpret_cast<const float4 *>(p + (size_t)s->halo * gw);
-            sg.src_down = reinterpret_cast<const float4 *>(p + (size_t)(s->halo + s->rows - t) * gw);
+            sg.src_up = reinterpret_cast<const float4 *>(p + (size_t)s->halo * rf);
+            sg.src_down = reinterpret_cast<const float4 *>(p + (size_t)(s->halo + s->rows - t) * rf);
             sg.dst_up = reinterpret_cast<float4 *>(s->link_up.planes + k * s->link_up.plane_floats +
-                                                   (size_t)(s->halo + s->link_up.rows) * gw);
+                                                   (size_t)(s->halo + s->link_up.rows) * rf);
             sg.dst_down = reinterpret_cast<float4 *>(s->link_down.planes + k * s->link_down.plane_floats +
-                                                     (size_t)(s->halo - t) * gw);
-            sg.n16 = (unsigned long long)t * gw / 4;
+                                                     (size_t)(s->halo - t) * rf);
+            sg.n16 = (unsigned long long)t * rf / 4;
         }
         return launch_halo_push(s, A);
     }
     std::vector<std::vector<Segment>> segs(local.size());
     for (size_t k = 0; k < local.size(); k++) {
         pfs_slab *s = local[k];
-        const size_t row = (size_t)s->gw * sizeof(float);
+        const size_t row = rf * sizeof(float);
         for (float *p : planes[k]) {
             char *b = reinterpret_cast<char *>(p);
             Segment sg;
@@ -1141,7 +1141,7 @@ extern "C" int pfs_slab_step_norms(pfs_slab *const *slabs, int n_local, float *c
 // just before the only kernel that overwrites the caller's buffers -- when it has long been written.  A raised flag
 // (never seen outside the tests that provoke it) discards the step's scratch results and reruns it with the exact bound.
 static int slab_fluid_step(pfs_slab *const *slabs, int n_local, float **vp, float **tmp, float dt, float viscosity,
-                           int n_diffuse, int n_pressure, void *const *streams, bool exact_bound)
+                           int n_diffuse, int n_pressure, void *const *streams, bool exact_bound, const float *const *forces)
 {
     const char *fn = "pfs_slab_simulate_fluid_step";
     std::vector<pfs_slab *> L;
@@ -1227,7 +1227,7 @@ static int slab_fluid_step(pfs_slab *const *slabs, int n_local, float **vp, floa
             Guard g(s->device);
             if (speculate) PFS_CUDA(cudaMemsetAsync(s->d_scalars + 4, 0, 3 * sizeof(float), s->stream));
             dim3 block(64, 4), grid((gw + 63) / 64, (s->rows + 3) / 4);
-            PFS_LAUNCH(advect_slab_kernel, grid, block, 0, s->stream, src[k], s->plane(0), s->plane(1), dt, gw, gh,
+            PFS_LAUNCH(advect_slab_kernel, grid, block, 0, s->stream, src[k], reinterpret_cast<float2 *>(s->plane(UV_A)), dt, gw, gh,
                        s->row0, s->rows, s->halo, reinterpret_cast<int *>(s->d_scalars + (speculate ? 6 : 2)),
                        speculate ? s->d_scalars + 4 : nullptr);
             if (speculate) {
@@ -1250,26 +1250,27 @@ static int slab_fluid_step(pfs_slab *const *slabs, int n_local, float **vp, floa
     // every slab: an exchange makes it `halo`; a pass of depth t needs t of them and -- by also recomputing the
     // e = valid-t rows just outside the band -- leaves e valid rows on its result.
     const int halo = L[0]->halo;
-    auto run_sweeps = [&](SweepOp op, int pa0, int pa1, int pb0, int pb1, int px0, int px1, const SweepParams &proto,
-                          int count, int *last0, int *last1, int *prev0, int *prev1, int *valid_out) -> int {
-        int cur0 = pa0, cur1 = pa1, oth0 = pb0, oth1 = pb1;
+    // `diffusion`: (u,v) planes through the packed kernel; else the pressure planes.  pa/pb: ping-pong plane units,
+    // px: the unit receiving iterate n-1.
+    auto run_sweeps = [&](bool diffusion, int pa, int pb, int px, const SweepParams &proto, int count, int *last,
+                          int *prev, int *valid_out, const float *const *force_bands) -> int {
+        int cur = pa, oth = pb;
         int left = count;
         int valid = 0;
         const bool vec = (gw % 4 == 0);
         SweepParams p0 = proto;
-        const bool packed = (op == SWEEP_DIFFUSE) && vec && packed_diffuse_supported(p0);
+        const bool packed = diffusion && vec && packed_diffuse_supported(p0);
         const int user_depth = pfs_get_fuse_depth();
         int depth = user_depth > 0 ? std::min(user_depth, MIN_HALO) : (packed ? default_diffuse_depth() : MIN_HALO);
+        if (diffusion && !packed) depth = 1;
         if (!vec) depth = 1;
+        const size_t rf = diffusion ? 2 * (size_t)gw : (size_t)gw;
         bool prev_in_extra = false;
         auto one_pass = [&](int t, bool final_pass) -> int {
             if (valid < t) {
                 std::vector<std::vector<float *>> pl(n);
-                for (int k = 0; k < n; k++) {
-                    pl[k].push_back(L[k]->plane(cur0));
-                    if (op == SWEEP_DIFFUSE) pl[k].push_back(L[k]->plane(cur1));
-                }
-                PFS_TRY(exchange_planes(L, pl, halo));
+                for (int k = 0; k < n; k++) pl[k].push_back(L[k]->plane(cur));
+                PFS_TRY(exchange_planes(L, pl, halo, rf));
                 valid = halo;
             }
             const int e = valid - t;                    // extra rows recomputed on each side of the band
@@ -1282,25 +1283,28 @@ static int slab_fluid_step(pfs_slab *const *slabs, int n_local, float **vp, floa
                 p.y_base = halo - e;
                 p.wrap = 0;
                 int flips = 0, wrote = 0;
-                float *a0 = s->plane(cur0), *a1 = s->plane(cur1), *b0 = s->plane(oth0), *b1 = s->plane(oth1);
-                float *x0 = (final_pass && t >= 2) ? s->plane(px0) : nullptr;
-                float *x1 = (final_pass && t >= 2) ? s->plane(px1) : nullptr;
-                const float *rhs = (op == SWEEP_PRESSURE) ? s->plane(6) : nullptr;
-                if (t == 1)
-                    PFS_TRY(launch_sweeps_basic(op, a0, a1, b0, b1, rhs, p, 1, &flips, s->stream));
-                else if (packed)
-                    PFS_TRY(launch_diffuse_packed(a0, a1, b0, b1, p, t, t, &flips, s->stream, x0, x1, &wrote));
+                float *a = s->plane(cur), *b = s->plane(oth);
+                float *x = (final_pass && t >= 2) ? s->plane(px) : nullptr;
+                ForceField ff{(force_bands && final_pass) ? force_bands[k] : nullptr, e, s->rows};
+                const ForceField *force = ff.aos ? &ff : nullptr;
+                if (diffusion && packed && t >= 2)
+                    PFS_TRY(launch_diffuse_packed(a, b, p, t, t, &flips, s->stream, x, &wrote, force));
+                else if (diffusion) {
+                    PFS_TRY(launch_diffuse_basic(a, b, p, 1, &flips, s->stream));
+                    if (force)
+                        PFS_TRY(launch_add_forces(b + (size_t)halo * rf, 2, force->aos, gw, s->rows, s->stream));
+                } else if (t == 1)
+                    PFS_TRY(launch_pressure_basic(a, b, s->plane(DIV), p, 1, &flips, s->stream));
                 else
-                    PFS_TRY(launch_sweeps_fused(op, a0, a1, b0, b1, rhs, p, t, t, &flips, s->stream, x0, x1, &wrote));
-                if (flips != 1 || (x0 != nullptr && !wrote)) {
+                    PFS_TRY(launch_pressure_fused(a, b, s->plane(DIV), p, t, t, &flips, s->stream, x, &wrote));
+                if (flips != 1 || (x != nullptr && !wrote)) {
                     set_error("slab sweeps: a pass of depth %d took %d hops (previous iterate stored: %d)", t, flips, wrote);
                     return PFS_ESTATE;
                 }
-                if (x0 != nullptr) prev_in_extra = true;
+                if (x != nullptr) prev_in_extra = true;
             }
-            valid = e;
-            std::swap(cur0, oth0);
-            std::swap(cur1, oth1);
+            valid = (force_bands && final_pass) ? 0 : e;   // rows outside the band got no force: exchange before the next use
+            std::swap(cur, oth);
             return PFS_OK;
         };
         while (left > 0) {
@@ -1310,10 +1314,8 @@ static int slab_fluid_step(pfs_slab *const *slabs, int n_local, float **vp, floa
             PFS_TRY(one_pass(t, left - t == 0));
             left -= t;
         }
-        *last0 = cur0;
-        *last1 = cur1;
-        *prev0 = prev_in_extra ? px0 : oth0;            // else: the set the last (single) sweep read
-        *prev1 = prev_in_extra ? px1 : oth1;
+        *last = cur;
+        *prev = prev_in_extra ? px : oth;               // else: the plane the last (single) sweep read
         *valid_out = valid;
         return PFS_OK;
     };
@@ -1324,9 +1326,9 @@ static int slab_fluid_step(pfs_slab *const *slabs, int n_local, float **vp, floa
     dp.alpha = viscosity * dt;
     dp.beta = (float)(1.0 + 4.0 * (double)dp.alpha);
     int d_valid = 0;
-    int dl0 = 0, dl1 = 1, dp0 = 2, dp1 = 3;                              // iterate n_d, iterate n_d - 1
+    int dl = UV_A, dpv = UV_B;                                            // iterate n_d, iterate n_d - 1
     next_phase(PFS_PHASE_DIFFUSE);
-    PFS_TRY(run_sweeps(SWEEP_DIFFUSE, 0, 1, 2, 3, 7, 8, dp, n_diffuse, &dl0, &dl1, &dp0, &dp1, &d_valid));
+    PFS_TRY(run_sweeps(true, UV_A, UV_B, UV_X, dp, n_diffuse, &dl, &dpv, &d_valid, forces));
     next_phase(PFS_PHASE_DIVERGENCE);
 
     // pointer choreography (pfs_simulate_fluid_step)
@@ -1341,16 +1343,15 @@ static int slab_fluid_step(pfs_slab *const *slabs, int n_local, float **vp, floa
     // ---- divergence (needs one halo row of v) + warm-start pressure; then the divergence halo ----
     {
         std::vector<std::vector<float *>> pl(n);
-        for (int k = 0; k < n; k++) pl[k].push_back(L[k]->plane(dl1));
-        if (d_valid < 1) PFS_TRY(exchange_planes(L, pl, 1));
+        for (int k = 0; k < n; k++) pl[k].push_back(L[k]->plane(dl));
+        if (d_valid < 1) PFS_TRY(exchange_planes(L, pl, 1, 2 * (size_t)gw));
         for (int k = 0; k < n; k++) {
             pfs_slab *s = L[k];
             Guard g(s->device);
-            PFS_TRY(launch_divergence(s->plane(dl0), s->plane(dl1), s->plane(6), Bv[k], s->plane(4), dt, gw, s->rows,
-                                      s->stream, halo, 0));
+            PFS_TRY(launch_divergence(s->plane(dl), s->plane(DIV), Bv[k], s->plane(P_A), dt, gw, s->rows, s->stream, halo, 0));
         }
-        for (int k = 0; k < n; k++) pl[k][0] = L[k]->plane(6);
-        PFS_TRY(exchange_planes(L, pl, halo));
+        for (int k = 0; k < n; k++) pl[k][0] = L[k]->plane(DIV);
+        PFS_TRY(exchange_planes(L, pl, halo, (size_t)gw));
     }
     SweepParams pp;
     pp.w = gw;
@@ -1358,9 +1359,9 @@ static int slab_fluid_step(pfs_slab *const *slabs, int n_local, float **vp, floa
     pp.alpha = 1.0f;
     pp.beta = 4.0f;
     int p_valid = 0;
-    int pl_last = 4, pl_prev = 5, unused0 = 0, unused1 = 0;
+    int pl_last = P_A, pl_prev = P_B;
     next_phase(PFS_PHASE_PRESSURE);
-    PFS_TRY(run_sweeps(SWEEP_PRESSURE, 4, 4, 5, 5, 9, 9, pp, n_pressure, &pl_last, &unused0, &pl_prev, &unused1, &p_valid));
+    PFS_TRY(run_sweeps(false, P_A, P_B, P_X, pp, n_pressure, &pl_last, &pl_prev, &p_valid, nullptr));
     next_phase(PFS_PHASE_PROJECT);
 
     // ---- late check of a speculative advect: everything so far only wrote scratch planes ----
@@ -1381,7 +1382,7 @@ static int slab_fluid_step(pfs_slab *const *slabs, int n_local, float **vp, floa
             // peer-transport timeout) is never touched here, so pfs_slab_check still sees whatever it holds
             delete ph;
             ph = nullptr;
-            return slab_fluid_step(slabs, n_local, vp, tmp, dt, viscosity, n_diffuse, n_pressure, streams, true);
+            return slab_fluid_step(slabs, n_local, vp, tmp, dt, viscosity, n_diffuse, n_pressure, streams, true, forces);
         }
     }
 
@@ -1389,14 +1390,13 @@ static int slab_fluid_step(pfs_slab *const *slabs, int n_local, float **vp, floa
     {
         std::vector<std::vector<float *>> pl(n);
         for (int k = 0; k < n; k++) pl[k].push_back(L[k]->plane(pl_last));
-        if (p_valid < 1) PFS_TRY(exchange_planes(L, pl, 1));
+        if (p_valid < 1) PFS_TRY(exchange_planes(L, pl, 1, (size_t)gw));
         for (int k = 0; k < n; k++) {
             pfs_slab *s = L[k];
             Guard g(s->device);
             const bool use_last = (Bp[k] == Bv[k]);
-            const float *u = s->plane(use_last ? dl0 : dp0), *v = s->plane(use_last ? dl1 : dp1);
-            PFS_TRY(launch_project_pack(u, v, s->plane(pl_last), s->plane(pl_prev), s->plane(6), Bq[k], Bp[k], dt, gw,
-                                        s->rows, s->stream, halo, 0));
+            PFS_TRY(launch_project_pack(s->plane(use_last ? dl : dpv), s->plane(pl_last), s->plane(pl_prev), s->plane(DIV),
+                                        Bq[k], Bp[k], dt, gw, s->rows, s->stream, halo, 0));
         }
     }
     for (int k = 0; k < n; k++) {
@@ -1409,7 +1409,24 @@ static int slab_fluid_step(pfs_slab *const *slabs, int n_local, float **vp, floa
 extern "C" int pfs_slab_simulate_fluid_step(pfs_slab *const *slabs, int n_local, float **vp, float **tmp, float dt,
                                             float viscosity, int n_diffuse, int n_pressure, void *const *streams)
 {
-    return slab_fluid_step(slabs, n_local, vp, tmp, dt, viscosity, n_diffuse, n_pressure, streams, false);
+    return slab_fluid_step(slabs, n_local, vp, tmp, dt, viscosity, n_diffuse, n_pressure, streams, false, nullptr);
+}
+
+// The same step with an external force at the addForces slot (pfs_simulate_fluid_step_forced): forces[k] is the k-th
+// local slab's band of the interleaved force field (rows x gw x 4 floats).
+extern "C" int pfs_slab_simulate_fluid_step_forced(pfs_slab *const *slabs, int n_local, float **vp, float **tmp, float dt,
+                                                   float viscosity, int n_diffuse, int n_pressure,
+                                                   const float *const *forces, void *const *streams)
+{
+    if (forces != nullptr) {
+        for (int k = 0; k < n_local; k++) {
+            if (!forces[k] || ((uintptr_t)forces[k] & 15)) {
+                set_error("pfs_slab_simulate_fluid_step_forced: slab %d: the force band must be a non-null, 16-byte aligned device buffer", k);
+                return PFS_EINVAL;
+            }
+        }
+    }
+    return slab_fluid_step(slabs, n_local, vp, tmp, dt, viscosity, n_diffuse, n_pressure, streams, false, forces);
 }
 
 // ---------------------------------------------------------------------------------------------

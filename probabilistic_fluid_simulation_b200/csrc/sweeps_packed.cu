@@ -4,70 +4,78 @@
 // The diffusion operator applies the same 5-point update with the same coefficients to channel 0
 // (u) and channel 1 (v).  sm_100 has two-wide FP32 instructions (add/mul/fma.rn.f32x2 -> FADD2 /
 // FMUL2 / FFMA2) that round each half exactly like the scalar instruction, so a lane keeps (u, v)
-// of a cell in one 64-bit register pair and issues ONE instruction per pair of updates.  The
-// structure is the warp-streaming scheme of sweeps_fused.cu:
-//   * a warp owns a strip of 128 columns x a chunk of L rows of BOTH planes; each lane holds, for
-//     every time level 0..T-1, the two most recent rows of its 4 cells x (u,v) (16*T registers);
-//   * per stream step one new row of u and of v arrives through a private cp.async ring in shared
-//     memory (no barriers anywhere), level l = 1..T produces row s-l, level T is stored;
+// of a cell in one 64-bit register pair and issues ONE instruction per pair of updates.  The velocity
+// planes are stored the same way -- (u, v) interleaved, 8 bytes per cell -- so a 16-byte load or store
+// moves two cells straight into / out of two register pairs, with no repacking.
+// The structure is the warp-streaming scheme of sweeps_fused.cu:
+//   * a warp owns a strip of 128 columns x a chunk of L rows; each lane holds, for every time level
+//     0..T-1, three rows of its 4 cells (24*T registers): the alpha products of the centre and the
+//     top row and the values of the centre row, so every value is multiplied by alpha exactly once
+//     per level (the reference multiplies it once per neighbour that reads it -- same value);
+//   * per stream step one new row arrives through a private cp.async ring in shared memory (no
+//     barriers anywhere), level l = 1..T produces row s-l, level T is stored;
 //   * x neighbours across lanes come by warp shuffle of the already-multiplied alpha*value pairs;
-//   * the division by beta = 1 + 4*alpha is the 3-instruction correctly rounded FMA division of
-//     div_const_fast() below, applied to pairs.  Its preconditions (numerator magnitude in
-//     [2^-96, 2^96], not -0) are not branched on in the hot loop: the loop keeps a running FMNMX3
-//     minimum of |numerator| and maximum of |input|; a warp whose extremes leave the safe range
-//     raises a flag for its work item, and a second ("repair") launch recomputes exactly those
-//     items with __fdiv_rn.  Real velocity fields never raise the flag; exact-zero regions do, and
-//     stay correct.
+//   * the division by beta = 1 + 4*alpha is a correctly rounded 2- or 3-instruction division by a
+//     constant (below), applied to pairs.  Its preconditions (numerator magnitude in [2^-96, 2^96],
+//     not -0) are not branched on in the hot loop: the loop keeps a running FMNMX3 minimum of
+//     |numerator| and maximum of |input|; a warp whose extremes leave the safe range recomputes its
+//     own work item with __fdiv_rn before it retires (same kernel, same warp, out of line).  Real
+//     velocity fields never take that path; exact-zero regions do, and stay correct.
 // Results are bit-identical to the one-sweep kernel and to fluid.cpp for every T.
 #include <math.h>
 #include <stdint.h>
 #include <stdlib.h>
 #include <string.h>
 
+#include <algorithm>
+#include <cmath>
 #include <map>
 #include <mutex>
 #include <thread>
-#include <vector>
-#include <algorithm>
-#include <cmath>
 #include <utility>
+#include <vector>
 
 #include "pfs_internal.cuh"
 
 namespace pfs {
 
-int pick_chunk_rows(int h, int columns_of_items, long long slots, int forced_rows);
-
 namespace {
 
-int env_int(const char *name, int dflt);
+int env_int(const char *name, int dflt)
+{
+    const char *v = getenv(name);
+    return (v && *v) ? atoi(v) : dflt;
+}
 
 constexpr int WARPS_PER_CTA = 4;
-#ifndef PFS_CARRY_MAX_DEPTH
-#define PFS_CARRY_MAX_DEPTH 6
-#endif
-constexpr int CARRY_MAX_DEPTH = PFS_CARRY_MAX_DEPTH;
-#ifndef PFS_RING_SLOTS
-#define PFS_RING_SLOTS 4
-#endif
-constexpr int RING_SLOTS = PFS_RING_SLOTS;   // cp.async ring depth per warp (rows), a power of two
-constexpr int PREFETCH = RING_SLOTS - 2;      // rows in flight ahead of the consumer
-constexpr int PRING_SLOTS = 4;                // the (opt-in) packed pressure kernel keeps its 4-slot ring (64 B x 32 lanes per slot)
-constexpr int PPREFETCH = PRING_SLOTS - 2;
+constexpr int MAX_DEPTH = 6;                  // deeper passes would not fit three rows per level in 255 registers
+// cp.async ring depth per warp (rows): eight slots (six rows in flight ahead of the consumer) where registers allow, four
+// (two rows in flight) at depth 6, where the second ring pointer pushed ptxas over the 255-register cap into spills.
+__host__ __device__ constexpr int ring_slots(int t) { return t >= 6 ? 4 : 8; }
+constexpr int UNROLL = 4;                     // stream steps per trip of the main loop; ring slots are immediates within a trip
+// Ring slot = one row of the strip (128 cells x 8 bytes).  Global loads are issued so that every cp.async instruction of
+// a warp covers 512 CONTIGUOUS bytes (lane i fetches 16-byte piece 32k+i of the row, k = 0,1) -- a lane fetching its own
+// 32 bytes as two pieces would touch half of every 32-byte sector per instruction, and the same pattern as a pure copy
+// runs at 3.8 instead of 5.7 TB/s (scripts/ubench/stream_copy*.cu).  In shared memory piece p (cells 2p, 2p+1) goes where
+// its OWNER lane o = p/2 reads it back with two conflict-free 16-byte loads: the lower pieces of all lanes in floats
+// [0,128), the upper pieces in [144,272) (the 64-byte skew keeps the asynchronous writes conflict-free as well).
+constexpr int SLOT_HI = 144;                  // float offset of the upper pieces within a slot
+constexpr int SLOT_FLOATS = 288;
 
 struct PackedParams {
-    const float *in_u, *in_v;
-    float *out_u, *out_v;
-    float *prev_u, *prev_v;     // optional: planes receiving iterate +T-1 as well (null = not wanted)
-    int *flags;                 // one int per work item (main kernel raises, repair kernel consumes)
+    const float *in;            // (u,v) plane of the current iterate
+    float *out;                 // (u,v) plane receiving iterate +T
+    float *prev;                // optional: (u,v) plane receiving iterate +T-1 as well (null = not wanted)
+    const float *force;         // optional: interleaved [rows][w][4] field whose channels 0,1 are added to iterate +T as
+                                // it is stored (the addForces slot, fluid.cpp:302); row 0 = output row force_skip
+    int force_skip, force_rows;
     int w, h;
     int strip_out, halo_cols;
     int n_strips, n_chunks, chunk_rows;
     int y_base, wrap;           // row map of the planes (SweepParams)
     float alpha, beta, rbeta;
-    float zh, zl;               // 2-instruction division (div_const_two2): RN(1/beta) and RN(1/beta - zh); used iff div2
-    int div2;
-    float guard_lo, guard_hi_in;   // |numerator| >= guard_lo and |input| <= guard_hi_in keep the FMA division exact
+    float zh, zl;               // 2-instruction division (div_const_two2): RN(1/beta) and RN(1/beta - zh)
+    float guard_lo, guard_hi_in;   // |numerator| >= guard_lo and |input| <= guard_hi_in keep the constant division exact
     float neg_zero;             // -0.0f, deliberately a RUN-TIME value: see mulc2()
 };
 
@@ -180,49 +188,51 @@ __device__ __forceinline__ float2 div_const_two2(float2 a, float2 zh, float2 zl)
     return fma2(a, zh, mul2(a, zl));
 }
 
-__device__ __forceinline__ void cp_async8(void *smem, const void *gmem)
+// Four cells = 32 bytes in one 256-bit store (STG.E.256, sm_100): a warp's row goes out as 1 KB without gaps.
+// WIDE = false (the out-of-line exact path) uses two 16-byte stores: ptxas 12.9 was seen to emit a single 32-bit STG for
+// the 256-bit inline-asm store inside code that also calls the IEEE-division slow path (only the first float of the row
+// reached memory).  tests/test_sass_stores.py checks the store forms of every instantiation in the built library.
+template <bool WIDE>
+__device__ __forceinline__ void store_row(float *p, const float2 (&c)[4])
 {
-    unsigned s = (unsigned)__cvta_generic_to_shared(smem);
-    asm volatile("cp.async.ca.shared.global [%0], [%1], 8;\n" ::"r"(s), "l"(gmem) : "memory");
+    if constexpr (WIDE) {
+        asm volatile("st.global.v8.f32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};" ::"l"(p), "f"(c[0].x), "f"(c[0].y), "f"(c[1].x),
+                     "f"(c[1].y), "f"(c[2].x), "f"(c[2].y), "f"(c[3].x), "f"(c[3].y)
+                     : "memory");
+    } else {
+        *reinterpret_cast<float4 *>(p) = make_float4(c[0].x, c[0].y, c[1].x, c[1].y);
+        *reinterpret_cast<float4 *>(p + 4) = make_float4(c[2].x, c[2].y, c[3].x, c[3].y);
+    }
 }
 
-// NC = cells per lane (4: 128-column strips, 16*T registers of state; 2: 64-column strips, 8*T registers,
-// i.e. twice the resident warps at a 7 % wider relative halo -- which one is faster is measured, not assumed:
-// profiles/r01_tuning.md).
-// UNR = stream steps per trip of the main loop (even: the row slots alternate with the step parity).  Steps past the
-// last one are harmless -- their prefetch is skipped and every store is masked by its row range -- so the trip count is
-// simply rounded up.  2 is the shipped value; 4 is an opt-in (PFS_DIFFUSE_UNROLL=4) that lets ptxas drop a third of the
-// register moves at the loop back-edge (13.4 instead of 14.4 instructions per update, scripts/sass_loop_stats.py) at
-// twice the loop body (20 KB); not measured on a GPU yet.
-template <int T, bool EXACT, int MINB, int NC, bool DIV2 = false, int UNR = 2>
-__global__ void __launch_bounds__(WARPS_PER_CTA * 32, MINB) diffuse_packed_kernel(const PackedParams P)
+// ---------------------------------------------------------------------------------------------
+// One work item (strip x chunk) streamed by one warp.  EXACT: IEEE division, no guard (the out-of-line repair
+// path); otherwise the constant division with the guard, returning "this lane saw a value outside the safe range".
+// Lane geometry in the (u,v) plane: the lane owns the unwrapped cells [xc, xc+4) -- 32 contiguous, 32-byte aligned bytes
+// (the halo and the width are multiples of four), stored with ONE 256-bit instruction per row; a warp's store covers
+// 1 KB without gaps.  Loads: see SLOT_FLOATS.
+// ---------------------------------------------------------------------------------------------
+// LAST: the pass that reaches sweep n -- the only one that may also store iterate +T-1 and add the external force; the
+// other passes (16 of 17 at 100 sweeps) carry neither the pointers nor the branches.
+template <int T, bool EXACT, bool DIV2, bool LAST>
+__device__ __forceinline__ bool stream_item(const PackedParams &P, const int item, float *my, const int lane)
 {
-    static_assert(NC == 4 || NC == 2, "4 or 2 cells per lane");
-    static_assert(UNR >= 2 && UNR % 2 == 0, "the unroll factor must be even");
-    __shared__ __align__(16) float ring[WARPS_PER_CTA][RING_SLOTS][2][32 * NC];
-
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int item = blockIdx.x * WARPS_PER_CTA + warp;
-    if (item >= P.n_strips * P.n_chunks) return;          // whole warp leaves together
-    if constexpr (EXACT) {
-        // repair launch: only flagged items.  It also clears the flag, so the buffer is all zero again when
-        // the next pass starts (no memset launch per pass).
-        int f = 0;
-        if (lane == 0) {
-            f = P.flags[item];
-            if (f) P.flags[item] = 0;
-        }
-        if (__shfl_sync(0xffffffffu, f, 0) == 0) return;
-    }
+    constexpr int RING_SLOTS = ring_slots(T);
+    constexpr int PREFETCH = RING_SLOTS - 2;              // rows in flight ahead of the consumer
     const int strip = item % P.n_strips;
     const int chunk = item / P.n_strips;
     const int w = P.w, h = P.h;
+    const long long rs = 2 * (long long)w;                // floats per plane row
 
     const int x0 = strip * P.strip_out;
-    const int xc = x0 - P.halo_cols + NC * lane;          // unwrapped first column of this lane
-    int xw = xc % w;
-    if (xw < 0) xw += w;
-    const bool store_lane = (xc >= x0) && (xc < x0 + P.strip_out) && (xc < w);
+    const int xc = x0 - P.halo_cols + 4 * lane;           // unwrapped first cell of this lane
+    const bool st = (xc >= x0) && (xc < min(x0 + P.strip_out, w));
+    // the two 16-byte pieces this lane FETCHES (not the ones it owns): cells xs + 2*lane and xs + 64 + 2*lane (+1), wrapped
+    int xlo = (x0 - P.halo_cols + 2 * lane) % w;
+    if (xlo < 0) xlo += w;
+    int xhi = (xlo + 64) % w;
+    // ... and where they go in a ring slot: owner lane o = 16k + lane/2, lower or upper piece by lane parity
+    float *const fetch = my - lane * 4 + (lane & 1) * SLOT_HI + 4 * (lane >> 1);
 
     const int y0 = chunk * P.chunk_rows;
     const int L = min(P.chunk_rows, h - y0);
@@ -231,49 +241,20 @@ __global__ void __launch_bounds__(WARPS_PER_CTA * 32, MINB) diffuse_packed_kerne
         ld_row %= h;
         if (ld_row < 0) ld_row += h;
     }
-    ld_row += P.y_base;
     const int wrap_at = P.wrap ? h : 0x7fffffff;
     const int n_steps = L + 2 * T;
+    const float *const in0 = P.in + (long long)P.y_base * rs;     // plane row of interior row 0
+    const float *ld_ptr = in0 + (long long)ld_row * rs;           // ld_row may be negative on a slab (halo rows)
+    const int off_lo = 2 * xlo, off_hi = 2 * xhi;
 
-    float *my = &ring[warp][0][0][lane * NC];
-    constexpr int PLANE_STRIDE = 32 * NC;                 // floats between the u and the v row of a slot
-    constexpr int SLOT_STRIDE = 2 * PLANE_STRIDE;
-
-    auto prefetch = [&](int s) {
-        if (s < n_steps) {
-            float *dst = my + (s & (RING_SLOTS - 1)) * SLOT_STRIDE;
-            const size_t off = (size_t)ld_row * w + xw;
-            if constexpr (NC == 4) {
-                cp_async16(dst, P.in_u + off);
-                cp_async16(dst + PLANE_STRIDE, P.in_v + off);
-            } else {
-                cp_async8(dst, P.in_u + off);
-                cp_async8(dst + PLANE_STRIDE, P.in_v + off);
-            }
-            ld_row = (ld_row + 1 == wrap_at) ? 0 : ld_row + 1;
-        }
-        cp_async_commit();
-    };
-#pragma unroll
-    for (int s = 0; s < PREFETCH; s++) prefetch(s);
-
-    // S[l][k][c]: level l, k alternates with the step parity, c = cell; .x = u, .y = v.
+    // S[l][k][c]: alpha products of level l's centre row (k = older^1) and top row (k = older); k alternates with
+    // the step parity.  A[l][c]: the centre row's values.  .x = u, .y = v.
     // Initialised to 1 (not 0) so that warm-up garbage never looks like a zero numerator.
-    float2 S[T][2][NC];
+    float2 S[T][2][4], A[T][4];
 #pragma unroll
     for (int l = 0; l < T; l++)
 #pragma unroll
-        for (int c = 0; c < NC; c++) S[l][0][c] = S[l][1][c] = make_float2(1.f, 1.f);
-    // Passes up to CARRY_MAX_DEPTH have registers to spare for a third row per level, so that the alpha product of a
-    // row, formed when the row arrives as the bottom row, is kept while the row is the centre and then the top row:
-    // every value is multiplied by alpha exactly once per level (the reference multiplies it four times, once per
-    // neighbour that reads it -- same value each time).  See the state layout at the prefix lambda below.
-    constexpr bool CARRY = (NC == 4 && T <= CARRY_MAX_DEPTH);
-    float2 A[CARRY ? T : 1][NC];
-#pragma unroll
-    for (int l = 0; l < (CARRY ? T : 1); l++)
-#pragma unroll
-        for (int c = 0; c < NC; c++) A[l][c] = make_float2(1.f, 1.f);
+        for (int c = 0; c < 4; c++) S[l][0][c] = S[l][1][c] = A[l][c] = make_float2(1.f, 1.f);
 
     const float2 alpha2 = make_float2(P.alpha, P.alpha);
     const float2 nz2 = make_float2(P.neg_zero, P.neg_zero);
@@ -284,86 +265,91 @@ __global__ void __launch_bounds__(WARPS_PER_CTA * 32, MINB) diffuse_packed_kerne
     float num_min = __int_as_float(0x7f800000);           // +inf
     float in_max = 0.f;
 
-    float *out_u = P.out_u + (size_t)(P.y_base + y0) * w + xc;
-    float *out_v = P.out_v + (size_t)(P.y_base + y0) * w + xc;
-    float *prev_u = P.prev_u ? P.prev_u + (size_t)(P.y_base + y0) * w + xc : nullptr;
-    float *prev_v = P.prev_v ? P.prev_v + (size_t)(P.y_base + y0) * w + xc : nullptr;
+    // row pointers of this lane's cells, advanced by one plane row per stream step: `op` is where the row produced at
+    // step s goes (output row s - 2T; dereferenced only for 0 <= row < L), `pp` the same for iterate +T-1 (row s-2T+1)
+    const long long cell0 = (long long)(P.y_base + y0) * rs + 2 * (long long)xc;
+    float *op = P.out + (cell0 - (long long)(2 * T) * rs);
+    float *pp = (LAST && P.prev) ? P.prev + (cell0 - (long long)(2 * T - 1) * rs) : nullptr;
+    const float *fp = nullptr;                            // force row of the output row, interleaved cells (4 floats each)
+    if (LAST && P.force) fp = P.force + 4 * ((long long)w * (long long)(y0 - P.force_skip - 2 * T) + (long long)xc);
 
-    for (int sb = 0; sb < n_steps; sb += UNR) {
+    // `slot` is a compile-time constant at every call site (the step loop is unrolled by UNROLL and starts at a multiple
+    // of it; with eight slots `ring` alternates between the two halves of the ring from trip to trip), so ring addresses
+    // are a base register plus an immediate
+    float *ring = my;                                     // owner view of the half being consumed (eight slots: it alternates)
+    const long long fetch_delta = fetch - my;             // the same slot seen through this lane's fetch position
+    auto prefetch = [&](int s, int slot, float *owner_base) {
+        float *base = owner_base + fetch_delta;
+        if (s < n_steps) {
+            float *dst = base + slot * SLOT_FLOATS;
+            cp_async16(dst, ld_ptr + off_lo);
+            cp_async16(dst + 64, ld_ptr + off_hi);
+            ld_ptr += rs;
+            if (++ld_row == wrap_at) {
+                ld_row = 0;
+                ld_ptr = in0;
+            }
+        }
+        cp_async_commit();
+    };
 #pragma unroll
-        for (int uu = 0; uu < UNR; uu++) {
-            const int u = uu & 1;
+    for (int s = 0; s < PREFETCH; s++) prefetch(s, s, my);
+
+    for (int sb = 0; sb < n_steps; sb += UNROLL) {
+        // the half of the ring this trip consumes, and the one the rows prefetched PREFETCH steps ahead land in
+        float *const other = (RING_SLOTS == 8) ? my + ((ring == my) ? UNROLL * SLOT_FLOATS : 0) : my;
+#pragma unroll
+        for (int uu = 0; uu < UNROLL; uu++) {
+            const int older = uu & 1;
             const int s = sb + uu;
-            prefetch(s + PREFETCH);
+            {
+                const int ahead = uu + PREFETCH;              // 2..5 (four slots) or 6..9 (eight slots) steps ahead
+                if constexpr (RING_SLOTS == 4)
+                    prefetch(s + PREFETCH, ahead % 4, my);
+                else
+                    prefetch(s + PREFETCH, ahead % 4, (ahead < 8) ? other : ring);
+            }
             cp_async_wait<PREFETCH>();
-            const float *slot = my + (s & (RING_SLOTS - 1)) * SLOT_STRIDE;
-            float2 fresh[NC];
-            if constexpr (NC == 4) {
-                const float4 ru = *reinterpret_cast<const float4 *>(slot);
-                const float4 rv = *reinterpret_cast<const float4 *>(slot + PLANE_STRIDE);
-                fresh[0] = make_float2(ru.x, rv.x); fresh[1] = make_float2(ru.y, rv.y);
-                fresh[2] = make_float2(ru.z, rv.z); fresh[3] = make_float2(ru.w, rv.w);
-            } else {
-                const float2 ru = *reinterpret_cast<const float2 *>(slot);
-                const float2 rv = *reinterpret_cast<const float2 *>(slot + PLANE_STRIDE);
-                fresh[0] = make_float2(ru.x, rv.x); fresh[1] = make_float2(ru.y, rv.y);
+            __syncwarp();     // cp.async completion is per thread, and the pieces a lane reads were fetched by two other lanes
+            const float *slot = ring + uu * SLOT_FLOATS;
+            float2 fresh[4];
+            {
+                const float4 lo = *reinterpret_cast<const float4 *>(slot);
+                const float4 hi = *reinterpret_cast<const float4 *>(slot + SLOT_HI);
+                fresh[0] = make_float2(lo.x, lo.y); fresh[1] = make_float2(lo.z, lo.w);
+                fresh[2] = make_float2(hi.x, hi.y); fresh[3] = make_float2(hi.z, hi.w);
             }
-            if constexpr (!EXACT) {
-#pragma unroll
-                for (int c = 0; c < NC; c++) in_max = max3abs(in_max, fresh[c].x, fresh[c].y);
-            }
-            const int older = u;
             // Software pipeline over the levels: the part of level l+1 that only needs rows stored in
-            // earlier steps -- the alpha products of its centre and top rows, the lane shuffles and
-            // (aL + aR) + aT -- is issued before the tail of level l, which depends on the row level l-1
-            // has just produced.  Two independent instruction streams per warp instead of one.
-            // State per level.  Without CARRY: slot [older^1] holds the centre row (s-l) as VALUES, slot [older] the top
-            // row (s-l-1) already MULTIPLIED by alpha (the product formed when that row was the centre row one step
-            // ago).  With CARRY both slots hold alpha products -- [older^1] the centre row's, [older] the top row's --
-            // and A[] holds the centre row's values; the top slot is dead after the prefix, so the product of the
-            // incoming bottom row is written straight into it and the slots just swap roles with the step parity.
-            float2 part[NC], part_next[NC], aCen[NC], aCen_next[NC];
-            auto prefix = [&](int l, float2(&dst)[NC], float2(&aC)[NC]) {
+            // earlier steps -- the lane shuffles of its centre row's alpha products and (aL + aR) + aT -- is issued
+            // before the tail of level l, which depends on the row level l-1 has just produced.  Two independent
+            // instruction streams per warp instead of one.  The top slot is dead after the prefix, so the product of
+            // the incoming bottom row is written straight into it and the slots just swap roles with the step parity.
+            float2 part[4], part_next[4];
+            auto prefix = [&](int l, float2(&dst)[4]) {
+                const float2(&aC)[4] = S[l - 1][older ^ 1];
+                const float2 aLft = shfl_up2(aC[3]);                      // alpha * (x-1) of cell 0
+                const float2 aRgt = shfl_down2(aC[0]);                    // alpha * (x+1) of cell 3
 #pragma unroll
-                for (int c = 0; c < NC; c++)        // alpha * centre row: carried from the step that produced it, or formed now
-                    aC[c] = CARRY ? S[l - 1][older ^ 1][c] : mulc2(S[l - 1][older ^ 1][c], alpha2, nz2);
-                const float2 aLft = shfl_up2(aC[NC - 1]);                 // alpha * (x-1) of cell 0
-                const float2 aRgt = shfl_down2(aC[0]);                    // alpha * (x+1) of the last cell
-#pragma unroll
-                for (int c = 0; c < NC; c++) {
+                for (int c = 0; c < 4; c++) {
                     const float2 lft = (c == 0) ? aLft : aC[c - 1];
-                    const float2 rgt = (c == NC - 1) ? aRgt : aC[c + 1];
+                    const float2 rgt = (c == 3) ? aRgt : aC[c + 1];
                     dst[c] = add2(add2(lft, rgt), S[l - 1][older][c]);    // (aL + aR) + aT, fluid.cpp:175-182
                 }
             };
-            prefix(1, part, aCen);
+            prefix(1, part);
 #pragma unroll
             for (int l = 1; l <= T; l++) {
-                float2 o[NC];
-                if (l == T && prev_u != nullptr) {
+                if (LAST && l == T && pp != nullptr) {
                     // `fresh` is row s-(T-1) of level T-1: the previous iterate, which the reference keeps in its
                     // other buffer (fluid.cpp:188-194); every column this lane stores is valid at that level too
-                    const int prow = s - 2 * T + 1;
-                    if (store_lane && prow >= 0 && prow < L) {
-                        if constexpr (NC == 4) {
-                            *reinterpret_cast<float4 *>(prev_u + (size_t)prow * w) =
-                                make_float4(fresh[0].x, fresh[1].x, fresh[2].x, fresh[3].x);
-                            *reinterpret_cast<float4 *>(prev_v + (size_t)prow * w) =
-                                make_float4(fresh[0].y, fresh[1].y, fresh[2].y, fresh[3].y);
-                        } else {
-                            *reinterpret_cast<float2 *>(prev_u + (size_t)prow * w) = make_float2(fresh[0].x, fresh[1].x);
-                            *reinterpret_cast<float2 *>(prev_v + (size_t)prow * w) = make_float2(fresh[0].y, fresh[1].y);
-                        }
-                    }
+                    if (st && (unsigned)(s - 2 * T + 1) < (unsigned)L) store_row<!EXACT>(pp, fresh);
                 }
-                if (l < T) prefix(l + 1, part_next, aCen_next);
-                float2 aBot[NC];
+                if (l < T) prefix(l + 1, part_next);
+                float2 o[4], aBot[4];
 #pragma unroll
-                for (int c = 0; c < NC; c++) {
-                    const float2 aB = mulc2(fresh[c], alpha2, nz2);       // alpha * bottom row (s-l+1)
-                    aBot[c] = aB;
-                    // ... + aB) + 1.0f*u_n
-                    const float2 num = add2(add2(part[c], aB), CARRY ? A[CARRY ? l - 1 : 0][c] : S[l - 1][older ^ 1][c]);
+                for (int c = 0; c < 4; c++) {
+                    aBot[c] = mulc2(fresh[c], alpha2, nz2);               // alpha * bottom row (s-l+1)
+                    const float2 num = add2(add2(part[c], aBot[c]), A[l - 1][c]);   // ... + aB) + 1.0f*u_n
                     if constexpr (EXACT) {
                         o[c] = make_float2(__fdiv_rn(num.x, beta), __fdiv_rn(num.y, beta));
                     } else {
@@ -372,271 +358,104 @@ __global__ void __launch_bounds__(WARPS_PER_CTA * 32, MINB) diffuse_packed_kerne
                     }
                 }
 #pragma unroll
-                for (int c = 0; c < NC; c++) {
-                    if constexpr (CARRY) {
-                        S[l - 1][older][c] = aBot[c];         // the dead top slot takes the new centre row's alpha product
-                        A[l - 1][c] = fresh[c];               // ... and A its values
-                    } else {
-                        S[l - 1][older ^ 1][c] = aCen[c];     // the centre row becomes the top row: keep its alpha product
-                        S[l - 1][older][c] = fresh[c];        // the bottom row becomes the centre row: keep its values
-                        aCen[c] = aCen_next[c];
-                    }
+                for (int c = 0; c < 4; c++) {
+                    S[l - 1][older][c] = aBot[c];         // the dead top slot takes the new centre row's alpha product
+                    A[l - 1][c] = fresh[c];               // ... and A its values
                     fresh[c] = o[c];
                     part[c] = part_next[c];
                 }
             }
-            const int orow = s - 2 * T;
-            if (store_lane && orow >= 0 && orow < L) {
-                if constexpr (NC == 4) {
-                    *reinterpret_cast<float4 *>(out_u + (size_t)orow * w) =
-                        make_float4(fresh[0].x, fresh[1].x, fresh[2].x, fresh[3].x);
-                    *reinterpret_cast<float4 *>(out_v + (size_t)orow * w) =
-                        make_float4(fresh[0].y, fresh[1].y, fresh[2].y, fresh[3].y);
-                } else {
-                    *reinterpret_cast<float2 *>(out_u + (size_t)orow * w) = make_float2(fresh[0].x, fresh[1].x);
-                    *reinterpret_cast<float2 *>(out_v + (size_t)orow * w) = make_float2(fresh[0].y, fresh[1].y);
+            if ((unsigned)(s - 2 * T) < (unsigned)L) {
+                if (LAST && fp != nullptr) {
+                    // addForces slot (fluid.cpp:302): channels 0,1 of the force field are added to the row being stored
+                    const int frow = y0 + (s - 2 * T) - P.force_skip;
+                    if ((unsigned)frow < (unsigned)P.force_rows) {
+#pragma unroll
+                        for (int c = 0; c < 4; c++) {
+                            if (st) {
+                                const float2 f = __ldg(reinterpret_cast<const float2 *>(fp + 4 * c));
+                                fresh[c] = make_float2(__fadd_rn(fresh[c].x, f.x), __fadd_rn(fresh[c].y, f.y));
+                            }
+                        }
+                    }
                 }
+                if (st) store_row<!EXACT>(op, fresh);
+            }
+            if constexpr (!EXACT) {
+                // the guard on the inputs, read from A[0] (= the level-0 row that arrived in this step) only now: right
+                // after the shared-memory load it made the warp sit out the load's latency instead of starting on the
+                // work that does not depend on the new row
+#pragma unroll
+                for (int c = 0; c < 4; c++) in_max = max3abs(in_max, A[0][c].x, A[0][c].y);
+            }
+            op += rs;
+            if constexpr (LAST) {
+                if (pp != nullptr) pp += rs;
+                if (fp != nullptr) fp += 4 * (long long)w;
             }
         }
+        ring = other;
     }
     cp_async_wait<0>();
-    if constexpr (!EXACT) {
-        // !(x >= lo) also catches a NaN minimum
-        const bool bad = !(num_min >= P.guard_lo) || !(in_max <= P.guard_hi_in);
-        if (__any_sync(0xffffffffu, bad) && lane == 0) P.flags[item] = 1;
-    }
+    if constexpr (EXACT) return false;
+    // !(x >= lo) also catches a NaN minimum
+    return !(num_min >= P.guard_lo) || !(in_max <= P.guard_hi_in);
 }
 
-// ---------------------------------------------------------------------------------------------
-// Packed pressure sweeps (fluid.cpp:239-258): the pressure field is one plane, so the two halves of a
-// register pair are two DIFFERENT strips (A = strip 2k, B = strip 2k+1) of the same rows: identical
-// instruction stream, independent data.  State per lane: 16*T registers of pressure rows plus 8*T of
-// divergence rows (window of T rows, rotating with period T; the step loop is unrolled by lcm(2,T)).
-// (((pL + pR) + pT) + pB) + b, then *0.25 -- the scaling is written as FFMA2(x, 0.25, -0) with a
-// run-time -0 so that ptxas cannot contract it into the next level's first add (see mulc2()).
-// ---------------------------------------------------------------------------------------------
-struct PressurePackedParams {
-    const float *in;
-    float *out;
-    const float *rhs;
-    int w, h;
-    int strip_out, halo_cols;
-    int n_strips, n_pairs, n_chunks, chunk_rows;
-    int y_base, wrap;
-    float neg_zero;
-};
-
+// The repair path, out of line so that it costs the hot loop neither registers nor instruction-cache footprint.
 template <int T>
-struct PressureUnroll {
-    static constexpr int value = (T % 2 == 0) ? T : 2 * T;
-};
-
-template <int T, int MINB>
-__global__ void __launch_bounds__(WARPS_PER_CTA * 32, MINB) pressure_packed_kernel(const PressurePackedParams P)
+__device__ __noinline__ void repair_item(const PackedParams &P, const int item, float *my, const int lane)
 {
-    constexpr int U = PressureUnroll<T>::value;
-    __shared__ float4 ring[WARPS_PER_CTA][PRING_SLOTS][4][32];   // per slot: p(A), p(B), div(A), div(B)
+    (void)stream_item<T, true, false, true>(P, item, my, lane);
+}
 
+template <int T, int MINB, bool DIV2, bool LAST>
+__global__ void __launch_bounds__(WARPS_PER_CTA * 32, MINB) diffuse_packed_kernel(const PackedParams P)
+{
+    __shared__ __align__(16) float ring[WARPS_PER_CTA][ring_slots(T) * SLOT_FLOATS];   // 18 or 36 KB per CTA
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int item = blockIdx.x * WARPS_PER_CTA + warp;
-    if (item >= P.n_pairs * P.n_chunks) return;
-    const int pair = item % P.n_pairs;
-    const int chunk = item / P.n_pairs;
-    const int w = P.w, h = P.h;
-
-    const int stripA = 2 * pair;
-    const bool haveB = (stripA + 1 < P.n_strips);
-    const int stripB = haveB ? stripA + 1 : stripA;          // an odd last strip is computed twice, stored once
-    const int x0A = stripA * P.strip_out, x0B = stripB * P.strip_out;
-    const int xcA = x0A - P.halo_cols + 4 * lane, xcB = x0B - P.halo_cols + 4 * lane;
-    int xwA = xcA % w, xwB = xcB % w;
-    if (xwA < 0) xwA += w;
-    if (xwB < 0) xwB += w;
-    const bool storeA = (xcA >= x0A) && (xcA < x0A + P.strip_out) && (xcA < w);
-    const bool storeB = haveB && (xcB >= x0B) && (xcB < x0B + P.strip_out) && (xcB < w);
-
-    const int y0 = chunk * P.chunk_rows;
-    const int L = min(P.chunk_rows, h - y0);
-    int ld_row = y0 - T;
-    if (P.wrap) {
-        ld_row %= h;
-        if (ld_row < 0) ld_row += h;
+    if (item >= P.n_strips * P.n_chunks) return;          // whole warp leaves together
+    float *my = &ring[warp][lane * 4];                    // owner view: lower piece at +0, upper at +SLOT_HI of a slot
+    if (P.guard_lo > 1e30f) {                 // test hook (PFS_DIFFUSE_FORCE_REPAIR=1): the exact path only
+        repair_item<T>(P, item, my, lane);
+        return;
     }
-    ld_row += P.y_base;
-    const int wrap_at = P.wrap ? h : 0x7fffffff;
-    const int n_steps = L + 2 * T;
-
-    float4 *my = &ring[warp][0][0][lane];
-    constexpr int SLOT_STRIDE = 4 * 32;
-
-    auto prefetch = [&](int s) {
-        if (s < n_steps) {
-            float4 *dst = my + (s & (PRING_SLOTS - 1)) * SLOT_STRIDE;
-            const size_t row = (size_t)ld_row * w;
-            cp_async16(dst, P.in + row + xwA);
-            cp_async16(dst + 32, P.in + row + xwB);
-            cp_async16(dst + 64, P.rhs + row + xwA);
-            cp_async16(dst + 96, P.rhs + row + xwB);
-            ld_row = (ld_row + 1 == wrap_at) ? 0 : ld_row + 1;
-        }
-        cp_async_commit();
-    };
-#pragma unroll
-    for (int s = 0; s < PPREFETCH; s++) prefetch(s);
-
-    float2 S[T][2][4];      // pressure rows: level, parity slot, cell; .x = strip A, .y = strip B
-    float2 Q[T][4];         // divergence rows s-T .. s-1; row r lives in Q[r mod T]
-#pragma unroll
-    for (int l = 0; l < T; l++)
-#pragma unroll
-        for (int c = 0; c < 4; c++) {
-            S[l][0][c] = S[l][1][c] = make_float2(0.f, 0.f);
-            Q[l][c] = make_float2(0.f, 0.f);
-        }
-    const float2 quarter2 = make_float2(0.25f, 0.25f);
-    const float2 nz2 = make_float2(P.neg_zero, P.neg_zero);
-
-    float *outA = P.out + (size_t)(P.y_base + y0) * w + xcA;
-    float *outB = P.out + (size_t)(P.y_base + y0) * w + xcB;
-
-    for (int sb = 0; sb < n_steps; sb += U) {
-#pragma unroll
-        for (int u = 0; u < U; u++) {
-            const int s = sb + u;
-            prefetch(s + PPREFETCH);
-            cp_async_wait<PPREFETCH>();
-            const float4 *slot = my + (s & (PRING_SLOTS - 1)) * SLOT_STRIDE;
-            const float4 pa = slot[0], pb = slot[32], qa = slot[64], qb = slot[96];
-            float2 fresh[4] = {make_float2(pa.x, pb.x), make_float2(pa.y, pb.y), make_float2(pa.z, pb.z),
-                               make_float2(pa.w, pb.w)};
-            const float2 qnew[4] = {make_float2(qa.x, qb.x), make_float2(qa.y, qb.y), make_float2(qa.z, qb.z),
-                                    make_float2(qa.w, qb.w)};
-            const int older = u & 1;
-#pragma unroll
-            for (int l = 1; l <= T; l++) {
-                float2 o[4];
-                const float2 lft = shfl_up2(S[l - 1][older ^ 1][3]);
-                const float2 rgt = shfl_down2(S[l - 1][older ^ 1][0]);
-#pragma unroll
-                for (int c = 0; c < 4; c++) {
-                    const float2 pl = (c == 0) ? lft : S[l - 1][older ^ 1][c - 1];
-                    const float2 pr = (c == 3) ? rgt : S[l - 1][older ^ 1][c + 1];
-                    // fluid.cpp:249-255: ((((pL + pR) + pT) + pB) + 1.0f*b) / 4.0f
-                    float2 sum = add2(add2(add2(pl, pr), S[l - 1][older][c]), fresh[c]);
-                    sum = add2(sum, Q[(u - l + 2 * U * T) % T][c]);
-                    o[c] = mulc2(sum, quarter2, nz2);
-                }
-#pragma unroll
-                for (int c = 0; c < 4; c++) {
-                    S[l - 1][older][c] = fresh[c];
-                    fresh[c] = o[c];
-                }
-            }
-#pragma unroll
-            for (int c = 0; c < 4; c++) Q[u % T][c] = qnew[c];
-            const int orow = s - 2 * T;
-            if (orow >= 0 && orow < L) {
-                if (storeA)
-                    *reinterpret_cast<float4 *>(outA + (size_t)orow * w) =
-                        make_float4(fresh[0].x, fresh[1].x, fresh[2].x, fresh[3].x);
-                if (storeB)
-                    *reinterpret_cast<float4 *>(outB + (size_t)orow * w) =
-                        make_float4(fresh[0].y, fresh[1].y, fresh[2].y, fresh[3].y);
-            }
-        }
-    }
-    cp_async_wait<0>();
+    const bool bad = stream_item<T, false, DIV2, LAST>(P, item, my, lane);
+    if (__any_sync(0xffffffffu, bad)) repair_item<T>(P, item, my, lane);
 }
+
+// resident CTAs per SM the kernel is compiled for (register cap 65536 / (128 * MINB)): depth 2 fits four, depth <= 4 three CTAs
+// (12 warps/SM), deeper passes get two (8 warps/SM, up to 255 registers)
+constexpr int packed_minb(int t) { return t > 4 ? 2 : (t > 2 ? 3 : 4); }
 
 template <int T>
-int launch_pressure_packed_t(const PressurePackedParams &P, cudaStream_t s)
-{
-    const int total = P.n_pairs * P.n_chunks;
-    const unsigned blocks = (unsigned)((total + WARPS_PER_CTA - 1) / WARPS_PER_CTA);
-    constexpr int MINB = (T > 2) ? 2 : 3;
-    PFS_LAUNCH((pressure_packed_kernel<T, MINB>), blocks, WARPS_PER_CTA * 32, 0, s, P);
-    return PFS_OK;
-}
-
-template <int T, int MINB, int NC>
-int launch_packed_mb(const PackedParams &P, cudaStream_t s)
+int launch_packed(const PackedParams &P, bool div2, cudaStream_t s)
 {
     const int total = P.n_strips * P.n_chunks;
     const unsigned blocks = (unsigned)((total + WARPS_PER_CTA - 1) / WARPS_PER_CTA);
-    static const int unroll = env_int("PFS_DIFFUSE_UNROLL", 2);
-    if (NC == 4 && P.div2 && unroll == 4)
-        PFS_LAUNCH((diffuse_packed_kernel<T, false, MINB, NC, (NC == 4), (NC == 4 ? 4 : 2)>), blocks, WARPS_PER_CTA * 32, 0,
-                   s, P);
-    else if (NC == 4 && P.div2)
-        PFS_LAUNCH((diffuse_packed_kernel<T, false, MINB, NC, (NC == 4)>), blocks, WARPS_PER_CTA * 32, 0, s, P);
+    const bool last = (P.prev != nullptr) || (P.force != nullptr);
+    if (div2 && last)
+        PFS_LAUNCH((diffuse_packed_kernel<T, packed_minb(T), true, true>), blocks, WARPS_PER_CTA * 32, 0, s, P);
+    else if (div2)
+        PFS_LAUNCH((diffuse_packed_kernel<T, packed_minb(T), true, false>), blocks, WARPS_PER_CTA * 32, 0, s, P);
+    else if (last)
+        PFS_LAUNCH((diffuse_packed_kernel<T, packed_minb(T), false, true>), blocks, WARPS_PER_CTA * 32, 0, s, P);
     else
-        PFS_LAUNCH((diffuse_packed_kernel<T, false, MINB, NC>), blocks, WARPS_PER_CTA * 32, 0, s, P);
-    PFS_LAUNCH((diffuse_packed_kernel<T, true, MINB, NC>), blocks, WARPS_PER_CTA * 32, 0, s, P);
-    --g_passes;     // the repair launch belongs to the same pass
+        PFS_LAUNCH((diffuse_packed_kernel<T, packed_minb(T), false, false>), blocks, WARPS_PER_CTA * 32, 0, s, P);
     return PFS_OK;
 }
 
-// resident CTAs per SM the kernel is compiled for (register cap 65536 / (128 * MINB)).  4 cells per lane:
-// depth <= 4 fits three CTAs (12 warps/SM) without spilling, deeper passes get two (8 warps/SM, up to 255
-// registers).  2 cells per lane: four CTAs (16 warps/SM, 128 registers).
-constexpr int packed_minb(int t, int nc) { return nc == 2 ? 4 : (t > 4 ? 2 : 3); }
-
-template <int T>
-int launch_packed(const PackedParams &P, int cells, cudaStream_t s)
-{
-    if (cells == 2) return launch_packed_mb<T, packed_minb(T, 2), 2>(P, s);
-    return launch_packed_mb<T, packed_minb(T, 4), 4>(P, s);
-}
-
-int launch_packed_depth(int t, const PackedParams &P, int cells, cudaStream_t s)
+int launch_packed_depth(int t, const PackedParams &P, bool div2, cudaStream_t s)
 {
     switch (t) {
-    case 1: return launch_packed<1>(P, cells, s);
-    case 2: return launch_packed<2>(P, cells, s);
-    case 3: return launch_packed<3>(P, cells, s);
-    case 4: return launch_packed<4>(P, cells, s);
-    case 5: return launch_packed<5>(P, cells, s);
-    case 6: return launch_packed<6>(P, cells, s);
-    case 7: return launch_packed<7>(P, cells, s);
-    case 8: return launch_packed<8>(P, cells, s);
+    case 2: return launch_packed<2>(P, div2, s);
+    case 3: return launch_packed<3>(P, div2, s);
+    case 4: return launch_packed<4>(P, div2, s);
+    case 5: return launch_packed<5>(P, div2, s);
+    case 6: return launch_packed<6>(P, div2, s);
     default: set_error("packed diffusion: unsupported depth %d", t); return PFS_EINVAL;
     }
-}
-
-// per-device flag buffers (grown on demand)
-struct FlagBuf {
-    int *ptr = nullptr;
-    size_t n = 0;
-};
-std::mutex g_flag_mutex;
-std::map<int, FlagBuf> g_flags;
-
-int get_flags(size_t n, int **out)
-{
-    int dev = 0;
-    PFS_CUDA(cudaGetDevice(&dev));
-    std::lock_guard<std::mutex> lock(g_flag_mutex);
-    FlagBuf &fb = g_flags[dev];
-    if (fb.n < n) {
-        if (fb.ptr) {
-            PFS_CUDA(cudaDeviceSynchronize());
-            PFS_CUDA(cudaFree(fb.ptr));
-            fb.ptr = nullptr;
-            fb.n = 0;
-        }
-        size_t want = n < 16384 ? 16384 : 2 * n;
-        PFS_CUDA(cudaMalloc((void **)&fb.ptr, want * sizeof(int)));
-        PFS_CUDA(cudaMemset(fb.ptr, 0, want * sizeof(int)));   // flags stay zero between passes: the repair kernel clears what it consumes
-        fb.n = want;
-    }
-    *out = fb.ptr;
-    return PFS_OK;
-}
-
-int env_int(const char *name, int dflt)
-{
-    const char *v = getenv(name);
-    return (v && *v) ? atoi(v) : dflt;
 }
 
 }  // namespace
@@ -709,15 +528,6 @@ int pick_chunk_rows(int h, int columns_of_items, long long slots, int forced_row
     return (h + n - 1) / n;            // equalise
 }
 
-void packed_release_device_buffers()
-{
-    std::lock_guard<std::mutex> lock(g_flag_mutex);
-    for (auto &kv : g_flags) {
-        if (kv.second.ptr && cudaSetDevice(kv.first) == cudaSuccess) cudaFree(kv.second.ptr);
-    }
-    g_flags.clear();
-}
-
 bool packed_diffuse_supported(const SweepParams &p)
 {
     // alpha >= 0 makes every sweep a convex combination (|values| never exceed the input maximum),
@@ -735,105 +545,67 @@ int packed_division_ops(float beta)
 int default_diffuse_depth()
 {
     static const int d = env_int("PFS_DIFFUSE_DEPTH", 0);
-    return (d > 0 && d <= 8) ? d : 6;      // measured best at 4096^2 (profiles/r01_tuning.md)
+    return (d > 0 && d <= MAX_DEPTH) ? d : 5;      // measured best at 4096^2: 1.45 ms per 100 sweeps against 1.49 at depth 6 (profiles/r02_tuning.md)
 }
 
-// n diffusion sweeps, up to `depth` per launch, ping-ponging (a0,a1) <-> (b0,b1).
-int launch_diffuse_packed(float *a0, float *a1, float *b0, float *b1, const SweepParams &p, int n, int depth,
-                          int *flips, cudaStream_t s, float *prev0, float *prev1, int *prev_written)
+// n diffusion sweeps on (u,v) planes, up to `depth` per launch, ping-ponging a <-> b.
+int launch_diffuse_packed(float *a, float *b, const SweepParams &p, int n, int depth, int *flips, cudaStream_t s,
+                          float *prev, int *prev_written, const ForceField *force)
 {
     if (prev_written) *prev_written = 0;
     static const int env_rows = env_int("PFS_DIFFUSE_ROWS", 0);
     static const int env_warps = env_int("PFS_DIFFUSE_WARPS_PER_SM", 0);
+    static const bool div2_env = !(getenv("PFS_DIFFUSE_DIV2") && getenv("PFS_DIFFUSE_DIV2")[0] == '0');
     if (depth <= 0) depth = default_diffuse_depth();
-    if (depth > 8) depth = 8;
-    int hops = 0;
-    float *cur0 = a0, *cur1 = a1, *oth0 = b0, *oth1 = b1;
-    int left = n;
-    while (left > 0) {
-        const int t = left < depth ? left : depth;
-        PackedParams P;
-        P.in_u = cur0; P.in_v = cur1; P.out_u = oth0; P.out_v = oth1;
-        const bool last_pass = (left - t == 0) && prev0 != nullptr && t >= 2;
-        P.prev_u = last_pass ? prev0 : nullptr;
-        P.prev_v = last_pass ? prev1 : nullptr;
-        if (last_pass && prev_written) *prev_written = 1;
-        P.w = p.w; P.h = p.h; P.y_base = p.y_base; P.wrap = p.wrap;
-        static const int env_cells = env_int("PFS_DIFFUSE_CELLS", 0);
-        const int cells = (env_cells == 2) ? 2 : 4;                         // cells per lane
-        P.halo_cols = cells * ((t + cells - 1) / cells);
-        P.strip_out = 32 * cells - 2 * P.halo_cols;
-        P.n_strips = (p.w + P.strip_out - 1) / P.strip_out;
-        // chunk height: one resident wave of warps if the grid allows it (pick_chunk_rows)
-        const int minb = packed_minb(t, cells);
-        const int warps_per_sm = env_warps > 0 ? env_warps : 4 * minb;
-        const long long slots = (long long)sm_count() * warps_per_sm;
-        P.chunk_rows = pick_chunk_rows(p.h, P.n_strips, slots, env_rows);
-        P.n_chunks = (p.h + P.chunk_rows - 1) / P.chunk_rows;
-        P.alpha = p.alpha; P.beta = p.beta; P.rbeta = 1.0f / p.beta;
-        P.guard_lo = 0x1p-96f;
-        static const bool div2_env = !(getenv("PFS_DIFFUSE_DIV2") && getenv("PFS_DIFFUSE_DIV2")[0] == '0');
-        const Div2Entry d2 = (div2_env && cells == 4) ? div2_constants(p.beta) : Div2Entry{false, 0.f, 0.f};
-        P.div2 = d2.ok ? 1 : 0;
-        P.zh = d2.zh;
-        P.zl = d2.zl;
-        if (d2.ok && d2.zl != 0.f)       // numerator * zl must stay a normal number (scale invariance of the proof)
-            P.guard_lo = std::max(P.guard_lo, 0x1p-124f / std::fabs(d2.zl));
-        P.guard_hi_in = 0x1p60f;
-        P.neg_zero = -0.0f;
-        PFS_TRY(get_flags((size_t)P.n_strips * P.n_chunks, &P.flags));
-        PFS_TRY(launch_packed_depth(t, P, cells, s));
-        float *t0 = cur0, *t1 = cur1;
-        cur0 = oth0; cur1 = oth1; oth0 = t0; oth1 = t1;
-        hops++;
-        left -= t;
-    }
-    *flips = hops;
-    return PFS_OK;
-}
-
-bool packed_pressure_supported(const SweepParams &p) { return (p.w % 4 == 0) && p.w >= 4 && p.h >= 1; }
-
-// n pressure sweeps, up to `depth` (even, <= 6) per launch, ping-ponging a <-> b; an odd remainder is one
-// plain sweep.
-int launch_pressure_packed(float *a, float *b, const float *rhs, const SweepParams &p, int n, int depth, int *flips,
-                           cudaStream_t s)
-{
-    static const int env_depth = env_int("PFS_PRESSURE_DEPTH", 0);
-    static const int env_rows = env_int("PFS_PRESSURE_ROWS", 0);
-    static const int env_warps = env_int("PFS_PRESSURE_WARPS_PER_SM", 0);
-    if (depth <= 0) depth = env_depth > 0 ? env_depth : 6;
-    if (depth > 8) depth = 8;
-    depth &= ~1;
+    if (depth > MAX_DEPTH) depth = MAX_DEPTH;
     int hops = 0;
     float *cur = a, *oth = b;
     int left = n;
+    // Pass depths as even as possible: ceil(n / depth) passes of depth d or d+1 (100 sweeps at depth 6: 15 x 6 + 2 x 5, not
+    // 16 x 6 + 4 -- shallow passes pay the same memory traffic for fewer sweeps).  A single sweep is left only for n == 1.
+    const int n_passes = (n + depth - 1) / depth;
+    const int base = n / n_passes, n_deeper = n % n_passes;
+    int pass = 0;
     while (left > 0) {
-        int t = (left >= depth) ? depth : (left & ~1);
-        if (depth < 2 || t < 2) {
+        const int t = std::min(left, base + (pass < n_deeper ? 1 : 0));
+        pass++;
+        if (t < 2) {
+            // a single sweep (n == 1, or depth 1): the plain kernel; iterate n-1 is then simply what it read
             int one = 0;
-            PFS_TRY(launch_sweeps_basic(SWEEP_PRESSURE, cur, cur, oth, oth, rhs, p, 1, &one, s));
-            t = 1;
+            PFS_TRY(launch_diffuse_basic(cur, oth, p, 1, &one, s));
+            if (left - 1 == 0 && force)
+                PFS_TRY(launch_add_forces(oth + (size_t)(p.y_base + force->skip_rows) * 2 * p.w, 2, force->aos, p.w,
+                                          force->rows, s));
         } else {
-            PressurePackedParams P;
-            P.in = cur; P.out = oth; P.rhs = rhs;
+            PackedParams P;
+            P.in = cur; P.out = oth;
+            const bool last_pass = (left - t == 0);
+            P.prev = (last_pass && prev != nullptr) ? prev : nullptr;
+            if (P.prev && prev_written) *prev_written = 1;
+            P.force = (last_pass && force) ? force->aos : nullptr;
+            P.force_skip = force ? force->skip_rows : 0;
+            P.force_rows = force ? force->rows : 0;
             P.w = p.w; P.h = p.h; P.y_base = p.y_base; P.wrap = p.wrap;
             P.halo_cols = 4 * ((t + 3) / 4);
             P.strip_out = 128 - 2 * P.halo_cols;
             P.n_strips = (p.w + P.strip_out - 1) / P.strip_out;
-            P.n_pairs = (P.n_strips + 1) / 2;
-            const int warps_per_sm = env_warps > 0 ? env_warps : 8;
+            // chunk height: one resident wave of warps if the grid allows it (pick_chunk_rows)
+            const int warps_per_sm = env_warps > 0 ? env_warps : WARPS_PER_CTA * packed_minb(t);
             const long long slots = (long long)sm_count() * warps_per_sm;
-            P.chunk_rows = pick_chunk_rows(p.h, P.n_pairs, slots, env_rows);
+            P.chunk_rows = pick_chunk_rows(p.h, P.n_strips, slots, env_rows);
             P.n_chunks = (p.h + P.chunk_rows - 1) / P.chunk_rows;
+            P.alpha = p.alpha; P.beta = p.beta; P.rbeta = 1.0f / p.beta;
+            P.guard_lo = 0x1p-96f;
+            const Div2Entry d2 = div2_env ? div2_constants(p.beta) : Div2Entry{false, 0.f, 0.f};
+            P.zh = d2.zh;
+            P.zl = d2.zl;
+            if (d2.ok && d2.zl != 0.f)       // numerator * zl must stay a normal number (scale invariance of the proof)
+                P.guard_lo = std::max(P.guard_lo, 0x1p-124f / std::fabs(d2.zl));
+            P.guard_hi_in = 0x1p60f;
+            static const bool force_exact = getenv("PFS_DIFFUSE_FORCE_REPAIR") && getenv("PFS_DIFFUSE_FORCE_REPAIR")[0] == '1';
+            if (force_exact) P.guard_lo = __builtin_inff();     // test hook: every work item takes the out-of-line exact path
             P.neg_zero = -0.0f;
-            switch (t) {
-            case 2: PFS_TRY(launch_pressure_packed_t<2>(P, s)); break;
-            case 4: PFS_TRY(launch_pressure_packed_t<4>(P, s)); break;
-            case 6: PFS_TRY(launch_pressure_packed_t<6>(P, s)); break;
-            case 8: PFS_TRY(launch_pressure_packed_t<8>(P, s)); break;
-            default: set_error("packed pressure: unsupported depth %d", t); return PFS_EINVAL;
-            }
+            PFS_TRY(launch_packed_depth(t, P, d2.ok, s));
         }
         std::swap(cur, oth);
         hops++;

@@ -136,7 +136,11 @@ def diffuse(vp: vp_field, vp_out: vp_field, viscosity: float, dt: float, n_sweep
 
 
 def addForces(vp: vp_field, forces=None) -> None:  # noqa: N802
+    """forces: None (the reference's empty body, fluid.cpp:198-208) or a CUDA tensor shaped like vp.data whose channels
+    0,1 are added to the velocity (pfs_add_forces)."""
     L = _cabi.lib()
+    if forces is not None and tuple(forces.shape) != tuple(vp.data.shape):
+        raise ValueError("forces must be shaped like vp.data")
     _check_buf(vp, "vp")
     _require_device("addForces", vp)
     with _dev_guard(vp.data):
@@ -196,8 +200,9 @@ def add_forces_stochastic(vp: vp_field, sigma: float, seed: int, step: int) -> N
 
 def simulate_fluid_step(vp: vp_field, tmp: vp_field, dt: float, viscosity: float,
                         n_diffuse: int = NUM_JACOBI_ITERS, n_pressure: int | None = None,
-                        sigma: float = 0.0, seed: int = 0, step: int = 0) -> None:
-    """sigma != 0 (device buffers only) adds the opt-in stochastic forcing at the addForces slot."""
+                        sigma: float = 0.0, seed: int = 0, step: int = 0, forces=None) -> None:
+    """sigma != 0 (device buffers only) adds the opt-in stochastic forcing at the addForces slot; `forces` (a CUDA tensor
+    shaped like vp.data) applies addForces(vp, forces) there (fluid.cpp:302; pfs_simulate_fluid_step_forced)."""
     L = _cabi.lib()
     n_pressure = n_diffuse if n_pressure is None else n_pressure
     _check_buf(vp, "vp"); _check_buf(tmp, "tmp")
@@ -208,7 +213,14 @@ def simulate_fluid_step(vp: vp_field, tmp: vp_field, dt: float, viscosity: float
     if vp.on_device:
         h = _Handles(vp, tmp)
         with _dev_guard(vp.data):
-            if sigma != 0.0:
+            if forces is not None:
+                if sigma != 0.0:
+                    raise ValueError("forces and sigma cannot be combined in one call")
+                if tuple(forces.shape) != tuple(vp.data.shape):
+                    raise ValueError("forces must be shaped like vp.data")
+                check(L.pfs_simulate_fluid_step_forced(h.ref(0), h.ref(1), dt, viscosity, vp.x, vp.y, vp.z, n_diffuse,
+                                                       n_pressure, forces.data_ptr(), _stream_of(vp.data)))
+            elif sigma != 0.0:
                 check(L.pfs_simulate_fluid_step_stochastic(h.ref(0), h.ref(1), dt, viscosity, vp.x, vp.y, vp.z,
                                                            n_diffuse, n_pressure, sigma, seed, step,
                                                            _stream_of(vp.data)))
@@ -217,12 +229,92 @@ def simulate_fluid_step(vp: vp_field, tmp: vp_field, dt: float, viscosity: float
                                                 n_diffuse, n_pressure, _stream_of(vp.data)))
         h.commit()
     else:
-        if sigma != 0.0:
-            raise ValueError("the stochastic forcing is available on device buffers only")
+        if sigma != 0.0 or forces is not None:
+            raise ValueError("the stochastic / external forcing is available on device buffers only")
         sv, st = _host_struct(vp), _host_struct(tmp)
         pairs = [(vp, sv), (tmp, st)]
         check(L.pfs_simulate_fluid_step_host(ctypes.byref(sv), ctypes.byref(st), dt, viscosity, n_diffuse, n_pressure))
         _commit_host(pairs)
+
+
+class FluidContext:
+    """Persistent-state context (pfs_ctx_*): the fields live on the device in the library's planar layout between steps;
+    the interleaved [H, W, 4] form exists only in upload() and download().  n steps leave behind, bit for bit, what n
+    calls of simulate_fluid_step + advect_color_step leave in the caller's buffers.
+
+        ctx = FluidContext(vx, vy, ix, iy); ctx.upload(vp, vtmp, image); ctx.step(100, dt, nu); vp, vtmp, image = ctx.download()
+    """
+
+    def __init__(self, vx: int, vy: int, ix: int = 0, iy: int = 0, device=None):
+        import torch
+        self.device = torch.device("cuda", torch.cuda.current_device() if device is None else device)
+        self.vx, self.vy, self.ix, self.iy = vx, vy, ix, iy
+        self._h = ctypes.c_void_p()
+        with torch.cuda.device(self.device):
+            check(_cabi.lib().pfs_ctx_create(ctypes.byref(self._h), vx, vy, ix, iy))
+
+    def close(self):
+        if self._h:
+            _cabi.lib().pfs_ctx_destroy(self._h)
+            self._h = ctypes.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def _stream(self):
+        import torch
+        return ctypes.c_void_p(torch.cuda.current_stream(self.device).cuda_stream)
+
+    @staticmethod
+    def _ptr(t, shape):
+        if t is None:
+            return None
+        import torch
+        if not (t.is_cuda and t.dtype == torch.float32 and t.is_contiguous() and tuple(t.shape) == shape):
+            raise ValueError(f"expected a contiguous float32 CUDA tensor of shape {shape}")
+        return t.data_ptr()
+
+    def upload(self, vp=None, vtmp=None, image=None) -> None:
+        """CUDA tensors [vy, vx, 4] / [iy, ix, 4]; None leaves that buffer's state alone."""
+        v, i = (self.vy, self.vx, 4), (self.iy, self.ix, 4)
+        check(_cabi.lib().pfs_ctx_upload(self._h, self._ptr(vp, v), self._ptr(vtmp, v), self._ptr(image, i), self._stream()))
+
+    def download(self, image_only: bool = False):
+        """-> (vp, vtmp, image) as new CUDA tensors (image None without one)."""
+        import torch
+        vp = vtmp = image = None
+        if not image_only:
+            vp = torch.empty((self.vy, self.vx, 4), dtype=torch.float32, device=self.device)
+            vtmp = torch.empty_like(vp)
+        if self.ix > 0:
+            image = torch.empty((self.iy, self.ix, 4), dtype=torch.float32, device=self.device)
+        check(_cabi.lib().pfs_ctx_download(self._h, None if vp is None else vp.data_ptr(), None if vtmp is None else vtmp.data_ptr(),
+                                           None if image is None else image.data_ptr(), self._stream()))
+        return vp, vtmp, image
+
+    def step(self, n_steps: int, dt: float, viscosity: float, n_diffuse: int = NUM_JACOBI_ITERS,
+             n_pressure: int | None = None) -> None:
+        n_pressure = n_diffuse if n_pressure is None else n_pressure
+        check(_cabi.lib().pfs_ctx_step(self._h, n_steps, dt, viscosity, n_diffuse, n_pressure, self._stream()))
+
+    def simulate_fluid_step(self, dt: float, viscosity: float, n_diffuse: int = NUM_JACOBI_ITERS, n_pressure: int | None = None,
+                            sigma: float = 0.0, seed: int = 0, step: int = 0, forces=None) -> None:
+        n_pressure = n_diffuse if n_pressure is None else n_pressure
+        L = _cabi.lib()
+        if forces is not None:
+            check(L.pfs_ctx_simulate_fluid_step_forced(self._h, dt, viscosity, n_diffuse, n_pressure,
+                                                       self._ptr(forces, (self.vy, self.vx, 4)), self._stream()))
+        elif sigma != 0.0:
+            check(L.pfs_ctx_simulate_fluid_step_stochastic(self._h, dt, viscosity, n_diffuse, n_pressure, sigma, seed, step,
+                                                           self._stream()))
+        else:
+            check(L.pfs_ctx_simulate_fluid_step(self._h, dt, viscosity, n_diffuse, n_pressure, self._stream()))
+
+    def advect_color_step(self, dt: float) -> None:
+        check(_cabi.lib().pfs_ctx_advect_color_step(self._h, dt, self._stream()))
 
 
 def advect_color_step(image: vp_field, itmp: vp_field, vp: vp_field, dt: float) -> None:

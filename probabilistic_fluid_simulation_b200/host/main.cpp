@@ -134,23 +134,47 @@ int main(int argc, char *argv[])
     std::cout << "Simulating [" << velocity_image.height << " x " << velocity_image.width << "] domain for "
               << n_timesteps << " timesteps at dt=" << delta_t << "..." << std::endl;
 
+    // The state lives in a persistent context of the library (pfs_ctx_*: planar layout between steps, the interleaved
+    // buffers above are only its upload source); PFS_DRIVER_STATELESS=1 drives the fluid.hpp entry points on the
+    // caller-owned buffers instead, exactly as the reference's loop does (main.cpp:222,225).  Same results either way.
+    const char *sl_env = getenv("PFS_DRIVER_STATELESS");
+    const bool stateless = sl_env && sl_env[0] == '1';
+    pfs_ctx *ctx = nullptr;
+    if (!stateless) {
+        if (pfs_ctx_create(&ctx, vp.x, vp.y, image.x, image.y) != PFS_OK ||
+            pfs_ctx_upload(ctx, d_vp, d_vtmp, d_image, nullptr) != PFS_OK) {
+            std::cerr << pfs_last_error() << std::endl;
+            return 1;
+        }
+    }
+
     auto time_start = std::chrono::high_resolution_clock::now();
     for (int i = 0; i < n_timesteps; i++) {
-        simulate_fluid_step(&d_vp, &d_vtmp, delta_t, viscosity, vp.x, vp.y, vp.z);
-        advect_color_step(&d_image, &d_itmp, &d_vp, delta_t, image.x, image.y, image.z, vp.x, vp.y, vp.z);
+        const float *frame_src = nullptr;
+        if (ctx) {
+            if (pfs_ctx_step(ctx, 1, delta_t, viscosity, NUM_JACOBI_ITERS, NUM_JACOBI_ITERS, nullptr) != PFS_OK ||
+                (flags == 0 && pfs_ctx_image(ctx, &frame_src) != PFS_OK)) {
+                std::cerr << pfs_last_error() << std::endl;
+                return 1;
+            }
+        } else {
+            simulate_fluid_step(&d_vp, &d_vtmp, delta_t, viscosity, vp.x, vp.y, vp.z);
+            advect_color_step(&d_image, &d_itmp, &d_vp, delta_t, image.x, image.y, image.z, vp.x, vp.y, vp.z);
+            frame_src = d_image;
+        }
         if (flags == 0) {
             std::string outpath = std::string(argv[6]);
             if (!outpath.empty() && outpath.back() != '/') outpath += "/";
             outpath += std::to_string(i) + ".png";
             std::cout << "[" << i << "] Writing to : " << outpath << std::endl;
             if (writer) {
-                if (!writer->submit(d_image, outpath)) {
+                if (!writer->submit(frame_src, outpath)) {
                     std::cerr << writer->error() << std::endl;
                     return 1;
                 }
                 continue;
             }
-            if (pfs_image_to_rgba8(d_image, d_frame, image.x, image.y, image.z, nullptr) != PFS_OK) {
+            if (pfs_image_to_rgba8(frame_src, d_frame, image.x, image.y, image.z, nullptr) != PFS_OK) {
                 std::cerr << pfs_last_error() << std::endl;
                 return 1;
             }
@@ -170,6 +194,7 @@ int main(int argc, char *argv[])
               << std::endl;
 
     delete writer;
+    pfs_ctx_destroy(ctx);
     cudaFreeHost(image.data);
     cudaFreeHost(vp.data);
     cudaFreeHost(vtmp.data);

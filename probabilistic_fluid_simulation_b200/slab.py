@@ -92,13 +92,20 @@ class SlabRing(_SlabBase):
         return _ptr_array([torch.cuda.current_stream(d).cuda_stream for d in self.devices])
 
     def simulate_fluid_step(self, vp: list, tmp: list, dt: float, viscosity: float,
-                            n_diffuse: int = NUM_JACOBI_ITERS, n_pressure: int | None = None) -> None:
-        """vp / tmp: lists of the bands (CUDA tensors); entries are exchanged as the reference would."""
+                            n_diffuse: int = NUM_JACOBI_ITERS, n_pressure: int | None = None, forces: list | None = None) -> None:
+        """vp / tmp: lists of the bands (CUDA tensors); entries are exchanged as the reference would.
+        forces: list of the bands of the force field (addForces slot), or None."""
         n_pressure = n_diffuse if n_pressure is None else n_pressure
         by_ptr = {t.data_ptr(): t for t in vp + tmp}
         pv, pt = _ptr_array([t.data_ptr() for t in vp]), _ptr_array([t.data_ptr() for t in tmp])
-        check(_cabi.lib().pfs_slab_simulate_fluid_step(_ptr_array([h.value for h in self._handles]), self.nranks, pv, pt,
-                                                       dt, viscosity, n_diffuse, n_pressure, self._streams()))
+        handles = _ptr_array([h.value for h in self._handles])
+        if forces is not None:
+            check(_cabi.lib().pfs_slab_simulate_fluid_step_forced(handles, self.nranks, pv, pt, dt, viscosity, n_diffuse,
+                                                                  n_pressure, _ptr_array([t.data_ptr() for t in forces]),
+                                                                  self._streams()))
+        else:
+            check(_cabi.lib().pfs_slab_simulate_fluid_step(handles, self.nranks, pv, pt, dt, viscosity, n_diffuse,
+                                                           n_pressure, self._streams()))
         for k in range(self.nranks):
             vp[k], tmp[k] = by_ptr[pv[k]], by_ptr[pt[k]]
 
@@ -154,12 +161,18 @@ class SlabRank(_SlabBase):
         return _ptr_array([torch.cuda.current_stream(t.device).cuda_stream])
 
     def simulate_fluid_step(self, vp: vp_field, tmp: vp_field, dt: float, viscosity: float,
-                            n_diffuse: int = NUM_JACOBI_ITERS, n_pressure: int | None = None) -> None:
+                            n_diffuse: int = NUM_JACOBI_ITERS, n_pressure: int | None = None, forces=None) -> None:
+        """forces: this rank's band of the force field (CUDA tensor shaped like vp.data), or None."""
         n_pressure = n_diffuse if n_pressure is None else n_pressure
         by_ptr = {vp.data.data_ptr(): vp.data, tmp.data.data_ptr(): tmp.data}
         pv, pt = _ptr_array([vp.data.data_ptr()]), _ptr_array([tmp.data.data_ptr()])
-        check(_cabi.lib().pfs_slab_simulate_fluid_step(_ptr_array([self._h.value]), 1, pv, pt, dt, viscosity,
-                                                       n_diffuse, n_pressure, self._stream(vp.data)))
+        if forces is not None:
+            check(_cabi.lib().pfs_slab_simulate_fluid_step_forced(_ptr_array([self._h.value]), 1, pv, pt, dt, viscosity,
+                                                                  n_diffuse, n_pressure, _ptr_array([forces.data_ptr()]),
+                                                                  self._stream(vp.data)))
+        else:
+            check(_cabi.lib().pfs_slab_simulate_fluid_step(_ptr_array([self._h.value]), 1, pv, pt, dt, viscosity,
+                                                           n_diffuse, n_pressure, self._stream(vp.data)))
         vp.data, tmp.data = by_ptr[pv[0]], by_ptr[pt[0]]
 
     def advect_color_step(self, image: vp_field, itmp: vp_field, vp: vp_field, dt: float) -> None:

@@ -139,6 +139,34 @@ def run(args, bench) -> None:
     value = cells_global * n / (ms_step * 1e-3)
     total_launches = int(sum_over_ranks(float(launches)))
 
+    # ---- the weak-scaling unit: the SAME band shape (w x rows-per-GPU) as one periodic grid on the regular 1-GPU path, measured
+    #      in this run on rank 0 while the other ranks wait, so that the N-GPU line carries its own denominator ----
+    unit = None
+    if not getattr(args, "no_unit", False):
+        if rank == 0:
+            uh = slab.rows
+            uvp, uvt, uimg, _ = bench.make_inputs(uh, w)
+            ctx = pfs.FluidContext(w, uh, w, uh)
+            ctx.upload(torch.from_numpy(uvp).cuda(), torch.from_numpy(uvt).cuda(), torch.from_numpy(uimg).cuda())
+            for _ in range(3):
+                ctx.step(1, DT, VISC, n, n)
+            u_steps = max(3, min(args.steps, 10))
+            u0, u1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            torch.cuda.synchronize()
+            u0.record()
+            for _ in range(u_steps):
+                ctx.step(1, DT, VISC, n, n)
+            u1.record()
+            torch.cuda.synchronize()
+            unit_ms = u0.elapsed_time(u1) / u_steps
+            ctx.close()
+            del ctx
+            torch.cuda.empty_cache()
+            unit = {"grid": [w, uh], "ms_per_step": unit_ms, "value": w * uh * n / (unit_ms * 1e-3), "unit": bench.UNIT,
+                    "steps": u_steps, "what": "one periodic grid of the per-GPU band shape on the regular single-GPU path "
+                                              "(persistent context), same run, rank 0"}
+        dist.barrier()
+
     # ---- end to end: every rank uploads its bands from pinned memory, steps, downloads them ----
     e2e = None
     if not args.no_e2e:
@@ -189,7 +217,9 @@ def run(args, bench) -> None:
                                                 "frac": step_bytes / (ms_step * 1e-3) / 1e9 / peak},
                 "cell_steps_per_s": cells_global / (ms_step * 1e-3), "phases_ms_rank0": per_phase, "kernels": kernels,
                 "transport": TRANSPORT_TEXT.get(slab.transport, slab.transport),
-                "rows_per_gpu": slab.rows, "parity": parity}
+                "rows_per_gpu": slab.rows, "parity": parity,
+                "weak_unit_1gpu": unit,
+                "efficiency_vs_unit": (unit["ms_per_step"] / ms_step) if unit else None}
         print(json.dumps(line), flush=True)
     dist.barrier()
     slab.close()

@@ -4,7 +4,8 @@ stall counts ptxas encoded (= the fewest cycles ONE warp needs per trip, nothing
 
     python scripts/sass_loop_stats.py <object-or-cubin> <substring of the mangled kernel name>
 
-The hot loop is taken to be the longest backward conditional branch of the kernel.  Control words are decoded
+The hot loop is taken to be the backward conditional branch whose body holds the most FP32 arithmetic (loops that call
+out of line or divide the slow way -- cold repair paths -- are skipped).  Control words are decoded
 from the second 64-bit word cuobjdump prints for every instruction (stall count: bits 41..44)."""
 import collections
 import re
@@ -52,13 +53,20 @@ def main():
     if not lines:
         sys.exit(f"no kernel matching {pattern!r} in {obj}")
     ins = instructions(lines[1:])
-    best = None
+    # candidate loops = backward conditional branches; the hot loop is the one with the most FP32 arithmetic that does
+    # not call out of line (a kernel may also carry a cold repair loop with IEEE divisions, which is longer)
+    best, best_score = None, -1
     for addr, text, _ in ins:
-        m = re.match(r"^@!?P\d\s+BRA\s+0x([0-9a-f]+)", text)
+        m = re.match(r"^@!?U?P\d\s+BRA(?:\.U)?\s+(?:!?UP\d,\s*)?0x([0-9a-f]+)", text)
         if m:
             tgt = int(m.group(1), 16)
-            if tgt < addr and (best is None or addr - tgt > best[1] - best[0]):
-                best = (tgt, addr)
+            if tgt < addr:
+                body = [opcode(t) for a, t, _ in ins if tgt <= a <= addr]
+                if "CALL" in body or "MUFU" in body:
+                    continue
+                score = sum(body.count(k) for k in ("FADD2", "FMUL2", "FFMA2", "FADD", "FMUL", "FFMA"))
+                if score > best_score:
+                    best, best_score = (tgt, addr), score
     if best is None:
         sys.exit("no backward conditional branch found")
     loop = [x for x in ins if best[0] <= x[0] <= best[1]]

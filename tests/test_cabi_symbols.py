@@ -41,7 +41,7 @@ def test_binding_covers_exactly_the_header():
 
 def test_version_and_knobs_without_gpu():
     L = _cabi.lib()
-    assert L.pfs_version() == 100
+    assert L.pfs_version() == 200
     assert L.pfs_set_fuse_depth(-1) == 1          # PFS_EINVAL
     assert b"depth" in L.pfs_last_error()
     assert L.pfs_set_fuse_depth(0) == 0

@@ -110,3 +110,11 @@ def test_b200_driver_unwritable_output_dir_is_not_fatal(writers, pngs, tmp_path)
     assert [ln for ln in lines if "Writing to" in ln] == [f"[{i}] Writing to : {missing}/{i}.png" for i in range(3)]
     assert lines[-1].startswith("3 timesteps took ") and lines[-1].endswith(" us.")
     assert r.stderr.count("warning: cannot write") == 3, r.stderr
+
+
+def test_b200_driver_on_the_stateless_entry_points(tmp_path):
+    """PFS_DRIVER_STATELESS=1: the driver loop calls the fluid.hpp entry points on caller-owned interleaved buffers, as
+    the reference's loop does (main.cpp:222,225), instead of a persistent context; same frames."""
+    name = "voronoi256_tulips"
+    lines, crcs, out = dc.run_driver(dc.B200, name, str(tmp_path), env={"PFS_DRIVER_STATELESS": "1"})
+    assert crcs == dc.load_driver_golden()["cases"][name]["frames_crc32"]

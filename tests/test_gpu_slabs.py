@@ -128,6 +128,26 @@ def test_ring_speculative_gather_depth_reruns_when_the_field_jumps(nranks):
     assert (c3 - c2) > 1.5 * (c2 - c1), (c1 - c0, c2 - c1, c3 - c2)   # the third step really ran twice
 
 
+@pytest.mark.parametrize("nranks", [1, 2, 3])
+@pytest.mark.parametrize("nd,npr", [(30, 30), (7, 10), (1, 2), (6, 6)])
+def test_ring_forced_step(nranks, nd, npr):
+    """The external force of the addForces slot on slabs: every rank gets its band of the force field; the rows a fused
+    pass recomputes outside its band get no force, so the halo is exchanged again before the divergence."""
+    h, w = 96, 128
+    vp, vtmp, _, _ = _state(h, w, 8, 8, 21)
+    force = (np.random.default_rng(22).standard_normal((h, w, 4)) * 0.1).astype(np.float32)
+    ring = SlabRing(nranks, w, h)
+    bv, bt, bf = ring.split(vp), ring.split(vtmp), ring.split(force)
+    orc = oracle.Oracle(nd, npr)
+    for _ in range(3):
+        ring.simulate_fluid_step(bv, bt, 0.5, 0.003, nd, npr, forces=bf)
+        vp, vtmp = orc.simulate_fluid_step_forced(vp, vtmp, 0.5, 0.003, force)
+    ring.check()
+    assert_bit_equal(ring.gather(bv), vp, f"vp (R={nranks})")
+    assert_bit_equal(ring.gather(bt), vtmp, f"vtmp (R={nranks})")
+    ring.close()
+
+
 @pytest.mark.parametrize("transport", ["p2p", "nccl"])
 @pytest.mark.parametrize("world", [2, 4, 8])
 def test_ring_of_processes(tmp_path, world, transport):

@@ -20,8 +20,11 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 def exe(tmp_path_factory):
     out = str(tmp_path_factory.mktemp("pngio") / "png_io_check")
     cxx = os.environ.get("CXX", "g++")
-    r = subprocess.run([cxx, "-std=c++17", "-O1", os.path.join(HERE, "png_io_check.cpp"), "-o", out, "-ldl"],
-                       capture_output=True, text=True)
+    # the same run-time hint host/Makefile compiles into the driver: where the python on PATH keeps Pillow's libpng16
+    import sysconfig
+    hint = os.path.join(sysconfig.get_paths()["purelib"], "pillow.libs", "libpng16*.so*")
+    r = subprocess.run([cxx, "-std=c++17", "-O1", f'-DPFS_LIBPNG_HINT="{hint}"', os.path.join(HERE, "png_io_check.cpp"),
+                        "-o", out, "-ldl"], capture_output=True, text=True)
     assert r.returncode == 0, r.stderr[-2000:]
     return out
 
