@@ -286,7 +286,16 @@ def ring_parity_check(rank: int, world: int, make_slab):
             slab.simulate_fluid_step(fv, ft, dt, visc, nd, npr)
             slab.advect_color_step(fi, fm, fv, dt)
         slab.check()
-        mine = {"rank": rank, "rows": (r0, rows), "irows": (i0, irows),
+        # ... and the same steps on resident state (pfs_slab_upload / _step / _download), the path the timed region uses
+        rv, rt, ri = (torch.from_numpy(x[a:a + m].copy()).cuda() for x, a, m in ((vp, r0, rows), (vtmp, r0, rows), (image, i0, irows)))
+        slab.upload(rv, rt, ri)
+        slab.step(steps, dt, visc, nd, npr)
+        slab.download(rv, rt, ri)
+        slab.check()
+        resident_equal = bool(torch.equal(rv.view(torch.int32), fv.data.view(torch.int32)) and
+                              torch.equal(rt.view(torch.int32), ft.data.view(torch.int32)) and
+                              torch.equal(ri.view(torch.int32), fi.data.view(torch.int32)))
+        mine = {"rank": rank, "rows": (r0, rows), "irows": (i0, irows), "resident_equal": resident_equal,
                 "vp": fv.data.cpu().numpy(), "vtmp": ft.data.cpu().numpy(), "image": fi.data.cpu().numpy()}
         parts = [None] * world
         dist.all_gather_object(parts, mine)
@@ -294,7 +303,7 @@ def ring_parity_check(rank: int, world: int, make_slab):
         if rank == 0:
             import oracle          # the checker: never on the timed or shipped path
             want = oracle.Oracle(nd, npr).run_steps(*(x.copy() for x in state), np.float32(dt), np.float32(visc), steps)
-            bad = []
+            bad = [f"rank {part['rank']}: resident state != stateless bands" for part in parts if not part["resident_equal"]]
             for part in parts:
                 a, n = part["rows"]
                 b, m = part["irows"]
@@ -313,7 +322,8 @@ def ring_parity_check(rank: int, world: int, make_slab):
         dist.barrier()
         slab.close()
     return {"ranks": world, "transport": transport, "bit_identical": ok_all, "checker": "oracle.Oracle (C restatement of "
-            "fluid.cpp, pinned against the compiled reference) on the whole grid, rank 0", "grid": [w, h], "image": [iw, ih],
+            "fluid.cpp, pinned against the compiled reference) on the whole grid, rank 0; stateless bands and resident state "
+            "(the timed path) both compared", "grid": [w, h], "image": [iw, ih],
             "sweeps": [nd, npr], "steps": steps, "cases": cases}
 
 

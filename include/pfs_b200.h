@@ -240,7 +240,20 @@ int pfs_slab_advect_color_step(pfs_slab *const *slabs, int n_local, float **imag
 int pfs_slab_simulate_fluid_step_forced(pfs_slab *const *slabs, int n_local, float **vp, float **tmp, float dt,
                                         float viscosity, int n_diffuse, int n_pressure, const float *const *forces,
                                         void *const *streams);
-/* Synchronises and reports an internal halo overflow (a bug, never expected). */
+/* Resident state on the slabs (the multi-GPU counterpart of pfs_ctx_*): upload the bands once, step, download.  Between
+ * steps the bands live in each slab's planes, so a step moves no interleaved data; n steps leave behind, bit for bit, what n
+ * calls of pfs_slab_simulate_fluid_step + pfs_slab_advect_color_step leave in the caller's bands.  vp/tmp/image: arrays
+ * over the local slabs of device pointers to the bands (image may be NULL when the slabs were created without one;
+ * download skips NULL arrays and NULL entries).  The gather depths of both advections are guessed from the previous
+ * step and verified by the kernels; a wrong guess is repaired before anything that depends on it is overwritten
+ * (pfs_slab_download and pfs_slab_check complete that verification for the last step). */
+int pfs_slab_upload(pfs_slab *const *slabs, int n_local, const float *const *vp, const float *const *tmp,
+                    const float *const *image, void *const *streams);
+int pfs_slab_step(pfs_slab *const *slabs, int n_local, int n_steps, float dt, float viscosity, int n_diffuse,
+                  int n_pressure, void *const *streams);
+int pfs_slab_download(pfs_slab *const *slabs, int n_local, float *const *vp, float *const *tmp, float *const *image,
+                      void *const *streams);
+/* Synchronises, completes deferred verification and reports an internal halo overflow (a bug, never expected). */
 int pfs_slab_check(pfs_slab *const *slabs, int n_local);
 
 /* ---- frame packing: the float -> byte half of write_png_from_array (includes/utils.hpp:129-131) -------- */

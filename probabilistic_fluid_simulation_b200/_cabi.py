@@ -76,6 +76,9 @@ SIGNATURES = {
     "pfs_slab_simulate_fluid_step": (_int, [_pp, _int, _pp, _pp, _f32, _f32, _int, _int, _pp]),
     "pfs_slab_advect_color_step": (_int, [_pp, _int, _pp, _pp, _pp, _f32, _pp]),
     "pfs_slab_simulate_fluid_step_forced": (_int, [_pp, _int, _pp, _pp, _f32, _f32, _int, _int, _pp, _pp]),
+    "pfs_slab_upload": (_int, [_pp, _int, _pp, _pp, _pp, _pp]),
+    "pfs_slab_step": (_int, [_pp, _int, _int, _f32, _f32, _int, _int, _pp]),
+    "pfs_slab_download": (_int, [_pp, _int, _pp, _pp, _pp, _pp]),
     "pfs_slab_check": (_int, [_pp, _int]),
     "pfs_image_to_rgba8": (_int, [_vp, _vp, _int, _int, _int, _vp]),
     "pfs_step_norms": (_int, [_vp, _vp, _int, _int, _int, ctypes.POINTER(ctypes.c_double), _vp]),

@@ -38,9 +38,10 @@ namespace pfs {
 
 constexpr int MAX_HALO = 32;   // halo rows per side: one exchange feeds MAX_HALO / depth fused passes
 constexpr int MIN_HALO = 8;    // >= the deepest fused pass
-constexpr int N_SLAB_PLANES = 10;   // units of plane_floats: (u,v) ping [0,1] | (u,v) pong [2,3] | p x2 [4][5] | div [6] |
-                                    // iterate n-1 of the last pass: (u,v) [7,8] | p [9].  A (u,v) plane is two units wide.
-constexpr int UV_A = 0, UV_B = 2, UV_X = 7, P_A = 4, P_B = 5, P_X = 9, DIV = 6;
+constexpr int N_SLAB_PLANES = 13;   // units of plane_floats: (u,v) ping [0,1] | (u,v) pong [2,3] | p x2 [4][5] | div [6] |
+                                    // iterate n-1 of the last pass: (u,v) [7,8] | p [9] | resident state: projected (u,v) [10,11],
+                                    // second divergence plane [12] (only until the first step after an upload).  A (u,v) plane is two units wide.
+constexpr int UV_A = 0, UV_B = 2, UV_X = 7, P_A = 4, P_B = 5, P_X = 9, DIV = 6, UV_S = 10, DIV2 = 12;
 constexpr int P2P_GATHER_ROWS = 64; // capacity (rows per side) of the peer-written gather halos; deeper gathers go through NCCL
 constexpr int P2P_FLAG_INTS = 16;
 
@@ -166,7 +167,8 @@ struct pfs_slab {
     float *d_scalars = nullptr;           // [0] max|v| (advect), [1] max|v| (advect_color), [2] sticky error word (as int: gather
                                           // overflow under an exact bound 1/2/3, peer-transport timeout 9; read by pfs_slab_check),
                                           // [3] setup scratch, [4] max|v| and [5] "a departure row was missing" (as float) of a
-                                          // speculative advect, [6] the same flag as the kernel raises it (int; reset every step)
+                                          // speculative advect, [6] the same flag as the kernel raises it (int; reset every step),
+                                          // [8] "row missing" flag of a speculative advect_color (int), [9] the same as float (all-reduced)
     float *h_scalars = nullptr;           // pinned mirror
     pfs::ncclComm_t comm = nullptr;
     // peer transport (one process per GPU, CUDA IPC): the ring neighbours' planes / gather halos / flags mapped here
@@ -188,7 +190,17 @@ struct pfs_slab {
     cudaEvent_t ev_ready = nullptr, ev_done = nullptr, ev_meas = nullptr, ev_fork = nullptr;
     cudaStream_t side = nullptr;          // carries the all-reduce + read-back of a speculative advect's (max|v|, flag)
     float vbound = -1.f;                  // max|v| of the field the last fluid step started from (< 0: not known yet)
+    // resident state (pfs_slab_upload / pfs_slab_step / pfs_slab_download): which plane unit holds which channel of the
+    // reference's two buffers -- vp = [uv UV_S, p pX, div dX], tmp = [uv uvY, p pY, div dY] -- and the image ping-pong
+    bool resident = false;
+    int uvY = pfs::UV_A, pX = pfs::P_A, pY = pfs::P_B, dX = pfs::DIV, dY = pfs::DIV2;
+    float *img[2] = {nullptr, nullptr};
+    int img_cur = 0;
+    bool pending_color = false;           // a speculative advect_color whose "row missing" flag has not been looked at yet
+    float pending_dt = 0.f;
+    cudaEvent_t ev_color = nullptr;
     float *plane(int k) const { return planes + (size_t)k * plane_floats; }
+    float *interior(int k, size_t row_floats) const { return plane(k) + (size_t)halo * row_floats; }
     int up() const { return (rank + nranks - 1) % nranks; }
     int down() const { return (rank + 1) % nranks; }
 };
@@ -213,11 +225,12 @@ struct Guard {   // cudaSetDevice for the scope of one slab's work
 // ---- small kernels of the slab path -----------------------------------------------------------
 __global__ void flag_to_float_kernel(const int *flag, float *out) { *out = (*flag != 0) ? 1.f : 0.f; }
 
-__global__ void __launch_bounds__(256) max_abs_v_kernel(const float4 *__restrict__ vp, size_t n, float *out)
+template <int CF>     // floats per cell: 4 = interleaved [u,v,p,div], 2 = (u,v) plane
+__global__ void __launch_bounds__(256) max_abs_v_kernel(const float *__restrict__ vp, size_t n, float *out)
 {
     float m = 0.f;
     for (size_t i = (size_t)blockIdx.x * 256 + threadIdx.x; i < n; i += (size_t)gridDim.x * 256) {
-        const float v = fabsf(__ldg(vp + i).y);
+        const float v = fabsf(__ldg(vp + i * CF + 1));
         m = (v > m || v != v) ? v : m;           // NaN propagates: the host then takes the all-gather path
     }
 #pragma unroll
@@ -231,27 +244,29 @@ __global__ void __launch_bounds__(256) max_abs_v_kernel(const float4 *__restrict
     }
 }
 
-// Rows of a periodic field of `total` rows, interleaved cells: the local band plus d halo rows received
-// from each ring neighbour (or the whole field: band0 = 0, band_n = total, d = 0).
+// Rows of a periodic field of `total` rows: the local band plus d halo rows received from each ring neighbour
+// (or the whole field: band0 = 0, band_n = total, d = 0).  Rows are `row_bytes` apart; the cell type is the kernel's business.
 struct RowSource {
-    const float4 *band, *above, *below;
-    int band0, band_n, d, total, width;
+    const char *band, *above, *below;
+    int band0, band_n, d, total;
+    size_t row_bytes;
 };
 
-__device__ __forceinline__ const float4 *source_row(const RowSource &S, int grow, int *overflow, int code)
+__device__ __forceinline__ const char *source_row(const RowSource &S, int grow, int *overflow, int code)
 {
     int r = grow - S.band0;
     if (r < -S.d) r += S.total;
     if (r >= S.band_n + S.d) r -= S.total;
-    if (r >= 0 && r < S.band_n) return S.band + (size_t)r * S.width;
-    if (r < 0 && r >= -S.d) return S.above + (size_t)(r + S.d) * S.width;
-    if (r >= S.band_n && r < S.band_n + S.d) return S.below + (size_t)(r - S.band_n) * S.width;
+    if (r >= 0 && r < S.band_n) return S.band + (size_t)r * S.row_bytes;
+    if (r < 0 && r >= -S.d) return S.above + (size_t)(r + S.d) * S.row_bytes;
+    if (r >= S.band_n && r < S.band_n + S.d) return S.below + (size_t)(r - S.band_n) * S.row_bytes;
     atomicExch(overflow, code);          // cannot happen if D was computed correctly; never read out of bounds
     return nullptr;
 }
 
 // advect (fluid.cpp:24-70) with GLOBAL indices: this rank produces rows [row0, row0+rows) of the gh-row
-// grid from the interleaved field (u,v in the first 8 bytes of a cell, as in the single-GPU kernel).
+// grid from a field whose cells are CF floats apart with (u,v) first (an interleaved buffer or a (u,v) plane).
+template <int CF>
 __global__ void __launch_bounds__(256)
     advect_slab_kernel(const RowSource S, float2 *__restrict__ uv_out, float dt, int w, int gh,
                        int row0, int rows, int y_base, int *overflow, float *vmax_out)
@@ -260,8 +275,9 @@ __global__ void __launch_bounds__(256)
     const bool live = (i < w && jl < rows);
     const int j = row0 + jl;
     const float fw = (float)w, fh = (float)gh;
-    const float4 *own = live ? source_row(S, j, overflow, 1) : nullptr;
-    const float2 uv = own ? __ldg(reinterpret_cast<const float2 *>(own + i)) : make_float2(0.f, 0.f);
+    auto cell = [](const char *row, int x) { return reinterpret_cast<const float2 *>(reinterpret_cast<const float *>(row) + (size_t)x * CF); };
+    const char *own = live ? source_row(S, j, overflow, 1) : nullptr;
+    const float2 uv = own ? __ldg(cell(own, i)) : make_float2(0.f, 0.f);
     if (vmax_out != nullptr) {
         // by-product: max|v| of the field being advected (what bounds the row displacement), NaN -> +inf.
         // Reduced over the whole CTA first (every thread gets here, dead ones with 0): ONE look at the running
@@ -297,18 +313,16 @@ __global__ void __launch_bounds__(256)
     xp = wrap_coord(xp, fw);
     yp = wrap_coord(yp, fh);
     const Bilinear b = make_bilinear(xp, yp, w, gh);
-    const float4 *r0 = source_row(S, b.j0, overflow, 1), *r1 = source_row(S, b.j1, overflow, 1);
+    const char *r0 = source_row(S, b.j0, overflow, 1), *r1 = source_row(S, b.j1, overflow, 1);
     if (!r0 || !r1) return;
-    const float2 f00 = __ldg(reinterpret_cast<const float2 *>(r0 + b.i0));
-    const float2 f10 = __ldg(reinterpret_cast<const float2 *>(r0 + b.i1));
-    const float2 f01 = __ldg(reinterpret_cast<const float2 *>(r1 + b.i0));
-    const float2 f11 = __ldg(reinterpret_cast<const float2 *>(r1 + b.i1));
+    const float2 f00 = __ldg(cell(r0, b.i0)), f10 = __ldg(cell(r0, b.i1)), f01 = __ldg(cell(r1, b.i0)), f11 = __ldg(cell(r1, b.i1));
     uv_out[(size_t)(y_base + jl) * w + i] = make_float2(bilerp(b, f00.x, f10.x, f01.x, f11.x), bilerp(b, f00.y, f10.y, f01.y, f11.y));
 }
 
 // advect_color (fluid.cpp:72-127) with GLOBAL indices: image rows [irow0, irow0+irows) of the ih-row
-// image; velocity rows [row0, row0+rows) (interleaved, local: the image bands are built so that the
+// image; velocity rows [row0, row0+rows) (local, cells VS floats apart: the image bands are built so that the
 // look-up of fluid.cpp:89-90 never leaves the rank's own velocity band).
+template <int VS>
 __global__ void __launch_bounds__(256)
     advect_color_slab_kernel(const RowSource S, float4 *__restrict__ out, const float *__restrict__ vp,
                              float dt_over_viw, float dt_over_vih, float viw, float vih, int iw, int ih, int irow0,
@@ -324,14 +338,15 @@ __global__ void __launch_bounds__(256)
         atomicExch(overflow, 2);
         return;
     }
-    const float2 uv = __ldg(reinterpret_cast<const float2 *>(vp + ((size_t)vj * vw + vi) * 4));
+    const float2 uv = __ldg(reinterpret_cast<const float2 *>(vp + ((size_t)vj * vw + vi) * VS));
     float xp = __fsub_rn((float)i, div_extent(__fmul_rn(dt_over_viw, uv.x), fiw, __frcp_rn(fiw)));
     float yp = __fsub_rn((float)j, div_extent(__fmul_rn(dt_over_vih, uv.y), fih, __frcp_rn(fih)));
     xp = wrap_coord(xp, fiw);
     yp = wrap_coord(yp, fih);
     const Bilinear b = make_bilinear(xp, yp, iw, ih);
-    const float4 *r0 = source_row(S, b.j0, overflow, 3), *r1 = source_row(S, b.j1, overflow, 3);
-    if (!r0 || !r1) return;
+    const char *c0 = source_row(S, b.j0, overflow, 3), *c1 = source_row(S, b.j1, overflow, 3);
+    if (!c0 || !c1) return;
+    const float4 *r0 = reinterpret_cast<const float4 *>(c0), *r1 = reinterpret_cast<const float4 *>(c1);
     const float4 f00 = __ldg(r0 + b.i0), f10 = __ldg(r0 + b.i1), f01 = __ldg(r1 + b.i0), f11 = __ldg(r1 + b.i1);
     float4 o;
     o.x = bilerp(b, f00.x, f10.x, f01.x, f11.x);
@@ -584,7 +599,8 @@ int ensure_bytes(void **ptr, size_t *have_rows, size_t want_rows, size_t row_byt
 // copy of the whole field assembled from every rank's band (always sufficient).
 struct FieldBands {
     int width, total;                         // cells per row, rows of the whole field
-    std::vector<const float4 *> band;         // local slabs' bands (caller memory)
+    size_t cell_bytes;                        // 16: interleaved cells, 8: a (u,v) plane
+    std::vector<const char *> band;           // local slabs' bands (first row of the band)
     std::vector<int> first, count;            // global first row / rows of each local band
     bool image;                               // selects the halo / whole buffers of the slab
 };
@@ -593,25 +609,28 @@ int build_row_sources(const std::vector<pfs_slab *> &local, const FieldBands &F,
                       std::vector<RowSource> *out)
 {
     const size_t n = local.size();
-    const size_t row = (size_t)F.width * sizeof(float4);
+    const size_t row = (size_t)F.width * F.cell_bytes;
     out->resize(n);
-    if (!whole && n == 1 && local[0]->p2p && D <= P2P_GATHER_ROWS && (F.image ? local[0]->ihalo_p2p : local[0]->vhalo_p2p)) {
+    if (!whole && n == 1 && local[0]->p2p && D <= P2P_GATHER_ROWS && row % 16 == 0 &&
+        (F.image ? local[0]->ihalo_p2p : local[0]->vhalo_p2p)) {
         // peer transport: my top D rows become the upper neighbour's "below" rows, my bottom D rows the lower
         // neighbour's "above" rows; both land in the fixed-capacity halos that were IPC-mapped at connect time
+        // (capacity: P2P_GATHER_ROWS rows of 16-byte cells per side; rows of 8-byte cells use half of it)
         pfs_slab *s = local[0];
         Guard g(s->device);
-        const size_t cap = (size_t)P2P_GATHER_ROWS * F.width;
+        const size_t cap = (size_t)P2P_GATHER_ROWS * F.width;            // float4 units per side
         float4 *mine = F.image ? s->ihalo_p2p : s->vhalo_p2p;
         float4 *up = F.image ? s->link_up.ihalo : s->link_up.vhalo;
         float4 *down = F.image ? s->link_down.ihalo : s->link_down.vhalo;
         PushArgs A;
         A.nseg = 1;
-        A.seg[0].src_up = F.band[0];
-        A.seg[0].src_down = F.band[0] + (size_t)(F.count[0] - D) * F.width;
+        A.seg[0].src_up = reinterpret_cast<const float4 *>(F.band[0]);
+        A.seg[0].src_down = reinterpret_cast<const float4 *>(F.band[0] + (size_t)(F.count[0] - D) * row);
         A.seg[0].dst_up = up + cap;                 // its rows [band_n, band_n + D)
         A.seg[0].dst_down = down;                   // its rows [-D, 0)
-        A.seg[0].n16 = (unsigned long long)D * F.width;
-        (*out)[0] = RowSource{F.band[0], mine, mine + cap, F.first[0], F.count[0], D, F.total, F.width};
+        A.seg[0].n16 = (unsigned long long)D * row / 16;
+        (*out)[0] = RowSource{F.band[0], reinterpret_cast<const char *>(mine), reinterpret_cast<const char *>(mine + cap),
+                              F.first[0], F.count[0], D, F.total, row};
         return launch_halo_push(s, A);
     }
     if (!whole) {
@@ -621,17 +640,17 @@ int build_row_sources(const std::vector<pfs_slab *> &local, const FieldBands &F,
             Guard g(s->device);
             float4 **hb = F.image ? &s->ihalo : &s->vhalo;
             size_t *cap = F.image ? &s->ihalo_rows : &s->vhalo_rows;
-            PFS_TRY(ensure_bytes((void **)hb, cap, 2 * (size_t)D, row));
-            float4 *above = *hb, *below = *hb + (size_t)D * F.width;
-            const char *b = reinterpret_cast<const char *>(F.band[k]);
+            PFS_TRY(ensure_bytes((void **)hb, cap, 2 * (size_t)D, (size_t)F.width * 16));
+            char *above = reinterpret_cast<char *>(*hb), *below = above + (size_t)D * row;
+            const char *b = F.band[k];
             Segment sg;
             sg.send_up = b;
             sg.send_down = b + (size_t)(F.count[k] - D) * row;
-            sg.recv_from_up = reinterpret_cast<char *>(above);
-            sg.recv_from_down = reinterpret_cast<char *>(below);
+            sg.recv_from_up = above;
+            sg.recv_from_down = below;
             sg.bytes = (size_t)D * row;
             segs[k].push_back(sg);
-            (*out)[k] = RowSource{F.band[k], above, below, F.first[k], F.count[k], D, F.total, F.width};
+            (*out)[k] = RowSource{F.band[k], above, below, F.first[k], F.count[k], D, F.total, row};
         }
         return ring_exchange(local, segs);
     }
@@ -642,12 +661,12 @@ int build_row_sources(const std::vector<pfs_slab *> &local, const FieldBands &F,
         Guard g(s->device);
         float4 **wb = F.image ? &s->iwhole : &s->vwhole;
         size_t *cap = F.image ? &s->iwhole_rows : &s->vwhole_rows;
-        PFS_TRY(ensure_bytes((void **)wb, cap, (size_t)F.total, row));
+        PFS_TRY(ensure_bytes((void **)wb, cap, (size_t)F.total, (size_t)F.width * 16));
         buf[k] = reinterpret_cast<char *>(*wb);
         if (F.count[k] > 0)
             PFS_CUDA(cudaMemcpyAsync(buf[k] + (size_t)F.first[k] * row, F.band[k], (size_t)F.count[k] * row,
                                      cudaMemcpyDeviceToDevice, s->stream));
-        (*out)[k] = RowSource{*wb, nullptr, nullptr, 0, F.total, 0, F.total, F.width};
+        (*out)[k] = RowSource{buf[k], nullptr, nullptr, 0, F.total, 0, F.total, row};
         if (s->comm != nullptr) {
             for (int r = 0; r < s->nranks; r++) {
                 int f, c;
@@ -795,9 +814,10 @@ extern "C" int pfs_slab_create(pfs_slab **out, int rank, int nranks, int gw, int
     };
     if ((e = cudaMalloc((void **)&s->planes, pfs::N_SLAB_PLANES * s->plane_floats * sizeof(float))) != cudaSuccess) fail(e, "cudaMalloc planes");
     if (st == PFS_OK && (e = cudaMemset(s->planes, 0, pfs::N_SLAB_PLANES * s->plane_floats * sizeof(float))) != cudaSuccess) fail(e, "cudaMemset");
-    if (st == PFS_OK && (e = cudaMalloc((void **)&s->d_scalars, 8 * sizeof(float))) != cudaSuccess) fail(e, "cudaMalloc scalars");
-    if (st == PFS_OK && (e = cudaMemset(s->d_scalars, 0, 8 * sizeof(float))) != cudaSuccess) fail(e, "cudaMemset");
-    if (st == PFS_OK && (e = cudaMallocHost((void **)&s->h_scalars, 8 * sizeof(float))) != cudaSuccess) fail(e, "cudaMallocHost");
+    if (st == PFS_OK && (e = cudaMalloc((void **)&s->d_scalars, 16 * sizeof(float))) != cudaSuccess) fail(e, "cudaMalloc scalars");
+    if (st == PFS_OK && (e = cudaMemset(s->d_scalars, 0, 16 * sizeof(float))) != cudaSuccess) fail(e, "cudaMemset");
+    if (st == PFS_OK && (e = cudaMallocHost((void **)&s->h_scalars, 16 * sizeof(float))) != cudaSuccess) fail(e, "cudaMallocHost");
+    if (st == PFS_OK && (e = cudaEventCreateWithFlags(&s->ev_color, cudaEventDisableTiming)) != cudaSuccess) fail(e, "event");
     if (st == PFS_OK && (e = cudaEventCreateWithFlags(&s->ev_ready, cudaEventDisableTiming)) != cudaSuccess) fail(e, "event");
     if (st == PFS_OK && (e = cudaEventCreateWithFlags(&s->ev_done, cudaEventDisableTiming)) != cudaSuccess) fail(e, "event");
     if (st == PFS_OK && (e = cudaEventCreateWithFlags(&s->ev_meas, cudaEventDisableTiming)) != cudaSuccess) fail(e, "event");
@@ -836,6 +856,9 @@ extern "C" int pfs_slab_destroy(pfs_slab *s)
     if (s->ev_done) cudaEventDestroy(s->ev_done);
     if (s->ev_meas) cudaEventDestroy(s->ev_meas);
     if (s->ev_fork) cudaEventDestroy(s->ev_fork);
+    if (s->ev_color) cudaEventDestroy(s->ev_color);
+    if (s->img[0]) cudaFree(s->img[0]);
+    if (s->img[1]) cudaFree(s->img[1]);
     if (s->side) cudaStreamDestroy(s->side);
     (void)cudaGetLastError();
     delete s;
@@ -1053,10 +1076,17 @@ extern "C" const char *pfs_slab_transport(const pfs_slab *s)
     return s->group.empty() ? "unconnected" : "local";
 }
 
+namespace pfs {
+namespace {
+int resolve_pending_color(const std::vector<pfs_slab *> &L);      // defined with the step functions below
+}
+}  // namespace pfs
+
 extern "C" int pfs_slab_check(pfs_slab *const *slabs, int n_local)
 {
     std::vector<pfs_slab *> local;
     PFS_TRY(check_local("pfs_slab_check", slabs, n_local, &local));
+    if (local[0]->resident) PFS_TRY(resolve_pending_color(local));   // streams: those of the last call
     for (pfs_slab *s : local) {
         Guard g(s->device);
         PFS_CUDA(cudaDeviceSynchronize());
@@ -1132,37 +1162,156 @@ extern "C" int pfs_slab_step_norms(pfs_slab *const *slabs, int n_local, float *c
 }
 
 // ---------------------------------------------------------------------------------------------
-// simulate_fluid_step on slabs.  vp[k] / tmp[k]: the k-th local slab's band of the interleaved buffers
-// (rows x gw x 4 floats, device memory of that slab's device).  Pointer exchange as pfs_simulate_fluid_step.
-// ---------------------------------------------------------------------------------------------
-// `exact_bound`: take the gather depth of the velocity advection from a max|v| reduction that the host waits for
+// simulate_fluid_step / advect_color_step on slabs.
+//
+// Two ways to hold the state:
+//   stateless  vp[k] / tmp[k] (image[k] / itmp[k]): the k-th local slab's band of the caller's interleaved buffers
+//              (rows x gw x 4 floats on that slab's device), read and rewritten every step; pointer exchange as
+//              pfs_simulate_fluid_step.
+//   resident   pfs_slab_upload / pfs_slab_step / pfs_slab_download: the bands live in the slab's own planes between steps,
+//              as in a pfs_ctx (pfs_ctx.cu explains the roles): advect gathers from the projected (u,v) plane, the pressure
+//              warm start is a plane of the last step, project writes a (u,v) plane -- no interleaved traffic at all.
+//
+// Gather depths.  `exact_bound`: take the depth of the velocity advection from a max|v| reduction that the host waits for
 // (one synchronisation at the start of the step).  Otherwise the depth is a guess from the previous step's maximum
 // (x2, +4 rows), the advect kernel raises a flag if a departure row is missing, and the flag is read back much later --
-// just before the only kernel that overwrites the caller's buffers -- when it has long been written.  A raised flag
+// just before the only kernel that overwrites the step's inputs (project) -- when it has long been written.  A raised flag
 // (never seen outside the tests that provoke it) discards the step's scratch results and reruns it with the exact bound.
-static int slab_fluid_step(pfs_slab *const *slabs, int n_local, float **vp, float **tmp, float dt, float viscosity,
-                           int n_diffuse, int n_pressure, void *const *streams, bool exact_bound, const float *const *forces)
+// Resident state gives advect_color the same treatment (the stateless call must measure: its result is the caller's at
+// once): its flag is looked at at the same point of the NEXT step -- or in pfs_slab_download / pfs_slab_check -- while the
+// old image and the velocity it was advected through are both still intact, and a miss reruns it with a measured depth.
+// ---------------------------------------------------------------------------------------------
+namespace pfs {
+namespace {
+
+struct StepIO {
+    bool resident;
+    float **vp, **tmp;                   // stateless only
+    const float *const *forces;          // optional force bands (addForces slot)
+};
+
+int min_band_rows(const pfs_slab *s, bool image)
 {
-    const char *fn = "pfs_slab_simulate_fluid_step";
-    std::vector<pfs_slab *> L;
-    PFS_TRY(check_local(fn, slabs, n_local, &L));
-    if (n_diffuse < 1 || n_pressure < 1) {
-        set_error("%s: sweep counts must be >= 1", fn);
-        return PFS_EINVAL;
-    }
-    if (!vp || !tmp) {
-        set_error("%s: vp / tmp arrays are null", fn);
-        return PFS_EINVAL;
-    }
-    const int n = n_local;
-    for (int k = 0; k < n; k++) {
-        if (!vp[k] || !tmp[k] || vp[k] == tmp[k] || ((uintptr_t)vp[k] & 15) || ((uintptr_t)tmp[k] & 15)) {
-            set_error("%s: slab %d: vp/tmp must be distinct, non-null, 16-byte aligned device buffers", fn, k);
-            return PFS_EINVAL;
+    int m = image ? s->ih : s->gh;
+    for (int r = 0; r < s->nranks; r++) {
+        int f, c;
+        band(s->gh, s->nranks, r, &f, &c);
+        if (image) {
+            int jf, jc;
+            image_band(s->ih, s->gh, f, c, &jf, &jc);
+            c = jc;
         }
-        L[k]->stream = streams ? (cudaStream_t)streams[k] : nullptr;
+        m = std::min(m, c);
     }
+    return m;
+}
+
+// advect_color on the bands: image_in[k] -> image_out[k] through the velocity band vel[k] (cells `vs` floats apart).
+// speculative: gather depth guessed from `vbound`, "row missing" flag raised in d_scalars[8] and left for resolve_pending_color().
+int color_step(const std::vector<pfs_slab *> &L, float *const *image_in, float *const *image_out, const float *const *vel, int vs,
+               float dt, bool speculative)
+{
+    const int n = (int)L.size();
+    const int iw = L[0]->iw, ih = L[0]->ih, gw = L[0]->gw, gh = L[0]->gh;
+    const float viw = (float)gw / (float)iw, vih = (float)gh / (float)ih;
+    const float dt_over_viw = dt / viw, dt_over_vih = dt / vih;
+    PhaseScope ph(PFS_PHASE_ADVECT_COLOR, L[0]->stream);
+    const int min_rows = min_band_rows(L[0], true);
+    bool whole = false;
+    int D = 0;
+    if (speculative) {
+        const double guess = 2.0 * std::fabs((double)dt_over_vih) * (double)L[0]->vbound / (double)ih;
+        if (guess * 1.001 + 5.0 < (double)min_rows) D = std::max(8, (int)std::ceil(guess * 1.001) + 4);
+        if (D == 0 || D + 3 >= min_rows) speculative = false;
+    }
+    if (!speculative) {
+        for (int k = 0; k < n; k++) {
+            pfs_slab *s = L[k];
+            Guard g(s->device);
+            PFS_CUDA(cudaMemsetAsync(s->d_scalars + 1, 0, sizeof(float), s->stream));
+            const size_t cells = (size_t)s->rows * gw;
+            if (vs == 2)
+                PFS_LAUNCH(max_abs_v_kernel<2>, 592, 256, 0, s->stream, vel[k], cells, s->d_scalars + 1);
+            else
+                PFS_LAUNCH(max_abs_v_kernel<4>, 592, 256, 0, s->stream, vel[k], cells, s->d_scalars + 1);
+        }
+        float vmax = 0.f;
+        PFS_TRY(global_max(L, 1, &vmax));
+        const double disp = std::fabs((double)dt_over_vih) * (double)vmax / (double)ih;
+        whole = !(disp * 1.001 + 3.0 < (double)min_rows);
+        D = whole ? 0 : (int)std::ceil(disp * 1.001) + 2;
+    }
+    FieldBands F{iw, ih, 16, {}, {}, {}, true};
+    for (int k = 0; k < n; k++) {
+        F.band.push_back(reinterpret_cast<const char *>(image_in[k]));
+        F.first.push_back(L[k]->irow0);
+        F.count.push_back(L[k]->irows);
+    }
+    std::vector<RowSource> src;
+    PFS_TRY(build_row_sources(L, F, D, whole, &src));
+    for (int k = 0; k < n; k++) {
+        pfs_slab *s = L[k];
+        Guard g(s->device);
+        int *flag = reinterpret_cast<int *>(s->d_scalars + (speculative ? 8 : 2));
+        if (speculative) PFS_CUDA(cudaMemsetAsync(s->d_scalars + 8, 0, 2 * sizeof(float), s->stream));
+        if (s->irows > 0) {
+            dim3 block(64, 4), grid((iw + 63) / 64, (s->irows + 3) / 4);
+            float4 *out = reinterpret_cast<float4 *>(image_out[k]);
+            if (vs == 2)
+                PFS_LAUNCH(advect_color_slab_kernel<2>, grid, block, 0, s->stream, src[k], out, vel[k], dt_over_viw, dt_over_vih,
+                           viw, vih, iw, ih, s->irow0, s->irows, gw, s->row0, s->rows, flag);
+            else
+                PFS_LAUNCH(advect_color_slab_kernel<4>, grid, block, 0, s->stream, src[k], out, vel[k], dt_over_viw, dt_over_vih,
+                           viw, vih, iw, ih, s->irow0, s->irows, gw, s->row0, s->rows, flag);
+        }
+        if (speculative) {
+            // "a row was missing" -> every rank, then the host; nobody waits for it yet
+            PFS_LAUNCH(flag_to_float_kernel, 1, 1, 0, s->stream, reinterpret_cast<const int *>(s->d_scalars + 8), s->d_scalars + 9);
+            PFS_CUDA(cudaEventRecord(s->ev_fork, s->stream));
+            PFS_CUDA(cudaStreamWaitEvent(s->side, s->ev_fork, 0));
+            if (s->comm != nullptr)
+                PFS_NCCL(nccl().AllReduce(s->d_scalars + 9, s->d_scalars + 9, 1, ncclFloat, ncclMax, s->comm, s->side));
+            PFS_CUDA(cudaMemcpyAsync(s->h_scalars + 9, s->d_scalars + 9, sizeof(float), cudaMemcpyDeviceToHost, s->side));
+            PFS_CUDA(cudaEventRecord(s->ev_color, s->side));
+            s->pending_color = true;
+            s->pending_dt = dt;
+        }
+    }
+    return PFS_OK;
+}
+
+// Resident state: look at the flag of the last speculative advect_color; on a miss run it again with a measured depth
+// (old image = img[cur^1], velocity = the projected plane: both untouched since).
+int resolve_pending_color(const std::vector<pfs_slab *> &L)
+{
+    if (!L[0]->pending_color) return PFS_OK;
+    bool missed = false;
+    for (pfs_slab *s : L) {
+        Guard g(s->device);
+        PFS_CUDA(cudaEventSynchronize(s->ev_color));
+        missed = missed || (s->h_scalars[9] != 0.f);
+        s->pending_color = false;
+    }
+    if (!missed) return PFS_OK;
+    std::vector<float *> in, out;
+    std::vector<const float *> vel;
+    for (pfs_slab *s : L) {
+        in.push_back(s->img[s->img_cur ^ 1]);
+        out.push_back(s->img[s->img_cur]);
+        vel.push_back(s->interior(UV_S, 2 * (size_t)s->gw));
+    }
+    return color_step(L, in.data(), out.data(), vel.data(), 2, L[0]->pending_dt, false);
+}
+
+int fluid_step(const std::vector<pfs_slab *> &L, const StepIO &io, float dt, float viscosity, int n_diffuse, int n_pressure,
+               bool exact_bound)
+{
+    const int n = (int)L.size();
     const int gw = L[0]->gw, gh = L[0]->gh;
+    const int halo = L[0]->halo;
+    const int cf = io.resident ? 2 : 4;                  // floats per cell of the field advect gathers from
+    std::vector<const float *> src_band(n);
+    for (int k = 0; k < n; k++) src_band[k] = io.resident ? L[k]->interior(UV_S, 2 * (size_t)gw) : io.vp[k];
 
     // phase timing (pfs_phase_times) follows the first local slab's stream
     cudaStream_t ts = L[0]->stream;
@@ -1177,12 +1326,7 @@ static int slab_fluid_step(pfs_slab *const *slabs, int n_local, float **vp, floa
     };
 
     // ---- advect: displacement bound -> halo depth D of the (u,v) gather source ----
-    int min_rows = gh;
-    for (int r = 0; r < L[0]->nranks; r++) {
-        int f, c;
-        band(gh, L[0]->nranks, r, &f, &c);
-        min_rows = std::min(min_rows, c);
-    }
+    const int min_rows = min_band_rows(L[0], false);
     static const bool spec_env = !(getenv("PFS_SLAB_SPECULATE") && !strcmp(getenv("PFS_SLAB_SPECULATE"), "0"));
     bool speculate = spec_env && !exact_bound && L[0]->vbound >= 0.f;
     bool whole = false;
@@ -1202,7 +1346,10 @@ static int slab_fluid_step(pfs_slab *const *slabs, int n_local, float **vp, floa
             Guard g(s->device);
             PFS_CUDA(cudaMemsetAsync(s->d_scalars, 0, sizeof(float), s->stream));
             const size_t cells = (size_t)s->rows * gw;
-            PFS_LAUNCH(max_abs_v_kernel, 592, 256, 0, s->stream, reinterpret_cast<const float4 *>(vp[k]), cells, s->d_scalars);
+            if (cf == 2)
+                PFS_LAUNCH(max_abs_v_kernel<2>, 592, 256, 0, s->stream, src_band[k], cells, s->d_scalars);
+            else
+                PFS_LAUNCH(max_abs_v_kernel<4>, 592, 256, 0, s->stream, src_band[k], cells, s->d_scalars);
         }
         float vmax = 0.f;
         PFS_TRY(global_max(L, 0, &vmax));
@@ -1214,9 +1361,9 @@ static int slab_fluid_step(pfs_slab *const *slabs, int n_local, float **vp, floa
         D = whole ? 0 : (int)std::ceil(disp * 1.001) + 2;
     }
     {
-        FieldBands F{gw, gh, {}, {}, {}, false};
+        FieldBands F{gw, gh, (size_t)cf * sizeof(float), {}, {}, {}, false};
         for (int k = 0; k < n; k++) {
-            F.band.push_back(reinterpret_cast<const float4 *>(vp[k]));
+            F.band.push_back(reinterpret_cast<const char *>(src_band[k]));
             F.first.push_back(L[k]->row0);
             F.count.push_back(L[k]->rows);
         }
@@ -1227,9 +1374,13 @@ static int slab_fluid_step(pfs_slab *const *slabs, int n_local, float **vp, floa
             Guard g(s->device);
             if (speculate) PFS_CUDA(cudaMemsetAsync(s->d_scalars + 4, 0, 3 * sizeof(float), s->stream));
             dim3 block(64, 4), grid((gw + 63) / 64, (s->rows + 3) / 4);
-            PFS_LAUNCH(advect_slab_kernel, grid, block, 0, s->stream, src[k], reinterpret_cast<float2 *>(s->plane(UV_A)), dt, gw, gh,
-                       s->row0, s->rows, s->halo, reinterpret_cast<int *>(s->d_scalars + (speculate ? 6 : 2)),
-                       speculate ? s->d_scalars + 4 : nullptr);
+            float2 *dst = reinterpret_cast<float2 *>(s->plane(UV_A));
+            int *flag = reinterpret_cast<int *>(s->d_scalars + (speculate ? 6 : 2));
+            float *vmax_out = speculate ? s->d_scalars + 4 : nullptr;
+            if (cf == 2)
+                PFS_LAUNCH(advect_slab_kernel<2>, grid, block, 0, s->stream, src[k], dst, dt, gw, gh, s->row0, s->rows, s->halo, flag, vmax_out);
+            else
+                PFS_LAUNCH(advect_slab_kernel<4>, grid, block, 0, s->stream, src[k], dst, dt, gw, gh, s->row0, s->rows, s->halo, flag, vmax_out);
             if (speculate) {
                 // (max|v| of this step's input, "a departure row was missing") -> every rank, then the host; nobody waits yet
                 // (on a side stream: the sweeps that follow do not depend on it)
@@ -1244,14 +1395,12 @@ static int slab_fluid_step(pfs_slab *const *slabs, int n_local, float **vp, floa
         }
     }
 
-    // n sweeps starting from iterate 0 in planes (pa0, pa1), all in fused passes; the pass that reaches sweep n also
-    // stores iterate n-1 into planes (px0, px1) (as pfs_api.cu's run_sweeps does), so both iterates the reference
+    // n sweeps starting from iterate 0 in plane unit pa, all in fused passes; the pass that reaches sweep n also
+    // stores iterate n-1 into unit px (as pfs_api.cu's run_diffuse / run_pressure do), so both iterates the reference
     // leaves behind exist afterwards.  `valid` tracks how many halo rows of the current iterate are correct on
     // every slab: an exchange makes it `halo`; a pass of depth t needs t of them and -- by also recomputing the
     // e = valid-t rows just outside the band -- leaves e valid rows on its result.
-    const int halo = L[0]->halo;
-    // `diffusion`: (u,v) planes through the packed kernel; else the pressure planes.  pa/pb: ping-pong plane units,
-    // px: the unit receiving iterate n-1.
+    // `diffusion`: (u,v) planes through the packed kernel; else the pressure planes.
     auto run_sweeps = [&](bool diffusion, int pa, int pb, int px, const SweepParams &proto, int count, int *last,
                           int *prev, int *valid_out, const float *const *force_bands) -> int {
         int cur = pa, oth = pb;
@@ -1307,10 +1456,14 @@ static int slab_fluid_step(pfs_slab *const *slabs, int n_local, float **vp, floa
             std::swap(cur, oth);
             return PFS_OK;
         };
-        while (left > 0) {
-            int t = std::min(left, depth);
+        // Diffusion: pass depths as even as possible, as launch_diffuse_packed plans them (ceil(count / depth) passes of
+        // depth d or d+1).  Pressure: full-depth passes, then the remainder (a depth-7 pass costs more per sweep than 8 or 4).
+        const int n_passes = (count + depth - 1) / depth;
+        const int base_t = count / n_passes, n_deeper = count % n_passes;
+        for (int pass = 0; left > 0; pass++) {
+            int t = diffusion ? std::min(left, base_t + (pass < n_deeper ? 1 : 0)) : std::min(left, depth);
             if (t < 1) t = 1;
-            if (left - t == 1 && t >= 3) t -= 1;        // never end on a lone single sweep: it could not store iterate n-1
+            if (!diffusion && left - t == 1 && t >= 3) t -= 1;      // never end on a lone single sweep: it could not store iterate n-1
             PFS_TRY(one_pass(t, left - t == 0));
             left -= t;
         }
@@ -1328,16 +1481,33 @@ static int slab_fluid_step(pfs_slab *const *slabs, int n_local, float **vp, floa
     int d_valid = 0;
     int dl = UV_A, dpv = UV_B;                                            // iterate n_d, iterate n_d - 1
     next_phase(PFS_PHASE_DIFFUSE);
-    PFS_TRY(run_sweeps(true, UV_A, UV_B, UV_X, dp, n_diffuse, &dl, &dpv, &d_valid, forces));
+    PFS_TRY(run_sweeps(true, UV_A, UV_B, UV_X, dp, n_diffuse, &dl, &dpv, &d_valid, io.forces));
     next_phase(PFS_PHASE_DIVERGENCE);
 
-    // pointer choreography (pfs_simulate_fluid_step)
+    // pointer choreography (pfs_simulate_fluid_step): struct `vp` points at buffer Bv after diffuse (the original vp buffer for
+    // an odd sweep count, else tmp's), its pressure channel is the warm start; struct `tmp` ends on the buffer holding p_N
+    const bool bv_is_x = (n_diffuse & 1) != 0;
+    const bool bp_is_bv = (n_pressure & 1) == 0;
     std::vector<float *> Bv(n), Bo(n), Bp(n), Bq(n);
-    for (int k = 0; k < n; k++) {
-        Bv[k] = (n_diffuse & 1) ? vp[k] : tmp[k];
-        Bo[k] = (n_diffuse & 1) ? tmp[k] : vp[k];
-        Bp[k] = (n_pressure & 1) ? Bo[k] : Bv[k];
-        Bq[k] = (n_pressure & 1) ? Bv[k] : Bo[k];
+    if (!io.resident) {
+        for (int k = 0; k < n; k++) {
+            Bv[k] = bv_is_x ? io.vp[k] : io.tmp[k];
+            Bo[k] = bv_is_x ? io.tmp[k] : io.vp[k];
+            Bp[k] = bp_is_bv ? Bv[k] : Bo[k];
+            Bq[k] = bp_is_bv ? Bo[k] : Bv[k];
+        }
+    }
+    // pressure plane units: stateless P_A (filled from the warm-start channel by the divergence kernel), P_B, P_X; resident:
+    // the warm-start plane of the last step and the two others (the same on every slab)
+    int p_warm = P_A, p_oth = P_B, p_ext = P_X;
+    if (io.resident) {
+        p_warm = bv_is_x ? L[0]->pX : L[0]->pY;
+        const int units[3] = {P_A, P_B, P_X};
+        int others[2], q = 0;
+        for (int u : units)
+            if (u != p_warm) others[q++] = u;
+        p_oth = others[0];
+        p_ext = others[1];
     }
 
     // ---- divergence (needs one halo row of v) + warm-start pressure; then the divergence halo ----
@@ -1348,7 +1518,8 @@ static int slab_fluid_step(pfs_slab *const *slabs, int n_local, float **vp, floa
         for (int k = 0; k < n; k++) {
             pfs_slab *s = L[k];
             Guard g(s->device);
-            PFS_TRY(launch_divergence(s->plane(dl), s->plane(DIV), Bv[k], s->plane(P_A), dt, gw, s->rows, s->stream, halo, 0));
+            PFS_TRY(launch_divergence(s->plane(dl), s->plane(DIV), io.resident ? nullptr : Bv[k], io.resident ? nullptr : s->plane(P_A),
+                                      dt, gw, s->rows, s->stream, halo, 0));
         }
         for (int k = 0; k < n; k++) pl[k][0] = L[k]->plane(DIV);
         PFS_TRY(exchange_planes(L, pl, halo, (size_t)gw));
@@ -1359,12 +1530,13 @@ static int slab_fluid_step(pfs_slab *const *slabs, int n_local, float **vp, floa
     pp.alpha = 1.0f;
     pp.beta = 4.0f;
     int p_valid = 0;
-    int pl_last = P_A, pl_prev = P_B;
+    int pl_last = p_warm, pl_prev = p_oth;
     next_phase(PFS_PHASE_PRESSURE);
-    PFS_TRY(run_sweeps(false, P_A, P_B, P_X, pp, n_pressure, &pl_last, &pl_prev, &p_valid, nullptr));
+    PFS_TRY(run_sweeps(false, p_warm, p_oth, p_ext, pp, n_pressure, &pl_last, &pl_prev, &p_valid, nullptr));
     next_phase(PFS_PHASE_PROJECT);
 
-    // ---- late check of a speculative advect: everything so far only wrote scratch planes ----
+    // ---- late checks: everything so far only wrote scratch planes ----
+    if (io.resident) PFS_TRY(resolve_pending_color(L));          // the last advect_color's flag, before project overwrites its velocity
     if (speculate) {
         float vmax = 0.f;
         bool missed = false;
@@ -1382,34 +1554,90 @@ static int slab_fluid_step(pfs_slab *const *slabs, int n_local, float **vp, floa
             // peer-transport timeout) is never touched here, so pfs_slab_check still sees whatever it holds
             delete ph;
             ph = nullptr;
-            return slab_fluid_step(slabs, n_local, vp, tmp, dt, viscosity, n_diffuse, n_pressure, streams, true, forces);
+            return fluid_step(L, io, dt, viscosity, n_diffuse, n_pressure, true);
         }
     }
 
-    // ---- gradient subtraction + write-back (needs one halo row of p_N) ----
+    // ---- gradient subtraction (needs one halo row of p_N) + write-back ----
     {
         std::vector<std::vector<float *>> pl(n);
         for (int k = 0; k < n; k++) pl[k].push_back(L[k]->plane(pl_last));
         if (p_valid < 1) PFS_TRY(exchange_planes(L, pl, 1, (size_t)gw));
+        const int uv_p = bp_is_bv ? dl : dpv;      // the (u,v) of the buffer holding p_N: diffusion iterate n if it is Bv, else n-1
         for (int k = 0; k < n; k++) {
             pfs_slab *s = L[k];
             Guard g(s->device);
-            const bool use_last = (Bp[k] == Bv[k]);
-            PFS_TRY(launch_project_pack(s->plane(use_last ? dl : dpv), s->plane(pl_last), s->plane(pl_prev), s->plane(DIV),
-                                        Bq[k], Bp[k], dt, gw, s->rows, s->stream, halo, 0));
+            if (io.resident)
+                PFS_TRY(launch_project_uv(s->plane(uv_p), s->plane(pl_last), s->plane(UV_S), dt, gw, s->rows, s->stream, halo, 0, nullptr));
+            else
+                PFS_TRY(launch_project_pack(s->plane(uv_p), s->plane(pl_last), s->plane(pl_prev), s->plane(DIV), Bq[k], Bp[k], dt, gw,
+                                            s->rows, s->stream, halo, 0));
+        }
+        if (io.resident) {
+            for (pfs_slab *s : L) {
+                s->uvY = uv_p;
+                s->pX = pl_prev;
+                s->pY = pl_last;
+                s->dX = s->dY = DIV;
+            }
         }
     }
-    for (int k = 0; k < n; k++) {
-        vp[k] = Bq[k];
-        tmp[k] = Bp[k];
+    if (!io.resident) {
+        for (int k = 0; k < n; k++) {
+            io.vp[k] = Bq[k];
+            io.tmp[k] = Bp[k];
+        }
     }
     return PFS_OK;
 }
 
+int begin_call(const char *fn, pfs_slab *const *slabs, int n_local, void *const *streams, std::vector<pfs_slab *> *L)
+{
+    PFS_TRY(check_local(fn, slabs, n_local, L));
+    for (int k = 0; k < n_local; k++) (*L)[k]->stream = streams ? (cudaStream_t)streams[k] : nullptr;
+    return PFS_OK;
+}
+
+int check_counts(const char *fn, int n_diffuse, int n_pressure)
+{
+    if (n_diffuse < 1 || n_pressure < 1) {
+        set_error("%s: sweep counts must be >= 1", fn);
+        return PFS_EINVAL;
+    }
+    return PFS_OK;
+}
+
+int stateless_fluid_step(const char *fn, pfs_slab *const *slabs, int n_local, float **vp, float **tmp, float dt, float viscosity,
+                         int n_diffuse, int n_pressure, const float *const *forces, void *const *streams)
+{
+    std::vector<pfs_slab *> L;
+    PFS_TRY(begin_call(fn, slabs, n_local, streams, &L));
+    PFS_TRY(check_counts(fn, n_diffuse, n_pressure));
+    if (!vp || !tmp) {
+        set_error("%s: vp / tmp arrays are null", fn);
+        return PFS_EINVAL;
+    }
+    for (int k = 0; k < n_local; k++) {
+        if (!vp[k] || !tmp[k] || vp[k] == tmp[k] || ((uintptr_t)vp[k] & 15) || ((uintptr_t)tmp[k] & 15)) {
+            set_error("%s: slab %d: vp/tmp must be distinct, non-null, 16-byte aligned device buffers", fn, k);
+            return PFS_EINVAL;
+        }
+        if (forces && (!forces[k] || ((uintptr_t)forces[k] & 15))) {
+            set_error("%s: slab %d: the force band must be a non-null, 16-byte aligned device buffer", fn, k);
+            return PFS_EINVAL;
+        }
+    }
+    return fluid_step(L, StepIO{false, vp, tmp, forces}, dt, viscosity, n_diffuse, n_pressure, false);
+}
+
+}  // namespace
+}  // namespace pfs
+
 extern "C" int pfs_slab_simulate_fluid_step(pfs_slab *const *slabs, int n_local, float **vp, float **tmp, float dt,
                                             float viscosity, int n_diffuse, int n_pressure, void *const *streams)
 {
-    return slab_fluid_step(slabs, n_local, vp, tmp, dt, viscosity, n_diffuse, n_pressure, streams, false, nullptr);
+    return stateless_fluid_step("pfs_slab_simulate_fluid_step", slabs, n_local, vp, tmp, dt, viscosity, n_diffuse, n_pressure, nullptr,
+                                streams);
 }
 
 // The same step with an external force at the addForces slot (pfs_simulate_fluid_step_forced): forces[k] is the k-th
@@ -1418,86 +1646,128 @@ extern "C" int pfs_slab_simulate_fluid_step_forced(pfs_slab *const *slabs, int n
                                                    float viscosity, int n_diffuse, int n_pressure,
                                                    const float *const *forces, void *const *streams)
 {
-    if (forces != nullptr) {
-        for (int k = 0; k < n_local; k++) {
-            if (!forces[k] || ((uintptr_t)forces[k] & 15)) {
-                set_error("pfs_slab_simulate_fluid_step_forced: slab %d: the force band must be a non-null, 16-byte aligned device buffer", k);
-                return PFS_EINVAL;
-            }
-        }
-    }
-    return slab_fluid_step(slabs, n_local, vp, tmp, dt, viscosity, n_diffuse, n_pressure, streams, false, forces);
+    return stateless_fluid_step("pfs_slab_simulate_fluid_step_forced", slabs, n_local, vp, tmp, dt, viscosity, n_diffuse, n_pressure,
+                                forces, streams);
 }
 
-// ---------------------------------------------------------------------------------------------
 // advect_color_step on slabs.  image[k] / itmp[k]: the k-th slab's band of image rows (irows x iw x 4);
 // vp[k]: its band of the (already stepped) velocity field.  image[k] and itmp[k] are exchanged.
-// ---------------------------------------------------------------------------------------------
 extern "C" int pfs_slab_advect_color_step(pfs_slab *const *slabs, int n_local, float **image, float **itmp,
                                           float *const *vp, float dt, void *const *streams)
 {
     const char *fn = "pfs_slab_advect_color_step";
     std::vector<pfs_slab *> L;
-    PFS_TRY(check_local(fn, slabs, n_local, &L));
+    PFS_TRY(begin_call(fn, slabs, n_local, streams, &L));
     if (!image || !itmp || !vp) {
         set_error("%s: null array argument", fn);
         return PFS_EINVAL;
     }
-    const int n = n_local;
-    const int iw = L[0]->iw, ih = L[0]->ih, gw = L[0]->gw, gh = L[0]->gh;
-    if (iw < 1 || ih < 1) {
+    if (L[0]->iw < 1 || L[0]->ih < 1) {
         set_error("%s: the slabs were created without an image", fn);
         return PFS_EINVAL;
     }
-    for (int k = 0; k < n; k++) {
+    for (int k = 0; k < n_local; k++) {
         if (!vp[k] || (L[k]->irows > 0 && (!image[k] || !itmp[k]))) {
             set_error("%s: slab %d: null buffer", fn, k);
             return PFS_EINVAL;
         }
-        L[k]->stream = streams ? (cudaStream_t)streams[k] : nullptr;
     }
-    const float viw = (float)gw / (float)iw, vih = (float)gh / (float)ih;
-    const float dt_over_viw = dt / viw, dt_over_vih = dt / vih;
-    PhaseScope ph(PFS_PHASE_ADVECT_COLOR, L[0]->stream);
+    PFS_TRY(color_step(L, image, itmp, vp, 4, dt, false));
+    for (int k = 0; k < n_local; k++) std::swap(image[k], itmp[k]);   // fluid.cpp:317-319
+    return PFS_OK;
+}
 
-    for (int k = 0; k < n; k++) {
+// ---------------------------------------------------------------------------------------------
+// Resident state: pfs_slab_upload / pfs_slab_step / pfs_slab_download
+// ---------------------------------------------------------------------------------------------
+extern "C" int pfs_slab_upload(pfs_slab *const *slabs, int n_local, const float *const *vp, const float *const *tmp,
+                               const float *const *image, void *const *streams)
+{
+    const char *fn = "pfs_slab_upload";
+    std::vector<pfs_slab *> L;
+    PFS_TRY(begin_call(fn, slabs, n_local, streams, &L));
+    if (!vp || !tmp || (L[0]->iw > 0 && !image)) {
+        set_error("%s: vp, tmp%s are needed", fn, L[0]->iw > 0 ? " and image" : "");
+        return PFS_EINVAL;
+    }
+    for (int k = 0; k < n_local; k++) {
+        pfs_slab *s = L[k];
+        if (!vp[k] || !tmp[k] || ((uintptr_t)vp[k] & 15) || ((uintptr_t)tmp[k] & 15) || (s->irows > 0 && (!image[k] || ((uintptr_t)image[k] & 15)))) {
+            set_error("%s: slab %d: bands must be non-null, 16-byte aligned device buffers", fn, k);
+            return PFS_EINVAL;
+        }
+        Guard g(s->device);
+        const size_t ibytes = (size_t)s->irows * s->iw * 4 * sizeof(float);
+        for (int q = 0; q < 2 && ibytes > 0; q++)
+            if (!s->img[q]) PFS_CUDA(cudaMalloc((void **)&s->img[q], ibytes));
+        const size_t gw = (size_t)s->gw;
+        s->uvY = UV_A; s->pX = P_A; s->pY = P_B; s->dX = DIV; s->dY = DIV2;
+        PFS_TRY(launch_unpack(vp[k], s->interior(UV_S, 2 * gw), s->interior(s->pX, gw), s->interior(s->dX, gw), s->gw, s->rows, s->stream));
+        PFS_TRY(launch_unpack(tmp[k], s->interior(s->uvY, 2 * gw), s->interior(s->pY, gw), s->interior(s->dY, gw), s->gw, s->rows, s->stream));
+        if (ibytes > 0) PFS_CUDA(cudaMemcpyAsync(s->img[0], image[k], ibytes, cudaMemcpyDefault, s->stream));
+        s->img_cur = 0;
+        s->resident = true;
+        s->pending_color = false;
+        s->vbound = -1.f;                 // the velocity is new: the first gather measures its bound
+    }
+    return PFS_OK;
+}
+
+extern "C" int pfs_slab_download(pfs_slab *const *slabs, int n_local, float *const *vp, float *const *tmp, float *const *image,
+                                 void *const *streams)
+{
+    const char *fn = "pfs_slab_download";
+    std::vector<pfs_slab *> L;
+    PFS_TRY(begin_call(fn, slabs, n_local, streams, &L));
+    for (pfs_slab *s : L) {
+        if (!s->resident) {
+            set_error("%s: the slabs hold no state (call pfs_slab_upload first)", fn);
+            return PFS_ESTATE;
+        }
+    }
+    PFS_TRY(resolve_pending_color(L));
+    for (int k = 0; k < n_local; k++) {
         pfs_slab *s = L[k];
         Guard g(s->device);
-        PFS_CUDA(cudaMemsetAsync(s->d_scalars + 1, 0, sizeof(float), s->stream));
-        const size_t cells = (size_t)s->rows * gw;
-        PFS_LAUNCH(max_abs_v_kernel, 592, 256, 0, s->stream, reinterpret_cast<const float4 *>(vp[k]), cells,
-                   s->d_scalars + 1);
+        const size_t gw = (size_t)s->gw;
+        if (vp && vp[k])
+            PFS_TRY(launch_pack(vp[k], s->interior(UV_S, 2 * gw), s->interior(s->pX, gw), s->interior(s->dX, gw), s->gw, s->rows, s->stream));
+        if (tmp && tmp[k])
+            PFS_TRY(launch_pack(tmp[k], s->interior(s->uvY, 2 * gw), s->interior(s->pY, gw), s->interior(s->dY, gw), s->gw, s->rows, s->stream));
+        if (image && image[k] && s->irows > 0)
+            PFS_CUDA(cudaMemcpyAsync(image[k], s->img[s->img_cur], (size_t)s->irows * s->iw * 4 * sizeof(float), cudaMemcpyDefault, s->stream));
     }
-    float vmax = 0.f;
-    PFS_TRY(global_max(L, 1, &vmax));
-    const double disp = std::fabs((double)dt_over_vih) * (double)vmax / (double)ih;
-    int min_rows = ih;
-    for (int r = 0; r < L[0]->nranks; r++) {
-        int f, c, jf, jc;
-        band(gh, L[0]->nranks, r, &f, &c);
-        image_band(ih, gh, f, c, &jf, &jc);
-        min_rows = std::min(min_rows, jc);
-    }
-    const bool whole = !(disp * 1.001 + 3.0 < (double)min_rows);
-    const int D = whole ? 0 : (int)std::ceil(disp * 1.001) + 2;
+    return PFS_OK;
+}
 
-    FieldBands F{iw, ih, {}, {}, {}, true};
-    for (int k = 0; k < n; k++) {
-        F.band.push_back(reinterpret_cast<const float4 *>(image[k]));
-        F.first.push_back(L[k]->irow0);
-        F.count.push_back(L[k]->irows);
+// n_steps iterations of the driver loop (main.cpp:236-239) on the resident state.
+extern "C" int pfs_slab_step(pfs_slab *const *slabs, int n_local, int n_steps, float dt, float viscosity, int n_diffuse,
+                             int n_pressure, void *const *streams)
+{
+    const char *fn = "pfs_slab_step";
+    std::vector<pfs_slab *> L;
+    PFS_TRY(begin_call(fn, slabs, n_local, streams, &L));
+    PFS_TRY(check_counts(fn, n_diffuse, n_pressure));
+    for (pfs_slab *s : L) {
+        if (!s->resident) {
+            set_error("%s: the slabs hold no state (call pfs_slab_upload first)", fn);
+            return PFS_ESTATE;
+        }
     }
-    std::vector<RowSource> src;
-    PFS_TRY(build_row_sources(L, F, D, whole, &src));
-    for (int k = 0; k < n; k++) {
-        pfs_slab *s = L[k];
-        if (s->irows == 0) continue;
-        Guard g(s->device);
-        dim3 block(64, 4), grid((iw + 63) / 64, (s->irows + 3) / 4);
-        PFS_LAUNCH(advect_color_slab_kernel, grid, block, 0, s->stream, src[k], reinterpret_cast<float4 *>(itmp[k]), vp[k],
-                   dt_over_viw, dt_over_vih, viw, vih, iw, ih, s->irow0, s->irows, gw, s->row0, s->rows,
-                   reinterpret_cast<int *>(s->d_scalars + 2));
+    static const bool spec_env = !(getenv("PFS_SLAB_SPECULATE") && !strcmp(getenv("PFS_SLAB_SPECULATE"), "0"));
+    const bool has_image = L[0]->iw > 0;
+    for (int it = 0; it < n_steps; it++) {
+        PFS_TRY(fluid_step(L, StepIO{true, nullptr, nullptr, nullptr}, dt, viscosity, n_diffuse, n_pressure, false));
+        if (!has_image) continue;
+        std::vector<float *> in, out;
+        std::vector<const float *> vel;
+        for (pfs_slab *s : L) {
+            in.push_back(s->img[s->img_cur]);
+            out.push_back(s->img[s->img_cur ^ 1]);
+            vel.push_back(s->interior(UV_S, 2 * (size_t)s->gw));
+        }
+        PFS_TRY(color_step(L, in.data(), out.data(), vel.data(), 2, dt, spec_env && L[0]->vbound >= 0.f));
+        for (pfs_slab *s : L) s->img_cur ^= 1;                 // fluid.cpp:317-319
     }
-    for (int k = 0; k < n; k++) std::swap(image[k], itmp[k]);   // fluid.cpp:317-319
     return PFS_OK;
 }

@@ -118,6 +118,26 @@ class SlabRing(_SlabBase):
         for k in range(self.nranks):
             image[k], itmp[k] = by_ptr[pi[k]], by_ptr[pm[k]]
 
+    # -- resident state (pfs_slab_upload / pfs_slab_step / pfs_slab_download) ---------------------
+    def upload(self, vp: list, tmp: list, image: list | None = None) -> None:
+        """The bands (lists of CUDA tensors) become the slabs' resident state."""
+        img = _ptr_array([t.data_ptr() for t in image]) if image is not None else None
+        check(_cabi.lib().pfs_slab_upload(_ptr_array([h.value for h in self._handles]), self.nranks,
+                                          _ptr_array([t.data_ptr() for t in vp]), _ptr_array([t.data_ptr() for t in tmp]), img,
+                                          self._streams()))
+
+    def step(self, n_steps: int, dt: float, viscosity: float, n_diffuse: int = NUM_JACOBI_ITERS, n_pressure: int | None = None) -> None:
+        n_pressure = n_diffuse if n_pressure is None else n_pressure
+        check(_cabi.lib().pfs_slab_step(_ptr_array([h.value for h in self._handles]), self.nranks, n_steps, dt, viscosity,
+                                        n_diffuse, n_pressure, self._streams()))
+
+    def download(self, vp: list, tmp: list, image: list | None = None) -> None:
+        """Writes the resident state into the given bands (lists of CUDA tensors of the band shapes)."""
+        img = _ptr_array([t.data_ptr() for t in image]) if image is not None else None
+        check(_cabi.lib().pfs_slab_download(_ptr_array([h.value for h in self._handles]), self.nranks,
+                                            _ptr_array([t.data_ptr() for t in vp]), _ptr_array([t.data_ptr() for t in tmp]), img,
+                                            self._streams()))
+
     def check(self) -> None:
         check(_cabi.lib().pfs_slab_check(_ptr_array([h.value for h in self._handles]), self.nranks))
 
@@ -182,6 +202,25 @@ class SlabRank(_SlabBase):
         check(_cabi.lib().pfs_slab_advect_color_step(_ptr_array([self._h.value]), 1, pi, pm, pv, dt,
                                                      self._stream(vp.data)))
         image.data, itmp.data = by_ptr[pi[0]], by_ptr[pm[0]]
+
+    # -- resident state (pfs_slab_upload / pfs_slab_step / pfs_slab_download) ---------------------
+    def upload(self, vp, tmp, image=None) -> None:
+        """This rank's bands (CUDA tensors [rows, gw, 4] / [irows, iw, 4]) become the slab's resident state."""
+        img = _ptr_array([image.data_ptr()]) if image is not None else None
+        check(_cabi.lib().pfs_slab_upload(_ptr_array([self._h.value]), 1, _ptr_array([vp.data_ptr()]), _ptr_array([tmp.data_ptr()]),
+                                          img, self._stream(vp)))
+
+    def step(self, n_steps: int, dt: float, viscosity: float, n_diffuse: int = NUM_JACOBI_ITERS, n_pressure: int | None = None,
+             device=None) -> None:
+        import torch
+        n_pressure = n_diffuse if n_pressure is None else n_pressure
+        stream = _ptr_array([torch.cuda.current_stream(device).cuda_stream])
+        check(_cabi.lib().pfs_slab_step(_ptr_array([self._h.value]), 1, n_steps, dt, viscosity, n_diffuse, n_pressure, stream))
+
+    def download(self, vp, tmp, image=None) -> None:
+        img = _ptr_array([image.data_ptr()]) if image is not None else None
+        check(_cabi.lib().pfs_slab_download(_ptr_array([self._h.value]), 1, _ptr_array([vp.data_ptr()]), _ptr_array([tmp.data_ptr()]),
+                                            img, self._stream(vp)))
 
     def check(self) -> None:
         check(_cabi.lib().pfs_slab_check(_ptr_array([self._h.value]), 1))

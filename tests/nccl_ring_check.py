@@ -98,6 +98,16 @@ def run_case(rank, world, h, w, ih, iw, dt, steps):
         slab.simulate_fluid_step(fv, ft, dt, visc, nd, npr)
         slab.advect_color_step(fi, fm, fv, dt)
     slab.check()
+    # the same run with the state resident in the slab's planes (pfs_slab_upload / _step / _download)
+    rv, rt = torch.from_numpy(vp[r0:r0 + rows].copy()).cuda(), torch.from_numpy(vtmp[r0:r0 + rows].copy()).cuda()
+    ri = torch.from_numpy(image[i0:i0 + irows].copy()).cuda()
+    slab.upload(rv, rt, ri)
+    slab.step(steps, dt, visc, nd, npr)
+    slab.download(rv, rt, ri)
+    slab.check()
+    assert torch.equal(rv.view(torch.int32), fv.data.view(torch.int32)), "resident vp != stateless vp"
+    assert torch.equal(rt.view(torch.int32), ft.data.view(torch.int32)), "resident vtmp != stateless vtmp"
+    assert torch.equal(ri.view(torch.int32), fi.data.view(torch.int32)), "resident image != stateless image"
     norms = slab.step_norms(fv, ft)          # all-reduced over the ring: identical on every rank
     parts = [None] * world
     dist.all_gather_object(parts, (fv.data.cpu().numpy(), ft.data.cpu().numpy(), fi.data.cpu().numpy()))

@@ -216,6 +216,35 @@ def test_diffuse_zero_and_tiny_fields(kind):
         assert_bit_equal(to_host(fb.data), rb, f"diffuse vp_out ({kind}, visc={visc})")
 
 
+def test_diffuse_exact_path_alone_in_a_child_process():
+    """PFS_DIFFUSE_FORCE_REPAIR=1 (read once per process) sends every work item of the packed passes through the
+    out-of-line exact-division path ONLY.  On ordinary fields the fast path is already right, so a broken exact path hides
+    behind it unless it runs alone -- that is how a miscompiled store in that path was found (tests/test_sass_stores.py)."""
+    import subprocess, sys, os
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    code = r"""
+import sys, numpy as np
+sys.path.insert(0, %r); sys.path.insert(0, %r)
+import oracle, probabilistic_fluid_simulation_b200 as pfs
+from gpu_util import to_dev, to_host
+rng = np.random.default_rng(5)
+for (h, w), n, depth in (((160, 384), 19, 0), ((72, 256), 6, 6), ((40, 128), 2, 2), ((64, 512), 7, 3), ((33, 260), 9, 4)):
+    pfs.set_fuse_depth(depth)
+    for scale in (1.0, 1e-36):
+        a = (rng.standard_normal((h, w, 4)) * 0.5).astype(np.float32); a[..., :2] *= np.float32(scale)
+        b = rng.standard_normal((h, w, 4)).astype(np.float32)
+        fa, fb = pfs.vp_field(to_dev(a)), pfs.vp_field(to_dev(b))
+        pfs.diffuse(fa, fb, 0.02, 1.5, n)
+        ra, rb = oracle.Oracle().diffuse(a, b, 0.02, 1.5, n)
+        assert np.array_equal(to_host(fa.data).view(np.uint32), ra.view(np.uint32)), (h, w, n, scale)
+        assert np.array_equal(to_host(fb.data).view(np.uint32), rb.view(np.uint32)), (h, w, n, scale)
+print("exact path ok")
+""" % (root, os.path.join(root, "tests"))
+    env = dict(os.environ, PFS_DIFFUSE_FORCE_REPAIR="1")
+    r = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, env=env, timeout=300)
+    assert r.returncode == 0 and "exact path ok" in r.stdout, r.stdout[-2000:] + r.stderr[-2000:]
+
+
 def test_diffuse_negative_viscosity_takes_the_exact_path():
     """alpha < 0 breaks the convexity argument of the guard: the library must not use the packed
     fast path, and must still match the reference."""

@@ -128,6 +128,76 @@ def test_ring_speculative_gather_depth_reruns_when_the_field_jumps(nranks):
     assert (c3 - c2) > 1.5 * (c2 - c1), (c1 - c0, c2 - c1, c3 - c2)   # the third step really ran twice
 
 
+def _run_ring_resident(nranks, state, dt, visc, nd, npr, steps, split_steps=False):
+    """The same run through pfs_slab_upload / pfs_slab_step / pfs_slab_download (state resident in the slabs' planes)."""
+    import torch
+    vp, vtmp, image, itmp = state
+    h, w = vp.shape[:2]
+    ih, iw = image.shape[:2]
+    ring = SlabRing(nranks, w, h, iw, ih)
+    bv, bt, bi = ring.split(vp), ring.split(vtmp), ring.split(image, image=True)
+    ring.upload(bv, bt, bi)
+    if split_steps:
+        for _ in range(steps):
+            ring.step(1, dt, visc, nd, npr)
+    else:
+        ring.step(steps, dt, visc, nd, npr)
+    ov, ot, oi = [torch.empty_like(t) for t in bv], [torch.empty_like(t) for t in bt], [torch.empty_like(t) for t in bi]
+    ring.download(ov, ot, oi)
+    ring.check()
+    out = ring.gather(ov), ring.gather(ot), ring.gather(oi)
+    ring.close()
+    return out
+
+
+@pytest.mark.parametrize("nranks", [1, 2, 3, 4])
+@pytest.mark.parametrize("dt,visc,nd,npr", [(0.5, 0.003, 30, 30), (40.0, 0.01, 7, 10), (3.0, 0.0, 3, 4), (2.0, 0.002, 1, 1), (2.0, 0.002, 2, 5)])
+def test_resident_ring_matches_oracle(nranks, dt, visc, nd, npr):
+    h, w, ih, iw = 96, 128, 96, 128
+    state = _state(h, w, ih, iw, 3)
+    got = _run_ring_resident(nranks, [x.copy() for x in state], dt, visc, nd, npr, 4)
+    want = oracle.Oracle(nd, npr).run_steps(*state, dt, visc, 4)
+    for name, g, wv in zip(("vp", "vtmp", "image"), got, want):
+        assert_bit_equal(g, wv, f"{name} (R={nranks})")
+
+
+@pytest.mark.parametrize("nranks", [2, 3])
+def test_resident_ring_image_ratio_and_large_displacement(nranks):
+    h, w, ih, iw = 72, 64, 96, 192
+    state = _state(h, w, ih, iw, 7)
+    for dt in (10.0, 3000.0):
+        got = _run_ring_resident(nranks, [x.copy() for x in state], dt, 0.001, 6, 8, 3, split_steps=True)
+        want = oracle.Oracle(6, 8).run_steps(*[x.copy() for x in state], dt, 0.001, 3)
+        for name, g, wv in zip(("vp", "vtmp", "image"), got, want):
+            assert_bit_equal(g, wv, f"{name} (R={nranks}, dt={dt})")
+
+
+def test_resident_ring_repairs_a_wrong_gather_guess():
+    """Resident state: both gather depths of step k are guessed from the field step k-1 started from.  Here the field is
+    replaced (a new upload keeps the old bound out of the picture) ... and, harder, the time step grows 100x between two
+    calls on the SAME state, so the guesses of the second call are far too shallow for the velocity advection and for the
+    image advection: both must be noticed and repaired, bit for bit."""
+    import torch
+    h, w = 256, 64
+    state = _state(h, w, h, w, 13)
+    vp, vtmp, image, itmp = [x.copy() for x in state]
+    ring = SlabRing(4, w, h, w, h)
+    bv, bt, bi = ring.split(vp), ring.split(vtmp), ring.split(image, image=True)
+    ring.upload(bv, bt, bi)
+    nd, npr, visc = 4, 4, 0.001
+    ring.step(2, 40.0, visc, nd, npr)
+    ring.step(2, 4000.0, visc, nd, npr)
+    ov, ot, oi = [torch.empty_like(t) for t in bv], [torch.empty_like(t) for t in bt], [torch.empty_like(t) for t in bi]
+    ring.download(ov, ot, oi)
+    ring.check()
+    orc = oracle.Oracle(nd, npr)
+    want = orc.run_steps(vp, vtmp, image, itmp, 40.0, visc, 2)
+    want = orc.run_steps(*want, 4000.0, visc, 2)
+    for name, g, wv in zip(("vp", "vtmp", "image"), (ring.gather(ov), ring.gather(ot), ring.gather(oi)), want):
+        assert_bit_equal(g, wv, name)
+    ring.close()
+
+
 @pytest.mark.parametrize("nranks", [1, 2, 3])
 @pytest.mark.parametrize("nd,npr", [(30, 30), (7, 10), (1, 2), (6, 6)])
 def test_ring_forced_step(nranks, nd, npr):
