@@ -243,14 +243,19 @@ int pfs_slab_simulate_fluid_step_forced(pfs_slab *const *slabs, int n_local, flo
 /* Resident state on the slabs (the multi-GPU counterpart of pfs_ctx_*): upload the bands once, step, download.  Between
  * steps the bands live in each slab's planes, so a step moves no interleaved data; n steps leave behind, bit for bit, what n
  * calls of pfs_slab_simulate_fluid_step + pfs_slab_advect_color_step leave in the caller's bands.  vp/tmp/image: arrays
- * over the local slabs of device pointers to the bands (image may be NULL when the slabs were created without one;
- * download skips NULL arrays and NULL entries).  The gather depths of both advections are guessed from the previous
+ * over the local slabs of device pointers to the bands.  The first upload needs all of them (image may be NULL when the
+ * slabs were created without one); later uploads may replace the velocity pair (vp AND tmp) or the image alone (NULL
+ * arrays are left as they are); download skips NULL arrays and NULL entries.  The gather depths of both advections are guessed from the previous
  * step and verified by the kernels; a wrong guess is repaired before anything that depends on it is overwritten
  * (pfs_slab_download and pfs_slab_check complete that verification for the last step). */
 int pfs_slab_upload(pfs_slab *const *slabs, int n_local, const float *const *vp, const float *const *tmp,
                     const float *const *image, void *const *streams);
 int pfs_slab_step(pfs_slab *const *slabs, int n_local, int n_steps, float dt, float viscosity, int n_diffuse,
                   int n_pressure, void *const *streams);
+/* The two halves of a resident step on their own (simulate_fluid_step / advect_color_step). */
+int pfs_slab_step_fluid(pfs_slab *const *slabs, int n_local, float dt, float viscosity, int n_diffuse, int n_pressure,
+                        void *const *streams);
+int pfs_slab_step_color(pfs_slab *const *slabs, int n_local, float dt, void *const *streams);
 int pfs_slab_download(pfs_slab *const *slabs, int n_local, float *const *vp, float *const *tmp, float *const *image,
                       void *const *streams);
 /* Synchronises, completes deferred verification and reports an internal halo overflow (a bug, never expected). */
@@ -282,6 +287,19 @@ int pfs_compute_pressure_adaptive(float **vp, float **vp_out, float dt, int vx, 
                                   void *stream);
 int pfs_slab_step_norms(pfs_slab *const *slabs, int n_local, float *const *vp, float *const *tmp, double out[4],
                         void *const *streams);
+/* The same run-time sweep count on a ring of slabs: vp[k] / vp_out[k] are the bands; the per-rank sums of squared updates are
+ * all-reduced (NCCL) after every batch, so every rank takes the same decision; one host synchronisation per batch, none
+ * inside it.  The bands end up bit-identical to pfs_compute_pressure with n_sweeps = *sweeps_out on the whole grid. */
+int pfs_slab_compute_pressure_adaptive(pfs_slab *const *slabs, int n_local, float **vp, float **vp_out, float dt, float tol,
+                                       int max_sweeps, int check_every, int *sweeps_out, double *update_rms_out,
+                                       void *const *streams);
+/* Red-black successive over-relaxation instead of Jacobi sweeps.  NOT the reference's solver and NOT a parity path: an opt-in
+ * alternative whose sweeps-to-tolerance is reported beside the Jacobi solve (profiles/).  Divergence as computePressure forms
+ * it (channel 3 of both buffers); the pressure is relaxed in place from channel 2 of vp with factor omega (0 < omega < 2)
+ * until the rms update of a full sweep is <= tol (looked at every check_every sweeps) or max_sweeps; result in channel 2
+ * of vp_out; pointers are not exchanged.  Single device. */
+int pfs_compute_pressure_sor(const float *vp, float *vp_out, float dt, int vx, int vy, int vz, float omega, float tol,
+                             int max_sweeps, int check_every, int *sweeps_out, double *update_rms_out, void *stream);
 
 /* ---- phase timing (diagnostics for bench.py; not on the reference's surface) --------------- */
 /* When enabled, pfs_simulate_fluid_step / pfs_advect_color_step bracket each phase with CUDA

@@ -79,11 +79,17 @@ SIGNATURES = {
     "pfs_slab_upload": (_int, [_pp, _int, _pp, _pp, _pp, _pp]),
     "pfs_slab_step": (_int, [_pp, _int, _int, _f32, _f32, _int, _int, _pp]),
     "pfs_slab_download": (_int, [_pp, _int, _pp, _pp, _pp, _pp]),
+    "pfs_slab_step_fluid": (_int, [_pp, _int, _f32, _f32, _int, _int, _pp]),
+    "pfs_slab_step_color": (_int, [_pp, _int, _f32, _pp]),
     "pfs_slab_check": (_int, [_pp, _int]),
     "pfs_image_to_rgba8": (_int, [_vp, _vp, _int, _int, _int, _vp]),
     "pfs_step_norms": (_int, [_vp, _vp, _int, _int, _int, ctypes.POINTER(ctypes.c_double), _vp]),
     "pfs_compute_pressure_adaptive": (_int, [_pp, _pp, _f32, _int, _int, _int, _f32, _int, _int, ctypes.POINTER(_int),
                                              ctypes.POINTER(ctypes.c_double), _vp]),
+    "pfs_slab_compute_pressure_adaptive": (_int, [_pp, _int, _pp, _pp, _f32, _f32, _int, _int, ctypes.POINTER(_int),
+                                                  ctypes.POINTER(ctypes.c_double), _pp]),
+    "pfs_compute_pressure_sor": (_int, [_vp, _vp, _f32, _int, _int, _int, _f32, _f32, _int, _int, ctypes.POINTER(_int),
+                                        ctypes.POINTER(ctypes.c_double), _vp]),
     "pfs_slab_transport": (ctypes.c_char_p, [_vp]),
     "pfs_slab_step_norms": (_int, [_pp, _int, _pp, _pp, ctypes.POINTER(ctypes.c_double), _pp]),
     "pfs_phase_timing_enable": (_int, [_int]),

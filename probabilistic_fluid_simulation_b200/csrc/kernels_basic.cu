@@ -28,6 +28,21 @@ __device__ __forceinline__ void load_vec(const float *p, float (&o)[V])
     }
 }
 
+// Four (u,v) cells = 32 contiguous, 32-byte aligned bytes in ONE 256-bit access (LDG/STG.E.256, sm_100): a warp covers
+// 1 KB without gaps.  Two 16-byte accesses per lane would touch half of every 32-byte sector per instruction.
+__device__ __forceinline__ void load_uv4(const float2 *p, float2 (&c)[4])
+{
+    asm volatile("ld.global.nc.v8.f32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];"
+                 : "=f"(c[0].x), "=f"(c[0].y), "=f"(c[1].x), "=f"(c[1].y), "=f"(c[2].x), "=f"(c[2].y), "=f"(c[3].x), "=f"(c[3].y)
+                 : "l"(p));
+}
+__device__ __forceinline__ void store_uv4(float2 *p, const float2 (&c)[4])
+{
+    asm volatile("st.global.v8.f32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};" ::"l"(p), "f"(c[0].x), "f"(c[0].y), "f"(c[1].x),
+                 "f"(c[1].y), "f"(c[2].x), "f"(c[2].y), "f"(c[3].x), "f"(c[3].y)
+                 : "memory");
+}
+
 template <int V>
 __device__ __forceinline__ void store_vec(float *p, const float (&o)[V])
 {
@@ -138,13 +153,17 @@ __global__ void __launch_bounds__(BX *BY)
     const float2 *rc = uv + (size_t)s.rj * w, *rt = uv + (size_t)s.jm * w, *rb = uv + (size_t)s.jp * w;
     float uc[V], vt[V], vb[V], o[V];
     if constexpr (V == 4) {
-        // four cells = two 16-byte loads per row; u comes from the centre row, v from the rows above and below
-        const float4 c0 = __ldg(reinterpret_cast<const float4 *>(rc + s.x)), c1 = __ldg(reinterpret_cast<const float4 *>(rc + s.x + 2));
-        const float4 t0 = __ldg(reinterpret_cast<const float4 *>(rt + s.x)), t1 = __ldg(reinterpret_cast<const float4 *>(rt + s.x + 2));
-        const float4 b0 = __ldg(reinterpret_cast<const float4 *>(rb + s.x)), b1 = __ldg(reinterpret_cast<const float4 *>(rb + s.x + 2));
-        uc[0] = c0.x; uc[1] = c0.z; uc[2] = c1.x; uc[3] = c1.z;
-        vt[0] = t0.y; vt[1] = t0.w; vt[2] = t1.y; vt[3] = t1.w;
-        vb[0] = b0.y; vb[1] = b0.w; vb[2] = b1.y; vb[3] = b1.w;
+        // four cells = one 256-bit load per row; u comes from the centre row, v from the rows above and below
+        float2 c[4], t[4], b[4];
+        load_uv4(rc + s.x, c);
+        load_uv4(rt + s.x, t);
+        load_uv4(rb + s.x, b);
+#pragma unroll
+        for (int k = 0; k < 4; k++) {
+            uc[k] = c[k].x;
+            vt[k] = t[k].y;
+            vb[k] = b[k].y;
+        }
     } else {
         uc[0] = __ldg(rc + s.x).x;
         vt[0] = __ldg(rt + s.x).y;
@@ -213,12 +232,10 @@ __global__ void __launch_bounds__(BX *BY)
         const float2 *src = uv + (size_t)s.rj * w + s.x;
         float2 *dst = uv_out + (size_t)s.rj * w + s.x;
         float2 v[V], o[V];
-        if constexpr (V == 4) {
-            const float4 a = __ldg(reinterpret_cast<const float4 *>(src)), b = __ldg(reinterpret_cast<const float4 *>(src + 2));
-            v[0] = make_float2(a.x, a.y); v[1] = make_float2(a.z, a.w); v[2] = make_float2(b.x, b.y); v[3] = make_float2(b.z, b.w);
-        } else {
+        if constexpr (V == 4)
+            load_uv4(src, v);
+        else
             v[0] = __ldg(src);
-        }
 #pragma unroll
         for (int k = 0; k < V; k++) {
             const float left = (k == 0) ? pl : pc[k - 1];
@@ -228,12 +245,10 @@ __global__ void __launch_bounds__(BX *BY)
             const float av = fabsf(o[k].y);
             m = (av > m || av != av) ? av : m;
         }
-        if constexpr (V == 4) {
-            *reinterpret_cast<float4 *>(dst) = make_float4(o[0].x, o[0].y, o[1].x, o[1].y);
-            *reinterpret_cast<float4 *>(dst + 2) = make_float4(o[2].x, o[2].y, o[3].x, o[3].y);
-        } else {
+        if constexpr (V == 4)
+            store_uv4(dst, o);
+        else
             *dst = o[0];
-        }
     }
     if (vmax != nullptr) {                      // every thread of the block gets here
         __shared__ float warp_max[BX * BY / 32];
@@ -282,7 +297,7 @@ __global__ void __launch_bounds__(256)
 // ---------------------------------------------------------------------------------------------
 template <int SS, int DS>     // floats per source / destination cell: 4 = interleaved [u,v,p,div], 2 = (u,v) plane
 __global__ void __launch_bounds__(256)
-    advect_kernel(const float *__restrict__ src, float *__restrict__ dst, float dt, int w, int h)
+    advect_kernel(const float *__restrict__ src, float *__restrict__ dst, float dt, int w, int h, float rfw, float rfh)
 {
     int i = blockIdx.x * 64 + threadIdx.x, j = blockIdx.y * 4 + threadIdx.y;
     if (i >= w || j >= h) return;
@@ -290,8 +305,9 @@ __global__ void __launch_bounds__(256)
     size_t cell = (size_t)j * w + i;
     float2 uv = __ldg(reinterpret_cast<const float2 *>(src + cell * SS));
     // fluid.cpp:39,41: (float)i - dt*u/fwidth  ==  i - ((dt*u)/fwidth)
-    float xp = __fsub_rn((float)i, div_extent(__fmul_rn(dt, uv.x), fw, __frcp_rn(fw)));
-    float yp = __fsub_rn((float)j, div_extent(__fmul_rn(dt, uv.y), fh, __frcp_rn(fh)));
+    // rfw, rfh: the correctly rounded reciprocals of the extents, formed once on the host (1.0f / fw)
+    float xp = __fsub_rn((float)i, div_extent(__fmul_rn(dt, uv.x), fw, rfw));
+    float yp = __fsub_rn((float)j, div_extent(__fmul_rn(dt, uv.y), fh, rfh));
     xp = wrap_coord(xp, fw);
     yp = wrap_coord(yp, fh);
     Bilinear b = make_bilinear(xp, yp, w, h);
@@ -312,7 +328,7 @@ __global__ void __launch_bounds__(256)
 template <int VS>     // floats per velocity cell: 4 = interleaved buffer, 2 = (u,v) plane
 __global__ void __launch_bounds__(256)
     advect_color_kernel(const float4 *__restrict__ image, float4 *__restrict__ out, const float *__restrict__ vp,
-                        float dt_over_viw, float dt_over_vih, float viw, float vih, int iw, int ih, int vw)
+                        float dt_over_viw, float dt_over_vih, float viw, float vih, int iw, int ih, int vw, float rfiw, float rfih)
 {
     int i = blockIdx.x * 64 + threadIdx.x, j = blockIdx.y * 4 + threadIdx.y;
     if (i >= iw || j >= ih) return;
@@ -321,8 +337,8 @@ __global__ void __launch_bounds__(256)
     int vj = (int)__fmul_rn((float)j, vih);   // fluid.cpp:90
     float2 uv = __ldg(reinterpret_cast<const float2 *>(vp + ((size_t)vj * vw + vi) * VS));
     // fluid.cpp:97-98: (float)i - (dt/viw) * u / fiwidth
-    float xp = __fsub_rn((float)i, div_extent(__fmul_rn(dt_over_viw, uv.x), fiw, __frcp_rn(fiw)));
-    float yp = __fsub_rn((float)j, div_extent(__fmul_rn(dt_over_vih, uv.y), fih, __frcp_rn(fih)));
+    float xp = __fsub_rn((float)i, div_extent(__fmul_rn(dt_over_viw, uv.x), fiw, rfiw));
+    float yp = __fsub_rn((float)j, div_extent(__fmul_rn(dt_over_vih, uv.y), fih, rfih));
     xp = wrap_coord(xp, fiw);
     yp = wrap_coord(yp, fih);
     Bilinear b = make_bilinear(xp, yp, iw, ih);
@@ -549,6 +565,45 @@ __global__ void __launch_bounds__(256) pack_rgba8_kernel(const float4 *__restric
     out[i] = make_uchar4(q(c.x), q(c.y), q(c.z), q(c.w));
 }
 
+// ---------------------------------------------------------------------------------------------
+// Red-black successive over-relaxation of the pressure equation -- NOT the reference's solver (fluid.cpp:239-266 is a
+// fixed number of Jacobi sweeps) and not a parity path: an opt-in alternative reported beside it.
+// One half-sweep per launch, in place: cells with (i + j) % 2 == colour take p <- p + omega * (jacobi(p) - p), where
+// jacobi(p) is the reference's update with the four neighbours of the other colour.  The sum of squared updates goes to
+// per-block partials (double), folded by norms_final_kernel.
+// ---------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256)
+    sor_half_sweep_kernel(float *__restrict__ p, const float *__restrict__ rhs, int w, int h, float omega, int colour,
+                          double *partials, int accumulate)
+{
+    const int j = blockIdx.y * 4 + threadIdx.y;
+    const int i = 2 * (blockIdx.x * 64 + threadIdx.x) + ((j + colour) & 1);
+    double d2 = 0.0;
+    if (i < w && j < h) {
+        const int im = (i == 0) ? w - 1 : i - 1, ip = (i + 1 >= w) ? 0 : i + 1;
+        const int jm = (j == 0) ? h - 1 : j - 1, jp = (j + 1 >= h) ? 0 : j + 1;
+        const size_t c = (size_t)j * w + i;
+        const float old = p[c];
+        const float gs = pressure_update(p[(size_t)j * w + im], p[(size_t)j * w + ip], p[(size_t)jm * w + i], p[(size_t)jp * w + i], rhs[c]);
+        const float upd = __fmul_rn(omega, __fsub_rn(gs, old));
+        p[c] = __fadd_rn(old, upd);
+        d2 = (double)upd * (double)upd;
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) d2 += __shfl_xor_sync(0xffffffffu, d2, o);
+    __shared__ double sh[8];
+    const int tid = threadIdx.y * 64 + threadIdx.x;
+    if ((tid & 31) == 0) sh[tid >> 5] = d2;
+    __syncthreads();
+    if (tid == 0) {
+        double t = 0;
+        for (int q = 0; q < 8; q++) t += sh[q];
+        double *o = partials + 4 * ((size_t)blockIdx.y * gridDim.x + blockIdx.x);
+        o[0] = accumulate ? o[0] + t : t;
+        o[1] = o[2] = o[3] = 0.0;
+    }
+}
+
 inline bool vec4_ok(int w, const void *a, const void *b = nullptr, const void *c = nullptr, const void *d = nullptr,
                     const void *e = nullptr, const void *f = nullptr)
 {
@@ -594,12 +649,13 @@ int launch_add_forces(float *dst, int dst_stride, const float *force_aos, int w,
 int launch_advect(const float *src, int src_stride, float *dst, int dst_stride, float dt, int w, int h, cudaStream_t s)
 {
     dim3 block(64, 4), grid((w + 63) / 64, (h + 3) / 4);
+    const float rfw = 1.0f / (float)w, rfh = 1.0f / (float)h;     // binary32 division on the host: correctly rounded, as __frcp_rn
     if (src_stride == 4 && dst_stride == 2)
-        PFS_LAUNCH((advect_kernel<4, 2>), grid, block, 0, s, src, dst, dt, w, h);
+        PFS_LAUNCH((advect_kernel<4, 2>), grid, block, 0, s, src, dst, dt, w, h, rfw, rfh);
     else if (src_stride == 2 && dst_stride == 2)
-        PFS_LAUNCH((advect_kernel<2, 2>), grid, block, 0, s, src, dst, dt, w, h);
+        PFS_LAUNCH((advect_kernel<2, 2>), grid, block, 0, s, src, dst, dt, w, h, rfw, rfh);
     else if (src_stride == 4 && dst_stride == 4)
-        PFS_LAUNCH((advect_kernel<4, 4>), grid, block, 0, s, src, dst, dt, w, h);
+        PFS_LAUNCH((advect_kernel<4, 4>), grid, block, 0, s, src, dst, dt, w, h, rfw, rfh);
     else {
         set_error("advect: unsupported cell strides %d -> %d", src_stride, dst_stride);
         return PFS_EINVAL;
@@ -710,6 +766,18 @@ int launch_step_norms(const float *vp_aos, const float *tmp_aos, size_t cells, d
     return PFS_OK;
 }
 
+int sor_partial_blocks(int w, int h) { return ((w / 2 + 1 + 63) / 64) * ((h + 3) / 4); }
+
+// One full red-black sweep (two launches) of p in place; the sum of squared updates lands in out4[0] (device).
+int launch_sor_sweep(float *p, const float *rhs, int w, int h, float omega, double *partials, double *out4, cudaStream_t s)
+{
+    dim3 block(64, 4), grid((w / 2 + 1 + 63) / 64, (h + 3) / 4);
+    PFS_LAUNCH(sor_half_sweep_kernel, grid, block, 0, s, p, rhs, w, h, omega, 0, partials, 0);
+    PFS_LAUNCH(sor_half_sweep_kernel, grid, block, 0, s, p, rhs, w, h, omega, 1, partials, 1);
+    if (out4) PFS_LAUNCH(norms_final_kernel, 1, 32, 0, s, partials, (int)(grid.x * grid.y), out4);
+    return PFS_OK;
+}
+
 int launch_stochastic_force(float *u, float *v, int stride, float sigma, unsigned long long seed, unsigned step, int w,
                             int h, int row0, int y_base, cudaStream_t s)
 {
@@ -732,10 +800,11 @@ int launch_advect_color(const float *image, float *out, const float *vel, int ve
     dim3 block(64, 4), grid((iw + 63) / 64, (ih + 3) / 4);
     const float4 *img = reinterpret_cast<const float4 *>(image);
     float4 *o4 = reinterpret_cast<float4 *>(out);
+    const float rfiw = 1.0f / (float)iw, rfih = 1.0f / (float)ih;
     if (vel_stride == 2)
-        PFS_LAUNCH(advect_color_kernel<2>, grid, block, 0, s, img, o4, vel, dt_over_viw, dt_over_vih, viw, vih, iw, ih, vw);
+        PFS_LAUNCH(advect_color_kernel<2>, grid, block, 0, s, img, o4, vel, dt_over_viw, dt_over_vih, viw, vih, iw, ih, vw, rfiw, rfih);
     else
-        PFS_LAUNCH(advect_color_kernel<4>, grid, block, 0, s, img, o4, vel, dt_over_viw, dt_over_vih, viw, vih, iw, ih, vw);
+        PFS_LAUNCH(advect_color_kernel<4>, grid, block, 0, s, img, o4, vel, dt_over_viw, dt_over_vih, viw, vih, iw, ih, vw, rfiw, rfih);
     return PFS_OK;
 }
 

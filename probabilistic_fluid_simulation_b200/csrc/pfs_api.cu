@@ -6,6 +6,7 @@
 #include <stdlib.h>
 #include <string.h>
 
+#include <algorithm>
 #include <map>
 #include <mutex>
 #include <vector>
@@ -564,6 +565,59 @@ extern "C" int pfs_compute_pressure_adaptive(float **vp, float **vp_out, float d
     PFS_TRY(launch_pack(buf_prev, nullptr, prev, div, vx, vy, s));
     *vp_out = buf_last;
     *vp = buf_prev;
+    if (sweeps_out) *sweeps_out = done;
+    if (update_rms_out) *update_rms_out = rms;
+    return PFS_OK;
+}
+
+// Red-black SOR variant of computePressure: NOT the reference's solver and not a parity path -- reported
+// beside the Jacobi solve as sweeps-to-tolerance.  Divergence as the reference forms it into channel 3 of both buffers; the
+// pressure is relaxed in place starting from channel 2 of vp until the rms update of a full sweep is <= tol (checked every
+// `check_every` sweeps) or max_sweeps is reached; the result goes to channel 2 of vp_out.  No pointer exchange.
+extern "C" int pfs_compute_pressure_sor(const float *vp, float *vp_out, float dt, int vx, int vy, int vz, float omega, float tol,
+                                        int max_sweeps, int check_every, int *sweeps_out, double *update_rms_out, void *stream)
+{
+    const char *fn = "pfs_compute_pressure_sor";
+    PFS_TRY(check_dims(fn, vx, vy, vz));
+    PFS_TRY(check_sweeps(fn, max_sweeps));
+    PFS_TRY(check_ptr(fn, "vp", vp));
+    PFS_TRY(check_ptr(fn, "vp_out", vp_out));
+    if (!(omega > 0.0f && omega < 2.0f) || check_every < 1 || !(tol >= 0.0f)) {
+        set_error("%s: need 0 < omega < 2, check_every >= 1, tol >= 0 (got %g, %d, %g)", fn, (double)omega, check_every, (double)tol);
+        return PFS_EINVAL;
+    }
+    cudaStream_t s = (cudaStream_t)stream;
+    DeviceScratch *sc;
+    const size_t cells = (size_t)vx * vy;
+    PFS_TRY(get_scratch(cells, &sc));
+    float *uv = sc->uv(0), *div = sc->div(), *p = sc->p(0);
+    PFS_TRY(launch_unpack(vp, uv, p, nullptr, vx, vy, s));
+    PFS_TRY(launch_divergence(uv, div, nullptr, nullptr, dt, vx, vy, s));
+    const int nb = sor_partial_blocks(vx, vy);
+    double *scratch = nullptr;
+    PFS_CUDA(cudaMalloc((void **)&scratch, (4 * (size_t)nb + 4) * sizeof(double)));
+    int done = 0, rc = PFS_OK;
+    double rms = 0.0;
+    while (done < max_sweeps && rc == PFS_OK) {
+        const int batch = std::min(check_every, max_sweeps - done);
+        for (int k = 0; k < batch && rc == PFS_OK; k++)
+            rc = launch_sor_sweep(p, div, vx, vy, omega, scratch, (k == batch - 1) ? scratch + 4 * (size_t)nb : nullptr, s);
+        if (rc != PFS_OK) break;
+        done += batch;
+        double host = 0.0;
+        cudaError_t e = cudaMemcpyAsync(&host, scratch + 4 * (size_t)nb, sizeof(double), cudaMemcpyDeviceToHost, s);
+        if (e == cudaSuccess) e = cudaStreamSynchronize(s);
+        if (e != cudaSuccess) {
+            rc = cuda_fail(e, fn, __FILE__, __LINE__);
+            break;
+        }
+        rms = sqrt(host / (double)cells);
+        if (rms <= (double)tol) break;
+    }
+    cudaFree(scratch);
+    if (rc != PFS_OK) return rc;
+    PFS_TRY(launch_pack(vp_out, nullptr, p, div, vx, vy, s));
+    PFS_TRY(launch_pack(const_cast<float *>(vp), nullptr, nullptr, div, vx, vy, s));     // channel 3 of the input buffer too (fluid.cpp:235-236)
     if (sweeps_out) *sweeps_out = done;
     if (update_rms_out) *update_rms_out = rms;
     return PFS_OK;

@@ -82,7 +82,7 @@ __device__ __forceinline__ float wrap_coord(float x, float ext)
     return fmodf(t, ext);
 }
 
-// a / ext, correctly rounded, for an extent with reciprocal rext = __frcp_rn(ext): the 3-instruction FMA
+// a / ext, correctly rounded, for an extent with correctly rounded reciprocal rext = RN(1/ext) (formed once on the host): the 3-instruction FMA
 // division whose exactness is established in sweeps_packed.cu (div_const_fast2) and
 // tests/exact_div_check.c; numerators outside its safe range (zero, tiny, huge, non-finite) take __fdiv_rn.
 __device__ __forceinline__ float div_extent(float a, float ext, float rext)
@@ -259,6 +259,10 @@ int launch_plane_diff_norms(const float *a, const float *b, size_t cells, double
                             cudaStream_t s);
 int launch_step_norms(const float *vp_aos, const float *tmp_aos, size_t cells, double *partials, int max_blocks,
                       double *out4, cudaStream_t s);
+
+// Red-black SOR of the pressure equation, one full sweep in place (not a parity path; kernels_basic.cu).
+int sor_partial_blocks(int w, int h);
+int launch_sor_sweep(float *p, const float *rhs, int w, int h, float omega, double *partials, double *out4, cudaStream_t s);
 
 // Opt-in Gaussian forcing of (u, v) at the addForces slot (kernels_basic.cu).  stride 2 = a (u,v) plane, 4 = interleaved.
 int launch_stochastic_force(float *u, float *v, int stride, float sigma, unsigned long long seed, unsigned step, int w,

@@ -269,7 +269,7 @@ __device__ __forceinline__ const char *source_row(const RowSource &S, int grow, 
 template <int CF>
 __global__ void __launch_bounds__(256)
     advect_slab_kernel(const RowSource S, float2 *__restrict__ uv_out, float dt, int w, int gh,
-                       int row0, int rows, int y_base, int *overflow, float *vmax_out)
+                       int row0, int rows, int y_base, int *overflow, float *vmax_out, float rfw, float rfh)
 {
     const int i = blockIdx.x * 64 + threadIdx.x, jl = blockIdx.y * 4 + threadIdx.y;
     const bool live = (i < w && jl < rows);
@@ -308,8 +308,8 @@ __global__ void __launch_bounds__(256)
         }
     }
     if (!own) return;
-    float xp = __fsub_rn((float)i, div_extent(__fmul_rn(dt, uv.x), fw, __frcp_rn(fw)));
-    float yp = __fsub_rn((float)j, div_extent(__fmul_rn(dt, uv.y), fh, __frcp_rn(fh)));
+    float xp = __fsub_rn((float)i, div_extent(__fmul_rn(dt, uv.x), fw, rfw));
+    float yp = __fsub_rn((float)j, div_extent(__fmul_rn(dt, uv.y), fh, rfh));
     xp = wrap_coord(xp, fw);
     yp = wrap_coord(yp, fh);
     const Bilinear b = make_bilinear(xp, yp, w, gh);
@@ -326,7 +326,7 @@ template <int VS>
 __global__ void __launch_bounds__(256)
     advect_color_slab_kernel(const RowSource S, float4 *__restrict__ out, const float *__restrict__ vp,
                              float dt_over_viw, float dt_over_vih, float viw, float vih, int iw, int ih, int irow0,
-                             int irows, int vw, int row0, int rows, int *overflow)
+                             int irows, int vw, int row0, int rows, int *overflow, float rfiw, float rfih)
 {
     const int i = blockIdx.x * 64 + threadIdx.x, jl = blockIdx.y * 4 + threadIdx.y;
     if (i >= iw || jl >= irows) return;
@@ -339,8 +339,8 @@ __global__ void __launch_bounds__(256)
         return;
     }
     const float2 uv = __ldg(reinterpret_cast<const float2 *>(vp + ((size_t)vj * vw + vi) * VS));
-    float xp = __fsub_rn((float)i, div_extent(__fmul_rn(dt_over_viw, uv.x), fiw, __frcp_rn(fiw)));
-    float yp = __fsub_rn((float)j, div_extent(__fmul_rn(dt_over_vih, uv.y), fih, __frcp_rn(fih)));
+    float xp = __fsub_rn((float)i, div_extent(__fmul_rn(dt_over_viw, uv.x), fiw, rfiw));
+    float yp = __fsub_rn((float)j, div_extent(__fmul_rn(dt_over_vih, uv.y), fih, rfih));
     xp = wrap_coord(xp, fiw);
     yp = wrap_coord(yp, fih);
     const Bilinear b = make_bilinear(xp, yp, iw, ih);
@@ -1259,10 +1259,10 @@ int color_step(const std::vector<pfs_slab *> &L, float *const *image_in, float *
             float4 *out = reinterpret_cast<float4 *>(image_out[k]);
             if (vs == 2)
                 PFS_LAUNCH(advect_color_slab_kernel<2>, grid, block, 0, s->stream, src[k], out, vel[k], dt_over_viw, dt_over_vih,
-                           viw, vih, iw, ih, s->irow0, s->irows, gw, s->row0, s->rows, flag);
+                           viw, vih, iw, ih, s->irow0, s->irows, gw, s->row0, s->rows, flag, 1.0f / (float)iw, 1.0f / (float)ih);
             else
                 PFS_LAUNCH(advect_color_slab_kernel<4>, grid, block, 0, s->stream, src[k], out, vel[k], dt_over_viw, dt_over_vih,
-                           viw, vih, iw, ih, s->irow0, s->irows, gw, s->row0, s->rows, flag);
+                           viw, vih, iw, ih, s->irow0, s->irows, gw, s->row0, s->rows, flag, 1.0f / (float)iw, 1.0f / (float)ih);
         }
         if (speculative) {
             // "a row was missing" -> every rank, then the host; nobody waits for it yet
@@ -1302,6 +1302,88 @@ int resolve_pending_color(const std::vector<pfs_slab *> &L)
     }
     return color_step(L, in.data(), out.data(), vel.data(), 2, L[0]->pending_dt, false);
 }
+
+    // n sweeps starting from iterate 0 in plane unit pa, all in fused passes; the pass that reaches sweep n also
+    // stores iterate n-1 into unit px (as pfs_api.cu's run_diffuse / run_pressure do), so both iterates the reference
+    // leaves behind exist afterwards.  `valid` tracks how many halo rows of the current iterate are correct on
+    // every slab: an exchange makes it `halo`; a pass of depth t needs t of them and -- by also recomputing the
+    // e = valid-t rows just outside the band -- leaves e valid rows on its result.
+// `diffusion`: (u,v) planes through the packed kernel; else the pressure planes.
+int run_sweeps(const std::vector<pfs_slab *> &L, bool diffusion, int pa, int pb, int px, const SweepParams &proto, int count, int *last,
+               int *prev, int *valid_io, const float *const *force_bands)
+{
+        const int n = (int)L.size();
+        const int gw = L[0]->gw, halo = L[0]->halo;
+        int cur = pa, oth = pb;
+        int left = count;
+        int valid = *valid_io;                          // valid halo rows of the iterate in `pa` on entry (0: exchange first)
+        const bool vec = (gw % 4 == 0);
+        SweepParams p0 = proto;
+        const bool packed = diffusion && vec && packed_diffuse_supported(p0);
+        const int user_depth = pfs_get_fuse_depth();
+        int depth = user_depth > 0 ? std::min(user_depth, MIN_HALO) : (packed ? default_diffuse_depth() : MIN_HALO);
+        if (diffusion && !packed) depth = 1;
+        if (!vec) depth = 1;
+        const size_t rf = diffusion ? 2 * (size_t)gw : (size_t)gw;
+        bool prev_in_extra = false;
+        auto one_pass = [&](int t, bool final_pass) -> int {
+            if (valid < t) {
+                std::vector<std::vector<float *>> pl(n);
+                for (int k = 0; k < n; k++) pl[k].push_back(L[k]->plane(cur));
+                PFS_TRY(exchange_planes(L, pl, halo, rf));
+                valid = halo;
+            }
+            const int e = valid - t;                    // extra rows recomputed on each side of the band
+            for (int k = 0; k < n; k++) {
+                pfs_slab *s = L[k];
+                Guard g(s->device);
+                SweepParams p = proto;
+                p.w = gw;
+                p.h = s->rows + 2 * e;
+                p.y_base = halo - e;
+                p.wrap = 0;
+                int flips = 0, wrote = 0;
+                float *a = s->plane(cur), *b = s->plane(oth);
+                float *x = (final_pass && t >= 2) ? s->plane(px) : nullptr;
+                ForceField ff{(force_bands && final_pass) ? force_bands[k] : nullptr, e, s->rows};
+                const ForceField *force = ff.aos ? &ff : nullptr;
+                if (diffusion && packed && t >= 2)
+                    PFS_TRY(launch_diffuse_packed(a, b, p, t, t, &flips, s->stream, x, &wrote, force));
+                else if (diffusion) {
+                    PFS_TRY(launch_diffuse_basic(a, b, p, 1, &flips, s->stream));
+                    if (force)
+                        PFS_TRY(launch_add_forces(b + (size_t)halo * rf, 2, force->aos, gw, s->rows, s->stream));
+                } else if (t == 1)
+                    PFS_TRY(launch_pressure_basic(a, b, s->plane(DIV), p, 1, &flips, s->stream));
+                else
+                    PFS_TRY(launch_pressure_fused(a, b, s->plane(DIV), p, t, t, &flips, s->stream, x, &wrote));
+                if (flips != 1 || (x != nullptr && !wrote)) {
+                    set_error("slab sweeps: a pass of depth %d took %d hops (previous iterate stored: %d)", t, flips, wrote);
+                    return PFS_ESTATE;
+                }
+                if (x != nullptr) prev_in_extra = true;
+            }
+            valid = (force_bands && final_pass) ? 0 : e;   // rows outside the band got no force: exchange before the next use
+            std::swap(cur, oth);
+            return PFS_OK;
+        };
+        // Diffusion: pass depths as even as possible, as launch_diffuse_packed plans them (ceil(count / depth) passes of
+        // depth d or d+1).  Pressure: full-depth passes, then the remainder (a depth-7 pass costs more per sweep than 8 or 4).
+        const int n_passes = (count + depth - 1) / depth;
+        const int base_t = count / n_passes, n_deeper = count % n_passes;
+        for (int pass = 0; left > 0; pass++) {
+            int t = diffusion ? std::min(left, base_t + (pass < n_deeper ? 1 : 0)) : std::min(left, depth);
+            if (t < 1) t = 1;
+            if (!diffusion && left - t == 1 && t >= 3) t -= 1;      // never end on a lone single sweep: it could not store iterate n-1
+            PFS_TRY(one_pass(t, left - t == 0));
+            left -= t;
+        }
+        *last = cur;
+        *prev = prev_in_extra ? px : oth;               // else: the plane the last (single) sweep read
+        *valid_io = valid;
+        return PFS_OK;
+}
+
 
 int fluid_step(const std::vector<pfs_slab *> &L, const StepIO &io, float dt, float viscosity, int n_diffuse, int n_pressure,
                bool exact_bound)
@@ -1378,9 +1460,9 @@ int fluid_step(const std::vector<pfs_slab *> &L, const StepIO &io, float dt, flo
             int *flag = reinterpret_cast<int *>(s->d_scalars + (speculate ? 6 : 2));
             float *vmax_out = speculate ? s->d_scalars + 4 : nullptr;
             if (cf == 2)
-                PFS_LAUNCH(advect_slab_kernel<2>, grid, block, 0, s->stream, src[k], dst, dt, gw, gh, s->row0, s->rows, s->halo, flag, vmax_out);
+                PFS_LAUNCH(advect_slab_kernel<2>, grid, block, 0, s->stream, src[k], dst, dt, gw, gh, s->row0, s->rows, s->halo, flag, vmax_out, 1.0f / (float)gw, 1.0f / (float)gh);
             else
-                PFS_LAUNCH(advect_slab_kernel<4>, grid, block, 0, s->stream, src[k], dst, dt, gw, gh, s->row0, s->rows, s->halo, flag, vmax_out);
+                PFS_LAUNCH(advect_slab_kernel<4>, grid, block, 0, s->stream, src[k], dst, dt, gw, gh, s->row0, s->rows, s->halo, flag, vmax_out, 1.0f / (float)gw, 1.0f / (float)gh);
             if (speculate) {
                 // (max|v| of this step's input, "a departure row was missing") -> every rank, then the host; nobody waits yet
                 // (on a side stream: the sweeps that follow do not depend on it)
@@ -1395,84 +1477,6 @@ int fluid_step(const std::vector<pfs_slab *> &L, const StepIO &io, float dt, flo
         }
     }
 
-    // n sweeps starting from iterate 0 in plane unit pa, all in fused passes; the pass that reaches sweep n also
-    // stores iterate n-1 into unit px (as pfs_api.cu's run_diffuse / run_pressure do), so both iterates the reference
-    // leaves behind exist afterwards.  `valid` tracks how many halo rows of the current iterate are correct on
-    // every slab: an exchange makes it `halo`; a pass of depth t needs t of them and -- by also recomputing the
-    // e = valid-t rows just outside the band -- leaves e valid rows on its result.
-    // `diffusion`: (u,v) planes through the packed kernel; else the pressure planes.
-    auto run_sweeps = [&](bool diffusion, int pa, int pb, int px, const SweepParams &proto, int count, int *last,
-                          int *prev, int *valid_out, const float *const *force_bands) -> int {
-        int cur = pa, oth = pb;
-        int left = count;
-        int valid = 0;
-        const bool vec = (gw % 4 == 0);
-        SweepParams p0 = proto;
-        const bool packed = diffusion && vec && packed_diffuse_supported(p0);
-        const int user_depth = pfs_get_fuse_depth();
-        int depth = user_depth > 0 ? std::min(user_depth, MIN_HALO) : (packed ? default_diffuse_depth() : MIN_HALO);
-        if (diffusion && !packed) depth = 1;
-        if (!vec) depth = 1;
-        const size_t rf = diffusion ? 2 * (size_t)gw : (size_t)gw;
-        bool prev_in_extra = false;
-        auto one_pass = [&](int t, bool final_pass) -> int {
-            if (valid < t) {
-                std::vector<std::vector<float *>> pl(n);
-                for (int k = 0; k < n; k++) pl[k].push_back(L[k]->plane(cur));
-                PFS_TRY(exchange_planes(L, pl, halo, rf));
-                valid = halo;
-            }
-            const int e = valid - t;                    // extra rows recomputed on each side of the band
-            for (int k = 0; k < n; k++) {
-                pfs_slab *s = L[k];
-                Guard g(s->device);
-                SweepParams p = proto;
-                p.w = gw;
-                p.h = s->rows + 2 * e;
-                p.y_base = halo - e;
-                p.wrap = 0;
-                int flips = 0, wrote = 0;
-                float *a = s->plane(cur), *b = s->plane(oth);
-                float *x = (final_pass && t >= 2) ? s->plane(px) : nullptr;
-                ForceField ff{(force_bands && final_pass) ? force_bands[k] : nullptr, e, s->rows};
-                const ForceField *force = ff.aos ? &ff : nullptr;
-                if (diffusion && packed && t >= 2)
-                    PFS_TRY(launch_diffuse_packed(a, b, p, t, t, &flips, s->stream, x, &wrote, force));
-                else if (diffusion) {
-                    PFS_TRY(launch_diffuse_basic(a, b, p, 1, &flips, s->stream));
-                    if (force)
-                        PFS_TRY(launch_add_forces(b + (size_t)halo * rf, 2, force->aos, gw, s->rows, s->stream));
-                } else if (t == 1)
-                    PFS_TRY(launch_pressure_basic(a, b, s->plane(DIV), p, 1, &flips, s->stream));
-                else
-                    PFS_TRY(launch_pressure_fused(a, b, s->plane(DIV), p, t, t, &flips, s->stream, x, &wrote));
-                if (flips != 1 || (x != nullptr && !wrote)) {
-                    set_error("slab sweeps: a pass of depth %d took %d hops (previous iterate stored: %d)", t, flips, wrote);
-                    return PFS_ESTATE;
-                }
-                if (x != nullptr) prev_in_extra = true;
-            }
-            valid = (force_bands && final_pass) ? 0 : e;   // rows outside the band got no force: exchange before the next use
-            std::swap(cur, oth);
-            return PFS_OK;
-        };
-        // Diffusion: pass depths as even as possible, as launch_diffuse_packed plans them (ceil(count / depth) passes of
-        // depth d or d+1).  Pressure: full-depth passes, then the remainder (a depth-7 pass costs more per sweep than 8 or 4).
-        const int n_passes = (count + depth - 1) / depth;
-        const int base_t = count / n_passes, n_deeper = count % n_passes;
-        for (int pass = 0; left > 0; pass++) {
-            int t = diffusion ? std::min(left, base_t + (pass < n_deeper ? 1 : 0)) : std::min(left, depth);
-            if (t < 1) t = 1;
-            if (!diffusion && left - t == 1 && t >= 3) t -= 1;      // never end on a lone single sweep: it could not store iterate n-1
-            PFS_TRY(one_pass(t, left - t == 0));
-            left -= t;
-        }
-        *last = cur;
-        *prev = prev_in_extra ? px : oth;               // else: the plane the last (single) sweep read
-        *valid_out = valid;
-        return PFS_OK;
-    };
-
     SweepParams dp;
     dp.w = gw;
     dp.h = L[0]->rows;
@@ -1481,7 +1485,7 @@ int fluid_step(const std::vector<pfs_slab *> &L, const StepIO &io, float dt, flo
     int d_valid = 0;
     int dl = UV_A, dpv = UV_B;                                            // iterate n_d, iterate n_d - 1
     next_phase(PFS_PHASE_DIFFUSE);
-    PFS_TRY(run_sweeps(true, UV_A, UV_B, UV_X, dp, n_diffuse, &dl, &dpv, &d_valid, io.forces));
+    PFS_TRY(run_sweeps(L, true, UV_A, UV_B, UV_X, dp, n_diffuse, &dl, &dpv, &d_valid, io.forces));
     next_phase(PFS_PHASE_DIVERGENCE);
 
     // pointer choreography (pfs_simulate_fluid_step): struct `vp` points at buffer Bv after diffuse (the original vp buffer for
@@ -1532,7 +1536,7 @@ int fluid_step(const std::vector<pfs_slab *> &L, const StepIO &io, float dt, flo
     int p_valid = 0;
     int pl_last = p_warm, pl_prev = p_oth;
     next_phase(PFS_PHASE_PRESSURE);
-    PFS_TRY(run_sweeps(false, p_warm, p_oth, p_ext, pp, n_pressure, &pl_last, &pl_prev, &p_valid, nullptr));
+    PFS_TRY(run_sweeps(L, false, p_warm, p_oth, p_ext, pp, n_pressure, &pl_last, &pl_prev, &p_valid, nullptr));
     next_phase(PFS_PHASE_PROJECT);
 
     // ---- late checks: everything so far only wrote scratch planes ----
@@ -1686,13 +1690,21 @@ extern "C" int pfs_slab_upload(pfs_slab *const *slabs, int n_local, const float 
     const char *fn = "pfs_slab_upload";
     std::vector<pfs_slab *> L;
     PFS_TRY(begin_call(fn, slabs, n_local, streams, &L));
-    if (!vp || !tmp || (L[0]->iw > 0 && !image)) {
-        set_error("%s: vp, tmp%s are needed", fn, L[0]->iw > 0 ? " and image" : "");
+    // The first upload needs everything; later ones may replace the velocity pair (vp AND tmp) or the image alone.
+    const bool first = !L[0]->resident;
+    if ((vp == nullptr) != (tmp == nullptr)) {
+        set_error("%s: vp and tmp are replaced together", fn);
         return PFS_EINVAL;
     }
+    if (first && (!vp || (L[0]->iw > 0 && !image))) {
+        set_error("%s: the first upload needs vp, tmp%s", fn, L[0]->iw > 0 ? " and image" : "");
+        return PFS_EINVAL;
+    }
+    if (!first && L[0]->pending_color) PFS_TRY(resolve_pending_color(L));
     for (int k = 0; k < n_local; k++) {
         pfs_slab *s = L[k];
-        if (!vp[k] || !tmp[k] || ((uintptr_t)vp[k] & 15) || ((uintptr_t)tmp[k] & 15) || (s->irows > 0 && (!image[k] || ((uintptr_t)image[k] & 15)))) {
+        if ((vp && (!vp[k] || !tmp[k] || ((uintptr_t)vp[k] & 15) || ((uintptr_t)tmp[k] & 15))) ||
+            (image && s->irows > 0 && (!image[k] || ((uintptr_t)image[k] & 15)))) {
             set_error("%s: slab %d: bands must be non-null, 16-byte aligned device buffers", fn, k);
             return PFS_EINVAL;
         }
@@ -1701,14 +1713,18 @@ extern "C" int pfs_slab_upload(pfs_slab *const *slabs, int n_local, const float 
         for (int q = 0; q < 2 && ibytes > 0; q++)
             if (!s->img[q]) PFS_CUDA(cudaMalloc((void **)&s->img[q], ibytes));
         const size_t gw = (size_t)s->gw;
-        s->uvY = UV_A; s->pX = P_A; s->pY = P_B; s->dX = DIV; s->dY = DIV2;
-        PFS_TRY(launch_unpack(vp[k], s->interior(UV_S, 2 * gw), s->interior(s->pX, gw), s->interior(s->dX, gw), s->gw, s->rows, s->stream));
-        PFS_TRY(launch_unpack(tmp[k], s->interior(s->uvY, 2 * gw), s->interior(s->pY, gw), s->interior(s->dY, gw), s->gw, s->rows, s->stream));
-        if (ibytes > 0) PFS_CUDA(cudaMemcpyAsync(s->img[0], image[k], ibytes, cudaMemcpyDefault, s->stream));
-        s->img_cur = 0;
+        if (vp) {
+            s->uvY = UV_A; s->pX = P_A; s->pY = P_B; s->dX = DIV; s->dY = DIV2;
+            PFS_TRY(launch_unpack(vp[k], s->interior(UV_S, 2 * gw), s->interior(s->pX, gw), s->interior(s->dX, gw), s->gw, s->rows, s->stream));
+            PFS_TRY(launch_unpack(tmp[k], s->interior(s->uvY, 2 * gw), s->interior(s->pY, gw), s->interior(s->dY, gw), s->gw, s->rows, s->stream));
+            s->vbound = -1.f;             // the velocity is new: the first gather measures its bound
+        }
+        if (image && ibytes > 0) {
+            if (first) s->img_cur = 0;
+            PFS_CUDA(cudaMemcpyAsync(s->img[s->img_cur], image[k], ibytes, cudaMemcpyDefault, s->stream));
+        }
         s->resident = true;
         s->pending_color = false;
-        s->vbound = -1.f;                 // the velocity is new: the first gather measures its bound
     }
     return PFS_OK;
 }
@@ -1740,34 +1756,188 @@ extern "C" int pfs_slab_download(pfs_slab *const *slabs, int n_local, float *con
     return PFS_OK;
 }
 
-// n_steps iterations of the driver loop (main.cpp:236-239) on the resident state.
-extern "C" int pfs_slab_step(pfs_slab *const *slabs, int n_local, int n_steps, float dt, float viscosity, int n_diffuse,
-                             int n_pressure, void *const *streams)
+namespace pfs {
+namespace {
+
+int begin_resident(const char *fn, pfs_slab *const *slabs, int n_local, void *const *streams, std::vector<pfs_slab *> *L)
 {
-    const char *fn = "pfs_slab_step";
-    std::vector<pfs_slab *> L;
-    PFS_TRY(begin_call(fn, slabs, n_local, streams, &L));
-    PFS_TRY(check_counts(fn, n_diffuse, n_pressure));
-    for (pfs_slab *s : L) {
+    PFS_TRY(begin_call(fn, slabs, n_local, streams, L));
+    for (pfs_slab *s : *L) {
         if (!s->resident) {
             set_error("%s: the slabs hold no state (call pfs_slab_upload first)", fn);
             return PFS_ESTATE;
         }
     }
+    return PFS_OK;
+}
+
+int resident_color_step(const std::vector<pfs_slab *> &L, float dt)
+{
     static const bool spec_env = !(getenv("PFS_SLAB_SPECULATE") && !strcmp(getenv("PFS_SLAB_SPECULATE"), "0"));
-    const bool has_image = L[0]->iw > 0;
+    PFS_TRY(resolve_pending_color(L));                         // two colour steps in a row: the flag words are about to be reused
+    std::vector<float *> in, out;
+    std::vector<const float *> vel;
+    for (pfs_slab *s : L) {
+        in.push_back(s->img[s->img_cur]);
+        out.push_back(s->img[s->img_cur ^ 1]);
+        vel.push_back(s->interior(UV_S, 2 * (size_t)s->gw));
+    }
+    PFS_TRY(color_step(L, in.data(), out.data(), vel.data(), 2, dt, spec_env && L[0]->vbound >= 0.f));
+    for (pfs_slab *s : L) s->img_cur ^= 1;                     // fluid.cpp:317-319
+    return PFS_OK;
+}
+
+}  // namespace
+}  // namespace pfs
+
+// n_steps iterations of the driver loop (main.cpp:236-239) on the resident state; and its two halves on their own
+// (simulate_fluid_step / advect_color_step, fluid.hpp:107,116), e.g. to overlap transfers with one of them.
+extern "C" int pfs_slab_step(pfs_slab *const *slabs, int n_local, int n_steps, float dt, float viscosity, int n_diffuse,
+                             int n_pressure, void *const *streams)
+{
+    const char *fn = "pfs_slab_step";
+    std::vector<pfs_slab *> L;
+    PFS_TRY(begin_resident(fn, slabs, n_local, streams, &L));
+    PFS_TRY(check_counts(fn, n_diffuse, n_pressure));
     for (int it = 0; it < n_steps; it++) {
         PFS_TRY(fluid_step(L, StepIO{true, nullptr, nullptr, nullptr}, dt, viscosity, n_diffuse, n_pressure, false));
-        if (!has_image) continue;
-        std::vector<float *> in, out;
-        std::vector<const float *> vel;
-        for (pfs_slab *s : L) {
-            in.push_back(s->img[s->img_cur]);
-            out.push_back(s->img[s->img_cur ^ 1]);
-            vel.push_back(s->interior(UV_S, 2 * (size_t)s->gw));
-        }
-        PFS_TRY(color_step(L, in.data(), out.data(), vel.data(), 2, dt, spec_env && L[0]->vbound >= 0.f));
-        for (pfs_slab *s : L) s->img_cur ^= 1;                 // fluid.cpp:317-319
+        if (L[0]->iw > 0) PFS_TRY(resident_color_step(L, dt));
     }
+    return PFS_OK;
+}
+
+extern "C" int pfs_slab_step_fluid(pfs_slab *const *slabs, int n_local, float dt, float viscosity, int n_diffuse, int n_pressure,
+                                   void *const *streams)
+{
+    const char *fn = "pfs_slab_step_fluid";
+    std::vector<pfs_slab *> L;
+    PFS_TRY(begin_resident(fn, slabs, n_local, streams, &L));
+    PFS_TRY(check_counts(fn, n_diffuse, n_pressure));
+    return fluid_step(L, StepIO{true, nullptr, nullptr, nullptr}, dt, viscosity, n_diffuse, n_pressure, false);
+}
+
+extern "C" int pfs_slab_step_color(pfs_slab *const *slabs, int n_local, float dt, void *const *streams)
+{
+    const char *fn = "pfs_slab_step_color";
+    std::vector<pfs_slab *> L;
+    PFS_TRY(begin_resident(fn, slabs, n_local, streams, &L));
+    if (L[0]->iw < 1) {
+        set_error("%s: the slabs were created without an image", fn);
+        return PFS_EINVAL;
+    }
+    return resident_color_step(L, dt);
+}
+
+// ---------------------------------------------------------------------------------------------
+// computePressure with a run-time sweep count on slabs (pfs_compute_pressure_adaptive over the ring).
+// Batches of `check_every` fused sweeps with the usual halo exchanges; after each batch the ranks' partial sums of
+// (p_N - p_{N-1})^2 (warp-shuffle + fixed-order block reduction, kernels_basic.cu) are all-reduced (NCCL, double) and the
+// global rms decides -- the same decision on every rank, one host synchronisation per batch, none inside a batch.  The
+// bands end up bit-identical to pfs_compute_pressure / the reference's computePressure with n_sweeps = the count returned.
+// ---------------------------------------------------------------------------------------------
+extern "C" int pfs_slab_compute_pressure_adaptive(pfs_slab *const *slabs, int n_local, float **vp, float **vp_out, float dt, float tol,
+                                                  int max_sweeps, int check_every, int *sweeps_out, double *update_rms_out,
+                                                  void *const *streams)
+{
+    const char *fn = "pfs_slab_compute_pressure_adaptive";
+    std::vector<pfs_slab *> L;
+    PFS_TRY(begin_call(fn, slabs, n_local, streams, &L));
+    if (!vp || !vp_out || max_sweeps < 1 || check_every < 2 || !(tol >= 0.0f)) {
+        set_error("%s: need vp, vp_out, max_sweeps >= 1, check_every >= 2 and tol >= 0", fn);
+        return PFS_EINVAL;
+    }
+    const int n = n_local;
+    for (int k = 0; k < n; k++) {
+        if (!vp[k] || !vp_out[k] || vp[k] == vp_out[k] || ((uintptr_t)vp[k] & 15) || ((uintptr_t)vp_out[k] & 15)) {
+            set_error("%s: slab %d: vp/vp_out must be distinct, non-null, 16-byte aligned device buffers", fn, k);
+            return PFS_EINVAL;
+        }
+    }
+    const int gw = L[0]->gw, halo = L[0]->halo;
+    const size_t gws = (size_t)gw;
+    constexpr int kBlocks = 1184;
+    std::vector<double *> scratch(n, nullptr);
+    struct Cleanup {
+        std::vector<double *> &v;
+        std::vector<pfs_slab *> &L;
+        ~Cleanup()
+        {
+            for (size_t k = 0; k < v.size(); k++)
+                if (v[k]) {
+                    Guard g(L[k]->device);
+                    cudaFree(v[k]);
+                }
+        }
+    } cleanup{scratch, L};
+    // (u,v) and the warm-start pressure of the bands -> planes; one halo row of v for the divergence; divergence + its halo
+    for (int k = 0; k < n; k++) {
+        pfs_slab *s = L[k];
+        Guard g(s->device);
+        PFS_CUDA(cudaMalloc((void **)&scratch[k], (4 * (size_t)kBlocks + 4) * sizeof(double)));
+        PFS_TRY(launch_unpack(vp[k], s->interior(UV_A, 2 * gws), s->interior(P_A, gws), nullptr, gw, s->rows, s->stream));
+    }
+    {
+        std::vector<std::vector<float *>> pl(n);
+        for (int k = 0; k < n; k++) pl[k].push_back(L[k]->plane(UV_A));
+        PFS_TRY(exchange_planes(L, pl, 1, 2 * gws));
+        for (int k = 0; k < n; k++) {
+            pfs_slab *s = L[k];
+            Guard g(s->device);
+            PFS_TRY(launch_divergence(s->plane(UV_A), s->plane(DIV), nullptr, nullptr, dt, gw, s->rows, s->stream, halo, 0));
+        }
+        for (int k = 0; k < n; k++) pl[k][0] = L[k]->plane(DIV);
+        PFS_TRY(exchange_planes(L, pl, halo, gws));
+    }
+    SweepParams pp;
+    pp.w = gw;
+    pp.h = L[0]->rows;
+    pp.alpha = 1.0f;
+    pp.beta = 4.0f;
+    int cur = P_A, oth = P_B, last = P_A, prev = P_B, valid = 0, done = 0;
+    double rms = 0.0;
+    const double cells_global = (double)gw * (double)L[0]->gh;
+    while (done < max_sweeps) {
+        int nb = std::min(check_every, max_sweeps - done);
+        if (max_sweeps - done - nb == 1) nb += 1;                 // never leave a batch of one sweep (it keeps no p_{N-1})
+        PFS_TRY(run_sweeps(L, false, cur, oth, P_X, pp, nb, &last, &prev, &valid, nullptr));
+        done += nb;
+        double sum = 0.0;
+        for (int k = 0; k < n; k++) {
+            pfs_slab *s = L[k];
+            Guard g(s->device);
+            double *res = scratch[k] + 4 * (size_t)kBlocks;
+            PFS_TRY(launch_plane_diff_norms(s->interior(last, gws), s->interior(prev, gws), (size_t)s->rows * gws, scratch[k], kBlocks, res,
+                                            s->stream));
+            if (s->comm != nullptr) PFS_NCCL(nccl().AllReduce(res, res, 1, ncclDouble, ncclSum, s->comm, s->stream));
+        }
+        for (int k = 0; k < n; k++) {
+            pfs_slab *s = L[k];
+            Guard g(s->device);
+            double host = 0.0;
+            PFS_CUDA(cudaMemcpyAsync(&host, scratch[k] + 4 * (size_t)kBlocks, sizeof(double), cudaMemcpyDeviceToHost, s->stream));
+            PFS_CUDA(cudaStreamSynchronize(s->stream));
+            sum = (s->comm != nullptr) ? host : sum + host;       // NCCL: already the global sum; in-process ring: fold the slabs
+        }
+        rms = std::sqrt(sum / cells_global);
+        if (rms <= (double)tol) break;
+        if (done < max_sweeps) {
+            cur = last;
+            oth = (last == P_A) ? P_B : P_A;                      // the ping-pong plane that does not hold iterate `done`
+        }
+    }
+    // write-back as pfs_compute_pressure: divergence into channel 3 of both buffers, channel 2 <- the iterate each buffer was
+    // last written with, data pointers as the reference's swaps leave them
+    for (int k = 0; k < n; k++) {
+        pfs_slab *s = L[k];
+        Guard g(s->device);
+        float *in0 = vp[k], *out0 = vp_out[k];
+        float *buf_last = (done & 1) ? out0 : in0, *buf_prev = (done & 1) ? in0 : out0;
+        PFS_TRY(launch_pack(buf_last, nullptr, s->interior(last, gws), s->interior(DIV, gws), gw, s->rows, s->stream));
+        PFS_TRY(launch_pack(buf_prev, nullptr, done >= 2 ? s->interior(prev, gws) : nullptr, s->interior(DIV, gws), gw, s->rows, s->stream));
+        vp_out[k] = buf_last;
+        vp[k] = buf_prev;
+    }
+    if (sweeps_out) *sweeps_out = done;
+    if (update_rms_out) *update_rms_out = rms;
     return PFS_OK;
 }

@@ -175,6 +175,20 @@ def computePressureAdaptive(vp: vp_field, vp_out: vp_field, dt: float, tol: floa
     return n.value, rms.value
 
 
+def computePressureSOR(vp: vp_field, vp_out: vp_field, dt: float, omega: float, tol: float, max_sweeps: int,  # noqa: N802
+                       check_every: int = 8) -> tuple[int, float]:
+    """Red-black SOR instead of the reference's Jacobi sweeps (pfs_compute_pressure_sor): NOT a parity path.  Divergence into
+    channel 3 of both buffers, relaxed pressure into channel 2 of vp_out.  -> (sweeps done, rms of the last sweep's update)."""
+    L = _cabi.lib()
+    _check_buf(vp, "vp"); _check_buf(vp_out, "vp_out")
+    _require_device("computePressureSOR", vp, vp_out)
+    n, rms = ctypes.c_int(0), ctypes.c_double(0.0)
+    with _dev_guard(vp.data):
+        check(L.pfs_compute_pressure_sor(vp.data.data_ptr(), vp_out.data.data_ptr(), dt, vp.x, vp.y, vp.z, omega, tol, max_sweeps,
+                                         check_every, ctypes.byref(n), ctypes.byref(rms), _stream_of(vp.data)))
+    return n.value, rms.value
+
+
 def subtractPressureGradient(vp: vp_field, vp_out: vp_field, dt: float) -> None:  # noqa: N802
     L = _cabi.lib()
     _check_buf(vp, "vp"); _check_buf(vp_out, "vp_out")

@@ -138,6 +138,18 @@ class SlabRing(_SlabBase):
                                             _ptr_array([t.data_ptr() for t in vp]), _ptr_array([t.data_ptr() for t in tmp]), img,
                                             self._streams()))
 
+    def compute_pressure_adaptive(self, vp: list, vp_out: list, dt: float, tol: float, max_sweeps: int, check_every: int = 16):
+        """computePressure with the sweep count chosen at run time, on the bands (pfs_slab_compute_pressure_adaptive).
+        -> (sweeps done, rms of the last update over the whole grid); entries of vp / vp_out are exchanged as the reference would."""
+        by_ptr = {t.data_ptr(): t for t in vp + vp_out}
+        pv, po = _ptr_array([t.data_ptr() for t in vp]), _ptr_array([t.data_ptr() for t in vp_out])
+        n, rms = ctypes.c_int(0), ctypes.c_double(0.0)
+        check(_cabi.lib().pfs_slab_compute_pressure_adaptive(_ptr_array([h.value for h in self._handles]), self.nranks, pv, po, dt, tol,
+                                                             max_sweeps, check_every, ctypes.byref(n), ctypes.byref(rms), self._streams()))
+        for k in range(self.nranks):
+            vp[k], vp_out[k] = by_ptr[pv[k]], by_ptr[po[k]]
+        return n.value, rms.value
+
     def check(self) -> None:
         check(_cabi.lib().pfs_slab_check(_ptr_array([h.value for h in self._handles]), self.nranks))
 
@@ -204,11 +216,26 @@ class SlabRank(_SlabBase):
         image.data, itmp.data = by_ptr[pi[0]], by_ptr[pm[0]]
 
     # -- resident state (pfs_slab_upload / pfs_slab_step / pfs_slab_download) ---------------------
-    def upload(self, vp, tmp, image=None) -> None:
-        """This rank's bands (CUDA tensors [rows, gw, 4] / [irows, iw, 4]) become the slab's resident state."""
+    def upload(self, vp=None, tmp=None, image=None, stream=None) -> None:
+        """This rank's bands (CUDA tensors [rows, gw, 4] / [irows, iw, 4]) become the slab's resident state.  After the first
+        upload the velocity pair (vp and tmp) or the image may be replaced on their own."""
         img = _ptr_array([image.data_ptr()]) if image is not None else None
-        check(_cabi.lib().pfs_slab_upload(_ptr_array([self._h.value]), 1, _ptr_array([vp.data_ptr()]), _ptr_array([tmp.data_ptr()]),
-                                          img, self._stream(vp)))
+        pv = _ptr_array([vp.data_ptr()]) if vp is not None else None
+        pt = _ptr_array([tmp.data_ptr()]) if tmp is not None else None
+        ref = vp if vp is not None else image
+        check(_cabi.lib().pfs_slab_upload(_ptr_array([self._h.value]), 1, pv, pt, img,
+                                          _ptr_array([stream]) if stream is not None else self._stream(ref)))
+
+    def step_fluid(self, dt: float, viscosity: float, n_diffuse: int = NUM_JACOBI_ITERS, n_pressure: int | None = None, stream=None) -> None:
+        import torch
+        n_pressure = n_diffuse if n_pressure is None else n_pressure
+        st = _ptr_array([stream if stream is not None else torch.cuda.current_stream().cuda_stream])
+        check(_cabi.lib().pfs_slab_step_fluid(_ptr_array([self._h.value]), 1, dt, viscosity, n_diffuse, n_pressure, st))
+
+    def step_color(self, dt: float, stream=None) -> None:
+        import torch
+        st = _ptr_array([stream if stream is not None else torch.cuda.current_stream().cuda_stream])
+        check(_cabi.lib().pfs_slab_step_color(_ptr_array([self._h.value]), 1, dt, st))
 
     def step(self, n_steps: int, dt: float, viscosity: float, n_diffuse: int = NUM_JACOBI_ITERS, n_pressure: int | None = None,
              device=None) -> None:
@@ -217,13 +244,26 @@ class SlabRank(_SlabBase):
         stream = _ptr_array([torch.cuda.current_stream(device).cuda_stream])
         check(_cabi.lib().pfs_slab_step(_ptr_array([self._h.value]), 1, n_steps, dt, viscosity, n_diffuse, n_pressure, stream))
 
-    def download(self, vp, tmp, image=None) -> None:
+    def download(self, vp=None, tmp=None, image=None, stream=None) -> None:
         img = _ptr_array([image.data_ptr()]) if image is not None else None
-        check(_cabi.lib().pfs_slab_download(_ptr_array([self._h.value]), 1, _ptr_array([vp.data_ptr()]), _ptr_array([tmp.data_ptr()]),
-                                            img, self._stream(vp)))
+        pv = _ptr_array([vp.data_ptr()]) if vp is not None else None
+        pt = _ptr_array([tmp.data_ptr()]) if tmp is not None else None
+        ref = vp if vp is not None else image
+        check(_cabi.lib().pfs_slab_download(_ptr_array([self._h.value]), 1, pv, pt, img,
+                                            _ptr_array([stream]) if stream is not None else self._stream(ref)))
 
     def check(self) -> None:
         check(_cabi.lib().pfs_slab_check(_ptr_array([self._h.value]), 1))
+
+    def compute_pressure_adaptive(self, vp: vp_field, vp_out: vp_field, dt: float, tol: float, max_sweeps: int, check_every: int = 16):
+        """This rank's part of pfs_slab_compute_pressure_adaptive (collective: the rms is all-reduced after every batch)."""
+        by_ptr = {vp.data.data_ptr(): vp.data, vp_out.data.data_ptr(): vp_out.data}
+        pv, po = _ptr_array([vp.data.data_ptr()]), _ptr_array([vp_out.data.data_ptr()])
+        n, rms = ctypes.c_int(0), ctypes.c_double(0.0)
+        check(_cabi.lib().pfs_slab_compute_pressure_adaptive(_ptr_array([self._h.value]), 1, pv, po, dt, tol, max_sweeps, check_every,
+                                                             ctypes.byref(n), ctypes.byref(rms), self._stream(vp.data)))
+        vp.data, vp_out.data = by_ptr[pv[0]], by_ptr[po[0]]
+        return n.value, rms.value
 
     def step_norms(self, vp: vp_field, tmp: vp_field) -> dict:
         """Norms of the WHOLE grid (all-reduced over the ring); the same on every rank."""

@@ -45,6 +45,32 @@ def sum_over_ranks(x: float, device="cuda") -> float:
     return float(t.item())
 
 
+# ---- host placement --------------------------------------------------------------------------------
+def bind_to_gpu_numa_node(local: int):
+    """Pin this process to the CPUs of the NUMA node its GPU hangs off, BEFORE any pinned host memory is allocated: the
+    default memory policy places pages on the allocating thread's node, so the rank's staging buffers end up next to its
+    own PCIe root instead of all eight ranks' buffers on one node (which is what made the 8-GPU end-to-end run host-bound).
+    -> {"node": n, "cpus": count} or None if the topology cannot be read (then nothing is changed)."""
+    try:
+        import torch
+        pr = torch.cuda.get_device_properties(local)
+        pci = f"{pr.pci_domain_id:04x}:{pr.pci_bus_id:02x}:{pr.pci_device_id:02x}.0"
+        node = int(open(f"/sys/bus/pci/devices/{pci}/numa_node").read().strip())
+        if node < 0:
+            return None
+        cpus = set()
+        for part in open(f"/sys/devices/system/node/node{node}/cpulist").read().strip().split(","):
+            a, _, b = part.partition("-")
+            cpus.update(range(int(a), int(b or a) + 1))
+        cpus &= os.sched_getaffinity(0)
+        if not cpus:
+            return None
+        os.sched_setaffinity(0, cpus)
+        return {"node": node, "cpus": len(cpus)}
+    except Exception:
+        return None
+
+
 # ---- the bench arm ---------------------------------------------------------------------------------
 TRANSPORT_TEXT = {
     "p2p": "halo rows stored straight into the ring neighbours' memory (CUDA IPC mappings over NVLink, one kernel per "
@@ -68,6 +94,7 @@ def run(args, bench) -> None:
         raise SystemExit(f"bench.py --gpus {args.gpus} needs WORLD_SIZE={args.gpus} (launch with torch.distributed.run); "
                          f"got WORLD_SIZE={world}")
     torch.cuda.set_device(local)
+    numa = bind_to_gpu_numa_node(local)
     w, h, n = bench.workload_shape(args)
     # NCCL announces its version on stdout when a communicator is created; stdout must carry exactly one
     # JSON line, so fd 1 points at stderr until both communicators (torch's and the library's) exist.
@@ -177,19 +204,46 @@ def run(args, bench) -> None:
         dist.barrier()
 
     # ---- end to end: every rank uploads its bands from pinned memory, steps, downloads them ----
+    # Pinned buffers are allocated after the process was bound to its GPU's NUMA node.  Uploads run on one stream, the
+    # kernels on the current one, downloads on a third, so the two PCIe directions overlap where the data dependencies
+    # allow: the image goes up while the fluid step runs, vp/vtmp come down while advect_color runs.
     e2e = None
     if not args.no_e2e:
         hv, ht, hi = (torch.from_numpy(x).pin_memory() for x in (vp, vtmp, image))
         e2e_steps = max(2, min(args.steps, 5))
+        s_up, s_down = torch.cuda.Stream(), torch.cuda.Stream()
+        main = torch.cuda.current_stream()
+        ev = [torch.cuda.Event() for _ in range(6)]
+
         def e2e_step():
-            fv.data.copy_(hv, non_blocking=True); ft.data.copy_(ht, non_blocking=True); fi.data.copy_(hi, non_blocking=True)
-            if resident:
-                slab.upload(fv.data, ft.data, fi.data)
-                slab.step(1, DT, VISC, n, n)
-                slab.download(fv.data, ft.data, fi.data)
-            else:
+            if not resident:
+                fv.data.copy_(hv, non_blocking=True); ft.data.copy_(ht, non_blocking=True); fi.data.copy_(hi, non_blocking=True)
                 step()
-            hv.copy_(fv.data, non_blocking=True); ht.copy_(ft.data, non_blocking=True); hi.copy_(fi.data, non_blocking=True)
+                hv.copy_(fv.data, non_blocking=True); ht.copy_(ft.data, non_blocking=True); hi.copy_(fi.data, non_blocking=True)
+                torch.cuda.synchronize()
+                return
+            s_up.wait_stream(main)
+            with torch.cuda.stream(s_up):
+                fv.data.copy_(hv, non_blocking=True); ft.data.copy_(ht, non_blocking=True)
+                ev[0].record()
+                fi.data.copy_(hi, non_blocking=True)
+                ev[1].record()
+            main.wait_event(ev[0])
+            slab.upload(fv.data, ft.data, None)
+            slab.step_fluid(DT, VISC, n, n)
+            slab.download(fv.data, ft.data, None)
+            ev[2].record()
+            with torch.cuda.stream(s_down):
+                s_down.wait_event(ev[2])
+                hv.copy_(fv.data, non_blocking=True); ht.copy_(ft.data, non_blocking=True)
+            main.wait_event(ev[1])
+            slab.upload(None, None, fi.data)
+            slab.step_color(DT)
+            slab.download(None, None, fi.data)
+            ev[3].record()
+            with torch.cuda.stream(s_down):
+                s_down.wait_event(ev[3])
+                hi.copy_(fi.data, non_blocking=True)
             torch.cuda.synchronize()
         e2e_step()
         dist.barrier()
@@ -200,8 +254,10 @@ def run(args, bench) -> None:
         e2e_s = max_over_ranks((time.perf_counter() - t0) / e2e_steps)
         e2e = {"value": cells_global * n / e2e_s, "unit": bench.UNIT, "ms_per_step": e2e_s * 1e3,
                "h2d_bytes_per_step": 3 * cells_global * 16, "d2h_bytes_per_step": 3 * cells_global * 16,
-               "api": "SlabRank.simulate_fluid_step + advect_color_step on each rank's band; every rank uploads vp, "
-                      "vtmp, image from pinned host memory and downloads them again each step", "steps": e2e_steps}
+               "api": "every rank: pinned host bands -> device (upload stream), pfs_slab_upload + pfs_slab_step_fluid / _color + "
+                      "pfs_slab_download, device -> pinned host bands (download stream); image upload overlaps the fluid step, "
+                      "velocity download overlaps advect_color", "steps": e2e_steps,
+               "host_placement": numa if numa else "NUMA topology not readable: default placement"}
 
     if rank == 0:
         peak, peak_src = bench.measured_peak_gbs()

@@ -30,6 +30,7 @@ def main():
     for case in CASES:
         run_case(rank, world, *case)
     run_jump_case(rank, world)
+    run_adaptive_case(rank, world)
     dist.barrier()
     dist.destroy_process_group()
 
@@ -74,6 +75,43 @@ def run_jump_case(rank, world):
         assert np.array_equal(got[0].view(np.uint32), wv.view(np.uint32)), "vp after the jump"
         assert np.array_equal(got[1].view(np.uint32), wt.view(np.uint32)), "vtmp after the jump"
         print("jump case matches oracle", flush=True)
+    dist.barrier()
+    slab.close()
+
+
+def run_adaptive_case(rank, world):
+    """pfs_slab_compute_pressure_adaptive across processes: every rank stops at the same count (the rms is all-reduced after
+    every batch), and the bands hold the reference's computePressure at that count."""
+    h, w, dt, every = 160, 96, 0.37, 8
+    rng = np.random.default_rng(7)
+    y, x = np.mgrid[0:h, 0:w]
+    a = np.zeros((h, w, 4), np.float32)
+    a[..., 0] = np.sin(2 * np.pi * x / w) * np.cos(2 * np.pi * y / h) + 0.05 * rng.standard_normal((h, w))
+    a[..., 1] = np.cos(4 * np.pi * x / w) * np.sin(2 * np.pi * y / h) + 0.05 * rng.standard_normal((h, w))
+    a[..., 2:] = rng.standard_normal((h, w, 2)).astype(np.float32)
+    b = np.ascontiguousarray(a[::-1])
+
+    def rms_at(n):
+        ra, rb = oracle.Oracle().compute_pressure(a.copy(), b.copy(), dt, n)
+        d = rb[..., 2].astype(np.float64) - ra[..., 2].astype(np.float64)
+        return ra, rb, float(np.sqrt(np.mean(d * d)))
+    tol = 0.5 * (rms_at(3 * every)[2] + rms_at(2 * every)[2])
+    slab = connect(rank, world, w, h, 0, 0)
+    r0, rows = slab.row0, slab.rows
+    fa, fb = vp_field(torch.from_numpy(a[r0:r0 + rows].copy()).cuda()), vp_field(torch.from_numpy(b[r0:r0 + rows].copy()).cuda())
+    n, rms = slab.compute_pressure_adaptive(fa, fb, dt, tol, 200, every)
+    slab.check()
+    parts = [None] * world
+    dist.all_gather_object(parts, (n, rms, fa.data.cpu().numpy(), fb.data.cpu().numpy()))
+    assert all(p[0] == n and p[1] == rms for p in parts), [(p[0], p[1]) for p in parts]
+    if rank == 0:
+        assert n == 3 * every, n
+        ra, rb, want = rms_at(n)
+        assert abs(rms - want) <= 1e-12 * max(1.0, want)
+        got = [np.concatenate([p[k] for p in parts], axis=0) for k in (2, 3)]
+        assert np.array_equal(got[0].view(np.uint32), ra.view(np.uint32)), "adaptive vp"
+        assert np.array_equal(got[1].view(np.uint32), rb.view(np.uint32)), "adaptive vp_out"
+        print("adaptive case matches oracle", flush=True)
     dist.barrier()
     slab.close()
 

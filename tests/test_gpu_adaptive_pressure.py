@@ -77,3 +77,55 @@ def test_adaptive_rejects_bad_arguments():
         pfs.computePressureAdaptive(fa, fb, 0.1, -1.0, 100, 8)
     with pytest.raises(pfs.PfsError):
         pfs.computePressureAdaptive(fa, fb, 0.1, float("nan"), 100, 8)
+
+
+@pytest.mark.parametrize("nranks", [1, 2, 3])
+@pytest.mark.parametrize("check_every,max_sweeps", [(8, 200), (5, 64)])
+def test_adaptive_on_a_ring_of_slabs(nranks, check_every, max_sweeps):
+    """pfs_slab_compute_pressure_adaptive: the rms is folded over the whole ring after every batch, so the ring stops at the
+    count the single-GPU solve stops at, and the bands hold the reference's computePressure at that count, bit for bit."""
+    from probabilistic_fluid_simulation_b200.slab import SlabRing
+    h, w = 96, 128
+    a, b = smooth_field(h, w, 41), smooth_field(h, w, 42)
+    dt = 0.37
+    target = 3 * check_every
+    tol = 0.5 * (oracle_rms(a, b, dt, target)[2] + oracle_rms(a, b, dt, target - check_every)[2])
+    fa, fb = pfs.vp_field(to_dev(a)), pfs.vp_field(to_dev(b))
+    n1, rms1 = pfs.computePressureAdaptive(fa, fb, dt, tol, max_sweeps, check_every)
+    ring = SlabRing(nranks, w, h)
+    ba, bb = ring.split(a), ring.split(b)
+    n, rms = ring.compute_pressure_adaptive(ba, bb, dt, tol, max_sweeps, check_every)
+    ring.check()
+    assert n == n1 and abs(rms - rms1) <= 1e-12 * max(1.0, rms1)
+    ra, rb, _ = oracle_rms(a, b, dt, n)
+    assert_bit_equal(ring.gather(ba), ra, f"ring vp (R={nranks})")
+    assert_bit_equal(ring.gather(bb), rb, f"ring vp_out (R={nranks})")
+    ring.close()
+
+
+def test_sor_reaches_the_tolerance_in_fewer_sweeps_than_jacobi():
+    """Red-black SOR is NOT a parity path: it is checked for what it claims -- the same discrete equation solved to the same
+    update tolerance in fewer sweeps.  Its result must satisfy the reference's own Jacobi fixed-point equation as well as
+    the Jacobi iterate at that tolerance does."""
+    from probabilistic_fluid_simulation_b200 import fixtures
+    h, w = 256, 256
+    a, b, _, _ = fixtures.make_state(fixtures.smooth_velocity_bytes(h, w), fixtures.random_image_bytes(8, 8, 1))
+    dt, tol = 1.0, 1e-3
+    fa, fb = pfs.vp_field(to_dev(a)), pfs.vp_field(to_dev(b))
+    n_jac, rms_jac = pfs.computePressureAdaptive(fa, fb, dt, tol, 20000, 8)
+    p_jac = to_host(fb.data if n_jac % 2 else fa.data)[..., 2].astype(np.float64)
+    ga, gb = pfs.vp_field(to_dev(a)), pfs.vp_field(to_dev(b))
+    n_sor, rms_sor = pfs.computePressureSOR(ga, gb, dt, 1.9, tol, 20000, 4)
+    out = to_host(gb.data)
+    p_sor, div = out[..., 2].astype(np.float64), out[..., 3].astype(np.float64)
+    assert rms_jac <= tol and rms_sor <= tol
+    assert n_sor * 3 < n_jac, (n_sor, n_jac)
+
+    def fixed_point_residual(p):
+        s = np.roll(p, 1, 1) + np.roll(p, -1, 1) + np.roll(p, 1, 0) + np.roll(p, -1, 0) + div
+        return float(np.sqrt(np.mean((0.25 * s - p) ** 2)))
+    assert fixed_point_residual(p_sor) <= 2.0 * max(fixed_point_residual(p_jac), tol)
+    # divergence channel as the reference forms it, in both buffers
+    ra, rb = oracle.Oracle().compute_pressure(a.copy(), b.copy(), dt, 1)
+    assert np.array_equal(out[..., 3].view(np.uint32), rb[..., 3].view(np.uint32))
+    assert np.array_equal(to_host(ga.data)[..., 3].view(np.uint32), ra[..., 3].view(np.uint32))

@@ -239,4 +239,5 @@ def test_ring_of_processes(tmp_path, world, transport):
     assert r.returncode == 0, r.stdout[-3000:] + r.stderr[-3000:]
     assert r.stdout.count("ring matches oracle") == 4, r.stdout[-3000:]
     assert "jump case matches oracle" in r.stdout, r.stdout[-3000:]
+    assert "adaptive case matches oracle" in r.stdout, r.stdout[-3000:]
     assert r.stdout.count(f"transport {transport}") == 4, r.stdout[-3000:]
