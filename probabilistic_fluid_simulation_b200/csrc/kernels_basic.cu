@@ -299,26 +299,25 @@ template <int SS, int DS>     // floats per source / destination cell: 4 = inter
 __global__ void __launch_bounds__(256)
     advect_kernel(const float *__restrict__ src, float *__restrict__ dst, float dt, int w, int h, float rfw, float rfh)
 {
-    int i = blockIdx.x * 64 + threadIdx.x, j = blockIdx.y * 4 + threadIdx.y;
+    const int i = blockIdx.x * 64 + threadIdx.x, j = blockIdx.y * 4 + threadIdx.y;
     if (i >= w || j >= h) return;
     const float fw = (float)w, fh = (float)h;
-    size_t cell = (size_t)j * w + i;
-    float2 uv = __ldg(reinterpret_cast<const float2 *>(src + cell * SS));
+    // a field has at most 2^28 cells (check_dims): 32-bit cell indices, one widening multiply-add per address
+    const unsigned uw = (unsigned)w, cell = (unsigned)j * uw + (unsigned)i;
+    const float2 uv = __ldg(reinterpret_cast<const float2 *>(src + (size_t)cell * SS));
     // fluid.cpp:39,41: (float)i - dt*u/fwidth  ==  i - ((dt*u)/fwidth)
     // rfw, rfh: the correctly rounded reciprocals of the extents, formed once on the host (1.0f / fw)
-    float xp = __fsub_rn((float)i, div_extent(__fmul_rn(dt, uv.x), fw, rfw));
-    float yp = __fsub_rn((float)j, div_extent(__fmul_rn(dt, uv.y), fh, rfh));
-    xp = wrap_coord(xp, fw);
-    yp = wrap_coord(yp, fh);
-    Bilinear b = make_bilinear(xp, yp, w, h);
-    const float *r0 = src + (size_t)b.j0 * w * SS, *r1 = src + (size_t)b.j1 * w * SS;
-    float2 f00 = __ldg(reinterpret_cast<const float2 *>(r0 + (size_t)b.i0 * SS));
-    float2 f10 = __ldg(reinterpret_cast<const float2 *>(r0 + (size_t)b.i1 * SS));
-    float2 f01 = __ldg(reinterpret_cast<const float2 *>(r1 + (size_t)b.i0 * SS));
-    float2 f11 = __ldg(reinterpret_cast<const float2 *>(r1 + (size_t)b.i1 * SS));
-    float un = bilerp(b, f00.x, f10.x, f01.x, f11.x);
-    float vn = bilerp(b, f00.y, f10.y, f01.y, f11.y);
-    *reinterpret_cast<float2 *>(dst + cell * DS) = make_float2(un, vn);
+    const float xp = backtrace_coord((float)i, __fmul_rn(dt, uv.x), fw, rfw);
+    const float yp = backtrace_coord((float)j, __fmul_rn(dt, uv.y), fh, rfh);
+    const Bilinear b = make_bilinear(xp, yp, w, h);
+    const unsigned r0 = (unsigned)b.j0 * uw, r1 = (unsigned)b.j1 * uw;
+    const float2 f00 = __ldg(reinterpret_cast<const float2 *>(src + (size_t)(r0 + (unsigned)b.i0) * SS));
+    const float2 f10 = __ldg(reinterpret_cast<const float2 *>(src + (size_t)(r0 + (unsigned)b.i1) * SS));
+    const float2 f01 = __ldg(reinterpret_cast<const float2 *>(src + (size_t)(r1 + (unsigned)b.i0) * SS));
+    const float2 f11 = __ldg(reinterpret_cast<const float2 *>(src + (size_t)(r1 + (unsigned)b.i1) * SS));
+    const float un = bilerp(b, f00.x, f10.x, f01.x, f11.x);
+    const float vn = bilerp(b, f00.y, f10.y, f01.y, f11.y);
+    *reinterpret_cast<float2 *>(dst + (size_t)cell * DS) = make_float2(un, vn);
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -330,26 +329,25 @@ __global__ void __launch_bounds__(256)
     advect_color_kernel(const float4 *__restrict__ image, float4 *__restrict__ out, const float *__restrict__ vp,
                         float dt_over_viw, float dt_over_vih, float viw, float vih, int iw, int ih, int vw, float rfiw, float rfih)
 {
-    int i = blockIdx.x * 64 + threadIdx.x, j = blockIdx.y * 4 + threadIdx.y;
+    const int i = blockIdx.x * 64 + threadIdx.x, j = blockIdx.y * 4 + threadIdx.y;
     if (i >= iw || j >= ih) return;
     const float fiw = (float)iw, fih = (float)ih;
-    int vi = (int)__fmul_rn((float)i, viw);   // fluid.cpp:89
-    int vj = (int)__fmul_rn((float)j, vih);   // fluid.cpp:90
-    float2 uv = __ldg(reinterpret_cast<const float2 *>(vp + ((size_t)vj * vw + vi) * VS));
+    const int vi = (int)__fmul_rn((float)i, viw);   // fluid.cpp:89
+    const int vj = (int)__fmul_rn((float)j, vih);   // fluid.cpp:90
+    const float2 uv = __ldg(reinterpret_cast<const float2 *>(vp + (size_t)((unsigned)vj * (unsigned)vw + (unsigned)vi) * VS));
     // fluid.cpp:97-98: (float)i - (dt/viw) * u / fiwidth
-    float xp = __fsub_rn((float)i, div_extent(__fmul_rn(dt_over_viw, uv.x), fiw, rfiw));
-    float yp = __fsub_rn((float)j, div_extent(__fmul_rn(dt_over_vih, uv.y), fih, rfih));
-    xp = wrap_coord(xp, fiw);
-    yp = wrap_coord(yp, fih);
-    Bilinear b = make_bilinear(xp, yp, iw, ih);
-    const float4 *r0 = image + (size_t)b.j0 * iw, *r1 = image + (size_t)b.j1 * iw;
-    float4 f00 = __ldg(r0 + b.i0), f10 = __ldg(r0 + b.i1), f01 = __ldg(r1 + b.i0), f11 = __ldg(r1 + b.i1);
+    const float xp = backtrace_coord((float)i, __fmul_rn(dt_over_viw, uv.x), fiw, rfiw);
+    const float yp = backtrace_coord((float)j, __fmul_rn(dt_over_vih, uv.y), fih, rfih);
+    const Bilinear b = make_bilinear(xp, yp, iw, ih);
+    const unsigned uw = (unsigned)iw, r0 = (unsigned)b.j0 * uw, r1 = (unsigned)b.j1 * uw;    // <= 2^28 pixels (check_dims)
+    const float4 f00 = __ldg(image + (r0 + (unsigned)b.i0)), f10 = __ldg(image + (r0 + (unsigned)b.i1));
+    const float4 f01 = __ldg(image + (r1 + (unsigned)b.i0)), f11 = __ldg(image + (r1 + (unsigned)b.i1));
     float4 o;
     o.x = bilerp(b, f00.x, f10.x, f01.x, f11.x);
     o.y = bilerp(b, f00.y, f10.y, f01.y, f11.y);
     o.z = bilerp(b, f00.z, f10.z, f01.z, f11.z);
     o.w = bilerp(b, f00.w, f10.w, f01.w, f11.w);
-    out[(size_t)j * iw + i] = o;
+    out[(unsigned)j * uw + (unsigned)i] = o;
 }
 
 // ---------------------------------------------------------------------------------------------

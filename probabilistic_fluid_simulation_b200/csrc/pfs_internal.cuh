@@ -96,6 +96,29 @@ __device__ __forceinline__ float div_extent(float a, float ext, float rext)
     return __fdiv_rn(a, ext);
 }
 
+// Back-traced coordinate of fluid.cpp:39-47 / 97-105: wrap(fi - a / ext), a = dt * velocity.  Almost every cell has a
+// displacement inside the division's safe range and a position within one period of the grid; for those the whole
+// thing is eight straight-line instructions (for |x| < ext, fmodf(x, ext) is x itself, so the first wrap_coord branch
+// is the identity, and x + ext >= 0).  Everything else -- tiny, huge or non-finite displacements, positions further out
+// -- goes through the general code out of line, so the common path carries no divergence bookkeeping.
+static __device__ __noinline__ float backtrace_coord_general(float fi, float a, float ext, float rext)
+{
+    return wrap_coord(__fsub_rn(fi, div_extent(a, ext, rext)), ext);
+}
+
+__device__ __forceinline__ float backtrace_coord(float fi, float a, float ext, float rext)
+{
+    const float aa = fabsf(a);
+    const float q0 = __fmul_rn(a, rext);
+    const float e = __fmaf_rn(-ext, q0, a);
+    const float q = __fmaf_rn(e, rext, q0);        // a == 0 gives a zero here too (its sign cannot matter: fi >= +0)
+    const float x = __fsub_rn(fi, q);
+    const float t = __fadd_rn(x, ext);
+    const bool ok = aa <= 0x1p96f && (aa >= 0x1p-96f || aa == 0.0f) && fabsf(x) < ext && t < __fadd_rn(ext, ext);
+    if (!ok) return backtrace_coord_general(fi, a, ext, rext);
+    return t >= ext ? __fsub_rn(t, ext) : t;
+}
+
 // fluid.cpp:19-21 with alpha = 1, beta = 4 (fluid.cpp:215-216,255): (((pL+pR)+pT)+pB + 1.0f*b)/4.0f.
 // Division by 4 and multiplication by 0.25 round identically (same real value, one rounding).
 __device__ __forceinline__ float pressure_update(float pl, float pr, float pt, float pb, float b)

@@ -308,10 +308,8 @@ __global__ void __launch_bounds__(256)
         }
     }
     if (!own) return;
-    float xp = __fsub_rn((float)i, div_extent(__fmul_rn(dt, uv.x), fw, rfw));
-    float yp = __fsub_rn((float)j, div_extent(__fmul_rn(dt, uv.y), fh, rfh));
-    xp = wrap_coord(xp, fw);
-    yp = wrap_coord(yp, fh);
+    const float xp = backtrace_coord((float)i, __fmul_rn(dt, uv.x), fw, rfw);
+    const float yp = backtrace_coord((float)j, __fmul_rn(dt, uv.y), fh, rfh);
     const Bilinear b = make_bilinear(xp, yp, w, gh);
     const char *r0 = source_row(S, b.j0, overflow, 1), *r1 = source_row(S, b.j1, overflow, 1);
     if (!r0 || !r1) return;
@@ -339,10 +337,8 @@ __global__ void __launch_bounds__(256)
         return;
     }
     const float2 uv = __ldg(reinterpret_cast<const float2 *>(vp + ((size_t)vj * vw + vi) * VS));
-    float xp = __fsub_rn((float)i, div_extent(__fmul_rn(dt_over_viw, uv.x), fiw, rfiw));
-    float yp = __fsub_rn((float)j, div_extent(__fmul_rn(dt_over_vih, uv.y), fih, rfih));
-    xp = wrap_coord(xp, fiw);
-    yp = wrap_coord(yp, fih);
+    const float xp = backtrace_coord((float)i, __fmul_rn(dt_over_viw, uv.x), fiw, rfiw);
+    const float yp = backtrace_coord((float)j, __fmul_rn(dt_over_vih, uv.y), fih, rfih);
     const Bilinear b = make_bilinear(xp, yp, iw, ih);
     const char *c0 = source_row(S, b.j0, overflow, 3), *c1 = source_row(S, b.j1, overflow, 3);
     if (!c0 || !c1) return;
