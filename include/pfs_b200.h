@@ -112,6 +112,9 @@ int pfs_simulate_fluid_step(float **vp, float **tmp, float dt, float viscosity,
  * (fluid.cpp:312-320: advect_color(image->itmp) then exchange *image and *itmp). */
 int pfs_advect_color_step(float **image, float **itmp, float **vp, float dt,
                           int ix, int iy, int iz, int vx, int vy, int vz, void *stream);
+/* pfs_advect_color_step whose kernel also stores the frame bytes of the new image (see pfs_ctx_advect_color_step_rgba8). */
+int pfs_advect_color_step_rgba8(float **image, float **itmp, float **vp, float dt, int ix, int iy, int iz,
+                                int vx, int vy, int vz, unsigned char *rgba8_out, void *stream);
 
 /* ---- device-pointer operator API: the six operators of includes/fluid.hpp ------------------ */
 /* Each one has the reference CPU operator's exact effect on the caller's interleaved buffers
@@ -173,6 +176,10 @@ int pfs_ctx_simulate_fluid_step_forced(pfs_ctx *c, float dt, float viscosity, in
 int pfs_ctx_simulate_fluid_step_stochastic(pfs_ctx *c, float dt, float viscosity, int n_diffuse, int n_pressure,
                                            float sigma, uint64_t seed, uint32_t step, void *stream);
 int pfs_ctx_advect_color_step(pfs_ctx *c, float dt, void *stream);
+/* The same step, its kernel also storing the frame of the NEW image as bytes (ix*iy*4, device memory, 4-byte aligned): what
+ * write_png_from_array (utils.hpp:129-131) would form, (png_byte)(x*255.0) per channel -- so a frame costs no extra pass
+ * over the image and only bytes cross PCIe. */
+int pfs_ctx_advect_color_step_rgba8(pfs_ctx *c, float dt, unsigned char *rgba8_out, void *stream);
 /* n_steps iterations of the driver loop: simulate_fluid_step + advect_color_step (the latter only with an image). */
 int pfs_ctx_step(pfs_ctx *c, int n_steps, float dt, float viscosity, int n_diffuse, int n_pressure, void *stream);
 /* Device pointer of the current image (interleaved RGBA floats), e.g. for pfs_image_to_rgba8; valid until the next step. */

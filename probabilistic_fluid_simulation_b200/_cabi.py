@@ -43,6 +43,7 @@ SIGNATURES = {
     "pfs_host_free": (_int, [_vp]),
     "pfs_simulate_fluid_step": (_int, [_pp, _pp, _f32, _f32, _int, _int, _int, _int, _int, _vp]),
     "pfs_advect_color_step": (_int, [_pp, _pp, _pp, _f32, _int, _int, _int, _int, _int, _int, _vp]),
+    "pfs_advect_color_step_rgba8": (_int, [_pp, _pp, _pp, _f32, _int, _int, _int, _int, _int, _int, _vp, _vp]),
     "pfs_advect": (_int, [_vp, _vp, _f32, _int, _int, _int, _vp]),
     "pfs_diffuse": (_int, [_pp, _pp, _f32, _f32, _int, _int, _int, _int, _vp]),
     "pfs_add_forces": (_int, [_vp, _vp, _int, _int, _int, _vp]),
@@ -61,6 +62,7 @@ SIGNATURES = {
     "pfs_ctx_simulate_fluid_step_forced": (_int, [_vp, _f32, _f32, _int, _int, _vp, _vp]),
     "pfs_ctx_simulate_fluid_step_stochastic": (_int, [_vp, _f32, _f32, _int, _int, _f32, ctypes.c_uint64, ctypes.c_uint32, _vp]),
     "pfs_ctx_advect_color_step": (_int, [_vp, _f32, _vp]),
+    "pfs_ctx_advect_color_step_rgba8": (_int, [_vp, _f32, _vp, _vp]),
     "pfs_ctx_step": (_int, [_vp, _int, _f32, _f32, _int, _int, _vp]),
     "pfs_ctx_image": (_int, [_vp, _pp]),
     "pfs_simulate_fluid_step_host": (_int, [_F, _F, _f32, _f32, _int, _int]),

@@ -324,10 +324,20 @@ __global__ void __launch_bounds__(256)
 // advect_color (fluid.cpp:72-127): one thread per pixel, velocity point-sampled at
 // ((int)(i*viw), (int)(j*vih)), four float4 texel gathers, one coalesced float4 store.
 // ---------------------------------------------------------------------------------------------
-template <int VS>     // floats per velocity cell: 4 = interleaved buffer, 2 = (u,v) plane
+// (png_byte)(x * 255.0) of includes/utils.hpp:129-131 without the double: the product of a binary32 and 255 rounded TOWARD
+// ZERO lies on the same side of every integer as the exact product (integers up to 2^24 are representable), so its
+// truncation is the truncation of the exact product -- which is what the reference's double multiply computes.
+__device__ __forceinline__ unsigned frame_byte(float x)
+{
+    const int t = __float2int_rz(__fmul_rz(x, 255.0f));
+    return (unsigned)min(max(t, 0), 255);           // outside [0, 256/255) the reference's cast is undefined; saturate
+}
+
+template <int VS, bool BYTES>     // floats per velocity cell: 4 = interleaved buffer, 2 = (u,v) plane; BYTES: also the frame
 __global__ void __launch_bounds__(256)
     advect_color_kernel(const float4 *__restrict__ image, float4 *__restrict__ out, const float *__restrict__ vp,
-                        float dt_over_viw, float dt_over_vih, float viw, float vih, int iw, int ih, int vw, float rfiw, float rfih)
+                        float dt_over_viw, float dt_over_vih, float viw, float vih, int iw, int ih, int vw, float rfiw, float rfih,
+                        unsigned *__restrict__ rgba8)
 {
     const int i = blockIdx.x * 64 + threadIdx.x, j = blockIdx.y * 4 + threadIdx.y;
     if (i >= iw || j >= ih) return;
@@ -348,6 +358,8 @@ __global__ void __launch_bounds__(256)
     o.z = bilerp(b, f00.z, f10.z, f01.z, f11.z);
     o.w = bilerp(b, f00.w, f10.w, f01.w, f11.w);
     out[(unsigned)j * uw + (unsigned)i] = o;
+    if (BYTES)      // the frame the reference's writer would form from this pixel: R, G, B, A in memory order
+        rgba8[(unsigned)j * uw + (unsigned)i] = frame_byte(o.x) | (frame_byte(o.y) << 8) | (frame_byte(o.z) << 16) | (frame_byte(o.w) << 24);
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -788,7 +800,7 @@ int launch_stochastic_force(float *u, float *v, int stride, float sigma, unsigne
 }
 
 int launch_advect_color(const float *image, float *out, const float *vel, int vel_stride, float dt, int iw, int ih, int vw,
-                        int vh, cudaStream_t s)
+                        int vh, cudaStream_t s, unsigned char *rgba8)
 {
     // fluid.cpp:82-83 and the (dt/viw), (dt/vih) factors of :97-98, all binary32
     const float viw = (float)vw / (float)iw;
@@ -799,10 +811,15 @@ int launch_advect_color(const float *image, float *out, const float *vel, int ve
     const float4 *img = reinterpret_cast<const float4 *>(image);
     float4 *o4 = reinterpret_cast<float4 *>(out);
     const float rfiw = 1.0f / (float)iw, rfih = 1.0f / (float)ih;
-    if (vel_stride == 2)
-        PFS_LAUNCH(advect_color_kernel<2>, grid, block, 0, s, img, o4, vel, dt_over_viw, dt_over_vih, viw, vih, iw, ih, vw, rfiw, rfih);
+    unsigned *b4 = reinterpret_cast<unsigned *>(rgba8);
+    if (vel_stride == 2 && rgba8)
+        PFS_LAUNCH((advect_color_kernel<2, true>), grid, block, 0, s, img, o4, vel, dt_over_viw, dt_over_vih, viw, vih, iw, ih, vw, rfiw, rfih, b4);
+    else if (vel_stride == 2)
+        PFS_LAUNCH((advect_color_kernel<2, false>), grid, block, 0, s, img, o4, vel, dt_over_viw, dt_over_vih, viw, vih, iw, ih, vw, rfiw, rfih, b4);
+    else if (rgba8)
+        PFS_LAUNCH((advect_color_kernel<4, true>), grid, block, 0, s, img, o4, vel, dt_over_viw, dt_over_vih, viw, vih, iw, ih, vw, rfiw, rfih, b4);
     else
-        PFS_LAUNCH(advect_color_kernel<4>, grid, block, 0, s, img, o4, vel, dt_over_viw, dt_over_vih, viw, vih, iw, ih, vw, rfiw, rfih);
+        PFS_LAUNCH((advect_color_kernel<4, false>), grid, block, 0, s, img, o4, vel, dt_over_viw, dt_over_vih, viw, vih, iw, ih, vw, rfiw, rfih, b4);
     return PFS_OK;
 }
 

@@ -952,6 +952,35 @@ extern "C" int pfs_advect_color_step(float **image, float **itmp, float **vp, fl
     return PFS_OK;
 }
 
+// advect_color_step whose kernel also stores the frame the reference's PNG writer would form from the new image
+extern "C" int pfs_advect_color_step_rgba8(float **image, float **itmp, float **vp, float dt, int ix, int iy, int iz, int vx,
+                                           int vy, int vz, unsigned char *rgba8_out, void *stream)
+{
+    const char *fn = "pfs_advect_color_step_rgba8";
+    if (!image || !itmp || !vp) {
+        set_error("%s: image / itmp / vp handle is null", fn);
+        return PFS_EINVAL;
+    }
+    PFS_TRY(check_dims(fn, ix, iy, iz));
+    PFS_TRY(check_dims(fn, vx, vy, vz));
+    PFS_TRY(check_ptr(fn, "image", *image));
+    PFS_TRY(check_ptr(fn, "itmp", *itmp));
+    PFS_TRY(check_ptr(fn, "vp", *vp));
+    if (!rgba8_out || (reinterpret_cast<uintptr_t>(rgba8_out) & 3u)) {
+        set_error("%s: rgba8_out must be a 4-byte aligned device pointer", fn);
+        return PFS_EINVAL;
+    }
+    cudaStream_t s = (cudaStream_t)stream;
+    {
+        PhaseScope ph(PFS_PHASE_ADVECT_COLOR, s);
+        PFS_TRY(launch_advect_color(*image, *itmp, *vp, 4, dt, ix, iy, vx, vy, s, rgba8_out));
+    }
+    float *t = *image;     // fluid.cpp:317-319
+    *image = *itmp;
+    *itmp = t;
+    return PFS_OK;
+}
+
 // =============================================================================================
 // host-buffer API
 // =============================================================================================

@@ -146,10 +146,10 @@ int enqueue_fluid(pfs_ctx *c, float dt, float viscosity, int nd, int np, float s
     return PFS_OK;
 }
 
-int enqueue_color(pfs_ctx *c, float dt, cudaStream_t s)
+int enqueue_color(pfs_ctx *c, float dt, cudaStream_t s, unsigned char *rgba8 = nullptr)
 {
     PhaseScope ph(PFS_PHASE_ADVECT_COLOR, s);
-    return launch_advect_color(c->img[c->cur], c->img[c->cur ^ 1], c->uv(c->uvX), 2, dt, c->ix, c->iy, c->vx, c->vy, s);
+    return launch_advect_color(c->img[c->cur], c->img[c->cur ^ 1], c->uv(c->uvX), 2, dt, c->ix, c->iy, c->vx, c->vy, s, rgba8);
 }
 
 void apply_roles(pfs_ctx *c, const Roles &r)
@@ -344,6 +344,28 @@ extern "C" int pfs_ctx_advect_color_step(pfs_ctx *c, float dt, void *stream)
     std::lock_guard<std::mutex> lock(c->m);
     DeviceGuard g(c->device);
     PFS_TRY(enqueue_color(c, dt, (cudaStream_t)stream));
+    c->cur ^= 1;                                             // fluid.cpp:317-319
+    return PFS_OK;
+}
+
+extern "C" int pfs_ctx_advect_color_step_rgba8(pfs_ctx *c, float dt, unsigned char *rgba8_out, void *stream)
+{
+    const char *fn = "pfs_ctx_advect_color_step_rgba8";
+    PFS_TRY(check_ctx(fn, c, true));
+    if (c->ix == 0) {
+        set_error("%s: the context was created without an image", fn);
+        return PFS_EINVAL;
+    }
+    if (!rgba8_out || (reinterpret_cast<uintptr_t>(rgba8_out) & 3u)) {
+        set_error("%s: rgba8_out must be a 4-byte aligned device pointer", fn);
+        return PFS_EINVAL;
+    }
+    std::lock_guard<std::mutex> lock(c->m);
+    DeviceGuard g(c->device);
+    {
+        PhaseScope ph(PFS_PHASE_ADVECT_COLOR, (cudaStream_t)stream);
+        PFS_TRY(enqueue_color(c, dt, (cudaStream_t)stream, rgba8_out));
+    }
     c->cur ^= 1;                                             // fluid.cpp:317-319
     return PFS_OK;
 }

@@ -292,8 +292,9 @@ int launch_stochastic_force(float *u, float *v, int stride, float sigma, unsigne
                             int h, int row0, int y_base, cudaStream_t s);
 
 // advect_color (fluid.cpp:72-127) on interleaved image buffers; the velocity is point-sampled from cells `vel_stride`
-// floats apart (4: interleaved buffer, 2: (u,v) plane).
+// floats apart (4: interleaved buffer, 2: (u,v) plane).  rgba8 != nullptr: the same kernel also stores the frame bytes of the
+// new image (iw*ih*4 bytes, 4-byte aligned), (png_byte)(x*255.0) per channel as includes/utils.hpp:129-131.
 int launch_advect_color(const float *image, float *out, const float *vel, int vel_stride, float dt, int iw, int ih, int vw,
-                        int vh, cudaStream_t s);
+                        int vh, cudaStream_t s, unsigned char *rgba8 = nullptr);
 
 }  // namespace pfs

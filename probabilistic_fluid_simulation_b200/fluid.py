@@ -327,11 +327,18 @@ class FluidContext:
         else:
             check(L.pfs_ctx_simulate_fluid_step(self._h, dt, viscosity, n_diffuse, n_pressure, self._stream()))
 
-    def advect_color_step(self, dt: float) -> None:
-        check(_cabi.lib().pfs_ctx_advect_color_step(self._h, dt, self._stream()))
+    def advect_color_step(self, dt: float, frame_out=None) -> None:
+        """frame_out: optional CUDA uint8 tensor of iy*ix*4 bytes; the advecting kernel then also stores the frame of the new
+        image, (png_byte)(x*255.0) per channel (pfs_ctx_advect_color_step_rgba8)."""
+        if frame_out is None:
+            check(_cabi.lib().pfs_ctx_advect_color_step(self._h, dt, self._stream()))
+        else:
+            check(_cabi.lib().pfs_ctx_advect_color_step_rgba8(self._h, dt, frame_out.data_ptr(), self._stream()))
 
 
-def advect_color_step(image: vp_field, itmp: vp_field, vp: vp_field, dt: float) -> None:
+def advect_color_step(image: vp_field, itmp: vp_field, vp: vp_field, dt: float, frame_out=None) -> None:
+    """frame_out (device fields only): CUDA uint8 tensor of iy*ix*4 bytes that receives the frame of the new image from the
+    same kernel (pfs_advect_color_step_rgba8)."""
     L = _cabi.lib()
     for f, n in ((image, "image"), (itmp, "itmp"), (vp, "vp")):
         _check_buf(f, n)
@@ -342,9 +349,15 @@ def advect_color_step(image: vp_field, itmp: vp_field, vp: vp_field, dt: float) 
     if vp.on_device:
         h = _Handles(image, itmp, vp)
         with _dev_guard(vp.data):
-            check(L.pfs_advect_color_step(h.ref(0), h.ref(1), h.ref(2), dt, image.x, image.y, image.z,
-                                          vp.x, vp.y, vp.z, _stream_of(vp.data)))
+            if frame_out is None:
+                check(L.pfs_advect_color_step(h.ref(0), h.ref(1), h.ref(2), dt, image.x, image.y, image.z,
+                                              vp.x, vp.y, vp.z, _stream_of(vp.data)))
+            else:
+                check(L.pfs_advect_color_step_rgba8(h.ref(0), h.ref(1), h.ref(2), dt, image.x, image.y, image.z,
+                                                    vp.x, vp.y, vp.z, frame_out.data_ptr(), _stream_of(vp.data)))
         h.commit()
+    elif frame_out is not None:
+        raise ValueError("frame_out needs device fields")
     else:
         si, st, sv = _host_struct(image), _host_struct(itmp), _host_struct(vp)
         pairs = [(image, si), (itmp, st)]

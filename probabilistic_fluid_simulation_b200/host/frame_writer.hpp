@@ -3,7 +3,8 @@
 // The reference's CUDA driver stops the device after every step, copies the float image back with a blocking cudaMemcpy
 // and encodes the PNG on the same thread (main.cpp:228-232, :243-245; the cudaMemcpyAsync over NUM_STREAMS streams it
 // gestures at is commented out).  Here a frame goes through a ring of slots:
-//   compute stream : pfs_image_to_rgba8 packs the float image to bytes in the slot's device buffer   (utils.hpp:129-131)
+//   compute stream : the bytes of the frame are formed in the slot's device buffer (utils.hpp:129-131): by the kernel that
+//                    advects the image (pfs_ctx_advect_color_step_rgba8) or by pfs_image_to_rgba8
 //   copy stream    : waits for that pack, copies the BYTES to the slot's pinned host buffer
 //   worker thread  : waits for the copy, encodes <dir>/<i>.png with libpng, frees the slot
 // so the next timestep starts while frame i is still being copied and encoded, and several frames encode in parallel.
@@ -59,15 +60,29 @@ public:
     // Blocks only while every slot is still in flight.  false: a CUDA call failed (message in error()).
     bool submit(const float *d_image, const std::string &path)
     {
-        Slot *s = nullptr;
-        {
-            std::unique_lock<std::mutex> lk(m_);
-            cv_free_.wait(lk, [this] { return !free_.empty(); });
-            s = free_.front();
-            free_.pop_front();
-        }
-        s->path = path;
-        if (pfs_image_to_rgba8(d_image, s->dev, w_, h_, c_, nullptr) != PFS_OK) return fail(pfs_last_error());
+        unsigned char *dst = begin(path);
+        if (pfs_image_to_rgba8(d_image, dst, w_, h_, c_, nullptr) != PFS_OK) return fail(pfs_last_error());
+        return commit();
+    }
+
+    // The two halves of submit for a producer that forms the bytes itself (pfs_ctx_advect_color_step_rgba8 stores the
+    // frame from the kernel that advects the image): begin hands out the device byte buffer of a free slot, commit is
+    // called once the producing kernel is enqueued on the legacy default stream.
+    unsigned char *begin(const std::string &path)
+    {
+        std::unique_lock<std::mutex> lk(m_);
+        cv_free_.wait(lk, [this] { return !free_.empty(); });
+        open_ = free_.front();
+        free_.pop_front();
+        open_->path = path;
+        return open_->dev;
+    }
+
+    bool commit()
+    {
+        Slot *s = open_;
+        open_ = nullptr;
+        if (!s) return fail("FrameWriter::commit without begin");
         if (cudaEventRecord(s->packed, nullptr) != cudaSuccess ||
             cudaStreamWaitEvent(copy_stream_, s->packed, 0) != cudaSuccess ||
             cudaMemcpyAsync(s->host, s->dev, bytes_, cudaMemcpyDeviceToHost, copy_stream_) != cudaSuccess ||
@@ -153,6 +168,7 @@ private:
     std::string error_;
     cudaStream_t copy_stream_ = nullptr;
     std::vector<Slot> slots_;
+    Slot *open_ = nullptr;              // slot handed out by begin(), waiting for commit()
     std::deque<Slot *> free_, queued_;
     std::vector<std::thread> workers_;
     std::mutex m_;

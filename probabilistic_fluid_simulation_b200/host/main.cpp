@@ -100,7 +100,8 @@ int main(int argc, char *argv[])
     if (!vtmp.data) return 1;
     for (size_t i = 0; i < vel_floats; i++) vtmp.data[i] = ((i % 4) == 3) ? 1.0f : -1.0f;
 
-    // frames leave the device as bytes: (png_byte)(x*255.0) is applied by pfs_image_to_rgba8 (utils.hpp:129-131)
+    // frames leave the device as bytes: (png_byte)(x*255.0) of utils.hpp:129-131 is applied on the device, by the kernel
+    // that advects the image (pfs_ctx_advect_color_step_rgba8) or, on the stateless path, by pfs_image_to_rgba8
     const size_t frame_bytes = img_floats;
     unsigned char *d_frame = nullptr, *h_frame = nullptr;
     int n_writers = (int)(std::thread::hardware_concurrency() / 2);   // PNG encoding is the slow part of a frame
@@ -151,9 +152,24 @@ int main(int argc, char *argv[])
     auto time_start = std::chrono::high_resolution_clock::now();
     for (int i = 0; i < n_timesteps; i++) {
         const float *frame_src = nullptr;
-        if (ctx) {
-            if (pfs_ctx_step(ctx, 1, delta_t, viscosity, NUM_JACOBI_ITERS, NUM_JACOBI_ITERS, nullptr) != PFS_OK ||
-                (flags == 0 && pfs_ctx_image(ctx, &frame_src) != PFS_OK)) {
+        std::string outpath;
+        if (flags == 0) {
+            outpath = std::string(argv[6]);
+            if (!outpath.empty() && outpath.back() != '/') outpath += "/";
+            outpath += std::to_string(i) + ".png";
+        }
+        bool frame_formed = false;
+        if (ctx && flags == 0) {
+            // frame mode: the kernel that advects the image also stores the frame's bytes (no separate pass over the image)
+            unsigned char *dst = writer ? writer->begin(outpath) : d_frame;
+            if (pfs_ctx_simulate_fluid_step(ctx, delta_t, viscosity, NUM_JACOBI_ITERS, NUM_JACOBI_ITERS, nullptr) != PFS_OK ||
+                pfs_ctx_advect_color_step_rgba8(ctx, delta_t, dst, nullptr) != PFS_OK) {
+                std::cerr << pfs_last_error() << std::endl;
+                return 1;
+            }
+            frame_formed = true;
+        } else if (ctx) {
+            if (pfs_ctx_step(ctx, 1, delta_t, viscosity, NUM_JACOBI_ITERS, NUM_JACOBI_ITERS, nullptr) != PFS_OK) {
                 std::cerr << pfs_last_error() << std::endl;
                 return 1;
             }
@@ -163,18 +179,15 @@ int main(int argc, char *argv[])
             frame_src = d_image;
         }
         if (flags == 0) {
-            std::string outpath = std::string(argv[6]);
-            if (!outpath.empty() && outpath.back() != '/') outpath += "/";
-            outpath += std::to_string(i) + ".png";
             std::cout << "[" << i << "] Writing to : " << outpath << std::endl;
             if (writer) {
-                if (!writer->submit(frame_src, outpath)) {
+                if (!(frame_formed ? writer->commit() : writer->submit(frame_src, outpath))) {
                     std::cerr << writer->error() << std::endl;
                     return 1;
                 }
                 continue;
             }
-            if (pfs_image_to_rgba8(frame_src, d_frame, image.x, image.y, image.z, nullptr) != PFS_OK) {
+            if (!frame_formed && pfs_image_to_rgba8(frame_src, d_frame, image.x, image.y, image.z, nullptr) != PFS_OK) {
                 std::cerr << pfs_last_error() << std::endl;
                 return 1;
             }

@@ -30,5 +30,26 @@ bi, bm = ring.split(image, image=True), ring.split(itmp, image=True)
 ring.simulate_fluid_step(bv, bt, 0.5, 0.002, 20, 20)
 ring.advect_color_step(bi, bm, bv, 0.5)
 ring.check()
+# round 2: forces fused into the last diffusion pass, persistent context (+ frame bytes from the advecting kernel), resident
+# slab state, adaptive solves (single device, ring), red-black SOR
+forces = torch.rand(h, w, 4, device="cuda")
+pfs.simulate_fluid_step(fv, ft, 0.5, 0.002, 11, 9, forces=forces)
+ctx = pfs.FluidContext(w, h, w, h)
+ctx.upload(fv.data, ft.data, fi.data)
+ctx.step(3, 0.5, 0.002, 12, 13)
+frame = torch.zeros(h, w, 4, dtype=torch.uint8, device="cuda")
+ctx.simulate_fluid_step(0.5, 0.002, 12, 13)
+ctx.advect_color_step(0.5, frame_out=frame)
+ctx.download()
+ctx.close()
+ring.upload(bv, bt, bi)
+ring.step(2, 0.5, 0.002, 20, 20)
+ring.download(bv, bt, bi)
+ring.check()
+ring.compute_pressure_adaptive(bv, bt, 0.5, 1e-30, 24, 8)
+ring.check()
+ga, gb = pfs.vp_field(torch.from_numpy(vp.copy()).cuda()), pfs.vp_field(torch.from_numpy(vtmp.copy()).cuda())
+pfs.computePressureAdaptive(ga, gb, 0.5, 1e-30, 24, 8)
+pfs.computePressureSOR(ga, gb, 0.5, 1.8, 1e-30, 12, 4)
 torch.cuda.synchronize()
 print("sanitize case done", pfs.kernel_launch_count())

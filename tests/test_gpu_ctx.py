@@ -166,3 +166,61 @@ def test_ctx_full_size_matches_stateless_path():
     for name, a, b in zip(("vp", "vtmp", "image"), g, (fv.data, ft.data, fi.data)):
         assert torch.equal(a.view(torch.int32), b.view(torch.int32)), name
     ctx.close()
+
+
+@pytest.mark.parametrize("ratio", ["same", "odd"])
+def test_frame_bytes_from_the_advecting_kernel(ratio):
+    """pfs_ctx_advect_color_step_rgba8 / pfs_advect_color_step_rgba8: the kernel that advects the image also stores the frame;
+    the bytes must be the reference writer's (png_byte)(x*255.0) (utils.hpp:129-131, through oracle.unit_float_to_bytes) of the
+    oracle's new image -- including values one ulp either side of every k/255 -- and the image itself is unchanged by it."""
+    import torch
+    h, w = 40, 64
+    ih, iw = (h, w) if ratio == "same" else (57, 131)
+    vp, vt = rand_field(h, w, 71, 0.8), rand_field(h, w, 72, 0.5)
+    vp[..., :2] = 0.0                       # zero velocity: the advected image is the input image, boundary values survive
+    rng = np.random.default_rng(73)
+    img = rng.random((ih, iw, 4)).astype(np.float32)
+    k255 = fixtures.bytes_to_unit_float(np.arange(256, dtype=np.uint8))
+    flat = img.reshape(-1)
+    flat[:256] = k255
+    flat[256:512] = np.nextafter(k255, np.float32(0))
+    flat[512:768] = np.nextafter(k255, np.float32(2))
+    flat[768:772] = [-0.25, 1.5, -0.0, 0.9999998]
+    _, want_img = oracle.Oracle().advect_color(img.copy(), np.zeros_like(img), vp, 0.3)     # (image, itmp): the result is in itmp
+    want_bytes = oracle.unit_float_to_bytes(np.clip(want_img, 0.0, np.float32(255.99 / 255.0)))
+    in_range = (want_img >= 0) & (want_img < np.float32(256.0 / 255.0))
+    # context
+    ctx = pfs.FluidContext(w, h, iw, ih)
+    ctx.upload(to_dev(vp), to_dev(vt), to_dev(img))
+    frame = torch.zeros((ih, iw, 4), dtype=torch.uint8, device="cuda")
+    ctx.advect_color_step(0.3, frame_out=frame)
+    got_img = to_host(ctx.download(image_only=True)[2])
+    ctx.close()
+    assert_bit_equal(got_img, want_img, "ctx image")
+    got = frame.cpu().numpy()
+    assert np.array_equal(got[in_range], want_bytes[in_range])
+    assert np.array_equal(got, pfs.image_to_rgba8(pfs.vp_field(to_dev(want_img))).cpu().numpy())     # saturation included
+    # stateless entry point
+    fi, fm, fv = pfs.vp_field(to_dev(img)), pfs.vp_field(to_dev(np.zeros_like(img))), pfs.vp_field(to_dev(vp))
+    frame2 = torch.zeros_like(frame)
+    pfs.advect_color_step(fi, fm, fv, 0.3, frame_out=frame2)
+    assert_bit_equal(to_host(fi.data), want_img, "stateless image")
+    assert torch.equal(frame2, frame)
+
+
+def test_frame_bytes_after_real_steps_equal_the_separate_pack():
+    h, w = 96, 160
+    vel = fixtures.smooth_velocity_bytes(h, w)
+    vp, vtmp, image, itmp = fixtures.make_state(vel, fixtures.random_image_bytes(2 * h, 2 * w, 3))
+    import torch
+    ctx = pfs.FluidContext(w, h, 2 * w, 2 * h)
+    ctx.upload(to_dev(vp), to_dev(vtmp), to_dev(image))
+    frame = torch.zeros((2 * h, 2 * w, 4), dtype=torch.uint8, device="cuda")
+    for _ in range(4):
+        ctx.simulate_fluid_step(50.0, 0.001, 9, 12)
+        ctx.advect_color_step(50.0, frame_out=frame)
+    got_img = ctx.download(image_only=True)[2]
+    ctx.close()
+    want = oracle.Oracle(9, 12).run_steps(vp, vtmp, image, itmp, 50.0, 0.001, 4)
+    assert_bit_equal(to_host(got_img), want[2], "image after 4 steps")
+    assert np.array_equal(frame.cpu().numpy(), oracle.unit_float_to_bytes(want[2]))
