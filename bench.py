@@ -255,7 +255,7 @@ def ring_parity_check(rank: int, world: int, make_slab):
     class, same transport) and compares every band, bit for bit, with the CPU oracle run on the whole grid by rank 0
     (reference semantics: fluid.cpp:298-320).  `make_slab(w, h, iw, ih)` returns a connected SlabRank.
     Grid 1024 x (64 * ranks), image 1536 x (96 * ranks) (image/grid ratio 1.5: the look-up factor of fluid.cpp:82-83 is
-    inexact in binary32), 7 + 10 sweeps, 3 steps; two time steps: one whose departure rows reach ~20 rows into the
+    inexact in binary32), 7 + 10 sweeps, 6 steps (so that the resident ring's captured sweep graphs are replayed, not only built); two time steps: one whose departure rows reach ~20 rows into the
     neighbouring bands (peer-written gather halos) and one whose departure rows lie beyond the neighbouring bands
     (whole-field gather).  -> the "parity" object of the JSON line (identical on every rank)."""
     import numpy as np
@@ -266,7 +266,7 @@ def ring_parity_check(rank: int, world: int, make_slab):
     from probabilistic_fluid_simulation_b200 import fixtures
 
     w, h, iw, ih = 1024, 64 * world, 1536, 96 * world
-    nd, npr, steps, visc = 7, 10, 3, 0.002
+    nd, npr, steps, visc = 7, 10, 6, 0.002
     vel = fixtures.smooth_velocity_bytes(h, w)
     noise = fixtures.hash_bytes(h, w, 2, 77).astype(np.int16) % 13 - 6
     vel[..., :2] = np.clip(vel[..., :2].astype(np.int16) + noise, 0, 255).astype(np.uint8)

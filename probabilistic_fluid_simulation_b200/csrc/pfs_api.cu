@@ -60,6 +60,12 @@ int sm_count()
     return n;
 }
 
+bool pdl_enabled()
+{
+    static const bool on = !(getenv("PFS_PDL") && getenv("PFS_PDL")[0] == '0');
+    return on;
+}
+
 int check_launch(const char *kernel, const char *file, int line)
 {
     cudaError_t e = cudaGetLastError();

@@ -50,6 +50,51 @@ int check_launch(const char *kernel, const char *file, int line);
         PFS_TRY(::pfs::check_launch(#kernel, __FILE__, __LINE__));             \
     } while (0)
 
+// Programmatic dependent launch (sm_90+): a kernel launched this way may have its CTAs placed on SMs the previous kernel of
+// the stream has already vacated, before that kernel has finished everywhere; they block in pdl_wait() until it has
+// completed and its writes are visible.  The fused sweep passes are one-wave kernels that follow each other 30+ times a
+// step, so the launch latency between two of them is otherwise paid on an idle machine.  Rules kept by every kernel
+// launched with PFS_LAUNCH_PDL: pdl_wait() is the first thing EVERY thread does after pdl_launch_dependents() -- before any
+// global access (reads of the previous kernel's output, and writes to planes it may still be reading) and before any
+// early exit, so that this kernel's completion implies the previous kernel's.  PFS_PDL=0 launches them the ordinary way.
+bool pdl_enabled();
+#ifdef __CUDACC__
+__device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;"); }
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+
+template <typename... KArgs, typename... Args>
+inline cudaError_t launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t s, Args... args)
+{
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = grid;
+    cfg.blockDim = block;
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = s;
+    cudaLaunchAttribute at[1];
+    at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    at[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = at;
+    // not inside a stream capture: graph replays showed no gain from programmatic edges and one slow outlier (profiles/r02_tuning.md)
+    cudaStreamCaptureStatus cap = cudaStreamCaptureStatusNone;
+    bool capturing = cap != cudaStreamCaptureStatusNone;
+    if (cudaStreamIsCapturing(s, &cap) != cudaSuccess) {
+        (void)cudaGetLastError();
+        capturing = true;
+    } else
+        capturing = cap != cudaStreamCaptureStatusNone;
+    cfg.numAttrs = (pdl_enabled() && !capturing) ? 1 : 0;
+    return cudaLaunchKernelEx(&cfg, kernel, KArgs(args)...);
+}
+#endif
+
+#define PFS_LAUNCH_PDL(kernel, grid, block, smem, stream, ...)                                \
+    do {                                                                                      \
+        (void)::pfs::launch_pdl(kernel, dim3(grid), dim3(block), (smem), (stream), __VA_ARGS__); \
+        ++::pfs::g_launches;                                                                  \
+        ++::pfs::g_passes;                                                                    \
+        PFS_TRY(::pfs::check_launch(#kernel, __FILE__, __LINE__));                            \
+    } while (0)
+
 // Brackets one phase of a step with CUDA events on `s` when pfs_phase_timing_enable(1) is set
 // (pfs_api.cu); a no-op otherwise.
 struct PhaseScope {

@@ -183,7 +183,22 @@ struct pfs_slab {
     PeerLink link_up, link_down;
     int *flags = nullptr;                 // [0] ready<-up [1] ready<-down [2] pushed<-up [3] pushed<-down [4] CTA counter
     float4 *vhalo_p2p = nullptr, *ihalo_p2p = nullptr;   // [above: P2P_GATHER_ROWS rows | below: same], written by the neighbours
-    int xseq = 0;                         // exchanges done over the peer transport (the same on every rank)
+    // Exchanges over the peer transport are numbered (the same on every rank); a push waits for / publishes its number in
+    // the neighbours' flag words.  The number is formed ON THE DEVICE as flags[5] + ordinal, so that a captured graph of
+    // pushes can be replayed: xord counts the pushes enqueued since flags[5] was last advanced (flush_seq).
+    int xord = 0;
+    // the sweeps of a resident step (diffusion, divergence, pressure and their halo exchanges) as replayable graphs
+    struct SegGraph {
+        int p_warm, nd, np, fuse, halo;
+        unsigned dt_bits, visc_bits;
+        cudaGraphExec_t exec;
+        unsigned long long launches, passes;
+        int dl, dpv, pl_last, pl_prev, p_valid;
+    };
+    std::vector<SegGraph> seg_graphs;
+    std::vector<SegGraph> seg_seen;       // keys launched one by one so far: a key is captured the second time it turns up
+    cudaStream_t capture_stream = nullptr;
+    int graph_mode = -1;                  // -1 unread, 0 off, 1 on (PFS_SLAB_GRAPH=0 disables)
     std::vector<void *> ipc_opened;
     std::vector<pfs_slab *> group;        // in-process transport: all ranks, indexed by rank (empty under NCCL)
     cudaStream_t stream = nullptr;        // stream of the call in flight
@@ -370,7 +385,7 @@ struct PushArgs {
     PushSeg seg[3];
     int nseg;
     int *mine, *up, *down, *error_flag;
-    int seq;
+    int ordinal;                          // this push is number mine[5] + ordinal
 };
 
 __device__ __forceinline__ void st_release_sys(int *p, int v)
@@ -400,15 +415,19 @@ __device__ __forceinline__ void wait_flag(const int *p, int seq, int *error_flag
     }
 }
 
+__global__ void advance_seq_kernel(int *base, int n) { *base += n; }
+
 __global__ void __launch_bounds__(256) halo_push_kernel(const PushArgs A)
 {
+    int seq = 0;
     if (threadIdx.x == 0) {
+        seq = *reinterpret_cast<volatile const int *>(A.mine + 5) + A.ordinal;     // advanced only between pushes, in stream order
         if (blockIdx.x == 0) {
-            st_release_sys(A.up + 1, A.seq);
-            st_release_sys(A.down + 0, A.seq);
+            st_release_sys(A.up + 1, seq);
+            st_release_sys(A.down + 0, seq);
         }
-        wait_flag(A.mine + 0, A.seq, A.error_flag);
-        wait_flag(A.mine + 1, A.seq, A.error_flag);
+        wait_flag(A.mine + 0, seq, A.error_flag);
+        wait_flag(A.mine + 1, seq, A.error_flag);
     }
     __syncthreads();
     const size_t tid = (size_t)blockIdx.x * 256 + threadIdx.x, nth = (size_t)gridDim.x * 256;
@@ -426,10 +445,10 @@ __global__ void __launch_bounds__(256) halo_push_kernel(const PushArgs A)
         if (done == (int)gridDim.x - 1) {
             atomicExch(A.mine + 4, 0);
             __threadfence_system();
-            st_release_sys(A.up + 3, A.seq);
-            st_release_sys(A.down + 2, A.seq);
-            wait_flag(A.mine + 2, A.seq, A.error_flag);
-            wait_flag(A.mine + 3, A.seq, A.error_flag);
+            st_release_sys(A.up + 3, seq);
+            st_release_sys(A.down + 2, seq);
+            wait_flag(A.mine + 2, seq, A.error_flag);
+            wait_flag(A.mine + 3, seq, A.error_flag);
         }
     }
 }
@@ -444,8 +463,18 @@ int launch_halo_push(pfs_slab *s, PushArgs &A)
     A.up = s->link_up.flags;
     A.down = s->link_down.flags;
     A.error_flag = reinterpret_cast<int *>(s->d_scalars + 2);
-    A.seq = ++s->xseq;
+    A.ordinal = ++s->xord;
     PFS_LAUNCH(halo_push_kernel, blocks, 256, 0, s->stream, A);
+    return PFS_OK;
+}
+
+// Folds the pushes enqueued so far into the device-side base (in stream order), so that the next push is number base + 1
+// again: called before a graph of pushes is captured or replayed, and as the last node of such a graph.
+int flush_seq(pfs_slab *s)
+{
+    if (!s->p2p || s->xord == 0) return PFS_OK;
+    PFS_LAUNCH(advance_seq_kernel, 1, 1, 0, s->stream, s->flags + 5, s->xord);
+    s->xord = 0;
     return PFS_OK;
 }
 
@@ -856,6 +885,9 @@ extern "C" int pfs_slab_destroy(pfs_slab *s)
     if (s->img[0]) cudaFree(s->img[0]);
     if (s->img[1]) cudaFree(s->img[1]);
     if (s->side) cudaStreamDestroy(s->side);
+    for (auto &gr : s->seg_graphs)
+        if (gr.exec) cudaGraphExecDestroy(gr.exec);
+    if (s->capture_stream) cudaStreamDestroy(s->capture_stream);
     (void)cudaGetLastError();
     delete s;
     return PFS_OK;
@@ -1040,7 +1072,7 @@ int p2p_setup(pfs_slab *s)
     PFS_CUDA(cudaMemset(s->planes, 0, sizeof(float)));
     PFS_CUDA(cudaMemset(s->flags + 8, 0, sizeof(int)));
     s->p2p = true;
-    s->xseq = 0;
+    s->xord = 0;
     return PFS_OK;
 }
 
@@ -1299,6 +1331,22 @@ int resolve_pending_color(const std::vector<pfs_slab *> &L)
     return color_step(L, in.data(), out.data(), vel.data(), 2, L[0]->pending_dt, false);
 }
 
+bool slab_graphs_enabled(pfs_slab *s)
+{
+    if (s->graph_mode < 0) {
+        const char *e = getenv("PFS_SLAB_GRAPH");
+        s->graph_mode = (e && e[0] == '0') ? 0 : 1;
+    }
+    return s->graph_mode == 1;
+}
+
+unsigned float_bits(float x)
+{
+    unsigned u;
+    memcpy(&u, &x, sizeof(u));
+    return u;
+}
+
     // n sweeps starting from iterate 0 in plane unit pa, all in fused passes; the pass that reaches sweep n also
     // stores iterate n-1 into unit px (as pfs_api.cu's run_diffuse / run_pressure do), so both iterates the reference
     // leaves behind exist afterwards.  `valid` tracks how many halo rows of the current iterate are correct on
@@ -1480,9 +1528,6 @@ int fluid_step(const std::vector<pfs_slab *> &L, const StepIO &io, float dt, flo
     dp.beta = (float)(1.0 + 4.0 * (double)dp.alpha);
     int d_valid = 0;
     int dl = UV_A, dpv = UV_B;                                            // iterate n_d, iterate n_d - 1
-    next_phase(PFS_PHASE_DIFFUSE);
-    PFS_TRY(run_sweeps(L, true, UV_A, UV_B, UV_X, dp, n_diffuse, &dl, &dpv, &d_valid, io.forces));
-    next_phase(PFS_PHASE_DIVERGENCE);
 
     // pointer choreography (pfs_simulate_fluid_step): struct `vp` points at buffer Bv after diffuse (the original vp buffer for
     // an odd sweep count, else tmp's), its pressure channel is the warm start; struct `tmp` ends on the buffer holding p_N
@@ -1509,21 +1554,6 @@ int fluid_step(const std::vector<pfs_slab *> &L, const StepIO &io, float dt, flo
         p_oth = others[0];
         p_ext = others[1];
     }
-
-    // ---- divergence (needs one halo row of v) + warm-start pressure; then the divergence halo ----
-    {
-        std::vector<std::vector<float *>> pl(n);
-        for (int k = 0; k < n; k++) pl[k].push_back(L[k]->plane(dl));
-        if (d_valid < 1) PFS_TRY(exchange_planes(L, pl, 1, 2 * (size_t)gw));
-        for (int k = 0; k < n; k++) {
-            pfs_slab *s = L[k];
-            Guard g(s->device);
-            PFS_TRY(launch_divergence(s->plane(dl), s->plane(DIV), io.resident ? nullptr : Bv[k], io.resident ? nullptr : s->plane(P_A),
-                                      dt, gw, s->rows, s->stream, halo, 0));
-        }
-        for (int k = 0; k < n; k++) pl[k][0] = L[k]->plane(DIV);
-        PFS_TRY(exchange_planes(L, pl, halo, (size_t)gw));
-    }
     SweepParams pp;
     pp.w = gw;
     pp.h = L[0]->rows;
@@ -1531,8 +1561,102 @@ int fluid_step(const std::vector<pfs_slab *> &L, const StepIO &io, float dt, flo
     pp.beta = 4.0f;
     int p_valid = 0;
     int pl_last = p_warm, pl_prev = p_oth;
-    next_phase(PFS_PHASE_PRESSURE);
-    PFS_TRY(run_sweeps(L, false, p_warm, p_oth, p_ext, pp, n_pressure, &pl_last, &pl_prev, &p_valid, nullptr));
+
+    // ---- the sweeps: diffusion | divergence (needs one halo row of v) + warm-start pressure, divergence halo | pressure ----
+    auto sweeps_segment = [&]() -> int {
+        next_phase(PFS_PHASE_DIFFUSE);
+        PFS_TRY(run_sweeps(L, true, UV_A, UV_B, UV_X, dp, n_diffuse, &dl, &dpv, &d_valid, io.forces));
+        next_phase(PFS_PHASE_DIVERGENCE);
+        {
+            std::vector<std::vector<float *>> pl(n);
+            for (int k = 0; k < n; k++) pl[k].push_back(L[k]->plane(dl));
+            if (d_valid < 1) PFS_TRY(exchange_planes(L, pl, 1, 2 * (size_t)gw));
+            for (int k = 0; k < n; k++) {
+                pfs_slab *s = L[k];
+                Guard g(s->device);
+                PFS_TRY(launch_divergence(s->plane(dl), s->plane(DIV), io.resident ? nullptr : Bv[k],
+                                          io.resident ? nullptr : s->plane(P_A), dt, gw, s->rows, s->stream, halo, 0));
+            }
+            for (int k = 0; k < n; k++) pl[k][0] = L[k]->plane(DIV);
+            PFS_TRY(exchange_planes(L, pl, halo, (size_t)gw));
+        }
+        next_phase(PFS_PHASE_PRESSURE);
+        PFS_TRY(run_sweeps(L, false, p_warm, p_oth, p_ext, pp, n_pressure, &pl_last, &pl_prev, &p_valid, nullptr));
+        return PFS_OK;
+    };
+    // One process per GPU over the peer transport, resident state: the segment is the same kernel sequence every step (the
+    // plane roles alternate with the sweep-count parities), ~50 launches that otherwise each pay their launch latency on an
+    // idle machine.  The second step with the same roles and parameters is captured, later ones replay the graph.  Every
+    // rank runs the same pushes in the same order whether it replays or launches them one by one.
+    pfs_slab *s0 = L[0];
+    bool seg_done = false;
+    if (io.resident && n == 1 && s0->p2p && !io.forces && slab_graphs_enabled(s0) && !phase_timing_on()) {
+        cudaStreamCaptureStatus cap = cudaStreamCaptureStatusNone;
+        const bool capturing = cudaStreamIsCapturing(s0->stream, &cap) != cudaSuccess || cap != cudaStreamCaptureStatusNone;
+        (void)cudaGetLastError();
+        pfs_slab::SegGraph key = {p_warm, n_diffuse, n_pressure, pfs_get_fuse_depth(), halo, float_bits(dt), float_bits(viscosity),
+                                  nullptr, 0, 0, 0, 0, 0, 0, 0};
+        auto same = [](const pfs_slab::SegGraph &x, const pfs_slab::SegGraph &y) {
+            return x.p_warm == y.p_warm && x.nd == y.nd && x.np == y.np && x.fuse == y.fuse && x.halo == y.halo && x.dt_bits == y.dt_bits &&
+                   x.visc_bits == y.visc_bits;
+        };
+        pfs_slab::SegGraph *hit = nullptr;
+        if (!capturing)
+            for (auto &gr : s0->seg_graphs)
+                if (same(gr, key)) hit = &gr;
+        Guard g(s0->device);
+        if (hit) {
+            PFS_TRY(flush_seq(s0));
+            PFS_CUDA(cudaGraphLaunch(hit->exec, s0->stream));
+            g_launches += hit->launches;
+            g_passes += hit->passes;
+            dl = hit->dl; dpv = hit->dpv; pl_last = hit->pl_last; pl_prev = hit->pl_prev; p_valid = hit->p_valid;
+            seg_done = true;
+        } else if (!capturing && std::any_of(s0->seg_seen.begin(), s0->seg_seen.end(),
+                                             [&](const pfs_slab::SegGraph &x) { return same(x, key); })) {
+            PFS_TRY(flush_seq(s0));
+            const unsigned long long l0 = g_launches, q0 = g_passes;
+            cudaStream_t user = s0->stream;
+            if (!s0->capture_stream) PFS_CUDA(cudaStreamCreateWithFlags(&s0->capture_stream, cudaStreamNonBlocking));
+            cudaGraph_t graph = nullptr;
+            cudaGraphExec_t exec = nullptr;
+            bool ok = cudaStreamBeginCapture(s0->capture_stream, cudaStreamCaptureModeRelaxed) == cudaSuccess;
+            if (ok) {
+                s0->stream = s0->capture_stream;
+                int rc = sweeps_segment();
+                if (rc == PFS_OK) rc = flush_seq(s0);
+                s0->stream = user;
+                ok = (cudaStreamEndCapture(s0->capture_stream, &graph) == cudaSuccess) && rc == PFS_OK && graph != nullptr;
+            }
+            if (ok) ok = cudaGraphInstantiate(&exec, graph, 0) == cudaSuccess;
+            if (graph) cudaGraphDestroy(graph);
+            if (ok) {
+                if (s0->seg_graphs.size() >= 8) {
+                    cudaGraphExecDestroy(s0->seg_graphs.front().exec);
+                    s0->seg_graphs.erase(s0->seg_graphs.begin());
+                }
+                key.exec = exec;
+                key.launches = g_launches - l0;
+                key.passes = g_passes - q0;
+                key.dl = dl; key.dpv = dpv; key.pl_last = pl_last; key.pl_prev = pl_prev; key.p_valid = p_valid;
+                s0->seg_graphs.push_back(key);
+                PFS_CUDA(cudaGraphLaunch(exec, s0->stream));      // the launches counted during capture are this replay's
+                seg_done = true;
+            } else {
+                (void)cudaGetLastError();                          // capture not possible here: launch one by one from now on
+                g_launches = l0;
+                g_passes = q0;
+                s0->xord = 0;                                      // the pushes of the failed capture never ran
+                s0->graph_mode = 0;
+                d_valid = 0; dl = UV_A; dpv = UV_B; p_valid = 0; pl_last = p_warm; pl_prev = p_oth;
+            }
+        }
+        if (!seg_done && !capturing) {
+            if (s0->seg_seen.size() >= 16) s0->seg_seen.erase(s0->seg_seen.begin());
+            s0->seg_seen.push_back(key);
+        }
+    }
+    if (!seg_done) PFS_TRY(sweeps_segment());
     next_phase(PFS_PHASE_PROJECT);
 
     // ---- late checks: everything so far only wrote scratch planes ----

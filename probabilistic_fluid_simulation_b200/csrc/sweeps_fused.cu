@@ -95,6 +95,8 @@ __global__ void __launch_bounds__(WARPS_PER_CTA * 32, MINB) fused_sweeps_kernel(
     constexpr int MODE = (U == RING_SLOTS) ? 0 : ((2 * U == RING_SLOTS) ? 1 : 2);
     __shared__ float4 ring[WARPS_PER_CTA][RING_SLOTS * SLOT];
 
+    pdl_launch_dependents();
+    pdl_wait();                                      // the pass before this one has finished; nothing global was touched yet
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int item = blockIdx.x * WARPS_PER_CTA + warp;
     if (item >= P.n_strips * P.n_chunks) return;     // whole warp leaves together
@@ -217,9 +219,9 @@ int launch_one(const FusedParams &P, cudaStream_t s)
     const unsigned blocks = (unsigned)((total + WARPS_PER_CTA - 1) / WARPS_PER_CTA);
     constexpr int MINB = (T >= 6) ? 3 : 4;
     if (P.prev != nullptr)
-        PFS_LAUNCH((fused_sweeps_kernel<T, MINB, true>), blocks, WARPS_PER_CTA * 32, 0, s, P);
+        PFS_LAUNCH_PDL((fused_sweeps_kernel<T, MINB, true>), blocks, WARPS_PER_CTA * 32, 0, s, P);
     else
-        PFS_LAUNCH((fused_sweeps_kernel<T, MINB, false>), blocks, WARPS_PER_CTA * 32, 0, s, P);
+        PFS_LAUNCH_PDL((fused_sweeps_kernel<T, MINB, false>), blocks, WARPS_PER_CTA * 32, 0, s, P);
     return PFS_OK;
 }
 

@@ -413,6 +413,8 @@ template <int T, int MINB, bool DIV2, bool LAST>
 __global__ void __launch_bounds__(WARPS_PER_CTA * 32, MINB) diffuse_packed_kernel(const PackedParams P)
 {
     __shared__ __align__(16) float ring[WARPS_PER_CTA][ring_slots(T) * SLOT_FLOATS];   // 18 or 36 KB per CTA
+    pdl_launch_dependents();
+    pdl_wait();                                           // the pass before this one has finished; nothing global was touched yet
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int item = blockIdx.x * WARPS_PER_CTA + warp;
     if (item >= P.n_strips * P.n_chunks) return;          // whole warp leaves together
@@ -436,13 +438,13 @@ int launch_packed(const PackedParams &P, bool div2, cudaStream_t s)
     const unsigned blocks = (unsigned)((total + WARPS_PER_CTA - 1) / WARPS_PER_CTA);
     const bool last = (P.prev != nullptr) || (P.force != nullptr);
     if (div2 && last)
-        PFS_LAUNCH((diffuse_packed_kernel<T, packed_minb(T), true, true>), blocks, WARPS_PER_CTA * 32, 0, s, P);
+        PFS_LAUNCH_PDL((diffuse_packed_kernel<T, packed_minb(T), true, true>), blocks, WARPS_PER_CTA * 32, 0, s, P);
     else if (div2)
-        PFS_LAUNCH((diffuse_packed_kernel<T, packed_minb(T), true, false>), blocks, WARPS_PER_CTA * 32, 0, s, P);
+        PFS_LAUNCH_PDL((diffuse_packed_kernel<T, packed_minb(T), true, false>), blocks, WARPS_PER_CTA * 32, 0, s, P);
     else if (last)
-        PFS_LAUNCH((diffuse_packed_kernel<T, packed_minb(T), false, true>), blocks, WARPS_PER_CTA * 32, 0, s, P);
+        PFS_LAUNCH_PDL((diffuse_packed_kernel<T, packed_minb(T), false, true>), blocks, WARPS_PER_CTA * 32, 0, s, P);
     else
-        PFS_LAUNCH((diffuse_packed_kernel<T, packed_minb(T), false, false>), blocks, WARPS_PER_CTA * 32, 0, s, P);
+        PFS_LAUNCH_PDL((diffuse_packed_kernel<T, packed_minb(T), false, false>), blocks, WARPS_PER_CTA * 32, 0, s, P);
     return PFS_OK;
 }
 
