@@ -168,7 +168,8 @@ struct pfs_slab {
                                           // overflow under an exact bound 1/2/3, peer-transport timeout 9; read by pfs_slab_check),
                                           // [3] setup scratch, [4] max|v| and [5] "a departure row was missing" (as float) of a
                                           // speculative advect, [6] the same flag as the kernel raises it (int; reset every step),
-                                          // [8] "row missing" flag of a speculative advect_color (int), [9] the same as float (all-reduced)
+                                          // [8] "row missing" flag of a speculative advect_color (int), [9] the same as float (all-reduced),
+                                          // [10] max|v| of the projected field of the last resident step (by-product of project)
     float *h_scalars = nullptr;           // pinned mirror
     pfs::ncclComm_t comm = nullptr;
     // peer transport (one process per GPU, CUDA IPC): the ring neighbours' planes / gather halos / flags mapped here
@@ -238,7 +239,12 @@ struct Guard {   // cudaSetDevice for the scope of one slab's work
 };
 
 // ---- small kernels of the slab path -----------------------------------------------------------
-__global__ void flag_to_float_kernel(const int *flag, float *out) { *out = (*flag != 0) ? 1.f : 0.f; }
+// flag -> out[1] as a float; vmax (optional: the running maximum a project kernel left) -> out[0]
+__global__ void flag_to_float_kernel(const int *flag, float *out, const float *vmax)
+{
+    out[1] = (*flag != 0) ? 1.f : 0.f;
+    if (vmax != nullptr) out[0] = *vmax;
+}
 
 template <int CF>     // floats per cell: 4 = interleaved [u,v,p,div], 2 = (u,v) plane
 __global__ void __launch_bounds__(256) max_abs_v_kernel(const float *__restrict__ vp, size_t n, float *out)
@@ -267,16 +273,20 @@ struct RowSource {
     size_t row_bytes;
 };
 
-__device__ __forceinline__ const char *source_row(const RowSource &S, int grow, int *overflow, int code)
+// The same lookup without branches, for the two bilinear rows of every cell: the three sources are one affine map each
+// (base + r * row_bytes with the base shifted so that r is the row relative to the band), chosen by two compares.  A row
+// outside all three raises *miss (the caller flags it once) and reads the band's first row, so nothing is out of bounds.
+__device__ __forceinline__ const char *source_row_select(const RowSource &S, int grow, bool *miss)
 {
     int r = grow - S.band0;
-    if (r < -S.d) r += S.total;
-    if (r >= S.band_n + S.d) r -= S.total;
-    if (r >= 0 && r < S.band_n) return S.band + (size_t)r * S.row_bytes;
-    if (r < 0 && r >= -S.d) return S.above + (size_t)(r + S.d) * S.row_bytes;
-    if (r >= S.band_n && r < S.band_n + S.d) return S.below + (size_t)(r - S.band_n) * S.row_bytes;
-    atomicExch(overflow, code);          // cannot happen if D was computed correctly; never read out of bounds
-    return nullptr;
+    r += (r < -S.d) ? S.total : 0;
+    r -= (r >= S.band_n + S.d) ? S.total : 0;
+    const bool out = (r < -S.d) || (r >= S.band_n + S.d);
+    *miss = *miss || out;
+    r = out ? 0 : r;
+    const char *base = (r < 0) ? S.above + (size_t)S.d * S.row_bytes
+                               : ((r >= S.band_n) ? S.below - (size_t)S.band_n * S.row_bytes : S.band);
+    return base + (ptrdiff_t)r * (ptrdiff_t)S.row_bytes;
 }
 
 // advect (fluid.cpp:24-70) with GLOBAL indices: this rank produces rows [row0, row0+rows) of the gh-row
@@ -291,8 +301,9 @@ __global__ void __launch_bounds__(256)
     const int j = row0 + jl;
     const float fw = (float)w, fh = (float)gh;
     auto cell = [](const char *row, int x) { return reinterpret_cast<const float2 *>(reinterpret_cast<const float *>(row) + (size_t)x * CF); };
-    const char *own = live ? source_row(S, j, overflow, 1) : nullptr;
-    const float2 uv = own ? __ldg(cell(own, i)) : make_float2(0.f, 0.f);
+    // the cell's own row is a row of the band (row0 <= j < row0 + rows, and the band source starts at band0 <= row0)
+    const bool own = live;
+    const float2 uv = own ? __ldg(cell(S.band + (size_t)(j - S.band0) * S.row_bytes, i)) : make_float2(0.f, 0.f);
     if (vmax_out != nullptr) {
         // by-product: max|v| of the field being advected (what bounds the row displacement), NaN -> +inf.
         // Reduced over the whole CTA first (every thread gets here, dead ones with 0): ONE look at the running
@@ -326,8 +337,12 @@ __global__ void __launch_bounds__(256)
     const float xp = backtrace_coord((float)i, __fmul_rn(dt, uv.x), fw, rfw);
     const float yp = backtrace_coord((float)j, __fmul_rn(dt, uv.y), fh, rfh);
     const Bilinear b = make_bilinear(xp, yp, w, gh);
-    const char *r0 = source_row(S, b.j0, overflow, 1), *r1 = source_row(S, b.j1, overflow, 1);
-    if (!r0 || !r1) return;
+    bool miss = false;
+    const char *r0 = source_row_select(S, b.j0, &miss), *r1 = source_row_select(S, b.j1, &miss);
+    if (miss) {
+        atomicExch(overflow, 1);         // cannot happen if D was computed correctly; a guessed D is verified through this word
+        return;
+    }
     const float2 f00 = __ldg(cell(r0, b.i0)), f10 = __ldg(cell(r0, b.i1)), f01 = __ldg(cell(r1, b.i0)), f11 = __ldg(cell(r1, b.i1));
     uv_out[(size_t)(y_base + jl) * w + i] = make_float2(bilerp(b, f00.x, f10.x, f01.x, f11.x), bilerp(b, f00.y, f10.y, f01.y, f11.y));
 }
@@ -355,8 +370,12 @@ __global__ void __launch_bounds__(256)
     const float xp = backtrace_coord((float)i, __fmul_rn(dt_over_viw, uv.x), fiw, rfiw);
     const float yp = backtrace_coord((float)j, __fmul_rn(dt_over_vih, uv.y), fih, rfih);
     const Bilinear b = make_bilinear(xp, yp, iw, ih);
-    const char *c0 = source_row(S, b.j0, overflow, 3), *c1 = source_row(S, b.j1, overflow, 3);
-    if (!c0 || !c1) return;
+    bool miss = false;
+    const char *c0 = source_row_select(S, b.j0, &miss), *c1 = source_row_select(S, b.j1, &miss);
+    if (miss) {
+        atomicExch(overflow, 3);
+        return;
+    }
     const float4 *r0 = reinterpret_cast<const float4 *>(c0), *r1 = reinterpret_cast<const float4 *>(c1);
     const float4 f00 = __ldg(r0 + b.i0), f10 = __ldg(r0 + b.i1), f01 = __ldg(r1 + b.i0), f11 = __ldg(r1 + b.i1);
     float4 o;
@@ -1294,7 +1313,7 @@ int color_step(const std::vector<pfs_slab *> &L, float *const *image_in, float *
         }
         if (speculative) {
             // "a row was missing" -> every rank, then the host; nobody waits for it yet
-            PFS_LAUNCH(flag_to_float_kernel, 1, 1, 0, s->stream, reinterpret_cast<const int *>(s->d_scalars + 8), s->d_scalars + 9);
+            PFS_LAUNCH(flag_to_float_kernel, 1, 1, 0, s->stream, reinterpret_cast<const int *>(s->d_scalars + 8), s->d_scalars + 8, nullptr);   // [9] = float([8] != 0)
             PFS_CUDA(cudaEventRecord(s->ev_fork, s->stream));
             PFS_CUDA(cudaStreamWaitEvent(s->side, s->ev_fork, 0));
             if (s->comm != nullptr)
@@ -1502,7 +1521,9 @@ int fluid_step(const std::vector<pfs_slab *> &L, const StepIO &io, float dt, flo
             dim3 block(64, 4), grid((gw + 63) / 64, (s->rows + 3) / 4);
             float2 *dst = reinterpret_cast<float2 *>(s->plane(UV_A));
             int *flag = reinterpret_cast<int *>(s->d_scalars + (speculate ? 6 : 2));
-            float *vmax_out = speculate ? s->d_scalars + 4 : nullptr;
+            // max|v| of the field being advected: on resident state the project kernel of the step that produced the field
+            // left it in [10] (it has spare issue slots; here the reduction costs a sixth of the kernel), else a by-product
+            float *vmax_out = (speculate && !io.resident) ? s->d_scalars + 4 : nullptr;
             if (cf == 2)
                 PFS_LAUNCH(advect_slab_kernel<2>, grid, block, 0, s->stream, src[k], dst, dt, gw, gh, s->row0, s->rows, s->halo, flag, vmax_out, 1.0f / (float)gw, 1.0f / (float)gh);
             else
@@ -1510,7 +1531,8 @@ int fluid_step(const std::vector<pfs_slab *> &L, const StepIO &io, float dt, flo
             if (speculate) {
                 // (max|v| of this step's input, "a departure row was missing") -> every rank, then the host; nobody waits yet
                 // (on a side stream: the sweeps that follow do not depend on it)
-                PFS_LAUNCH(flag_to_float_kernel, 1, 1, 0, s->stream, reinterpret_cast<const int *>(s->d_scalars + 6), s->d_scalars + 5);
+                PFS_LAUNCH(flag_to_float_kernel, 1, 1, 0, s->stream, reinterpret_cast<const int *>(s->d_scalars + 6), s->d_scalars + 4,
+                           io.resident ? s->d_scalars + 10 : nullptr);
                 PFS_CUDA(cudaEventRecord(s->ev_fork, s->stream));
                 PFS_CUDA(cudaStreamWaitEvent(s->side, s->ev_fork, 0));
                 if (s->comm != nullptr)
@@ -1577,8 +1599,13 @@ int fluid_step(const std::vector<pfs_slab *> &L, const StepIO &io, float dt, flo
                 PFS_TRY(launch_divergence(s->plane(dl), s->plane(DIV), io.resident ? nullptr : Bv[k],
                                           io.resident ? nullptr : s->plane(P_A), dt, gw, s->rows, s->stream, halo, 0));
             }
-            for (int k = 0; k < n; k++) pl[k][0] = L[k]->plane(DIV);
+            // the divergence halo and the first pressure halo (the warm start is final by now) in ONE exchange
+            for (int k = 0; k < n; k++) {
+                pl[k][0] = L[k]->plane(DIV);
+                pl[k].push_back(L[k]->plane(p_warm));
+            }
             PFS_TRY(exchange_planes(L, pl, halo, (size_t)gw));
+            p_valid = halo;
         }
         next_phase(PFS_PHASE_PRESSURE);
         PFS_TRY(run_sweeps(L, false, p_warm, p_oth, p_ext, pp, n_pressure, &pl_last, &pl_prev, &p_valid, nullptr));
@@ -1691,8 +1718,11 @@ int fluid_step(const std::vector<pfs_slab *> &L, const StepIO &io, float dt, flo
         for (int k = 0; k < n; k++) {
             pfs_slab *s = L[k];
             Guard g(s->device);
-            if (io.resident)
-                PFS_TRY(launch_project_uv(s->plane(uv_p), s->plane(pl_last), s->plane(UV_S), dt, gw, s->rows, s->stream, halo, 0, nullptr));
+            if (io.resident) {
+                PFS_CUDA(cudaMemsetAsync(s->d_scalars + 10, 0, sizeof(float), s->stream));
+                PFS_TRY(launch_project_uv(s->plane(uv_p), s->plane(pl_last), s->plane(UV_S), dt, gw, s->rows, s->stream, halo, 0,
+                                          s->d_scalars + 10));     // max|v| of the new field, for the next step's advect
+            }
             else
                 PFS_TRY(launch_project_pack(s->plane(uv_p), s->plane(pl_last), s->plane(pl_prev), s->plane(DIV), Bq[k], Bp[k], dt, gw,
                                             s->rows, s->stream, halo, 0));
