@@ -483,7 +483,9 @@ def run_single_gpu(args):
                 "unit": "GB/s", "frac": kernels[dom]["frac"], "traffic": traffic, "peak_source": peak_src,
                 "alg_bytes_per_launch": kernels[dom]["alg_bytes_per_launch"],
                 "avg_launch_ms": kernels[dom]["avg_launch_ms"],
-                "note": "algorithmic bytes give no credit for temporal blocking, so frac may exceed 1"}
+                "note": "algorithmic bytes give no credit for temporal blocking, so frac may exceed 1; measured DRAM bytes per launch are in "
+                        "`traffic`; after temporal blocking the fused sweeps are bound by FP32 instruction dispatch, not HBM "
+                        "(DESIGN.md 3.4: ~20 cycles per (u,v) update per SM sub-partition is the floor, 22.7 measured)"}
     step_bytes = (88 + 16 * n + 12 * n) * cells
     whole_step = {"alg_bytes": step_bytes, "achieved_gbs": step_bytes / (ms_step * 1e-3) / 1e9,
                   "frac": step_bytes / (ms_step * 1e-3) / 1e9 / peak}
