@@ -139,6 +139,10 @@ def run(args, bench) -> None:
             slab.simulate_fluid_step(fv, ft, DT, VISC, n, n)
             slab.advect_color_step(fi, fm, fv, DT)
 
+    # setup, as in the N = 1 arm: resident slabs capture their sweep segment once per plane-role assignment (period 2, the
+    # second occurrence is captured); run through that before the warm-up so that warm-up and timed region are steady state
+    for _ in range(bench.PRIME_STEPS):
+        step()
     for _ in range(args.warmup):
         step()
     slab.check()
@@ -196,7 +200,7 @@ def run(args, bench) -> None:
             uvp, uvt, uimg, _ = bench.make_inputs(uh, w)
             ctx = pfs.FluidContext(w, uh, w, uh)
             ctx.upload(torch.from_numpy(uvp).cuda(), torch.from_numpy(uvt).cuda(), torch.from_numpy(uimg).cuda())
-            for _ in range(3):
+            for _ in range(bench.PRIME_STEPS + 3):          # graph priming + warm-up, as in the N = 1 arm
                 ctx.step(1, DT, VISC, n, n)
             u_steps = max(3, min(args.steps, 10))
             u0, u1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
