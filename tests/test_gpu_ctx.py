@@ -122,8 +122,11 @@ def test_ctx_forced_and_stochastic_steps():
     ctx.close()
 
 
-def test_ctx_without_step_graphs_in_a_child_process():
-    """PFS_STEP_GRAPH=0 is read once per context: eager launches must give the same bits as graph replays."""
+@pytest.mark.parametrize("env_extra", [{"PFS_STEP_GRAPH": "0"}, {"PFS_STEP_GRAPH": "0", "PFS_PDL": "0"}, {"PFS_PDL": "0"}],
+                         ids=["eager+pdl", "eager", "graphs-no-pdl"])
+def test_ctx_without_step_graphs_in_a_child_process(env_extra):
+    """PFS_STEP_GRAPH / PFS_PDL are read once per process: eager launches (with and without programmatic dependent launch of
+    the fused passes) must give the same bits as graph replays."""
     code = r'''
 import sys, numpy as np
 sys.path.insert(0, %r); sys.path.insert(0, %r)
@@ -140,7 +143,7 @@ for g, w in zip(ctx.download(), want):
     assert np.array_equal(to_host(g).view(np.uint32), w.view(np.uint32))
 print("eager ctx ok")
 ''' % (ROOT, os.path.join(ROOT, "tests"))
-    env = dict(os.environ, PFS_STEP_GRAPH="0")
+    env = dict(os.environ, **env_extra)
     r = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, env=env, timeout=300)
     assert r.returncode == 0 and "eager ctx ok" in r.stdout, r.stdout[-2000:] + r.stderr[-2000:]
 

@@ -225,14 +225,24 @@ def test_ring_of_processes(tmp_path, world, transport):
     (the default when every rank can map its neighbours); "nccl": send/recv.  Both must reproduce the oracle bit for bit
     (tests/nccl_ring_check.py: bands of different heights, a 25-row gather, a gather deeper than the peer halos, the
     whole-field path, the rerun after a field jump).  Skipped only when fewer than `world` GPUs are visible."""
+    _ring_of_processes(world, transport, {})
+
+
+def test_ring_of_two_processes_without_sweep_graphs():
+    """The resident ring's sweep segment launched kernel by kernel (PFS_SLAB_GRAPH=0) and without programmatic dependent
+    launch: the same checks as test_ring_of_processes[2-p2p], whose resident case replays captured graphs."""
+    _ring_of_processes(2, "p2p", {"PFS_SLAB_GRAPH": "0", "PFS_PDL": "0"}, port_offset=40)
+
+
+def _ring_of_processes(world, transport, env_extra, port_offset=0):
     import torch
     if torch.cuda.device_count() < world:
         pytest.skip(f"needs {world} GPUs, {torch.cuda.device_count()} visible")
-    env = dict(os.environ)
+    env = dict(os.environ, **env_extra)
     env.pop("PFS_SLAB_TRANSPORT", None)
     if transport == "nccl":
         env["PFS_SLAB_TRANSPORT"] = "nccl"
-    port = 29541 + 2 * world + (0 if transport == "p2p" else 1)
+    port = 29541 + 2 * world + (0 if transport == "p2p" else 1) + port_offset
     cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", f"--nproc-per-node={world}", "--master-addr",
            "127.0.0.1", "--master-port", str(port), os.path.join(ROOT, "tests", "nccl_ring_check.py")]
     r = subprocess.run(cmd, capture_output=True, text=True, timeout=900, cwd=ROOT, env=env)
