@@ -295,29 +295,55 @@ __global__ void __launch_bounds__(256)
 // a (u,v) plane.  One 8-byte load fetches both components of a corner; neighbouring threads'
 // corners share 32-byte sectors, so the gather runs out of L1 for coherent flows.
 // ---------------------------------------------------------------------------------------------
-template <int SS, int DS>     // floats per source / destination cell: 4 = interleaved [u,v,p,div], 2 = (u,v) plane
+// R rows per thread (rows j and j + 4 of an 8-row tile for R = 2): the kernel is two dependent round trips to memory per
+// cell (own velocity, then the four corners) with ~120 instructions between and after them; at one cell per thread it
+// spent most of its time waiting on the scoreboard (ncu: issue 66 %, long-scoreboard stalls dominant).  Two independent
+// cells per thread, staged (all own loads, all index arithmetic, all gathers, all blends), overlap those waits.
+template <int SS, int DS, int R>     // floats per source / destination cell: 4 = interleaved [u,v,p,div], 2 = (u,v) plane
 __global__ void __launch_bounds__(256)
     advect_kernel(const float *__restrict__ src, float *__restrict__ dst, float dt, int w, int h, float rfw, float rfh)
 {
-    const int i = blockIdx.x * 64 + threadIdx.x, j = blockIdx.y * 4 + threadIdx.y;
-    if (i >= w || j >= h) return;
+    const int i = blockIdx.x * 64 + threadIdx.x, j0 = blockIdx.y * (4 * R) + threadIdx.y;
+    if (i >= w || j0 >= h) return;
     const float fw = (float)w, fh = (float)h;
     // a field has at most 2^28 cells (check_dims): 32-bit cell indices, one widening multiply-add per address
-    const unsigned uw = (unsigned)w, cell = (unsigned)j * uw + (unsigned)i;
-    const float2 uv = __ldg(reinterpret_cast<const float2 *>(src + (size_t)cell * SS));
-    // fluid.cpp:39,41: (float)i - dt*u/fwidth  ==  i - ((dt*u)/fwidth)
-    // rfw, rfh: the correctly rounded reciprocals of the extents, formed once on the host (1.0f / fw)
-    const float xp = backtrace_coord((float)i, __fmul_rn(dt, uv.x), fw, rfw);
-    const float yp = backtrace_coord((float)j, __fmul_rn(dt, uv.y), fh, rfh);
-    const Bilinear b = make_bilinear(xp, yp, w, h);
-    const unsigned r0 = (unsigned)b.j0 * uw, r1 = (unsigned)b.j1 * uw;
-    const float2 f00 = __ldg(reinterpret_cast<const float2 *>(src + (size_t)(r0 + (unsigned)b.i0) * SS));
-    const float2 f10 = __ldg(reinterpret_cast<const float2 *>(src + (size_t)(r0 + (unsigned)b.i1) * SS));
-    const float2 f01 = __ldg(reinterpret_cast<const float2 *>(src + (size_t)(r1 + (unsigned)b.i0) * SS));
-    const float2 f11 = __ldg(reinterpret_cast<const float2 *>(src + (size_t)(r1 + (unsigned)b.i1) * SS));
-    const float un = bilerp(b, f00.x, f10.x, f01.x, f11.x);
-    const float vn = bilerp(b, f00.y, f10.y, f01.y, f11.y);
-    *reinterpret_cast<float2 *>(dst + (size_t)cell * DS) = make_float2(un, vn);
+    const unsigned uw = (unsigned)w;
+    bool live[R];
+    unsigned cell[R];
+    float2 uv[R];
+#pragma unroll
+    for (int r = 0; r < R; r++) {
+        const int j = j0 + 4 * r;
+        live[r] = j < h;
+        cell[r] = (unsigned)(live[r] ? j : j0) * uw + (unsigned)i;
+        uv[r] = __ldg(reinterpret_cast<const float2 *>(src + (size_t)cell[r] * SS));
+    }
+    Bilinear b[R];
+    unsigned r0[R], r1[R];
+#pragma unroll
+    for (int r = 0; r < R; r++) {
+        // fluid.cpp:39,41: (float)i - dt*u/fwidth  ==  i - ((dt*u)/fwidth)
+        // rfw, rfh: the correctly rounded reciprocals of the extents, formed once on the host (1.0f / fw)
+        const float xp = backtrace_coord((float)i, __fmul_rn(dt, uv[r].x), fw, rfw);
+        const float yp = backtrace_coord((float)(live[r] ? j0 + 4 * r : j0), __fmul_rn(dt, uv[r].y), fh, rfh);
+        b[r] = make_bilinear(xp, yp, w, h);
+        r0[r] = (unsigned)b[r].j0 * uw;
+        r1[r] = (unsigned)b[r].j1 * uw;
+    }
+    float2 f00[R], f10[R], f01[R], f11[R];
+#pragma unroll
+    for (int r = 0; r < R; r++) {
+        f00[r] = __ldg(reinterpret_cast<const float2 *>(src + (size_t)(r0[r] + (unsigned)b[r].i0) * SS));
+        f10[r] = __ldg(reinterpret_cast<const float2 *>(src + (size_t)(r0[r] + (unsigned)b[r].i1) * SS));
+        f01[r] = __ldg(reinterpret_cast<const float2 *>(src + (size_t)(r1[r] + (unsigned)b[r].i0) * SS));
+        f11[r] = __ldg(reinterpret_cast<const float2 *>(src + (size_t)(r1[r] + (unsigned)b[r].i1) * SS));
+    }
+#pragma unroll
+    for (int r = 0; r < R; r++) {
+        const float un = bilerp(b[r], f00[r].x, f10[r].x, f01[r].x, f11[r].x);
+        const float vn = bilerp(b[r], f00[r].y, f10[r].y, f01[r].y, f11[r].y);
+        if (live[r]) *reinterpret_cast<float2 *>(dst + (size_t)cell[r] * DS) = make_float2(un, vn);
+    }
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -333,33 +359,60 @@ __device__ __forceinline__ unsigned frame_byte(float x)
     return (unsigned)min(max(t, 0), 255);           // outside [0, 256/255) the reference's cast is undefined; saturate
 }
 
-template <int VS, bool BYTES>     // floats per velocity cell: 4 = interleaved buffer, 2 = (u,v) plane; BYTES: also the frame
-__global__ void __launch_bounds__(256)
+template <int VS, bool BYTES, int R>     // floats per velocity cell: 4 = interleaved buffer, 2 = (u,v) plane; BYTES: also the frame;
+__global__ void __launch_bounds__(256)   // R rows per thread, staged as in advect_kernel
     advect_color_kernel(const float4 *__restrict__ image, float4 *__restrict__ out, const float *__restrict__ vp,
                         float dt_over_viw, float dt_over_vih, float viw, float vih, int iw, int ih, int vw, float rfiw, float rfih,
                         unsigned *__restrict__ rgba8)
 {
-    const int i = blockIdx.x * 64 + threadIdx.x, j = blockIdx.y * 4 + threadIdx.y;
-    if (i >= iw || j >= ih) return;
+    const int i = blockIdx.x * 64 + threadIdx.x, jb = blockIdx.y * (4 * R) + threadIdx.y;
+    if (i >= iw || jb >= ih) return;
     const float fiw = (float)iw, fih = (float)ih;
+    const unsigned uw = (unsigned)iw;    // <= 2^28 pixels (check_dims)
     const int vi = (int)__fmul_rn((float)i, viw);   // fluid.cpp:89
-    const int vj = (int)__fmul_rn((float)j, vih);   // fluid.cpp:90
-    const float2 uv = __ldg(reinterpret_cast<const float2 *>(vp + (size_t)((unsigned)vj * (unsigned)vw + (unsigned)vi) * VS));
-    // fluid.cpp:97-98: (float)i - (dt/viw) * u / fiwidth
-    const float xp = backtrace_coord((float)i, __fmul_rn(dt_over_viw, uv.x), fiw, rfiw);
-    const float yp = backtrace_coord((float)j, __fmul_rn(dt_over_vih, uv.y), fih, rfih);
-    const Bilinear b = make_bilinear(xp, yp, iw, ih);
-    const unsigned uw = (unsigned)iw, r0 = (unsigned)b.j0 * uw, r1 = (unsigned)b.j1 * uw;    // <= 2^28 pixels (check_dims)
-    const float4 f00 = __ldg(image + (r0 + (unsigned)b.i0)), f10 = __ldg(image + (r0 + (unsigned)b.i1));
-    const float4 f01 = __ldg(image + (r1 + (unsigned)b.i0)), f11 = __ldg(image + (r1 + (unsigned)b.i1));
-    float4 o;
-    o.x = bilerp(b, f00.x, f10.x, f01.x, f11.x);
-    o.y = bilerp(b, f00.y, f10.y, f01.y, f11.y);
-    o.z = bilerp(b, f00.z, f10.z, f01.z, f11.z);
-    o.w = bilerp(b, f00.w, f10.w, f01.w, f11.w);
-    out[(unsigned)j * uw + (unsigned)i] = o;
-    if (BYTES)      // the frame the reference's writer would form from this pixel: R, G, B, A in memory order
-        rgba8[(unsigned)j * uw + (unsigned)i] = frame_byte(o.x) | (frame_byte(o.y) << 8) | (frame_byte(o.z) << 16) | (frame_byte(o.w) << 24);
+    bool live[R];
+    int jj[R];
+    float2 uv[R];
+#pragma unroll
+    for (int r = 0; r < R; r++) {
+        live[r] = jb + 4 * r < ih;
+        jj[r] = live[r] ? jb + 4 * r : jb;
+        const int vj = (int)__fmul_rn((float)jj[r], vih);   // fluid.cpp:90
+        uv[r] = __ldg(reinterpret_cast<const float2 *>(vp + (size_t)((unsigned)vj * (unsigned)vw + (unsigned)vi) * VS));
+    }
+    Bilinear b[R];
+    unsigned r0[R], r1[R];
+#pragma unroll
+    for (int r = 0; r < R; r++) {
+        // fluid.cpp:97-98: (float)i - (dt/viw) * u / fiwidth
+        const float xp = backtrace_coord((float)i, __fmul_rn(dt_over_viw, uv[r].x), fiw, rfiw);
+        const float yp = backtrace_coord((float)jj[r], __fmul_rn(dt_over_vih, uv[r].y), fih, rfih);
+        b[r] = make_bilinear(xp, yp, iw, ih);
+        r0[r] = (unsigned)b[r].j0 * uw;
+        r1[r] = (unsigned)b[r].j1 * uw;
+    }
+    float4 f00[R], f10[R], f01[R], f11[R];
+#pragma unroll
+    for (int r = 0; r < R; r++) {
+        f00[r] = __ldg(image + (r0[r] + (unsigned)b[r].i0));
+        f10[r] = __ldg(image + (r0[r] + (unsigned)b[r].i1));
+        f01[r] = __ldg(image + (r1[r] + (unsigned)b[r].i0));
+        f11[r] = __ldg(image + (r1[r] + (unsigned)b[r].i1));
+    }
+#pragma unroll
+    for (int r = 0; r < R; r++) {
+        float4 o;
+        o.x = bilerp(b[r], f00[r].x, f10[r].x, f01[r].x, f11[r].x);
+        o.y = bilerp(b[r], f00[r].y, f10[r].y, f01[r].y, f11[r].y);
+        o.z = bilerp(b[r], f00[r].z, f10[r].z, f01[r].z, f11[r].z);
+        o.w = bilerp(b[r], f00[r].w, f10[r].w, f01[r].w, f11[r].w);
+        if (live[r]) {
+            const unsigned pix = (unsigned)jj[r] * uw + (unsigned)i;
+            out[pix] = o;
+            if (BYTES)      // the frame the reference's writer would form from this pixel: R, G, B, A in memory order
+                rgba8[pix] = frame_byte(o.x) | (frame_byte(o.y) << 8) | (frame_byte(o.z) << 16) | (frame_byte(o.w) << 24);
+        }
+    }
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -626,6 +679,13 @@ inline bool vec4_ok(int w, const void *a, const void *b = nullptr, const void *c
 // ---------------------------------------------------------------------------------------------
 // host wrappers
 // ---------------------------------------------------------------------------------------------
+// rows per thread of the two gather kernels (PFS_GATHER_ROWS=1|2, default 2; see advect_kernel)
+static int env_rows_per_thread()
+{
+    const char *e = getenv("PFS_GATHER_ROWS");
+    return (e && e[0] == '1') ? 1 : 2;
+}
+
 int launch_unpack(const float *aos, float *uv, float *p, float *div, int w, int h, cudaStream_t s)
 {
     size_t n = (size_t)w * h;
@@ -658,14 +718,22 @@ int launch_add_forces(float *dst, int dst_stride, const float *force_aos, int w,
 
 int launch_advect(const float *src, int src_stride, float *dst, int dst_stride, float dt, int w, int h, cudaStream_t s)
 {
-    dim3 block(64, 4), grid((w + 63) / 64, (h + 3) / 4);
+    static const int rows_env = env_rows_per_thread();
+    const int R = rows_env;
+    dim3 block(64, 4), grid((w + 63) / 64, (h + 4 * R - 1) / (4 * R));
     const float rfw = 1.0f / (float)w, rfh = 1.0f / (float)h;     // binary32 division on the host: correctly rounded, as __frcp_rn
-    if (src_stride == 4 && dst_stride == 2)
-        PFS_LAUNCH((advect_kernel<4, 2>), grid, block, 0, s, src, dst, dt, w, h, rfw, rfh);
+    if (src_stride == 4 && dst_stride == 2 && R == 2)
+        PFS_LAUNCH((advect_kernel<4, 2, 2>), grid, block, 0, s, src, dst, dt, w, h, rfw, rfh);
+    else if (src_stride == 4 && dst_stride == 2)
+        PFS_LAUNCH((advect_kernel<4, 2, 1>), grid, block, 0, s, src, dst, dt, w, h, rfw, rfh);
+    else if (src_stride == 2 && dst_stride == 2 && R == 2)
+        PFS_LAUNCH((advect_kernel<2, 2, 2>), grid, block, 0, s, src, dst, dt, w, h, rfw, rfh);
     else if (src_stride == 2 && dst_stride == 2)
-        PFS_LAUNCH((advect_kernel<2, 2>), grid, block, 0, s, src, dst, dt, w, h, rfw, rfh);
+        PFS_LAUNCH((advect_kernel<2, 2, 1>), grid, block, 0, s, src, dst, dt, w, h, rfw, rfh);
+    else if (src_stride == 4 && dst_stride == 4 && R == 2)
+        PFS_LAUNCH((advect_kernel<4, 4, 2>), grid, block, 0, s, src, dst, dt, w, h, rfw, rfh);
     else if (src_stride == 4 && dst_stride == 4)
-        PFS_LAUNCH((advect_kernel<4, 4>), grid, block, 0, s, src, dst, dt, w, h, rfw, rfh);
+        PFS_LAUNCH((advect_kernel<4, 4, 1>), grid, block, 0, s, src, dst, dt, w, h, rfw, rfh);
     else {
         set_error("advect: unsupported cell strides %d -> %d", src_stride, dst_stride);
         return PFS_EINVAL;
@@ -807,19 +875,27 @@ int launch_advect_color(const float *image, float *out, const float *vel, int ve
     const float vih = (float)vh / (float)ih;
     const float dt_over_viw = dt / viw;
     const float dt_over_vih = dt / vih;
-    dim3 block(64, 4), grid((iw + 63) / 64, (ih + 3) / 4);
+    static const int R = env_rows_per_thread();
+    dim3 block(64, 4), grid((iw + 63) / 64, (ih + 4 * R - 1) / (4 * R));
     const float4 *img = reinterpret_cast<const float4 *>(image);
     float4 *o4 = reinterpret_cast<float4 *>(out);
     const float rfiw = 1.0f / (float)iw, rfih = 1.0f / (float)ih;
     unsigned *b4 = reinterpret_cast<unsigned *>(rgba8);
-    if (vel_stride == 2 && rgba8)
-        PFS_LAUNCH((advect_color_kernel<2, true>), grid, block, 0, s, img, o4, vel, dt_over_viw, dt_over_vih, viw, vih, iw, ih, vw, rfiw, rfih, b4);
-    else if (vel_stride == 2)
-        PFS_LAUNCH((advect_color_kernel<2, false>), grid, block, 0, s, img, o4, vel, dt_over_viw, dt_over_vih, viw, vih, iw, ih, vw, rfiw, rfih, b4);
-    else if (rgba8)
-        PFS_LAUNCH((advect_color_kernel<4, true>), grid, block, 0, s, img, o4, vel, dt_over_viw, dt_over_vih, viw, vih, iw, ih, vw, rfiw, rfih, b4);
-    else
-        PFS_LAUNCH((advect_color_kernel<4, false>), grid, block, 0, s, img, o4, vel, dt_over_viw, dt_over_vih, viw, vih, iw, ih, vw, rfiw, rfih, b4);
+#define PFS_COLOR(VS_, BY_, R_)                                                                                                   \
+    PFS_LAUNCH((advect_color_kernel<VS_, BY_, R_>), grid, block, 0, s, img, o4, vel, dt_over_viw, dt_over_vih, viw, vih, iw, ih, vw, \
+               rfiw, rfih, b4)
+    const int variant = (vel_stride == 2 ? 0 : 4) + (rgba8 ? 2 : 0) + (R == 2 ? 1 : 0);
+    switch (variant) {
+    case 0: PFS_COLOR(2, false, 1); break;
+    case 1: PFS_COLOR(2, false, 2); break;
+    case 2: PFS_COLOR(2, true, 1); break;
+    case 3: PFS_COLOR(2, true, 2); break;
+    case 4: PFS_COLOR(4, false, 1); break;
+    case 5: PFS_COLOR(4, false, 2); break;
+    case 6: PFS_COLOR(4, true, 1); break;
+    default: PFS_COLOR(4, true, 2); break;
+    }
+#undef PFS_COLOR
     return PFS_OK;
 }
 

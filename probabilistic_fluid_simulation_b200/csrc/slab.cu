@@ -291,26 +291,40 @@ __device__ __forceinline__ const char *source_row_select(const RowSource &S, int
 
 // advect (fluid.cpp:24-70) with GLOBAL indices: this rank produces rows [row0, row0+rows) of the gh-row
 // grid from a field whose cells are CF floats apart with (u,v) first (an interleaved buffer or a (u,v) plane).
+constexpr int GATHER_ROWS = 2;      // rows per thread of the two gather kernels (rows jl and jl + 4 of an 8-row tile), staged so
+                                    // that the two cells' memory round trips overlap (kernels_basic.cu: advect_kernel)
+
 template <int CF>
 __global__ void __launch_bounds__(256)
     advect_slab_kernel(const RowSource S, float2 *__restrict__ uv_out, float dt, int w, int gh,
                        int row0, int rows, int y_base, int *overflow, float *vmax_out, float rfw, float rfh)
 {
-    const int i = blockIdx.x * 64 + threadIdx.x, jl = blockIdx.y * 4 + threadIdx.y;
-    const bool live = (i < w && jl < rows);
-    const int j = row0 + jl;
+    constexpr int R = GATHER_ROWS;
+    const int i = blockIdx.x * 64 + threadIdx.x, jb = blockIdx.y * (4 * R) + threadIdx.y;
     const float fw = (float)w, fh = (float)gh;
     auto cell = [](const char *row, int x) { return reinterpret_cast<const float2 *>(reinterpret_cast<const float *>(row) + (size_t)x * CF); };
-    // the cell's own row is a row of the band (row0 <= j < row0 + rows, and the band source starts at band0 <= row0)
-    const bool own = live;
-    const float2 uv = own ? __ldg(cell(S.band + (size_t)(j - S.band0) * S.row_bytes, i)) : make_float2(0.f, 0.f);
+    bool live[R];
+    int jl[R];
+    float2 uv[R];
+#pragma unroll
+    for (int r = 0; r < R; r++) {
+        jl[r] = jb + 4 * r;
+        live[r] = (i < w && jl[r] < rows);
+        // the cell's own row is a row of the band (row0 <= j < row0 + rows, and the band source starts at band0 <= row0)
+        uv[r] = live[r] ? __ldg(cell(S.band + (size_t)(row0 + jl[r] - S.band0) * S.row_bytes, i)) : make_float2(0.f, 0.f);
+    }
     if (vmax_out != nullptr) {
         // by-product: max|v| of the field being advected (what bounds the row displacement), NaN -> +inf.
         // Reduced over the whole CTA first (every thread gets here, dead ones with 0): ONE look at the running
         // maximum per CTA, and an atomic only when the CTA would raise it -- a look per warp was a million loads of
         // one address per step, all served by the same L2 slice.
         __shared__ float warp_max[8];
-        float m = fabsf(uv.y);
+        float m = 0.f;
+#pragma unroll
+        for (int r = 0; r < R; r++) {
+            const float a = fabsf(uv[r].y);
+            m = (a > m || a != a) ? a : m;
+        }
 #pragma unroll
         for (int o = 16; o > 0; o >>= 1) {
             const float t = __shfl_xor_sync(0xffffffffu, m, o);
@@ -333,18 +347,34 @@ __global__ void __launch_bounds__(256)
             }
         }
     }
-    if (!own) return;
-    const float xp = backtrace_coord((float)i, __fmul_rn(dt, uv.x), fw, rfw);
-    const float yp = backtrace_coord((float)j, __fmul_rn(dt, uv.y), fh, rfh);
-    const Bilinear b = make_bilinear(xp, yp, w, gh);
+    Bilinear b[R];
+    const char *r0[R], *r1[R];
     bool miss = false;
-    const char *r0 = source_row_select(S, b.j0, &miss), *r1 = source_row_select(S, b.j1, &miss);
-    if (miss) {
-        atomicExch(overflow, 1);         // cannot happen if D was computed correctly; a guessed D is verified through this word
-        return;
+#pragma unroll
+    for (int r = 0; r < R; r++) {
+        const float xp = backtrace_coord((float)i, __fmul_rn(dt, uv[r].x), fw, rfw);
+        const float yp = backtrace_coord((float)(row0 + (live[r] ? jl[r] : 0)), __fmul_rn(dt, uv[r].y), fh, rfh);
+        b[r] = make_bilinear(xp, yp, w, gh);
+        bool mr = false;
+        r0[r] = source_row_select(S, b[r].j0, &mr);
+        r1[r] = source_row_select(S, b[r].j1, &mr);
+        miss = miss || (mr && live[r]);
     }
-    const float2 f00 = __ldg(cell(r0, b.i0)), f10 = __ldg(cell(r0, b.i1)), f01 = __ldg(cell(r1, b.i0)), f11 = __ldg(cell(r1, b.i1));
-    uv_out[(size_t)(y_base + jl) * w + i] = make_float2(bilerp(b, f00.x, f10.x, f01.x, f11.x), bilerp(b, f00.y, f10.y, f01.y, f11.y));
+    if (miss) atomicExch(overflow, 1);       // cannot happen if D was computed correctly; a guessed D is verified through this word
+    float2 f00[R], f10[R], f01[R], f11[R];
+#pragma unroll
+    for (int r = 0; r < R; r++) {
+        const int x0 = live[r] ? b[r].i0 : 0, x1 = live[r] ? b[r].i1 : 0;     // dead threads read cell 0 of a valid row
+        f00[r] = __ldg(cell(r0[r], x0));
+        f10[r] = __ldg(cell(r0[r], x1));
+        f01[r] = __ldg(cell(r1[r], x0));
+        f11[r] = __ldg(cell(r1[r], x1));
+    }
+#pragma unroll
+    for (int r = 0; r < R; r++)
+        if (live[r])
+            uv_out[(size_t)(y_base + jl[r]) * w + i] =
+                make_float2(bilerp(b[r], f00[r].x, f10[r].x, f01[r].x, f11[r].x), bilerp(b[r], f00[r].y, f10[r].y, f01[r].y, f11[r].y));
 }
 
 // advect_color (fluid.cpp:72-127) with GLOBAL indices: image rows [irow0, irow0+irows) of the ih-row
@@ -356,34 +386,63 @@ __global__ void __launch_bounds__(256)
                              float dt_over_viw, float dt_over_vih, float viw, float vih, int iw, int ih, int irow0,
                              int irows, int vw, int row0, int rows, int *overflow, float rfiw, float rfih)
 {
-    const int i = blockIdx.x * 64 + threadIdx.x, jl = blockIdx.y * 4 + threadIdx.y;
-    if (i >= iw || jl >= irows) return;
-    const int j = irow0 + jl;
+    constexpr int R = GATHER_ROWS;
+    const int i = blockIdx.x * 64 + threadIdx.x, jb = blockIdx.y * (4 * R) + threadIdx.y;
+    if (i >= iw || jb >= irows) return;
     const float fiw = (float)iw, fih = (float)ih;
     const int vi = (int)__fmul_rn((float)i, viw);
-    const int vj = (int)__fmul_rn((float)j, vih) - row0;
-    if (vj < 0 || vj >= rows) {
+    bool live[R];
+    int jl[R];
+    float2 uv[R];
+    bool vmiss = false;
+#pragma unroll
+    for (int r = 0; r < R; r++) {
+        live[r] = jb + 4 * r < irows;
+        jl[r] = live[r] ? jb + 4 * r : jb;
+        int vj = (int)__fmul_rn((float)(irow0 + jl[r]), vih) - row0;
+        if (vj < 0 || vj >= rows) {
+            vmiss = true;
+            vj = 0;
+        }
+        uv[r] = __ldg(reinterpret_cast<const float2 *>(vp + ((size_t)vj * vw + vi) * VS));
+    }
+    if (vmiss) {
         atomicExch(overflow, 2);
         return;
     }
-    const float2 uv = __ldg(reinterpret_cast<const float2 *>(vp + ((size_t)vj * vw + vi) * VS));
-    const float xp = backtrace_coord((float)i, __fmul_rn(dt_over_viw, uv.x), fiw, rfiw);
-    const float yp = backtrace_coord((float)j, __fmul_rn(dt_over_vih, uv.y), fih, rfih);
-    const Bilinear b = make_bilinear(xp, yp, iw, ih);
+    Bilinear b[R];
+    const char *c0[R], *c1[R];
     bool miss = false;
-    const char *c0 = source_row_select(S, b.j0, &miss), *c1 = source_row_select(S, b.j1, &miss);
+#pragma unroll
+    for (int r = 0; r < R; r++) {
+        const float xp = backtrace_coord((float)i, __fmul_rn(dt_over_viw, uv[r].x), fiw, rfiw);
+        const float yp = backtrace_coord((float)(irow0 + jl[r]), __fmul_rn(dt_over_vih, uv[r].y), fih, rfih);
+        b[r] = make_bilinear(xp, yp, iw, ih);
+        c0[r] = source_row_select(S, b[r].j0, &miss);
+        c1[r] = source_row_select(S, b[r].j1, &miss);
+    }
     if (miss) {
         atomicExch(overflow, 3);
         return;
     }
-    const float4 *r0 = reinterpret_cast<const float4 *>(c0), *r1 = reinterpret_cast<const float4 *>(c1);
-    const float4 f00 = __ldg(r0 + b.i0), f10 = __ldg(r0 + b.i1), f01 = __ldg(r1 + b.i0), f11 = __ldg(r1 + b.i1);
-    float4 o;
-    o.x = bilerp(b, f00.x, f10.x, f01.x, f11.x);
-    o.y = bilerp(b, f00.y, f10.y, f01.y, f11.y);
-    o.z = bilerp(b, f00.z, f10.z, f01.z, f11.z);
-    o.w = bilerp(b, f00.w, f10.w, f01.w, f11.w);
-    out[(size_t)jl * iw + i] = o;
+    float4 f00[R], f10[R], f01[R], f11[R];
+#pragma unroll
+    for (int r = 0; r < R; r++) {
+        const float4 *q0 = reinterpret_cast<const float4 *>(c0[r]), *q1 = reinterpret_cast<const float4 *>(c1[r]);
+        f00[r] = __ldg(q0 + b[r].i0);
+        f10[r] = __ldg(q0 + b[r].i1);
+        f01[r] = __ldg(q1 + b[r].i0);
+        f11[r] = __ldg(q1 + b[r].i1);
+    }
+#pragma unroll
+    for (int r = 0; r < R; r++) {
+        float4 o;
+        o.x = bilerp(b[r], f00[r].x, f10[r].x, f01[r].x, f11[r].x);
+        o.y = bilerp(b[r], f00[r].y, f10[r].y, f01[r].y, f11[r].y);
+        o.z = bilerp(b[r], f00[r].z, f10[r].z, f01[r].z, f11[r].z);
+        o.w = bilerp(b[r], f00[r].w, f10[r].w, f01[r].w, f11[r].w);
+        if (live[r]) out[(size_t)jl[r] * iw + i] = o;
+    }
 }
 
 // ---- peer transport: halo rows stored straight into the ring neighbours' memory -------------------------------
@@ -1302,7 +1361,7 @@ int color_step(const std::vector<pfs_slab *> &L, float *const *image_in, float *
         int *flag = reinterpret_cast<int *>(s->d_scalars + (speculative ? 8 : 2));
         if (speculative) PFS_CUDA(cudaMemsetAsync(s->d_scalars + 8, 0, 2 * sizeof(float), s->stream));
         if (s->irows > 0) {
-            dim3 block(64, 4), grid((iw + 63) / 64, (s->irows + 3) / 4);
+            dim3 block(64, 4), grid((iw + 63) / 64, (s->irows + 4 * GATHER_ROWS - 1) / (4 * GATHER_ROWS));
             float4 *out = reinterpret_cast<float4 *>(image_out[k]);
             if (vs == 2)
                 PFS_LAUNCH(advect_color_slab_kernel<2>, grid, block, 0, s->stream, src[k], out, vel[k], dt_over_viw, dt_over_vih,
@@ -1518,7 +1577,7 @@ int fluid_step(const std::vector<pfs_slab *> &L, const StepIO &io, float dt, flo
             pfs_slab *s = L[k];
             Guard g(s->device);
             if (speculate) PFS_CUDA(cudaMemsetAsync(s->d_scalars + 4, 0, 3 * sizeof(float), s->stream));
-            dim3 block(64, 4), grid((gw + 63) / 64, (s->rows + 3) / 4);
+            dim3 block(64, 4), grid((gw + 63) / 64, (s->rows + 4 * GATHER_ROWS - 1) / (4 * GATHER_ROWS));
             float2 *dst = reinterpret_cast<float2 *>(s->plane(UV_A));
             int *flag = reinterpret_cast<int *>(s->d_scalars + (speculate ? 6 : 2));
             // max|v| of the field being advected: on resident state the project kernel of the step that produced the field
