@@ -219,8 +219,8 @@ int pfs_timestep_host(pfs_field *vp, pfs_field *vtmp, pfs_field *image, pfs_fiel
 /* Not on the reference's surface (the reference is single-device); same operators, same
  * results bit for bit.  Rank r of R owns a contiguous band of velocity rows and the band of image rows
  * whose velocity look-up (fluid.cpp:89-90) falls into it; the caller's interleaved buffers are split the
- * same way (band rows x width x 4 floats each).  Halo rows move between ring neighbours before every
- * fused pass (csrc/slab.cu).  Transports: NCCL, one process per GPU (pfs_slab_connect_nccl), or direct
+ * same way (band rows x width x 4 floats each).  32 halo rows move between ring neighbours about every 30 sweeps
+ * (a fused pass also recomputes the rows just outside its band, csrc/slab.cu).  Transports: NCCL, one process per GPU (pfs_slab_connect_nccl), or direct
  * copies between slabs living in one process on any devices (pfs_slab_connect_local). */
 typedef struct pfs_slab pfs_slab;
 /* Pure host arithmetic: the bands of rank `rank` (works without a GPU). */
