@@ -491,6 +491,7 @@ def run_single_gpu(args):
             traffic = None
     roofline = {"bound": "hbm", "kernel": dom, "achieved": kernels[dom]["achieved_gbs"], "peak": peak,
                 "unit": "GB/s", "frac": kernels[dom]["frac"], "traffic": traffic, "peak_source": peak_src,
+                "frac_of_nominal_8000_gbs": kernels[dom]["achieved_gbs"] / 8000.0,
                 "alg_bytes_per_launch": kernels[dom]["alg_bytes_per_launch"],
                 "avg_launch_ms": kernels[dom]["avg_launch_ms"],
                 "note": "algorithmic bytes give no credit for temporal blocking, so frac may exceed 1; measured DRAM bytes per launch are in "

@@ -292,7 +292,8 @@ def run(args, bench) -> None:
         if dom:
             roofline = {"bound": "hbm", "kernel": dom + " phase (fused passes + halo exchanges), per GPU",
                         "achieved": kernels[dom]["achieved_gbs"], "peak": peak, "unit": "GB/s", "frac": kernels[dom]["frac"],
-                        "traffic": None, "peak_source": peak_src}
+                        "traffic": None, "peak_source": peak_src,
+                        "frac_of_nominal_8000_gbs": kernels[dom]["achieved_gbs"] / 8000.0}
         step_bytes = (88 + 16 * n + 12 * n) * cells_local
         line = {"metric": bench.METRIC, "value": value, "unit": bench.UNIT, "n_gpus": world, "steps": args.steps,
                 "warmup": args.warmup, "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak",
